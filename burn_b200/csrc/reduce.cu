@@ -1,0 +1,737 @@
+// Path (b): axis / full reductions with a fuse-on-read prologue tape and a
+// fuse-on-write epilogue tape.
+//
+// Replaces reduce_kernel_fused (crates/burn-cubecl-fusion/src/optim/reduce/
+// optimization.rs:503) and the eager reduce entry points sum / reduce_dim
+// (crates/burn-cubecl/src/kernel/reduce/base.rs:108-150).  Semantics follow the
+// CPU oracle: keepdim outputs (crates/burn-ndarray/src/ops/macros.rs:1-60),
+// mean = sum / len, argmax/argmin = first extreme with first-NaN-wins
+// (crates/burn-ndarray/src/ops/base.rs:1715-1757), max/min propagate NaN
+// (default max_dim = gather(argmax), crates/burn-backend/src/backend/ops/tensor.rs:1609-1614).
+//
+// The input is viewed as [outer, R, inner] (R = reduced axis).  Three mappings:
+//   ROW_WARP  inner == 1, short rows : one warp per row, shuffle tree.
+//   ROW_CTA   inner == 1, long rows  : one CTA per (row, split); splits are
+//             combined by the last-arriving CTA (ticket), deterministically.
+//   COL       inner  > 1             : a CTA owns TX column-vectors x TY row
+//             groups; R is split across a thread-block cluster and the CTAs'
+//             partials are combined through distributed shared memory.
+// Roofline: HBM bandwidth; algorithmic bytes = input bytes + output bytes.
+#include <cooperative_groups.h>
+
+#include "tape_host.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace b200 {
+
+// from elemwise.cu (same translation-unit-local helpers re-declared here)
+__device__ __forceinline__ void r_cp_async_16(uint32_t smem_addr, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(g));
+}
+__device__ __forceinline__ void r_cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+struct Acc {
+  uint32_t v;  // f32 or i32 bits
+  int32_t i;   // index along the reduced axis (arg kinds)
+};
+
+struct ReduceParams {
+  TapeParams rd;  // fuse-on-read tape, geometry = input shape
+  TapeParams wr;  // fuse-on-write tape, geometry = output shape; INPUT(0) = reduced value
+  int32_t kind;
+  int32_t is_int;       // lanes are i32 (else f32)
+  uint32_t outer, R, inner;
+  uint32_t r_vec;       // R / VEC      (ROW mappings)
+  uint32_t inner_vec;   // inner / VEC  (COL mapping)
+  uint32_t splits;      // ROW_CTA: CTAs per row;  COL: cluster size along R
+  uint32_t rows_per_split;  // COL: rows of R per cluster rank; ROW_CTA: vectors per split
+  Acc *partials;        // ROW_CTA with splits > 1
+  uint32_t *tickets;
+  float mean_div;       // (float)R
+};
+
+// ----------------------------------------------------------------- combine
+__device__ __forceinline__ Acc acc_identity(int kind, int is_int) {
+  Acc a;
+  a.i = 0x7fffffff;
+  switch (kind) {
+    case B200_RED_SUM: case B200_RED_MEAN: case B200_RED_ANY: a.v = 0u; break;  // 0.0f == 0
+    case B200_RED_PROD: a.v = is_int ? 1u : u_of(1.0f); break;
+    case B200_RED_ALL: a.v = 1u; break;
+    case B200_RED_MAX: case B200_RED_ARGMAX:
+      a.v = is_int ? 0x80000000u : u_of(-INFINITY); break;
+    case B200_RED_MIN: case B200_RED_ARGMIN:
+      a.v = is_int ? 0x7fffffffu : u_of(INFINITY); break;
+    case B200_RED_MAXABS: a.v = 0u; break;
+    default: a.v = 0u; break;
+  }
+  return a;
+}
+
+// Element → accumulator domain (ANY/ALL test non-zero; MAXABS takes |x|).
+__device__ __forceinline__ uint32_t acc_map(int kind, int is_int, uint32_t x) {
+  switch (kind) {
+    case B200_RED_ANY: case B200_RED_ALL:
+      return is_int ? (x != 0u) : (f_of(x) != 0.0f);
+    case B200_RED_MAXABS:
+      return is_int ? (uint32_t)abs((int32_t)x) : (x & 0x7fffffffu);
+    default: return x;
+  }
+}
+
+// Associative, commutative combine — safe for any tree shape.
+__device__ __forceinline__ Acc acc_combine(int kind, int is_int, Acc a, Acc b) {
+  Acc r = a;
+  switch (kind) {
+    case B200_RED_SUM: case B200_RED_MEAN:
+      r.v = is_int ? a.v + b.v : u_of(__fadd_rn(f_of(a.v), f_of(b.v)));
+      break;
+    case B200_RED_PROD:
+      r.v = is_int ? a.v * b.v : u_of(__fmul_rn(f_of(a.v), f_of(b.v)));
+      break;
+    case B200_RED_ANY: r.v = a.v | b.v; break;
+    case B200_RED_ALL: r.v = a.v & b.v; break;
+    case B200_RED_MAX: case B200_RED_MAXABS: case B200_RED_MIN: {
+      const bool is_min = kind == B200_RED_MIN;
+      if (is_int) {
+        const int32_t x = (int32_t)a.v, y = (int32_t)b.v;
+        r.v = (uint32_t)(is_min ? min(x, y) : max(x, y));
+      } else {
+        const float x = f_of(a.v), y = f_of(b.v);
+        if (x != x) r.v = a.v;
+        else if (y != y) r.v = b.v;
+        else r.v = u_of(is_min ? fminf(x, y) : fmaxf(x, y));
+      }
+      break;
+    }
+    case B200_RED_ARGMAX: case B200_RED_ARGMIN: {
+      const bool is_min = kind == B200_RED_ARGMIN;
+      bool take_b;
+      if (is_int) {
+        const int32_t x = (int32_t)a.v, y = (int32_t)b.v;
+        take_b = is_min ? (y < x) : (y > x);
+        take_b = take_b || (y == x && b.i < a.i);
+      } else {
+        const float x = f_of(a.v), y = f_of(b.v);
+        const bool xn = x != x, yn = y != y;
+        if (xn || yn) {
+          take_b = yn && (!xn || b.i < a.i);
+        } else {
+          take_b = is_min ? (y < x) : (y > x);
+          take_b = take_b || (y == x && b.i < a.i);
+        }
+      }
+      if (take_b) r = b;
+      break;
+    }
+    default: break;
+  }
+  return r;
+}
+
+__device__ __forceinline__ Acc acc_shfl_xor(Acc a, int m) {
+  Acc r;
+  r.v = __shfl_xor_sync(0xffffffffu, a.v, m);
+  r.i = __shfl_xor_sync(0xffffffffu, a.i, m);
+  return r;
+}
+
+__device__ __forceinline__ Acc warp_reduce(int kind, int is_int, Acc a) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) a = acc_combine(kind, is_int, a, acc_shfl_xor(a, m));
+  return a;
+}
+
+// ----------------------------------------------------------------- tile IO
+__device__ __forceinline__ int64_t r_operand_offset(const OperandDesc &d, int rank,
+                                                    const uint32_t (&coord)[kMaxDims]) {
+  int64_t off = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxDims; ++k)
+    if (k < rank) off += (int64_t)coord[k] * d.strides[k];
+  return off;
+}
+
+template <int VEC, int U>
+__device__ __forceinline__ void load_inputs(const TapeParams &p, const SlotFile<VEC, U> &slots,
+                                            const uint32_t (&coord)[U][kMaxDims],
+                                            const bool (&ok)[U]) {
+  for (int k = 0; k < p.n_in; ++k) {
+    const OperandDesc &d = p.in[k];
+    if (VEC == 4 && d.mode == kModeVec && (d.dtype == B200_F32 || d.dtype == B200_I32)) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const int64_t off = r_operand_offset(d, p.rank, coord[u]);
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(
+            slots.base + (size_t)(k * U + u) * kTapeBlock * 4);
+        r_cp_async_16(sa, reinterpret_cast<const uint32_t *>(d.ptr) + off);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        uint32_t r[VEC];
+        if (ok[u]) {
+          load_operand<VEC>(d, p.rank, coord[u], r);
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) r[j] = 0;
+        }
+        slots.put(k, u, r);
+      }
+    }
+  }
+  if constexpr (VEC == 4) r_cp_async_wait_all();
+}
+
+// Evaluates the read tape for U vectors and leaves the values in `val`.
+template <int VEC, int U>
+__device__ __forceinline__ void eval_read(const ReduceParams &P, const SlotFile<VEC, U> &slots,
+                                          const uint32_t (&vidx)[U], const bool (&ok)[U],
+                                          uint32_t (&val)[U][VEC]) {
+  uint32_t coord[U][kMaxDims];
+#pragma unroll
+  for (int u = 0; u < U; ++u) vec_coords<VEC>(P.rd, ok[u] ? vidx[u] : 0u, coord[u]);
+  load_inputs<VEC, U>(P.rd, slots, coord, ok);
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) val[u][j] = 0;
+  run_tape<VEC, U>(P.rd, slots, val, [&](int o, const uint32_t(&x)[U][VEC]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (ok[u]) store_operand<VEC>(P.rd.out[o], P.rd.rank, coord[u], x[u]);
+  });
+}
+
+// Applies mean division, runs the write tape and stores VECW consecutive outputs
+// starting at output vector index `ovec`.
+template <int VECW>
+__device__ __forceinline__ void finalize(const ReduceParams &P, uint32_t *wr_smem, uint32_t ovec,
+                                         const Acc (&a)[VECW]) {
+  const SlotFile<VECW, 1> slots = make_slots<VECW, 1>(wr_smem, threadIdx.x);
+  uint32_t red[VECW];
+  const bool is_arg = P.kind == B200_RED_ARGMAX || P.kind == B200_RED_ARGMIN;
+#pragma unroll
+  for (int j = 0; j < VECW; ++j) {
+    uint32_t v = is_arg ? (uint32_t)a[j].i : a[j].v;
+    if (P.kind == B200_RED_MEAN)
+      v = P.is_int ? (uint32_t)((int32_t)v / (int32_t)P.R) : u_of(__fdiv_rn(f_of(v), P.mean_div));
+    red[j] = v;
+  }
+  uint32_t coord[kMaxDims];
+  vec_coords<VECW>(P.wr, ovec, coord);
+  slots.put(0, 0, red);
+  for (int k = 1; k < P.wr.n_in; ++k) {
+    uint32_t r[VECW];
+    load_operand<VECW>(P.wr.in[k], P.wr.rank, coord, r);
+    slots.put(k, 0, r);
+  }
+  uint32_t acc[1][VECW];
+#pragma unroll
+  for (int j = 0; j < VECW; ++j) acc[0][j] = red[j];
+  run_tape<VECW, 1>(P.wr, slots, acc, [&](int o, const uint32_t(&x)[1][VECW]) {
+    store_operand<VECW>(P.wr.out[o], P.wr.rank, coord, x[0]);
+  });
+}
+
+// Folds the VEC lanes of U vectors of a ROW mapping into one Acc.
+template <int VEC, int U>
+__device__ __forceinline__ Acc fold_row(const ReduceParams &P, Acc a, const uint32_t (&val)[U][VEC],
+                                        const uint32_t (&ridx)[U], const bool (&ok)[U]) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (!ok[u]) continue;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      Acc e;
+      e.v = acc_map(P.kind, P.is_int, val[u][j]);
+      e.i = (int32_t)(ridx[u] * VEC + j);
+      a = acc_combine(P.kind, P.is_int, a, e);
+    }
+  }
+  return a;
+}
+
+constexpr int kWarps = kTapeBlock / 32;
+
+// ----------------------------------------------------------------- ROW_WARP
+template <int VEC, int U>
+__global__ void __launch_bounds__(kTapeBlock)
+reduce_row_warp_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const SlotFile<VEC, U> slots = make_slots<VEC, U>(smem, threadIdx.x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_rows = P.outer;
+  for (uint32_t row = blockIdx.x * kWarps + warp; row < n_rows; row += gridDim.x * kWarps) {
+    Acc a = acc_identity(P.kind, P.is_int);
+    for (uint32_t base = 0; base < P.r_vec; base += 32 * U) {
+      uint32_t vidx[U], ridx[U];
+      bool ok[U];
+      uint32_t val[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ridx[u] = base + u * 32 + lane;
+        ok[u] = ridx[u] < P.r_vec;
+        vidx[u] = row * P.r_vec + ridx[u];
+      }
+      eval_read<VEC, U>(P, slots, vidx, ok, val);
+      a = fold_row<VEC, U>(P, a, val, ridx, ok);
+    }
+    a = warp_reduce(P.kind, P.is_int, a);
+    if (lane == 0) {
+      const Acc one[1] = {a};
+      finalize<1>(P, smem + rd_words, row, one);
+    }
+    __syncwarp();
+  }
+}
+
+// ----------------------------------------------------------------- ROW_CTA
+__device__ __forceinline__ Acc block_reduce(int kind, int is_int, Acc a, Acc *scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a = warp_reduce(kind, is_int, a);
+  __syncthreads();  // scratch reuse across calls
+  if (lane == 0) scratch[warp] = a;
+  __syncthreads();
+  Acc r = (lane < kWarps) ? scratch[lane] : acc_identity(kind, is_int);
+  r = warp_reduce(kind, is_int, r);
+  return r;  // valid in every thread of warp 0 (and all warps, same data)
+}
+
+template <int VEC, int U>
+__global__ void __launch_bounds__(kTapeBlock)
+reduce_row_cta_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words, uint32_t slot_words) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const SlotFile<VEC, U> slots = make_slots<VEC, U>(smem, threadIdx.x);
+  Acc *scratch = reinterpret_cast<Acc *>(smem + slot_words);
+  __shared__ uint32_t s_last;
+  const uint32_t n_work = P.outer * P.splits;
+  for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const uint32_t row = w / P.splits, split = w - row * P.splits;
+    const uint32_t begin = split * P.rows_per_split;
+    const uint32_t end = min(P.r_vec, begin + P.rows_per_split);
+    Acc a = acc_identity(P.kind, P.is_int);
+    for (uint32_t base = begin; base < end; base += kTapeBlock * U) {
+      uint32_t vidx[U], ridx[U];
+      bool ok[U];
+      uint32_t val[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ridx[u] = base + u * kTapeBlock + threadIdx.x;
+        ok[u] = ridx[u] < end;
+        vidx[u] = row * P.r_vec + ridx[u];
+      }
+      eval_read<VEC, U>(P, slots, vidx, ok, val);
+      a = fold_row<VEC, U>(P, a, val, ridx, ok);
+    }
+    a = block_reduce(P.kind, P.is_int, a, scratch);
+    if (P.splits == 1) {
+      if (threadIdx.x == 0) {
+        const Acc one[1] = {a};
+        finalize<1>(P, smem + rd_words, row, one);
+      }
+    } else {
+      if (threadIdx.x == 0) {
+        P.partials[(size_t)row * P.splits + split] = a;
+        __threadfence();
+        const uint32_t t = atomicAdd(&P.tickets[row], 1u);
+        s_last = (t == P.splits - 1) ? 1u : 0u;
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        Acc b = acc_identity(P.kind, P.is_int);
+        for (uint32_t s = threadIdx.x; s < P.splits; s += kTapeBlock) {
+          const uint2 raw = __ldcg(reinterpret_cast<const uint2 *>(&P.partials[(size_t)row * P.splits + s]));
+          Acc e;
+          e.v = raw.x;
+          e.i = (int32_t)raw.y;
+          b = acc_combine(P.kind, P.is_int, b, e);
+        }
+        b = block_reduce(P.kind, P.is_int, b, scratch);
+        if (threadIdx.x == 0) {
+          const Acc one[1] = {b};
+          finalize<1>(P, smem + rd_words, row, one);
+          P.tickets[row] = 0u;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------- COL
+// blockDim = (TX, TY): TX column-vectors x TY row groups.  gridDim = (col tiles,
+// splits) with cluster dims (1, splits, 1).
+template <int VEC, int U>
+__global__ void __launch_bounds__(kTapeBlock)
+reduce_col_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words, uint32_t slot_words) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  // slot file indexed by flat thread id
+  SlotFile<VEC, U> slots;
+  slots.base = smem + (VEC == 4 ? tid * 4 : tid);
+  Acc *scratch = reinterpret_cast<Acc *>(smem + slot_words);  // [TY][TX][VEC], then cta result [TX][VEC]
+
+  const uint32_t TX = blockDim.x, TY = blockDim.y;
+  const uint32_t tiles_per_outer = (P.inner_vec + TX - 1) / TX;
+  const uint32_t o = blockIdx.x / tiles_per_outer;
+  const uint32_t cvec = (blockIdx.x - o * tiles_per_outer) * TX + threadIdx.x;
+  const bool col_ok = cvec < P.inner_vec;
+  const uint32_t split = blockIdx.y;
+  const uint32_t r_begin = split * P.rows_per_split;
+  const uint32_t r_end = min(P.R, r_begin + P.rows_per_split);
+
+  Acc a[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) a[j] = acc_identity(P.kind, P.is_int);
+
+  for (uint32_t base = r_begin; base < r_end; base += TY * U) {
+    uint32_t vidx[U], r[U];
+    bool ok[U];
+    uint32_t val[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      r[u] = base + u * TY + threadIdx.y;
+      ok[u] = col_ok && r[u] < r_end;
+      vidx[u] = (o * P.R + r[u]) * P.inner_vec + cvec;
+    }
+    eval_read<VEC, U>(P, slots, vidx, ok, val);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        Acc e;
+        e.v = acc_map(P.kind, P.is_int, val[u][j]);
+        e.i = (int32_t)r[u];
+        a[j] = acc_combine(P.kind, P.is_int, a[j], e);
+      }
+    }
+  }
+
+  // combine the TY row groups through shared memory (fixed order)
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) scratch[(threadIdx.y * TX + threadIdx.x) * VEC + j] = a[j];
+  __syncthreads();
+  Acc *cta_result = scratch + TY * TX * VEC;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      Acc b = scratch[threadIdx.x * VEC + j];
+      for (uint32_t y = 1; y < TY; ++y)
+        b = acc_combine(P.kind, P.is_int, b, scratch[(y * TX + threadIdx.x) * VEC + j]);
+      a[j] = b;
+      cta_result[threadIdx.x * VEC + j] = b;
+    }
+  }
+
+  if (P.splits > 1) {
+    // cross-CTA combine over distributed shared memory
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (cluster.block_rank() == 0 && threadIdx.y == 0) {
+      for (uint32_t rk = 1; rk < P.splits; ++rk) {
+        const Acc *remote = cluster.map_shared_rank(cta_result, rk);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          a[j] = acc_combine(P.kind, P.is_int, a[j], remote[threadIdx.x * VEC + j]);
+      }
+    }
+    cluster.sync();  // keep remote smem alive until rank 0 has read it
+    if (cluster.block_rank() != 0) return;
+  }
+  if (threadIdx.y == 0 && col_ok) finalize<VEC>(P, smem + rd_words, o * P.inner_vec + cvec, a);
+}
+
+// ----------------------------------------------------------------- host planning
+struct ReducePlan {
+  ReduceParams P;
+  int vec;
+  bool col;
+};
+
+static int32_t plan_side(const b200_tape *tape, const b200_tensor *ins, int n_ins,
+                         const b200_tensor *outs, int n_outs, int rank, const int64_t *shape,
+                         bool first_input_virtual, TapeParams &tp,
+                         std::vector<PlannedOperand> &planned, CollapsedLayout &L) {
+  int32_t st = plan_tape(tape, n_ins + (first_input_virtual ? 1 : 0), n_outs, tp);
+  if (st != B200_OK) return st;
+  planned.assign(n_ins + n_outs, PlannedOperand{});
+  std::vector<PlannedOperand *> all;
+  for (int i = 0; i < n_ins; ++i) {
+    st = broadcast_operand(ins[i], rank, shape, "reduce input", i, planned[i]);
+    if (st != B200_OK) return st;
+    all.push_back(&planned[i]);
+  }
+  for (int i = 0; i < n_outs; ++i) {
+    st = broadcast_operand(outs[i], rank, shape, "reduce output", i, planned[n_ins + i]);
+    if (st != B200_OK) return st;
+    for (int d = 0; d < rank; ++d)
+      B200_REQUIRE(outs[i].shape[d] == shape[d], B200_ERR_SHAPE,
+                   "reduce output %d: dim %d is %lld, expected %lld", i, d,
+                   (long long)outs[i].shape[d], (long long)shape[d]);
+    all.push_back(&planned[n_ins + i]);
+  }
+  L = collapse_dims(rank, shape, all);
+  return B200_OK;
+}
+
+static void fill_side(TapeParams &tp, const std::vector<PlannedOperand> &planned, int n_ins,
+                      int n_outs, const CollapsedLayout &L, int vec, bool first_input_virtual) {
+  fill_geometry(tp, L, vec);
+  const int shift = first_input_virtual ? 1 : 0;
+  if (first_input_virtual) {
+    memset(&tp.in[0], 0, sizeof(OperandDesc));
+    tp.in[0].mode = kModeGather;
+  }
+  for (int i = 0; i < n_ins; ++i) fill_desc(tp.in[i + shift], planned[i], L.rank, vec);
+  for (int i = 0; i < n_outs; ++i) {
+    fill_desc(tp.out[i], planned[n_ins + i], L.rank, vec);
+    if (tp.out[i].mode == kModeBcast) tp.out[i].mode = kModeGather;
+  }
+}
+
+static bool is_int_dtype(int32_t dt) {
+  return dt == B200_I32 || dt == B200_I64 || dt == B200_BOOL || dt == B200_U8;
+}
+
+// Core entry: the input shape is `shape` (rank dims); dims [ax_begin, ax_end) are
+// reduced together (ax_end - ax_begin == 1 for an axis reduce; the whole range
+// for a full reduce, which requires it to be all dims).
+static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_begin, int ax_end,
+                           const b200_tape *read, const b200_tensor *inputs, int n_inputs,
+                           const b200_tape *write, const b200_tensor *write_inputs,
+                           int n_write_inputs, const b200_tensor *outputs, int n_outputs,
+                           const int64_t *out_shape, int out_rank, int32_t value_is_int,
+                           b200_stream s) {
+  B200_REQUIRE(kind >= B200_RED_SUM && kind <= B200_RED_ALL, B200_ERR_INVALID, "bad reduce kind %d", kind);
+  int64_t outer = 1, R = 1, inner = 1;
+  for (int d = 0; d < ax_begin; ++d) outer *= shape[d];
+  for (int d = ax_begin; d < ax_end; ++d) R *= shape[d];
+  for (int d = ax_end; d < rank; ++d) inner *= shape[d];
+  const int64_t numel = outer * R * inner;
+  B200_REQUIRE(numel < (1ll << 31), B200_ERR_UNSUPPORTED, "reduce over %lld elements exceeds 2^31", (long long)numel);
+  const bool is_arg = kind == B200_RED_ARGMAX || kind == B200_RED_ARGMIN;
+  if (is_arg) B200_REQUIRE(R > 0, B200_ERR_SHAPE, "Cannot compute arg over an empty axis");
+  if (outer * inner == 0) return B200_OK;
+
+  ReducePlan plan;
+  ReduceParams &P = plan.P;
+  memset(&P, 0, sizeof(P));
+
+  // ---- read side
+  b200_tape_op mov_in = {B200_OP_MOV, (uint8_t)B200_ARG_INPUT(0), 0, 0, B200_DST_NONE, B200_DST_NONE, {0, 0}};
+  b200_tape default_read = {&mov_in, 1, nullptr, 0};
+  if (!read) {
+    B200_REQUIRE(n_inputs == 1, B200_ERR_INVALID, "a reduce without a read tape takes exactly one input");
+    read = &default_read;
+  }
+  // outputs of the read tape are not supported through this entry (n_out = 0)
+  std::vector<PlannedOperand> rd_planned;
+  CollapsedLayout rdL;
+  int32_t st = plan_side(read, inputs, n_inputs, nullptr, 0, rank, shape, false, P.rd, rd_planned, rdL);
+  if (st != B200_OK) return st;
+
+  // ---- write side
+  b200_tape_op mov_out = {B200_OP_MOV, (uint8_t)B200_ARG_INPUT(0), 0, 0, B200_DST_NONE, 0, {0, 0}};
+  b200_tape default_write = {&mov_out, 1, nullptr, 0};
+  if (!write) {
+    B200_REQUIRE(n_outputs == 1, B200_ERR_INVALID, "a reduce without a write tape has exactly one output");
+    write = &default_write;
+  }
+  std::vector<PlannedOperand> wr_planned;
+  CollapsedLayout wrL;
+  st = plan_side(write, write_inputs, n_write_inputs, outputs, n_outputs, out_rank, out_shape, true,
+                 P.wr, wr_planned, wrL);
+  if (st != B200_OK) return st;
+
+  // ---- mapping
+  const bool col = inner > 1;
+  int vec = 4;
+  if (rdL.shape[rdL.rank - 1] % 4 != 0) vec = 1;
+  if (col ? (inner % 4 != 0) : (R % 4 != 0)) vec = 1;
+  int vecw = 1;
+  if (col && vec == 4 && wrL.shape[wrL.rank - 1] % 4 == 0) vecw = 4;
+  if (col && vec == 4 && vecw != 4) vec = 1;  // keep read/write lane counts equal in COL
+  fill_side(P.rd, rd_planned, n_inputs, 0, rdL, vec, false);
+  fill_side(P.wr, wr_planned, n_write_inputs, n_outputs, wrL, col ? vec : 1, true);
+  P.rd.n_vec = (uint32_t)(numel / vec);
+  P.wr.n_vec = (uint32_t)(outer * inner / (col ? vec : 1));
+  P.kind = kind;
+  P.is_int = value_is_int;
+  P.outer = (uint32_t)outer;
+  P.R = (uint32_t)R;
+  P.inner = (uint32_t)inner;
+  P.r_vec = (uint32_t)(R / vec);
+  P.inner_vec = (uint32_t)(inner / vec);
+  P.mean_div = (float)R;
+  P.splits = 1;
+
+  cudaStream_t stream = resolve_stream(s);
+  const int sms = sm_count();
+  const int U = (vec == 4) ? 2 : 4;
+  const size_t rd_slots = slot_file_bytes(std::max(1, P.rd.n_in + P.rd.n_tmp), vec, U);
+  const size_t wr_slots = slot_file_bytes(std::max(1, P.wr.n_in + P.wr.n_tmp), col ? vec : 1, 1);
+  const size_t slot_bytes = rd_slots + wr_slots;
+  const uint32_t rd_words = (uint32_t)(rd_slots / 4);
+  const uint32_t slot_words = (uint32_t)(slot_bytes / 4);
+
+  if (R == 0) {
+    // empty axis: identity (sum → 0, prod → 1, mean → NaN like 0/0)
+    // handled by running the kernels with zero iterations.
+  }
+
+  if (!col) {
+    const uint32_t n_rows = P.outer;
+    const bool warp_rows = (P.r_vec <= 32u * U * 4u) && n_rows >= (uint32_t)(sms * kWarps);
+    if (warp_rows) {
+      const size_t smem = slot_bytes;
+      auto launch = [&](auto kern) -> int32_t {
+        if (smem > 48 * 1024)
+          B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTapeBlock, smem));
+        per_sm = std::max(per_sm, 1);
+        const uint32_t need = (n_rows + kWarps - 1) / kWarps;
+        const unsigned grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)(sms * per_sm)));
+        kern<<<grid, kTapeBlock, smem, stream>>>(P, rd_words);
+        B200_LAUNCH_CHECK();
+        return B200_OK;
+      };
+      return vec == 4 ? launch(reduce_row_warp_kernel<4, 2>) : launch(reduce_row_warp_kernel<1, 4>);
+    }
+    // CTA per (row, split)
+    const size_t smem = slot_bytes + sizeof(Acc) * kWarps;
+    const uint32_t tile = kTapeBlock * U;
+    uint32_t splits = 1;
+    const uint32_t target = (uint32_t)sms * 4u;
+    if (n_rows < target && P.r_vec > tile * 8u) {
+      splits = std::min<uint32_t>((target + n_rows - 1) / n_rows, (P.r_vec + tile * 4u - 1) / (tile * 4u));
+      splits = std::max(1u, std::min(splits, 1024u));
+    }
+    uint32_t per_split = (P.r_vec + splits - 1) / splits;
+    per_split = ((per_split + tile - 1) / tile) * tile;
+    if (per_split == 0) per_split = tile;
+    splits = std::max(1u, (P.r_vec + per_split - 1) / per_split);
+    P.splits = splits;
+    P.rows_per_split = per_split;
+    void *ws = nullptr;
+    if (splits > 1) {
+      const size_t pbytes = sizeof(Acc) * (size_t)n_rows * splits;
+      const size_t tbytes = sizeof(uint32_t) * (size_t)n_rows;
+      B200_CUDA(cudaMallocAsync(&ws, pbytes + tbytes, stream));
+      P.partials = reinterpret_cast<Acc *>(ws);
+      P.tickets = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(ws) + pbytes);
+      B200_CUDA(cudaMemsetAsync(P.tickets, 0, tbytes, stream));
+    }
+    auto launch = [&](auto kern) -> int32_t {
+      if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTapeBlock, smem));
+      per_sm = std::max(per_sm, 1);
+      const uint64_t work = (uint64_t)n_rows * splits;
+      const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(work, (uint64_t)sms * per_sm));
+      kern<<<grid, kTapeBlock, smem, stream>>>(P, rd_words, slot_words);
+      B200_LAUNCH_CHECK();
+      return B200_OK;
+    };
+    st = vec == 4 ? launch(reduce_row_cta_kernel<4, 2>) : launch(reduce_row_cta_kernel<1, 4>);
+    if (ws) cudaFreeAsync(ws, stream);
+    return st;
+  }
+
+  // ---- COL mapping
+  uint32_t TX = 32;
+  uint32_t tiles = P.outer * ((P.inner_vec + TX - 1) / TX);
+  if (tiles * 8u < (uint32_t)sms && P.inner_vec > 8) {
+    TX = 8;
+    tiles = P.outer * ((P.inner_vec + TX - 1) / TX);
+  }
+  const uint32_t TY = kTapeBlock / TX;
+  uint32_t splits = 1;
+  const uint32_t target = (uint32_t)sms * 4u;
+  while (splits < 8 && tiles * splits < target && P.R / (splits * 2) >= TY * (uint32_t)U * 2u) splits *= 2;
+  P.splits = splits;
+  P.rows_per_split = (P.R + splits - 1) / splits;
+  const size_t scratch = sizeof(Acc) * (size_t)(TY * TX * vec + TX * vec);
+  const size_t smem = slot_bytes + scratch;
+
+  auto launch = [&](auto kern) -> int32_t {
+    if (smem > 48 * 1024)
+      B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(tiles, splits, 1);
+    cfg.blockDim = dim3(TX, TY, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = splits;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, P, rd_words, slot_words));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  };
+  return vec == 4 ? launch(reduce_col_kernel<4, 2>) : launch(reduce_col_kernel<1, 4>);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int32_t b200_launch_reduce(int32_t kind, int32_t axis, int32_t rank,
+                                      const int64_t *in_shape, const b200_tape *read,
+                                      const b200_tensor *inputs, int32_t n_inputs,
+                                      const b200_tape *write, const b200_tensor *write_inputs,
+                                      int32_t n_write_inputs, const b200_tensor *outputs,
+                                      int32_t n_outputs, b200_stream s) {
+  B200_REQUIRE(rank >= 1 && rank <= B200_MAX_RANK, B200_ERR_INVALID, "rank %d out of range", rank);
+  B200_REQUIRE(in_shape && inputs && outputs, B200_ERR_INVALID, "null argument");
+  B200_REQUIRE(n_inputs >= 1 && n_outputs >= 1, B200_ERR_INVALID, "reduce needs >=1 input and output");
+  B200_REQUIRE(axis >= 0 && axis < rank, B200_ERR_SHAPE, "reduce axis %d out of range for rank %d", axis, rank);
+  int64_t out_shape[B200_MAX_RANK];
+  for (int d = 0; d < rank; ++d) out_shape[d] = in_shape[d];
+  out_shape[axis] = 1;
+  // The reduced lanes are int when the value feeding the reduce is int: decided by
+  // the dtype of input 0 when there is no read tape, else by the last read op.
+  int32_t is_int = is_int_dtype(inputs[0].dtype);
+  if (read && read->n_ops > 0) {
+    const int op = read->ops[read->n_ops - 1].op;
+    if (op == B200_OP_MOV || op == B200_OP_SELECT) {
+      // keeps the class of its source; approximate with input 0
+    } else {
+      is_int = (op >= B200_OP_EQ_F && op <= B200_OP_ISINF_F) || (op >= B200_OP_ADD_I && op <= B200_OP_NOT_B) ||
+               op == B200_OP_F2I || op == B200_OP_B2I || op == B200_OP_F2B || op == B200_OP_I2B;
+    }
+  }
+  return reduce_impl(kind, rank, in_shape, axis, axis + 1, read, inputs, n_inputs, write,
+                     write_inputs, n_write_inputs, outputs, n_outputs, out_shape, rank, is_int, s);
+}
+
+extern "C" int32_t b200_launch_reduce_full(int32_t kind, const b200_tensor *input,
+                                           const b200_tensor *output, b200_stream s) {
+  B200_REQUIRE(input && output, B200_ERR_INVALID, "null argument");
+  B200_REQUIRE(input->rank >= 1 && input->rank <= B200_MAX_RANK, B200_ERR_INVALID, "bad rank");
+  B200_REQUIRE(kind != B200_RED_ARGMAX && kind != B200_RED_ARGMIN, B200_ERR_UNSUPPORTED,
+               "full arg reductions are expressed as reshape + axis reduce");
+  B200_REQUIRE(numel_of(output->shape, output->rank) == 1, B200_ERR_SHAPE,
+               "full reduce output must hold exactly one element");
+  b200_tensor out1 = *output;
+  out1.rank = 1;
+  out1.shape[0] = 1;
+  out1.strides[0] = 1;
+  const int64_t one = 1;
+  return reduce_impl(kind, input->rank, input->shape, 0, input->rank, nullptr, input, 1, nullptr,
+                     nullptr, 0, &out1, 1, &one, 1, is_int_dtype(input->dtype), s);
+}

@@ -1,0 +1,353 @@
+/*
+ * burn_b200.h — C ABI of libburn_b200.so, the sm_100a CUDA library behind the
+ * `burn-b200` backend (Burn `Backend` trait + burn-fusion `FusionRuntime`).
+ *
+ * This is the drop-in boundary: every entry point below is what the Rust crate
+ * `crates/burn-b200` binds with `extern "C"` (see INTEGRATION.md for the Rust
+ * declarations).  Signatures carry only plain pointers, sizes and PODs.  Each
+ * entry point cites the reference interface it serves (paths relative to the
+ * tracel-ai/burn tree, version 0.22.0-pre.2).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative b200_status otherwise;
+ *    b200_last_error() returns a thread-local message.  The Rust shim turns a
+ *    non-zero status into panic!/ExecutionError exactly where the reference
+ *    panics (crates/burn-backend/src/backend/ops/tensor.rs — shape/dtype errors
+ *    panic; only sync / into_data return Result).
+ *  - tensors are described by b200_tensor: device pointer, dtype, rank, shape
+ *    and strides IN ELEMENTS (stride 0 = broadcast).  This mirrors
+ *    CubeTensor{handle, meta(shape+strides), dtype}
+ *    (crates/burn-cubecl/src/tensor/base.rs:20-33).
+ *  - all launches are asynchronous on the given b200_stream (NULL = the
+ *    library's per-device default stream).
+ *  - there is no CPU fallback anywhere in this library.
+ */
+#ifndef BURN_B200_H
+#define BURN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+#define B200_MAX_RANK 8
+#define B200_MAX_TAPE_OPS 64     /* crates/burn-cubecl-fusion/src/engine/fuser.rs:857 */
+#define B200_MAX_TAPE_INPUTS 12
+#define B200_MAX_TAPE_OUTPUTS 8
+#define B200_MAX_TAPE_TEMPS 8
+#define B200_MAX_TAPE_SCALARS 32
+
+typedef enum {
+  B200_OK = 0,
+  B200_ERR_CUDA = -1,        /* a CUDA runtime/driver call failed */
+  B200_ERR_INVALID = -2,     /* bad argument (rank, dtype, null pointer …) */
+  B200_ERR_SHAPE = -3,       /* shape mismatch — the reference panics here */
+  B200_ERR_UNSUPPORTED = -4, /* valid request this library does not implement */
+  B200_ERR_NCCL = -5,
+  B200_ERR_NO_DEVICE = -6
+} b200_status;
+
+/* DType subset of crates/burn-std/src/tensor/dtype.rs:10-26.  Bool is stored as
+ * one byte per element (BoolStore::U8 — the CUDA default,
+ * crates/burn-backend/src/lib.rs:98-107). */
+typedef enum {
+  B200_F32 = 0,
+  B200_F16 = 1,
+  B200_BF16 = 2,
+  B200_I32 = 3,
+  B200_I64 = 4,
+  B200_BOOL = 5, /* u8, 0 or 1 */
+  B200_U8 = 6,
+  B200_DTYPE_COUNT = 7
+} b200_dtype;
+
+typedef struct {
+  void *ptr;
+  int32_t dtype; /* b200_dtype */
+  int32_t rank;
+  int64_t shape[B200_MAX_RANK];
+  int64_t strides[B200_MAX_RANK]; /* in elements; 0 = broadcast */
+} b200_tensor;
+
+typedef void *b200_stream; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ runtime */
+/* Backend::{name, device_count, sync, seed, memory_cleanup}
+ * (crates/burn-backend/src/backend/base.rs:112-250). */
+int32_t b200_abi_version(void);
+int32_t b200_device_count(int32_t *count);
+int32_t b200_init(int32_t device);              /* idempotent; selects device */
+int32_t b200_set_device(int32_t device);
+int32_t b200_device_info(int32_t device, int32_t *sm_count, int32_t *cc_major,
+                         int32_t *cc_minor, uint64_t *total_mem);
+int32_t b200_stream_create(b200_stream *out, int32_t high_priority);
+int32_t b200_stream_destroy(b200_stream s);
+int32_t b200_stream_sync(b200_stream s);        /* Backend::sync */
+int32_t b200_device_sync(void);
+const char *b200_last_error(void);
+/* CUDA events on the launching stream — what bench.py times kernels with. */
+typedef void *b200_event;
+int32_t b200_event_create(b200_event *out);
+int32_t b200_event_destroy(b200_event e);
+int32_t b200_event_record(b200_event e, b200_stream s);
+int32_t b200_event_elapsed_ms(b200_event start, b200_event stop, float *ms); /* syncs on stop */
+
+/* Stream-ordered caching allocator (cudaMallocAsync pool, never trimmed until
+ * b200_memory_cleanup).  Replaces cubecl's memory pools behind
+ * CubeTensor::handle; b200_retain/b200_free give the refcount semantics of
+ * Handle::can_mut (crates/burn-ir/src/handle.rs:92-111). */
+int32_t b200_alloc(void **out, uint64_t bytes, b200_stream s);
+int32_t b200_free(void *ptr, b200_stream s);
+int32_t b200_memory_cleanup(void);
+int32_t b200_memset(void *ptr, int32_t byte, uint64_t bytes, b200_stream s);
+
+/* float_from_data / float_into_data / float_to_device
+ * (crates/burn-backend/src/backend/ops/tensor.rs:25,109,123).  Host buffers
+ * may be pageable; pinned buffers (b200_host_alloc) make the copy truly async. */
+int32_t b200_host_alloc(void **out, uint64_t bytes);
+int32_t b200_host_free(void *ptr);
+int32_t b200_memcpy_h2d(void *dst, const void *src, uint64_t bytes, b200_stream s);
+int32_t b200_memcpy_d2h(void *dst, const void *src, uint64_t bytes, b200_stream s);
+int32_t b200_memcpy_d2d(void *dst, const void *src, uint64_t bytes, b200_stream s);
+
+/* ---------------------------------------------------- path (a): op tapes */
+/*
+ * A tape is the register-resident program one fused kernel runs per element.
+ * It is what `TraceOperationFuser` builds as Vec<FuseOp>
+ * (crates/burn-cubecl-fusion/src/engine/fuser.rs:33-839,
+ *  crates/burn-cubecl-fusion/src/engine/codegen/ir.rs:135-195), flattened to an
+ * accumulator machine: every op writes the accumulator (ACC); it may also save
+ * the result into a temp slot and/or store it to an output tensor.
+ *
+ * Operand byte: bits 7..6 kind, bits 5..0 index.
+ */
+#define B200_ARG_ACC 0x00u             /* result of the previous tape op */
+#define B200_ARG_INPUT(i) (0x40u | (uint8_t)(i))
+#define B200_ARG_TEMP(i) (0x80u | (uint8_t)(i))
+#define B200_ARG_SCALAR(i) (0xC0u | (uint8_t)(i))
+#define B200_DST_NONE 0xFFu
+
+typedef enum {
+  /* float (f32 math; f16/bf16 are storage types converted at load/store) */
+  B200_OP_MOV = 0, /* FuseOp::Assign */
+  B200_OP_ADD_F, B200_OP_SUB_F, B200_OP_MUL_F, B200_OP_DIV_F, B200_OP_REM_F,
+  B200_OP_POW_F, B200_OP_MIN_F, B200_OP_MAX_F, B200_OP_ATAN2_F,
+  B200_OP_NEG_F, B200_OP_ABS_F, B200_OP_EXP_F, B200_OP_LOG_F, B200_OP_LOG1P_F,
+  B200_OP_SQRT_F, B200_OP_RECIP_F, B200_OP_SIN_F, B200_OP_COS_F, B200_OP_TAN_F,
+  B200_OP_TANH_F, B200_OP_ERF_F, B200_OP_FLOOR_F, B200_OP_CEIL_F,
+  B200_OP_ROUND_F, B200_OP_TRUNC_F, B200_OP_SIGN_F, B200_OP_SINH_F,
+  B200_OP_COSH_F, B200_OP_ASIN_F, B200_OP_ACOS_F, B200_OP_ATAN_F,
+  B200_OP_ASINH_F, B200_OP_ACOSH_F, B200_OP_ATANH_F, B200_OP_SIGMOID_F,
+  B200_OP_CLAMP_F, /* a, lo=b, hi=c */
+  /* float comparisons -> bool */
+  B200_OP_EQ_F, B200_OP_NE_F, B200_OP_LT_F, B200_OP_LE_F, B200_OP_GT_F,
+  B200_OP_GE_F, B200_OP_ISNAN_F, B200_OP_ISINF_F,
+  /* int (i32 math; i64 is a storage type) */
+  B200_OP_ADD_I, B200_OP_SUB_I, B200_OP_MUL_I, B200_OP_DIV_I, B200_OP_REM_I,
+  B200_OP_MIN_I, B200_OP_MAX_I, B200_OP_NEG_I, B200_OP_ABS_I, B200_OP_SIGN_I,
+  B200_OP_AND_I, B200_OP_OR_I, B200_OP_XOR_I, B200_OP_NOT_I, B200_OP_SHL_I,
+  B200_OP_SHR_I, B200_OP_CLAMP_I,
+  B200_OP_EQ_I, B200_OP_NE_I, B200_OP_LT_I, B200_OP_LE_I, B200_OP_GT_I,
+  B200_OP_GE_I,
+  /* bool */
+  B200_OP_AND_B, B200_OP_OR_B, B200_OP_XOR_B, B200_OP_NOT_B,
+  /* select: out = cond(c) ? b : a  — FuseOp::ConditionalAssign; mask_fill is
+   * a=input, b=scalar, c=mask; mask_where is a=input, b=source, c=mask
+   * (crates/burn-ndarray/src/ops/base.rs:78-104). */
+  B200_OP_SELECT,
+  /* casts (FuseOp::Assign with a dtype change; Rust `as` semantics) */
+  B200_OP_F2I, B200_OP_I2F, B200_OP_B2F, B200_OP_B2I, B200_OP_F2B, B200_OP_I2B,
+  B200_OP_COUNT
+} b200_opcode;
+
+typedef struct {
+  uint8_t op;      /* b200_opcode */
+  uint8_t a, b, c; /* operand bytes */
+  uint8_t dst_temp;/* temp slot to save the result into, or B200_DST_NONE */
+  uint8_t dst_out; /* output tensor index to store the result to, or NONE */
+  uint8_t pad[2];
+} b200_tape_op;
+
+typedef struct {
+  const b200_tape_op *ops;
+  int32_t n_ops;
+  const uint32_t *scalars; /* raw 32-bit patterns (f32 or i32) */
+  int32_t n_scalars;
+} b200_tape;
+
+/*
+ * Fused elementwise launch — ElemwiseOptimization::execute →
+ * elemwise_fuse::launch_unchecked
+ * (crates/burn-cubecl-fusion/src/optim/elemwise/optimization.rs:81-171).
+ * `ref_shape` is the block's output shape; every input/output descriptor must
+ * have rank == `rank` and be broadcast-compatible with it (size-1 dims are
+ * given stride 0 by the caller or by the library).  Outputs may alias inputs
+ * (in-place reuse, crates/burn-cubecl-fusion/src/engine/launch/output.rs:47-55)
+ * when they have the same layout.
+ */
+int32_t b200_launch_elemwise(const b200_tape *tape, const b200_tensor *inputs,
+                             int32_t n_inputs, const b200_tensor *outputs,
+                             int32_t n_outputs, int32_t rank,
+                             const int64_t *ref_shape, b200_stream s);
+
+/* ------------------------------------------------ path (b): reductions */
+/* ReduceDimOpIr{input,out,axis} (crates/burn-ir/src/operation.rs:1008-1020);
+ * kinds accepted by the Reduce fuser
+ * (crates/burn-cubecl-fusion/src/optim/reduce/fuser.rs:221-300). */
+typedef enum {
+  B200_RED_SUM = 0,
+  B200_RED_MEAN = 1,
+  B200_RED_PROD = 2,
+  B200_RED_MAX = 3,
+  B200_RED_MIN = 4,
+  B200_RED_ARGMAX = 5, /* first max, first NaN wins: burn-ndarray base.rs:1715-1757 */
+  B200_RED_ARGMIN = 6,
+  B200_RED_MAXABS = 7,
+  B200_RED_ANY = 8,
+  B200_RED_ALL = 9
+} b200_reduce_kind;
+
+/*
+ * Fused reduce: out = write_tape( reduce_axis( read_tape(inputs…) ) ), keepdim.
+ * reduce_kernel_fused (crates/burn-cubecl-fusion/src/optim/reduce/optimization.rs:503).
+ *  - `read`  (optional, may be NULL): fuse-on-read tape over `inputs`, evaluated
+ *    at the reduce INPUT shape `in_shape`; its last ACC value is what is reduced.
+ *    With read == NULL the single input tensor inputs[0] is reduced directly.
+ *  - `write` (optional): fuse-on-write tape evaluated at the OUTPUT shape
+ *    (in_shape with in_shape[axis] = 1); its INPUT(0) is the reduced value and
+ *    INPUT(1…) are `write_inputs`; results go to `outputs`.  With write == NULL
+ *    the reduced value is stored to outputs[0].
+ *  Float reductions accumulate in f32; arg reductions write i32 or i64 per the
+ *  output dtype.  axis == -1 with rank-1 output shape [1] reduces everything
+ *  (float_sum, crates/burn-backend/src/backend/ops/tensor.rs:883).
+ */
+int32_t b200_launch_reduce(int32_t kind, int32_t axis, int32_t rank,
+                           const int64_t *in_shape, const b200_tape *read,
+                           const b200_tensor *inputs, int32_t n_inputs,
+                           const b200_tape *write,
+                           const b200_tensor *write_inputs,
+                           int32_t n_write_inputs, const b200_tensor *outputs,
+                           int32_t n_outputs, b200_stream s);
+
+/* Full reduction of a tensor to shape [1] (Sum/Mean/Prod/Max/Min/Any/All).
+ * float_sum → sum_view (crates/burn-ndarray/src/ops/base.rs:940-943). */
+int32_t b200_launch_reduce_full(int32_t kind, const b200_tensor *input,
+                                const b200_tensor *output, b200_stream s);
+
+/* ------------------------------------------------ path (c): float_matmul */
+typedef enum {
+  B200_MM_TF32 = 0,   /* f32 operands fed to tcgen05 kind::tf32, f32 accumulate */
+  B200_MM_BF16 = 1,   /* operands rounded to bf16 (RN), kind::f16, f32 accumulate */
+  B200_MM_F32X3 = 2   /* 3xTF32 split: near-f32 accuracy on the tensor pipe */
+} b200_mm_precision;
+
+/*
+ * C[..., M, N] = A[..., M, K] · B[..., K, N] with numpy-style broadcast of the
+ * leading dims (crates/burn-ndarray/src/ops/matmul.rs:9-183) and arbitrary
+ * (transposed-view) strides on the last two dims of A and B — the NT/TN GEMMs
+ * autodiff issues (crates/burn-autodiff/src/ops/tensor.rs:560-616).
+ * `epilogue` (optional) is a fuse-on-write tape run on the accumulator before
+ * the store — MatmulOptimization (crates/burn-cubecl-fusion/src/optim/matmul/
+ * optimization.rs:97-140): INPUT(0) is the accumulator, INPUT(1…) are
+ * `epi_inputs` described at the OUTPUT shape (broadcast strides allowed).
+ * All of a, b, c must have the same rank >= 2.  c must be row-major contiguous.
+ * `workspace` (may be NULL) is scratch for operand conversion; query its size
+ * with b200_matmul_workspace_bytes.
+ */
+int32_t b200_matmul_workspace_bytes(const b200_tensor *a, const b200_tensor *b,
+                                    int32_t precision, uint64_t *bytes);
+int32_t b200_launch_matmul(const b200_tensor *a, const b200_tensor *b,
+                           const b200_tensor *c, int32_t precision,
+                           const b200_tape *epilogue,
+                           const b200_tensor *epi_inputs, int32_t n_epi_inputs,
+                           void *workspace, uint64_t workspace_bytes,
+                           b200_stream s);
+
+/* ------------------------------------------------ indexing / data movement */
+/* strided → contiguous copy with optional dtype cast (float_cast, into_contiguous;
+ * crates/burn-cubecl/src/kernel/contiguous.rs, kernel/cast/base.rs:13). */
+int32_t b200_launch_copy(const b200_tensor *src, const b200_tensor *dst, b200_stream s);
+/* float_gather / int_gather: out[..i..] = t[.. idx[..i..] ..] along dim
+ * (crates/burn-ndarray/src/ops/base.rs:106-138). */
+int32_t b200_launch_gather(int32_t dim, const b200_tensor *input,
+                           const b200_tensor *indices, const b200_tensor *out,
+                           b200_stream s);
+/* float_scatter_add: t[.. idx ..] += value, sequential along dim per lane —
+ * deterministic and bit-identical to the oracle
+ * (crates/burn-cubecl/src/kernel/index/scatter.rs:13-71,
+ *  crates/burn-ndarray/src/ops/base.rs:140-183).  `tensor` is updated in place. */
+int32_t b200_launch_scatter_add(int32_t dim, const b200_tensor *tensor,
+                                const b200_tensor *indices,
+                                const b200_tensor *value, b200_stream s);
+/* float_select: out = t.index_select(dim, indices[1-D])
+ * (crates/burn-backend/src/backend/ops/tensor.rs:518). */
+int32_t b200_launch_select(int32_t dim, const b200_tensor *input,
+                           const b200_tensor *indices, const b200_tensor *out,
+                           b200_stream s);
+/* float_select_add: t.index_add(dim, indices, value) in place, deterministic
+ * (sequential over indices per lane) — embedding backward
+ * (crates/burn-backend/src/backend/ops/modules/base.rs:161-180). */
+int32_t b200_launch_select_add(int32_t dim, const b200_tensor *tensor,
+                               const b200_tensor *indices,
+                               const b200_tensor *value, b200_stream s);
+/* float_random (crates/burn-backend/src/backend/ops/tensor.rs:39): Philox4x32-10.
+ * kind 0 = uniform[lo,hi), 1 = normal(mean=lo,std=hi), 2 = bernoulli(p=lo). */
+int32_t b200_launch_random(const b200_tensor *out, int32_t kind, double lo,
+                           double hi, uint64_t seed, uint64_t offset,
+                           b200_stream s);
+/* int_arange (crates/burn-backend/src/backend/ops/int_tensor.rs:1287). */
+int32_t b200_launch_arange(const b200_tensor *out, int64_t start, int64_t step,
+                           b200_stream s);
+
+/* ------------------------------------------------ row-resident fused chains */
+/* softmax / log_softmax along the last axis in one pass (the ReduceBroadcasted
+ * analogue, crates/burn-cubecl-fusion/src/optim/reduce_broadcasted/; op chain
+ * crates/burn-backend/src/backend/ops/activation.rs:250-287). */
+int32_t b200_launch_softmax(const b200_tensor *input, const b200_tensor *out,
+                            int32_t log_softmax, b200_stream s);
+/* layer_norm over the last axis: (x-mean)/sqrt(var+eps)*gamma+beta
+ * (crates/burn-backend/src/backend/ops/modules/base.rs:846-877).  gamma/beta
+ * may be NULL. */
+int32_t b200_launch_layer_norm(const b200_tensor *input, const b200_tensor *gamma,
+                               const b200_tensor *beta, double eps,
+                               const b200_tensor *out, b200_stream s);
+
+/* ------------------------------------------------ collectives */
+/* DistributedOps::{all_reduce, sync_collective}
+ * (crates/burn-backend/src/backend/distributed/ops.rs:116-131; reference impl
+ * crates/burn-cubecl/src/ops/distributed.rs:17-55).  One communicator per
+ * process (one process per GPU); the 128-byte unique id is produced on rank 0
+ * and distributed by the host (torch.distributed / any bootstrap). */
+#define B200_NCCL_UNIQUE_ID_BYTES 128
+typedef void *b200_comm;
+typedef enum { B200_REDUCE_SUM = 0, B200_REDUCE_MEAN = 1 } b200_reduce_op;
+int32_t b200_comm_unique_id(uint8_t id[B200_NCCL_UNIQUE_ID_BYTES]);
+int32_t b200_comm_init(b200_comm *out, const uint8_t id[B200_NCCL_UNIQUE_ID_BYTES],
+                       int32_t rank, int32_t world_size);
+int32_t b200_comm_destroy(b200_comm comm);
+/* In-place all-reduce (sendbuff == recvbuff, as the reference does) on the
+ * communicator's dedicated stream, ordered after everything already queued on
+ * `producer` (event fence). */
+int32_t b200_all_reduce(b200_comm comm, void *ptr, uint64_t count, int32_t dtype,
+                        int32_t op, b200_stream producer);
+/* Bucketed variant: n tensors reduced inside one ncclGroup. */
+int32_t b200_all_reduce_multi(b200_comm comm, void *const *ptrs,
+                              const uint64_t *counts, int32_t n, int32_t dtype,
+                              int32_t op, b200_stream producer);
+/* Makes `consumer` wait for every collective issued so far
+ * (DistributedOps::sync_collective). */
+int32_t b200_collective_sync(b200_comm comm, b200_stream consumer);
+
+/* ------------------------------------------------ introspection */
+/* Number of kernels this library has launched since load (bench.py's
+ * gpu_launches claim) and a reset. */
+uint64_t b200_launch_count(void);
+void b200_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BURN_B200_H */

@@ -1,0 +1,79 @@
+"""Shared helpers for the GPU parity tests: run single ops / fused chains through
+the C ABI and compare with the CPU oracle."""
+from __future__ import annotations
+
+import numpy as np
+
+from burn_b200 import _abi as abi
+from burn_b200 import device as dv
+from burn_b200.device import DeviceTensor, TapeBuilder
+
+# parity tolerances stated by BASELINE.json north_star
+REL_ELEMWISE = 1e-6
+REL_REDUCE = 1e-5
+
+
+def up(a, dtype=None) -> DeviceTensor:
+    return DeviceTensor.from_numpy(np.asarray(a), dtype=dtype)
+
+
+def run_tape(tb: TapeBuilder, inputs, out_shape, out_dtypes=(abi.F32,)):
+    outs = [DeviceTensor.empty(out_shape, dt) for dt in out_dtypes]
+    dv.launch_elemwise(tb.build(), inputs, outs, out_shape)
+    res = [o.numpy() for o in outs]
+    return res[0] if len(res) == 1 else res
+
+
+def binary(opname: str, a: DeviceTensor, b: DeviceTensor, out_dtype=abi.F32):
+    shape = np.broadcast_shapes(a.shape, b.shape)
+    tb = TapeBuilder().op(opname, ("in", 0), ("in", 1), out=0)
+    return run_tape(tb, [a.expand(shape), b.expand(shape)], shape, (out_dtype,))
+
+
+def binary_scalar(opname: str, a: DeviceTensor, s, kind="f", out_dtype=abi.F32):
+    tb = TapeBuilder().op(opname, ("in", 0), (kind, s), out=0)
+    return run_tape(tb, [a], a.shape, (out_dtype,))
+
+
+def unary(opname: str, a: DeviceTensor, out_dtype=abi.F32):
+    tb = TapeBuilder().op(opname, ("in", 0), out=0)
+    return run_tape(tb, [a], a.shape, (out_dtype,))
+
+
+def gelu_tape(tb: TapeBuilder, src, out=None):
+    """gelu(x) = x * (erf(x / sqrt2) + 1) / 2 as the 5 primitive ops burn-fusion sees
+    (crates/burn-backend/src/backend/ops/activation.rs:69-76).  `src` must be re-readable
+    (an input or a temp)."""
+    tb.op("DIV_F", src, ("f", 1.4142135623730951))
+    tb.op("ERF_F", "acc")
+    tb.op("ADD_F", "acc", ("f", 1.0))
+    tb.op("MUL_F", src, "acc")
+    tb.op("DIV_F", "acc", ("f", 2.0), out=out)
+    return tb
+
+
+def assert_close(got, want, rel, abs_=0.0, what=""):
+    from oracle import oracle
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    ok = oracle.approx_eq_mask(got, want, rel, abs_)
+    if not ok.all():
+        bad = np.argwhere(~ok)
+        i = tuple(bad[0])
+        raise AssertionError(
+            f"{what}: {bad.shape[0]} / {ok.size} elements differ beyond rel={rel} abs={abs_}; "
+            f"first at {i}: got {got[i]!r} want {want[i]!r}")
+
+
+def assert_exact(got, want, what=""):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    if got.dtype.kind == "f":
+        same = (got == want) | (np.isnan(got) & np.isnan(want))
+    else:
+        same = got.astype(np.int64) == want.astype(np.int64)
+    if not same.all():
+        i = tuple(np.argwhere(~same)[0])
+        raise AssertionError(f"{what}: {np.count_nonzero(~same)} mismatches; first at {i}: got {got[i]!r} want {want[i]!r}")
