@@ -8,161 +8,238 @@
 //  kernel/mask/{mask_fill,mask_where}.rs, kernel/cast/base.rs).
 //
 // HBM layout: every operand is read exactly once and every output written once,
-// as 128-bit accesses; vector-eligible operands go global→shared with
-// cp.async (no register staging, all of a thread's loads in flight at once),
-// the tape then runs out of the thread-private slot file.  Roofline: HBM
-// bandwidth; algorithmic bytes = Σ operand element sizes per element.
+// as 128-bit accesses.  Vector-eligible operands stream global→shared through a
+// multi-stage cp.async ring (no register staging): while the tape runs on tile t
+// out of the thread-private slot file, the loads of tiles t+1 … t+S-1 are in
+// flight, so HBM latency is hidden without needing high occupancy.
+// Roofline: HBM bandwidth; algorithmic bytes = Σ operand element sizes per element.
 #include "tape_host.cuh"
 
 namespace b200 {
 
-__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void *g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(g));
-}
-__device__ __forceinline__ void cp_async_8(uint32_t smem_addr, const void *g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr), "l"(g));
-}
-__device__ __forceinline__ void cp_async_4(uint32_t smem_addr, const void *g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(g));
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
-}
+constexpr int kEwBlock = 128;  // threads per CTA (vectorised kernel)
+constexpr int kEwU = 4;        // 16-byte vectors per thread per tile → 16 elements
+constexpr int kEw1Block = 256; // scalar fallback kernel
+constexpr int kEw1U = 4;
 
-// Expands a raw 16-byte slot word loaded by cp.async into 32-bit lanes.
-__device__ __forceinline__ void expand_raw(int32_t dtype, uint32_t (&r)[4]) {
-  if (dtype == B200_BF16) {
-    const uint32_t x = r[0], y = r[1];
-    r[0] = x << 16; r[1] = x & 0xFFFF0000u; r[2] = y << 16; r[3] = y & 0xFFFF0000u;
-  } else if (dtype == B200_F16) {
-    const uint32_t x = r[0], y = r[1];
-    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&x));
-    const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&y));
-    r[0] = u_of(f0.x); r[1] = u_of(f0.y); r[2] = u_of(f1.x); r[3] = u_of(f1.y);
-  } else {  // BOOL / U8
-    const uint32_t v = r[0];
-    r[0] = v & 0xFFu; r[1] = (v >> 8) & 0xFFu; r[2] = (v >> 16) & 0xFFu; r[3] = v >> 24;
-  }
-}
-
-__device__ __forceinline__ int64_t operand_offset(const OperandDesc &d, int rank,
-                                                  const uint32_t (&coord)[kMaxDims]) {
-  int64_t off = 0;
+// Issues the asynchronous loads of the vector-eligible inputs of one tile into
+// ring stage `stage`.
+template <int U, int BLOCK, int RM>
+__device__ __forceinline__ void prefetch_tile(const TapeParams &p, const SlotFile<4, U, BLOCK> &slots,
+                                              int stage, uint32_t tile) {
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(slots.smem);
+  const uint32_t v0 = tile * (BLOCK * U) + threadIdx.x;
+  Coord3 c[U];
 #pragma unroll
-  for (int k = 0; k < kMaxDims; ++k)
-    if (k < rank) off += (int64_t)coord[k] * d.strides[k];
-  return off;
-}
-
-// Fills the input slots of one tile.  Shared with the reduce kernels.
-template <int VEC, int U>
-__device__ __forceinline__ void load_tile_inputs(const TapeParams &p, const SlotFile<VEC, U> &slots,
-                                                 const uint32_t (&coord)[U][kMaxDims],
-                                                 const bool (&ok)[U]) {
-  bool needs_expand = false;
+  for (int u = 0; u < U; ++u) c[u] = coords3<4, RM>(p, v0 + u * BLOCK);
   for (int k = 0; k < p.n_in; ++k) {
     const OperandDesc &d = p.in[k];
-    if (VEC == 4 && d.mode == kModeVec && d.dtype != B200_I64) {
-      const int es = (d.dtype == B200_F32 || d.dtype == B200_I32) ? 4
-                     : (d.dtype == B200_BF16 || d.dtype == B200_F16) ? 2 : 1;
-      needs_expand |= (es != 4);
+    const int es = d.async_es;
+    if (es == 0) continue;
+    const char *base = reinterpret_cast<const char *>(d.ptr);
+    const uint32_t sa = smem_base + slots.private_word(stage * p.n_in + k, 0) * 16u;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!ok[u]) continue;
-        const int64_t off = operand_offset(d, p.rank, coord[u]);
-        const char *g = reinterpret_cast<const char *>(d.ptr) + off * es;
-        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(
-            slots.base + (size_t)(k * U + u) * kTapeBlock * 4);
-        if (es == 4) cp_async_16(sa, g);
-        else if (es == 2) cp_async_8(sa, g);
-        else cp_async_4(sa, g);
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        uint32_t r[VEC];
-        if (ok[u]) {
-          load_operand<VEC>(d, p.rank, coord[u], r);
-        } else {
-#pragma unroll
-          for (int j = 0; j < VEC; ++j) r[j] = 0;
-        }
-        slots.put(k, u, r);
-      }
-    }
-  }
-  if constexpr (VEC == 4) {
-    cp_async_wait_all();
-    if (needs_expand) {
-      for (int k = 0; k < p.n_in; ++k) {
-        const OperandDesc &d = p.in[k];
-        if (d.mode == kModeVec && d.dtype != B200_F32 && d.dtype != B200_I32 &&
-            d.dtype != B200_I64) {
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            uint32_t r[VEC];
-            slots.get(k, u, r);
-            expand_raw(d.dtype, r);
-            slots.put(k, u, r);
-          }
-        }
-      }
+    for (int u = 0; u < U; ++u) {
+      const uint32_t v = v0 + u * BLOCK;
+      if (v >= p.n_vec) continue;
+      const char *g = base + operand_offset<4, RM>(p, d, v, c[u]) * es;
+      if (es == 4) cp_async_16(sa + u * (BLOCK * 16u), g);
+      else if (es == 2) cp_async_8(sa + u * (BLOCK * 16u), g);
+      else cp_async_4(sa + u * (BLOCK * 16u), g);
     }
   }
 }
 
-template <int VEC, int U>
-__global__ void __launch_bounds__(kTapeBlock)
-elemwise_tape_kernel(const __grid_constant__ TapeParams p) {
+// Vectorised kernel: VEC = 4, S-stage ring.
+template <int U, int BLOCK, int RM>
+__global__ void __launch_bounds__(BLOCK)
+elemwise_tape_kernel_v4(const __grid_constant__ TapeParams p, int stages, uint32_t flags) {
   extern __shared__ __align__(16) uint32_t smem[];
-  const SlotFile<VEC, U> slots = make_slots<VEC, U>(smem, threadIdx.x);
-  constexpr uint32_t kTileVecs = kTapeBlock * U;
+  SlotFile<4, U, BLOCK> slots;
+  slots.smem = smem;
+  slots.tid = threadIdx.x;
+  constexpr uint32_t kTileVecs = BLOCK * U;
   const uint32_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
+  const int tmp_base = stages * p.n_in;
+  const bool has_sync_inputs = flags & 1u;   // some input is not cp.async-eligible
+  const bool needs_expand = flags & 2u;      // some cp.async input is 8/16-bit
 
+  if (p.n_scalars > 0) {
+    init_scalars<4, U, BLOCK>(p, slots, tmp_base + p.n_tmp);
+    __syncthreads();
+  }
+
+  // prologue: fill S-1 stages
+  uint32_t next = blockIdx.x;
+  for (int s = 0; s < stages - 1; ++s) {
+    if (next < n_tiles) prefetch_tile<U, BLOCK, RM>(p, slots, s, next);
+    cp_async_commit();
+    next += gridDim.x;
+  }
+
+  int stage = 0;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    uint32_t coord[U][kMaxDims];
-    bool ok[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t v = tile * kTileVecs + u * kTapeBlock + threadIdx.x;
-      ok[u] = v < p.n_vec;
-      vec_coords<VEC>(p, ok[u] ? v : 0u, coord[u]);
+    {  // keep the ring full: the stage consumed last iteration is free again
+      int ps = stage + stages - 1;
+      if (ps >= stages) ps -= stages;
+      if (next < n_tiles) prefetch_tile<U, BLOCK, RM>(p, slots, ps, next);
+      cp_async_commit();
+      next += gridDim.x;
     }
-    load_tile_inputs<VEC, U>(p, slots, coord, ok);
+    cp_async_wait_dyn(stages - 1);
 
-    uint32_t acc[U][VEC];
+    const int in_base = stage * p.n_in;
+    const uint32_t v0 = tile * kTileVecs + threadIdx.x;
+    if (has_sync_inputs || needs_expand) {
+      for (int k = 0; k < p.n_in; ++k) {
+        const OperandDesc &d = p.in[k];
+        if (d.async_es == 4) continue;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t v = v0 + u * BLOCK;
+          uint32_t r[4];
+          if (d.async_es != 0) {
+            slots.get(in_base + k, u, r);
+            expand_raw(d.dtype, r);
+          } else if (v < p.n_vec) {
+            load_operand<4, RM>(p, d, v, coords3<4, RM>(p, v), r);
+          } else {
+            r[0] = r[1] = r[2] = r[3] = 0;
+          }
+          slots.put(in_base + k, u, r);
+        }
+      }
+    }
+
+    uint32_t acc[U][4];
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) acc[u][j] = 0;
+      for (int j = 0; j < 4; ++j) acc[u][j] = 0;
 
-    run_tape<VEC, U>(p, slots, acc, [&](int o, const uint32_t(&val)[U][VEC]) {
+    run_tape<4, U, BLOCK>(
+        p, slots, acc,
+        [&](int o, const uint32_t(&val)[U][4]) {
+          const OperandDesc &d = p.out[o];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (ok[u]) store_operand<VEC>(p.out[o], p.rank, coord[u], val[u]);
-    });
+          for (int u = 0; u < U; ++u) {
+            const uint32_t v = v0 + u * BLOCK;
+            if (v < p.n_vec) store_operand<4, RM>(p, d, v, coords3<4, RM>(p, v), val[u]);
+          }
+        },
+        in_base, tmp_base);
+
+    if (++stage == stages) stage = 0;
+  }
+  cp_async_wait_all();
+}
+
+// Scalar fallback (innermost collapsed dim not a multiple of 4): VEC = 1.
+template <int U, int BLOCK, int RM>
+__global__ void __launch_bounds__(BLOCK)
+elemwise_tape_kernel_v1(const __grid_constant__ TapeParams p) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  SlotFile<1, U, BLOCK> slots;
+  slots.smem = smem;
+  slots.tid = threadIdx.x;
+  constexpr uint32_t kTileVecs = BLOCK * U;
+  const uint32_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
+  if (p.n_scalars > 0) {
+    init_scalars<1, U, BLOCK>(p, slots, p.n_in + p.n_tmp);
+    __syncthreads();
+  }
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t v0 = tile * kTileVecs + threadIdx.x;
+    for (int k = 0; k < p.n_in; ++k) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t v = v0 + u * BLOCK;
+        uint32_t r[1] = {0u};
+        if (v < p.n_vec) load_operand<1, RM>(p, p.in[k], v, coords3<1, RM>(p, v), r);
+        slots.put(k, u, r);
+      }
+    }
+    uint32_t acc[U][1];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u][0] = 0;
+    run_tape<1, U, BLOCK>(
+        p, slots, acc,
+        [&](int o, const uint32_t(&val)[U][1]) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t v = v0 + u * BLOCK;
+            if (v < p.n_vec) store_operand<1, RM>(p, p.out[o], v, coords3<1, RM>(p, v), val[u]);
+          }
+        },
+        0, p.n_in);
   }
 }
 
-template <int VEC, int U>
-static int32_t launch_elemwise_impl(const TapeParams &p, cudaStream_t stream) {
-  const int n_slots = p.n_in + p.n_tmp;
-  const size_t smem = slot_file_bytes(n_slots > 0 ? n_slots : 1, VEC, U);
-  B200_REQUIRE((int)smem <= max_smem_optin(), B200_ERR_UNSUPPORTED,
-               "tape needs %zu B of slot file (limit %d)", smem, max_smem_optin());
-  auto kern = elemwise_tape_kernel<VEC, U>;
+template <typename Kern, typename... Args>
+static int32_t launch_persistent(Kern kern, int block, size_t smem, uint64_t n_tiles, cudaStream_t stream,
+                                 Args... args) {
   if (smem > 48 * 1024)
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTapeBlock, smem));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
   if (per_sm < 1) per_sm = 1;
-  const uint32_t tile_vecs = kTapeBlock * U;
-  const uint64_t n_tiles = ((uint64_t)p.n_vec + tile_vecs - 1) / tile_vecs;
   const uint64_t resident = (uint64_t)sm_count() * per_sm;
   const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, resident));
-  kern<<<grid, kTapeBlock, smem, stream>>>(p);
+  kern<<<grid, block, smem, stream>>>(args...);
   B200_LAUNCH_CHECK();
   return B200_OK;
+}
+
+static int32_t launch_v4(const CompiledTape &ct, TapeParams &p, int rm, cudaStream_t stream) {
+  constexpr int U = kEwU, BLOCK = kEwBlock;
+  uint32_t flags = 0;
+  int n_async = 0;
+  for (int k = 0; k < ct.n_in; ++k) {
+    const OperandDesc &d = p.in[k];
+    if (d.async_es == 0) flags |= 1u;
+    else {
+      ++n_async;
+      if (d.async_es != 4) flags |= 2u;
+    }
+  }
+  // ring depth: keep >= ~16 x 16 B in flight per thread, bounded by shared memory so
+  // that at least 2-3 CTAs stay resident per SM
+  int stages = 1;
+  if (n_async > 0) stages = std::max(2, std::min(4, 16 / (n_async * U) + 1));
+  const size_t smem_cap = 100 * 1024;
+  auto bytes_for = [&](int s) { return slot_file_bytes(s * ct.n_in + ct.n_tmp, (int)ct.scalars.size(), 4, U, BLOCK); };
+  while (stages > 1 && bytes_for(stages) > smem_cap) --stages;
+  const size_t smem = std::max<size_t>(bytes_for(stages), 16);
+  B200_REQUIRE((int)smem <= max_smem_optin(), B200_ERR_UNSUPPORTED,
+               "tape needs %zu B of slot file (limit %d)", smem, max_smem_optin());
+  int32_t st = finalize_tape(ct, U, BLOCK, stages, p);
+  if (st != B200_OK) return st;
+  const uint64_t n_tiles = ((uint64_t)p.n_vec + BLOCK * U - 1) / (BLOCK * U);
+  switch (rm) {
+    case kRankLinear:
+      return launch_persistent(elemwise_tape_kernel_v4<U, BLOCK, kRankLinear>, BLOCK, smem, n_tiles, stream, p, stages, flags);
+    case kRank3:
+      return launch_persistent(elemwise_tape_kernel_v4<U, BLOCK, kRank3>, BLOCK, smem, n_tiles, stream, p, stages, flags);
+    default:
+      return launch_persistent(elemwise_tape_kernel_v4<U, BLOCK, kRankGeneric>, BLOCK, smem, n_tiles, stream, p, stages, flags);
+  }
+}
+
+static int32_t launch_v1(const CompiledTape &ct, TapeParams &p, int rm, cudaStream_t stream) {
+  constexpr int U = kEw1U, BLOCK = kEw1Block;
+  const size_t smem = std::max<size_t>(
+      slot_file_bytes(ct.n_in + ct.n_tmp, (int)ct.scalars.size(), 1, U, BLOCK), 16);
+  int32_t st = finalize_tape(ct, U, BLOCK, 1, p);
+  if (st != B200_OK) return st;
+  const uint64_t n_tiles = ((uint64_t)p.n_vec + BLOCK * U - 1) / (BLOCK * U);
+  switch (rm) {
+    case kRankLinear:
+      return launch_persistent(elemwise_tape_kernel_v1<U, BLOCK, kRankLinear>, BLOCK, smem, n_tiles, stream, p);
+    case kRank3:
+      return launch_persistent(elemwise_tape_kernel_v1<U, BLOCK, kRank3>, BLOCK, smem, n_tiles, stream, p);
+    default:
+      return launch_persistent(elemwise_tape_kernel_v1<U, BLOCK, kRankGeneric>, BLOCK, smem, n_tiles, stream, p);
+  }
 }
 
 }  // namespace b200
@@ -176,14 +253,13 @@ extern "C" int32_t b200_launch_elemwise(const b200_tape *tape, const b200_tensor
   B200_REQUIRE(rank >= 1 && rank <= B200_MAX_RANK, B200_ERR_INVALID, "rank %d out of range", rank);
   B200_REQUIRE(ref_shape, B200_ERR_INVALID, "ref_shape is null");
   B200_REQUIRE(n_outputs >= 1, B200_ERR_INVALID, "an elementwise launch needs at least one output");
-  TapeParams p;
-  memset(&p, 0, sizeof(p));
-  int32_t st = plan_tape(tape, n_inputs, n_outputs, p);
+  CompiledTape ct;
+  int32_t st = compile_tape(tape, n_inputs, n_outputs, ct);
   if (st != B200_OK) return st;
 
-  const int64_t numel = numel_of(ref_shape, rank);
   for (int d = 0; d < rank; ++d)
     B200_REQUIRE(ref_shape[d] >= 0, B200_ERR_SHAPE, "negative dim %d", d);
+  const int64_t numel = numel_of(ref_shape, rank);
   if (numel == 0) return B200_OK;  // empty tensors: nothing to launch
   B200_REQUIRE(numel < (1ll << 31), B200_ERR_UNSUPPORTED,
                "elementwise launch over %lld elements exceeds the 2^31 index range", (long long)numel);
@@ -208,7 +284,10 @@ extern "C" int32_t b200_launch_elemwise(const b200_tape *tape, const b200_tensor
   }
   const CollapsedLayout L = collapse_dims(rank, ref_shape, all);
   const int vec = (L.shape[L.rank - 1] % 4 == 0) ? 4 : 1;
-  fill_geometry(p, L, vec);
+  const int rm = rank_mode(L, all);
+  TapeParams p;
+  memset(&p, 0, sizeof(p));
+  fill_geometry(p, L, vec, rm);
   for (int i = 0; i < n_inputs; ++i) fill_desc(p.in[i], planned[i], L.rank, vec);
   for (int i = 0; i < n_outputs; ++i) {
     fill_desc(p.out[i], planned[n_inputs + i], L.rank, vec);
@@ -217,6 +296,5 @@ extern "C" int32_t b200_launch_elemwise(const b200_tape *tape, const b200_tensor
   p.n_vec = (uint32_t)(numel / vec);
 
   cudaStream_t stream = resolve_stream(s);
-  if (vec == 4) return launch_elemwise_impl<4, 2>(p, stream);
-  return launch_elemwise_impl<1, 4>(p, stream);
+  return vec == 4 ? launch_v4(ct, p, rm, stream) : launch_v1(ct, p, rm, stream);
 }

@@ -25,13 +25,7 @@ namespace cg = cooperative_groups;
 
 namespace b200 {
 
-// from elemwise.cu (same translation-unit-local helpers re-declared here)
-__device__ __forceinline__ void r_cp_async_16(uint32_t smem_addr, const void *g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(g));
-}
-__device__ __forceinline__ void r_cp_async_wait_all() {
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
-}
+constexpr int kRedBlock = 256;  // threads per CTA in reduce kernels
 
 struct Acc {
   uint32_t v;  // f32 or i32 bits
@@ -146,36 +140,23 @@ __device__ __forceinline__ Acc warp_reduce(int kind, int is_int, Acc a) {
 }
 
 // ----------------------------------------------------------------- tile IO
-__device__ __forceinline__ int64_t r_operand_offset(const OperandDesc &d, int rank,
-                                                    const uint32_t (&coord)[kMaxDims]) {
-  int64_t off = 0;
+template <int VEC, int U, int RM>
+__device__ __forceinline__ void load_inputs(const TapeParams &p, const SlotFile<VEC, U, kRedBlock> &slots,
+                                            const uint32_t (&vidx)[U], const bool (&ok)[U]) {
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(slots.smem);
 #pragma unroll
-  for (int k = 0; k < kMaxDims; ++k)
-    if (k < rank) off += (int64_t)coord[k] * d.strides[k];
-  return off;
-}
-
-template <int VEC, int U>
-__device__ __forceinline__ void load_inputs(const TapeParams &p, const SlotFile<VEC, U> &slots,
-                                            const uint32_t (&coord)[U][kMaxDims],
-                                            const bool (&ok)[U]) {
-  for (int k = 0; k < p.n_in; ++k) {
-    const OperandDesc &d = p.in[k];
-    if (VEC == 4 && d.mode == kModeVec && (d.dtype == B200_F32 || d.dtype == B200_I32)) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
+  for (int u = 0; u < U; ++u) {
+    const Coord3 c = coords3<VEC, RM>(p, ok[u] ? vidx[u] : 0u);
+    for (int k = 0; k < p.n_in; ++k) {
+      const OperandDesc &d = p.in[k];
+      if (VEC == 4 && d.mode == kModeVec && (d.dtype == B200_F32 || d.dtype == B200_I32)) {
         if (!ok[u]) continue;
-        const int64_t off = r_operand_offset(d, p.rank, coord[u]);
-        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(
-            slots.base + (size_t)(k * U + u) * kTapeBlock * 4);
-        r_cp_async_16(sa, reinterpret_cast<const uint32_t *>(d.ptr) + off);
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
+        const int64_t off = operand_offset<VEC, RM>(p, d, vidx[u], c);
+        cp_async_16(smem_base + slots.private_word(k, u) * 16u, reinterpret_cast<const uint32_t *>(d.ptr) + off);
+      } else {
         uint32_t r[VEC];
         if (ok[u]) {
-          load_operand<VEC>(d, p.rank, coord[u], r);
+          load_operand<VEC, RM>(p, d, vidx[u], c, r);
         } else {
 #pragma unroll
           for (int j = 0; j < VEC; ++j) r[j] = 0;
@@ -184,35 +165,37 @@ __device__ __forceinline__ void load_inputs(const TapeParams &p, const SlotFile<
       }
     }
   }
-  if constexpr (VEC == 4) r_cp_async_wait_all();
+  if constexpr (VEC == 4) cp_async_wait_all();
 }
 
 // Evaluates the read tape for U vectors and leaves the values in `val`.
-template <int VEC, int U>
-__device__ __forceinline__ void eval_read(const ReduceParams &P, const SlotFile<VEC, U> &slots,
+template <int VEC, int U, int RM>
+__device__ __forceinline__ void eval_read(const ReduceParams &P, const SlotFile<VEC, U, kRedBlock> &slots,
                                           const uint32_t (&vidx)[U], const bool (&ok)[U],
                                           uint32_t (&val)[U][VEC]) {
-  uint32_t coord[U][kMaxDims];
-#pragma unroll
-  for (int u = 0; u < U; ++u) vec_coords<VEC>(P.rd, ok[u] ? vidx[u] : 0u, coord[u]);
-  load_inputs<VEC, U>(P.rd, slots, coord, ok);
+  load_inputs<VEC, U, RM>(P.rd, slots, vidx, ok);
 #pragma unroll
   for (int u = 0; u < U; ++u)
 #pragma unroll
     for (int j = 0; j < VEC; ++j) val[u][j] = 0;
-  run_tape<VEC, U>(P.rd, slots, val, [&](int o, const uint32_t(&x)[U][VEC]) {
+  run_tape<VEC, U, kRedBlock>(
+      P.rd, slots, val,
+      [&](int o, const uint32_t(&x)[U][VEC]) {
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (ok[u]) store_operand<VEC>(P.rd.out[o], P.rd.rank, coord[u], x[u]);
-  });
+        for (int u = 0; u < U; ++u)
+          if (ok[u]) store_operand<VEC, RM>(P.rd, P.rd.out[o], vidx[u], coords3<VEC, RM>(P.rd, vidx[u]), x[u]);
+      },
+      0, P.rd.n_in);
 }
 
 // Applies mean division, runs the write tape and stores VECW consecutive outputs
 // starting at output vector index `ovec`.
-template <int VECW>
-__device__ __forceinline__ void finalize(const ReduceParams &P, uint32_t *wr_smem, uint32_t ovec,
+template <int VECW, int WRM>
+__device__ __forceinline__ void finalize(const ReduceParams &P, uint32_t *wr_smem, int tid, uint32_t ovec,
                                          const Acc (&a)[VECW]) {
-  const SlotFile<VECW, 1> slots = make_slots<VECW, 1>(wr_smem, threadIdx.x);
+  SlotFile<VECW, 1, kRedBlock> slots;
+  slots.smem = wr_smem;
+  slots.tid = tid;
   uint32_t red[VECW];
   const bool is_arg = P.kind == B200_RED_ARGMAX || P.kind == B200_RED_ARGMIN;
 #pragma unroll
@@ -222,20 +205,34 @@ __device__ __forceinline__ void finalize(const ReduceParams &P, uint32_t *wr_sme
       v = P.is_int ? (uint32_t)((int32_t)v / (int32_t)P.R) : u_of(__fdiv_rn(f_of(v), P.mean_div));
     red[j] = v;
   }
-  uint32_t coord[kMaxDims];
-  vec_coords<VECW>(P.wr, ovec, coord);
+  const Coord3 c = coords3<VECW, WRM>(P.wr, ovec);
   slots.put(0, 0, red);
   for (int k = 1; k < P.wr.n_in; ++k) {
     uint32_t r[VECW];
-    load_operand<VECW>(P.wr.in[k], P.wr.rank, coord, r);
+    load_operand<VECW, WRM>(P.wr, P.wr.in[k], ovec, c, r);
     slots.put(k, 0, r);
   }
   uint32_t acc[1][VECW];
 #pragma unroll
   for (int j = 0; j < VECW; ++j) acc[0][j] = red[j];
-  run_tape<VECW, 1>(P.wr, slots, acc, [&](int o, const uint32_t(&x)[1][VECW]) {
-    store_operand<VECW>(P.wr.out[o], P.wr.rank, coord, x[0]);
-  });
+  run_tape<VECW, 1, kRedBlock>(
+      P.wr, slots, acc,
+      [&](int o, const uint32_t(&x)[1][VECW]) { store_operand<VECW, WRM>(P.wr, P.wr.out[o], ovec, c, x[0]); }, 0,
+      P.wr.n_in);
+}
+
+// Writes the shared scalar words of both tapes; all threads must call it.
+template <int VEC, int U, int VECW>
+__device__ __forceinline__ void init_both_scalars(const ReduceParams &P, uint32_t *smem, uint32_t rd_words, int tid) {
+  SlotFile<VEC, U, kRedBlock> rs;
+  rs.smem = smem;
+  rs.tid = tid;
+  init_scalars<VEC, U, kRedBlock>(P.rd, rs, P.rd.n_in + P.rd.n_tmp);
+  SlotFile<VECW, 1, kRedBlock> ws;
+  ws.smem = smem + rd_words;
+  ws.tid = tid;
+  init_scalars<VECW, 1, kRedBlock>(P.wr, ws, P.wr.n_in + P.wr.n_tmp);
+  __syncthreads();
 }
 
 // Folds the VEC lanes of U vectors of a ROW mapping into one Acc.
@@ -256,14 +253,17 @@ __device__ __forceinline__ Acc fold_row(const ReduceParams &P, Acc a, const uint
   return a;
 }
 
-constexpr int kWarps = kTapeBlock / 32;
+constexpr int kWarps = kRedBlock / 32;
 
 // ----------------------------------------------------------------- ROW_WARP
-template <int VEC, int U>
-__global__ void __launch_bounds__(kTapeBlock)
+template <int VEC, int U, int RM>
+__global__ void __launch_bounds__(kRedBlock)
 reduce_row_warp_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words) {
   extern __shared__ __align__(16) uint32_t smem[];
-  const SlotFile<VEC, U> slots = make_slots<VEC, U>(smem, threadIdx.x);
+  SlotFile<VEC, U, kRedBlock> slots;
+  slots.smem = smem;
+  slots.tid = threadIdx.x;
+  init_both_scalars<VEC, U, 1>(P, smem, rd_words, threadIdx.x);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_rows = P.outer;
   for (uint32_t row = blockIdx.x * kWarps + warp; row < n_rows; row += gridDim.x * kWarps) {
@@ -278,13 +278,13 @@ reduce_row_warp_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words
         ok[u] = ridx[u] < P.r_vec;
         vidx[u] = row * P.r_vec + ridx[u];
       }
-      eval_read<VEC, U>(P, slots, vidx, ok, val);
+      eval_read<VEC, U, RM>(P, slots, vidx, ok, val);
       a = fold_row<VEC, U>(P, a, val, ridx, ok);
     }
     a = warp_reduce(P.kind, P.is_int, a);
     if (lane == 0) {
       const Acc one[1] = {a};
-      finalize<1>(P, smem + rd_words, row, one);
+      finalize<1, kRankGeneric>(P, smem + rd_words, threadIdx.x, row, one);
     }
     __syncwarp();
   }
@@ -302,11 +302,14 @@ __device__ __forceinline__ Acc block_reduce(int kind, int is_int, Acc a, Acc *sc
   return r;  // valid in every thread of warp 0 (and all warps, same data)
 }
 
-template <int VEC, int U>
-__global__ void __launch_bounds__(kTapeBlock)
+template <int VEC, int U, int RM>
+__global__ void __launch_bounds__(kRedBlock)
 reduce_row_cta_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words, uint32_t slot_words) {
   extern __shared__ __align__(16) uint32_t smem[];
-  const SlotFile<VEC, U> slots = make_slots<VEC, U>(smem, threadIdx.x);
+  SlotFile<VEC, U, kRedBlock> slots;
+  slots.smem = smem;
+  slots.tid = threadIdx.x;
+  init_both_scalars<VEC, U, 1>(P, smem, rd_words, threadIdx.x);
   Acc *scratch = reinterpret_cast<Acc *>(smem + slot_words);
   __shared__ uint32_t s_last;
   const uint32_t n_work = P.outer * P.splits;
@@ -315,24 +318,24 @@ reduce_row_cta_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words,
     const uint32_t begin = split * P.rows_per_split;
     const uint32_t end = min(P.r_vec, begin + P.rows_per_split);
     Acc a = acc_identity(P.kind, P.is_int);
-    for (uint32_t base = begin; base < end; base += kTapeBlock * U) {
+    for (uint32_t base = begin; base < end; base += kRedBlock * U) {
       uint32_t vidx[U], ridx[U];
       bool ok[U];
       uint32_t val[U][VEC];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        ridx[u] = base + u * kTapeBlock + threadIdx.x;
+        ridx[u] = base + u * kRedBlock + threadIdx.x;
         ok[u] = ridx[u] < end;
         vidx[u] = row * P.r_vec + ridx[u];
       }
-      eval_read<VEC, U>(P, slots, vidx, ok, val);
+      eval_read<VEC, U, RM>(P, slots, vidx, ok, val);
       a = fold_row<VEC, U>(P, a, val, ridx, ok);
     }
     a = block_reduce(P.kind, P.is_int, a, scratch);
     if (P.splits == 1) {
       if (threadIdx.x == 0) {
         const Acc one[1] = {a};
-        finalize<1>(P, smem + rd_words, row, one);
+        finalize<1, kRankGeneric>(P, smem + rd_words, threadIdx.x, row, one);
       }
     } else {
       if (threadIdx.x == 0) {
@@ -345,7 +348,7 @@ reduce_row_cta_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words,
       if (s_last) {
         __threadfence();
         Acc b = acc_identity(P.kind, P.is_int);
-        for (uint32_t s = threadIdx.x; s < P.splits; s += kTapeBlock) {
+        for (uint32_t s = threadIdx.x; s < P.splits; s += kRedBlock) {
           const uint2 raw = __ldcg(reinterpret_cast<const uint2 *>(&P.partials[(size_t)row * P.splits + s]));
           Acc e;
           e.v = raw.x;
@@ -355,7 +358,7 @@ reduce_row_cta_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words,
         b = block_reduce(P.kind, P.is_int, b, scratch);
         if (threadIdx.x == 0) {
           const Acc one[1] = {b};
-          finalize<1>(P, smem + rd_words, row, one);
+          finalize<1, kRankGeneric>(P, smem + rd_words, threadIdx.x, row, one);
           P.tickets[row] = 0u;
         }
       }
@@ -367,14 +370,16 @@ reduce_row_cta_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words,
 // ----------------------------------------------------------------- COL
 // blockDim = (TX, TY): TX column-vectors x TY row groups.  gridDim = (col tiles,
 // splits) with cluster dims (1, splits, 1).
-template <int VEC, int U>
-__global__ void __launch_bounds__(kTapeBlock)
+template <int VEC, int U, int RM>
+__global__ void __launch_bounds__(kRedBlock)
 reduce_col_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words, uint32_t slot_words) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   // slot file indexed by flat thread id
-  SlotFile<VEC, U> slots;
-  slots.base = smem + (VEC == 4 ? tid * 4 : tid);
+  SlotFile<VEC, U, kRedBlock> slots;
+  slots.smem = smem;
+  slots.tid = tid;
+  init_both_scalars<VEC, U, VEC>(P, smem, rd_words, tid);
   Acc *scratch = reinterpret_cast<Acc *>(smem + slot_words);  // [TY][TX][VEC], then cta result [TX][VEC]
 
   const uint32_t TX = blockDim.x, TY = blockDim.y;
@@ -400,7 +405,7 @@ reduce_col_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words, uin
       ok[u] = col_ok && r[u] < r_end;
       vidx[u] = (o * P.R + r[u]) * P.inner_vec + cvec;
     }
-    eval_read<VEC, U>(P, slots, vidx, ok, val);
+    eval_read<VEC, U, RM>(P, slots, vidx, ok, val);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (!ok[u]) continue;
@@ -446,7 +451,7 @@ reduce_col_kernel(const __grid_constant__ ReduceParams P, uint32_t rd_words, uin
     cluster.sync();  // keep remote smem alive until rank 0 has read it
     if (cluster.block_rank() != 0) return;
   }
-  if (threadIdx.y == 0 && col_ok) finalize<VEC>(P, smem + rd_words, o * P.inner_vec + cvec, a);
+  if (threadIdx.y == 0 && col_ok) finalize<VEC, kRankGeneric>(P, smem + rd_words, tid, o * P.inner_vec + cvec, a);
 }
 
 // ----------------------------------------------------------------- host planning
@@ -458,9 +463,9 @@ struct ReducePlan {
 
 static int32_t plan_side(const b200_tape *tape, const b200_tensor *ins, int n_ins,
                          const b200_tensor *outs, int n_outs, int rank, const int64_t *shape,
-                         bool first_input_virtual, TapeParams &tp,
-                         std::vector<PlannedOperand> &planned, CollapsedLayout &L) {
-  int32_t st = plan_tape(tape, n_ins + (first_input_virtual ? 1 : 0), n_outs, tp);
+                         bool first_input_virtual, CompiledTape &ct,
+                         std::vector<PlannedOperand> &planned, CollapsedLayout &L, int &rm) {
+  int32_t st = compile_tape(tape, n_ins + (first_input_virtual ? 1 : 0), n_outs, ct);
   if (st != B200_OK) return st;
   planned.assign(n_ins + n_outs, PlannedOperand{});
   std::vector<PlannedOperand *> all;
@@ -479,12 +484,13 @@ static int32_t plan_side(const b200_tape *tape, const b200_tensor *ins, int n_in
     all.push_back(&planned[n_ins + i]);
   }
   L = collapse_dims(rank, shape, all);
+  rm = rank_mode(L, all);
   return B200_OK;
 }
 
 static void fill_side(TapeParams &tp, const std::vector<PlannedOperand> &planned, int n_ins,
-                      int n_outs, const CollapsedLayout &L, int vec, bool first_input_virtual) {
-  fill_geometry(tp, L, vec);
+                      int n_outs, const CollapsedLayout &L, int vec, bool first_input_virtual, int rm) {
+  fill_geometry(tp, L, vec, rm);
   const int shift = first_input_virtual ? 1 : 0;
   if (first_input_virtual) {
     memset(&tp.in[0], 0, sizeof(OperandDesc));
@@ -535,7 +541,9 @@ static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_
   // outputs of the read tape are not supported through this entry (n_out = 0)
   std::vector<PlannedOperand> rd_planned;
   CollapsedLayout rdL;
-  int32_t st = plan_side(read, inputs, n_inputs, nullptr, 0, rank, shape, false, P.rd, rd_planned, rdL);
+  CompiledTape rd_ct, wr_ct;
+  int rm = kRankGeneric, wrm = kRankGeneric;
+  int32_t st = plan_side(read, inputs, n_inputs, nullptr, 0, rank, shape, false, rd_ct, rd_planned, rdL, rm);
   if (st != B200_OK) return st;
 
   // ---- write side
@@ -548,7 +556,7 @@ static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_
   std::vector<PlannedOperand> wr_planned;
   CollapsedLayout wrL;
   st = plan_side(write, write_inputs, n_write_inputs, outputs, n_outputs, out_rank, out_shape, true,
-                 P.wr, wr_planned, wrL);
+                 wr_ct, wr_planned, wrL, wrm);
   if (st != B200_OK) return st;
 
   // ---- mapping
@@ -559,8 +567,8 @@ static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_
   int vecw = 1;
   if (col && vec == 4 && wrL.shape[wrL.rank - 1] % 4 == 0) vecw = 4;
   if (col && vec == 4 && vecw != 4) vec = 1;  // keep read/write lane counts equal in COL
-  fill_side(P.rd, rd_planned, n_inputs, 0, rdL, vec, false);
-  fill_side(P.wr, wr_planned, n_write_inputs, n_outputs, wrL, col ? vec : 1, true);
+  fill_side(P.rd, rd_planned, n_inputs, 0, rdL, vec, false, rm);
+  fill_side(P.wr, wr_planned, n_write_inputs, n_outputs, wrL, col ? vec : 1, true, kRankGeneric);
   P.rd.n_vec = (uint32_t)(numel / vec);
   P.wr.n_vec = (uint32_t)(outer * inner / (col ? vec : 1));
   P.kind = kind;
@@ -576,8 +584,13 @@ static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_
   cudaStream_t stream = resolve_stream(s);
   const int sms = sm_count();
   const int U = (vec == 4) ? 2 : 4;
-  const size_t rd_slots = slot_file_bytes(std::max(1, P.rd.n_in + P.rd.n_tmp), vec, U);
-  const size_t wr_slots = slot_file_bytes(std::max(1, P.wr.n_in + P.wr.n_tmp), col ? vec : 1, 1);
+  st = finalize_tape(rd_ct, U, kRedBlock, 1, P.rd);
+  if (st != B200_OK) return st;
+  st = finalize_tape(wr_ct, 1, kRedBlock, 1, P.wr);
+  if (st != B200_OK) return st;
+  auto round16 = [](size_t b) { return (b + 15) / 16 * 16; };
+  const size_t rd_slots = round16(slot_file_bytes(std::max(1, P.rd.n_in + P.rd.n_tmp), P.rd.n_scalars, vec, U, kRedBlock));
+  const size_t wr_slots = round16(slot_file_bytes(std::max(1, P.wr.n_in + P.wr.n_tmp), P.wr.n_scalars, col ? vec : 1, 1, kRedBlock));
   const size_t slot_bytes = rd_slots + wr_slots;
   const uint32_t rd_words = (uint32_t)(rd_slots / 4);
   const uint32_t slot_words = (uint32_t)(slot_bytes / 4);
@@ -596,19 +609,26 @@ static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_
         if (smem > 48 * 1024)
           B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTapeBlock, smem));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRedBlock, smem));
         per_sm = std::max(per_sm, 1);
         const uint32_t need = (n_rows + kWarps - 1) / kWarps;
         const unsigned grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)(sms * per_sm)));
-        kern<<<grid, kTapeBlock, smem, stream>>>(P, rd_words);
+        kern<<<grid, kRedBlock, smem, stream>>>(P, rd_words);
         B200_LAUNCH_CHECK();
         return B200_OK;
       };
-      return vec == 4 ? launch(reduce_row_warp_kernel<4, 2>) : launch(reduce_row_warp_kernel<1, 4>);
+      if (vec == 4) {
+        if (rm == kRankLinear) return launch(reduce_row_warp_kernel<4, 2, kRankLinear>);
+        if (rm == kRank3) return launch(reduce_row_warp_kernel<4, 2, kRank3>);
+        return launch(reduce_row_warp_kernel<4, 2, kRankGeneric>);
+      }
+      if (rm == kRankLinear) return launch(reduce_row_warp_kernel<1, 4, kRankLinear>);
+      if (rm == kRank3) return launch(reduce_row_warp_kernel<1, 4, kRank3>);
+      return launch(reduce_row_warp_kernel<1, 4, kRankGeneric>);
     }
     // CTA per (row, split)
     const size_t smem = slot_bytes + sizeof(Acc) * kWarps;
-    const uint32_t tile = kTapeBlock * U;
+    const uint32_t tile = kRedBlock * U;
     uint32_t splits = 1;
     const uint32_t target = (uint32_t)sms * 4u;
     if (n_rows < target && P.r_vec > tile * 8u) {
@@ -634,15 +654,23 @@ static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_
       if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 0;
-      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTapeBlock, smem));
+      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRedBlock, smem));
       per_sm = std::max(per_sm, 1);
       const uint64_t work = (uint64_t)n_rows * splits;
       const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(work, (uint64_t)sms * per_sm));
-      kern<<<grid, kTapeBlock, smem, stream>>>(P, rd_words, slot_words);
+      kern<<<grid, kRedBlock, smem, stream>>>(P, rd_words, slot_words);
       B200_LAUNCH_CHECK();
       return B200_OK;
     };
-    st = vec == 4 ? launch(reduce_row_cta_kernel<4, 2>) : launch(reduce_row_cta_kernel<1, 4>);
+    if (vec == 4) {
+      st = rm == kRankLinear ? launch(reduce_row_cta_kernel<4, 2, kRankLinear>)
+           : rm == kRank3    ? launch(reduce_row_cta_kernel<4, 2, kRank3>)
+                             : launch(reduce_row_cta_kernel<4, 2, kRankGeneric>);
+    } else {
+      st = rm == kRankLinear ? launch(reduce_row_cta_kernel<1, 4, kRankLinear>)
+           : rm == kRank3    ? launch(reduce_row_cta_kernel<1, 4, kRank3>)
+                             : launch(reduce_row_cta_kernel<1, 4, kRankGeneric>);
+    }
     if (ws) cudaFreeAsync(ws, stream);
     return st;
   }
@@ -654,7 +682,7 @@ static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_
     TX = 8;
     tiles = P.outer * ((P.inner_vec + TX - 1) / TX);
   }
-  const uint32_t TY = kTapeBlock / TX;
+  const uint32_t TY = kRedBlock / TX;
   uint32_t splits = 1;
   const uint32_t target = (uint32_t)sms * 4u;
   while (splits < 8 && tiles * splits < target && P.R / (splits * 2) >= TY * (uint32_t)U * 2u) splits *= 2;
@@ -683,7 +711,14 @@ static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_
     B200_LAUNCH_CHECK();
     return B200_OK;
   };
-  return vec == 4 ? launch(reduce_col_kernel<4, 2>) : launch(reduce_col_kernel<1, 4>);
+  if (vec == 4) {
+    if (rm == kRankLinear) return launch(reduce_col_kernel<4, 2, kRankLinear>);
+    if (rm == kRank3) return launch(reduce_col_kernel<4, 2, kRank3>);
+    return launch(reduce_col_kernel<4, 2, kRankGeneric>);
+  }
+  if (rm == kRankLinear) return launch(reduce_col_kernel<1, 4, kRankLinear>);
+  if (rm == kRank3) return launch(reduce_col_kernel<1, 4, kRank3>);
+  return launch(reduce_col_kernel<1, 4, kRankGeneric>);
 }
 
 }  // namespace b200

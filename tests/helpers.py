@@ -11,6 +11,9 @@ from burn_b200.device import DeviceTensor, TapeBuilder
 # parity tolerances stated by BASELINE.json north_star
 REL_ELEMWISE = 1e-6
 REL_REDUCE = 1e-5
+# gelu = x*(1+erf(x/sqrt2))/2: for negative x the 1+erf cancels, so one f32 ulp of erf
+# (2^-24 = 6e-8, times |x|/2 <= 2) is the absolute floor of any f32 implementation
+ABS_GELU = 1.2e-7
 
 
 def up(a, dtype=None) -> DeviceTensor:
@@ -77,3 +80,22 @@ def assert_exact(got, want, what=""):
     if not same.all():
         i = tuple(np.argwhere(~same)[0])
         raise AssertionError(f"{what}: {np.count_nonzero(~same)} mismatches; first at {i}: got {got[i]!r} want {want[i]!r}")
+
+
+def assert_ulp(got, want, max_ulp: int, max_mismatch_frac: float, what=""):
+    """f32 results within `max_ulp` units in the last place, and bit-identical for all but
+    `max_mismatch_frac` of the elements."""
+    got = np.asarray(got, dtype=np.float32)
+    want = np.asarray(want, dtype=np.float32)
+    assert got.shape == want.shape
+
+    def ordered(a):
+        i = a.view(np.int32).astype(np.int64)
+        return np.where(i < 0, -(i & 0x7FFFFFFF), i)
+
+    fin = np.isfinite(want)
+    assert np.array_equal(got[~fin], want[~fin], equal_nan=True), f"{what}: non-finite values differ"
+    d = np.abs(ordered(got[fin]) - ordered(want[fin]))
+    assert d.max(initial=0) <= max_ulp, f"{what}: max ulp distance {d.max()} > {max_ulp}"
+    frac = np.count_nonzero(d) / max(d.size, 1)
+    assert frac <= max_mismatch_frac, f"{what}: {frac:.4%} of elements differ (limit {max_mismatch_frac:.2%})"

@@ -68,10 +68,16 @@ def test_unary(dev, op, fn, lo, hi):
     H.assert_close(got, fn(a), H.REL_ELEMWISE, 0.0, op)
 
 
-def test_erf_tanh_match_oracle_bits(dev):
-    # the oracle evaluates erf / tanh in f64 and rounds; so do we
-    a = rnd((1 << 16,), -5, 5)
-    H.assert_exact(H.unary("ERF_F", H.up(a)), oracle.float_erf(a), "erf")
+def test_erf_within_one_ulp_of_oracle_and_tanh_exact(dev):
+    # The oracle evaluates erf / tanh in f64 and rounds.  tanh does the same here (bit-exact);
+    # erf is an f32 routine designed to land within 1 ulp of the correctly rounded value
+    # (scripts/fit_erf.py): <= 1 ulp everywhere and identical for > 97 % of inputs.
+    a = np.concatenate([rnd((1 << 18,), -5, 5), rnd((1 << 18,), -0.5, 0.5),
+                        np.array([0.0, -0.0, 0.5, -0.5, 4.0, -4.0, 3.9999998, 1e-30, -1e-38, np.inf, -np.inf],
+                                 dtype=np.float32)])
+    got = H.unary("ERF_F", H.up(a))
+    H.assert_ulp(got, oracle.float_erf(a), 1, 0.03, "erf")
+    assert np.isnan(H.unary("ERF_F", H.up(np.array([np.nan], dtype=np.float32)))[0])
     H.assert_exact(H.unary("TANH_F", H.up(a)), oracle.float_tanh(a), "tanh")
 
 
@@ -125,7 +131,8 @@ def test_gelu_fused_chain(dev, shape):
     x = rnd(shape, -4, 4)
     tb = H.gelu_tape(TapeBuilder(), ("in", 0), out=0)
     got = H.run_tape(tb, [H.up(x)], shape)
-    H.assert_exact(got, oracle.gelu(x), "gelu")
+    # 1 + erf cancels for negative x: one f32 ulp of erf (6e-8) is the absolute floor
+    H.assert_close(got, oracle.gelu(x), H.REL_ELEMWISE, H.ABS_GELU, "gelu")
 
 
 def bench_chain_tape():
@@ -144,7 +151,7 @@ def test_bench_chain_matches_oracle(dev, shape):
     m = a < 0
     want = oracle.float_mask_fill(oracle.gelu(oracle.float_add(oracle.float_mul(a, b), c)), m, 0.0)
     got = H.run_tape(bench_chain_tape(), [H.up(a), H.up(b), H.up(c), H.up(m)], shape)
-    H.assert_exact(got, want, "bench chain")
+    H.assert_close(got, want, H.REL_ELEMWISE, 0.0, "bench chain")
     np.testing.assert_array_equal(want, oracle.bench_chain_unfused(a, b, c, m))
 
 
@@ -155,11 +162,11 @@ def test_bench_chain_variants_broadcast_and_transposed(dev):
     m = a < 0
     want = oracle.float_mask_fill(oracle.gelu(oracle.float_add(oracle.float_mul(a, b), c_row)), m, 0.0)
     got = H.run_tape(bench_chain_tape(), [H.up(a), H.up(b), H.up(c_row).expand(shape), H.up(m)], shape)
-    H.assert_exact(got, want, "chain with broadcast c")
+    H.assert_close(got, want, H.REL_ELEMWISE, 0.0, "chain with broadcast c")
     # `a` given as a transposed view of a [512, 256] buffer
     at = H.up(np.ascontiguousarray(a.T)).swap_dims(0, 1)
     got = H.run_tape(bench_chain_tape(), [at, H.up(b), H.up(c_row).expand(shape), H.up(m)], shape)
-    H.assert_exact(got, want, "chain with transposed a")
+    H.assert_close(got, want, H.REL_ELEMWISE, 0.0, "chain with transposed a")
 
 
 def test_multiple_outputs_and_temps(dev):
@@ -254,6 +261,6 @@ def test_full_size_chain_properties(dev):
     assert np.all(got[m] == 0.0)
     blk = (slice(4000, 4256), slice(0, 8192))
     want = oracle.float_mask_fill(oracle.gelu(oracle.float_add(oracle.float_mul(a[blk], b[blk]), c[blk])), m[blk], 0.0)
-    H.assert_exact(got[blk], want, "sampled block")
+    H.assert_close(got[blk], want, H.REL_ELEMWISE, 0.0, "sampled block")
     again = H.run_tape(bench_chain_tape(), [da, db, dc, dm], (n, n))
     assert np.array_equal(got, again)
