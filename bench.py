@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric on its configs[1] workload.
+
+metric   : fused elemwise/reduce GB/s vs HBM
+workload : on a synthetic [8192, 8192] f32 batch, one step =
+             y  = mask_fill(gelu(a*b + c), m, 0)       one fused kernel (17 B/elem algorithmic)
+             sum_dim(y, 1), sum_dim(y, 0), mean_dim(y, 1), argmax(y, 1), sum(y)
+           all through the burn_b200 C ABI (the entry points burn-fusion's Optimization::execute
+           would call).  value = algorithmic bytes of the step / step time.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm
+  python bench.py --impl reference --gpus N --steps K --warmup W   # burn-ndarray restatement on CPU
+
+N > 1 (torchrun): every rank runs the step on its own shard of independent tensors (weak
+scaling, no data-path collective); timing is barrier + device sync on both sides, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ROWS, N_COLS = 8192, 8192
+ELEMS = N_ROWS * N_COLS
+CHAIN_BYTES_PER_ELEM = 17  # a, b, c (f32) + mask (u8) + out (f32): SURVEY.md §8(d)
+
+
+def reduce_bytes(rows: int, cols: int) -> int:
+    """input once + one 4-byte output per kept index."""
+    return rows * cols * 4 + max(rows, cols) * 4
+
+
+def step_bytes(rows: int, cols: int) -> int:
+    e = rows * cols
+    return (e * CHAIN_BYTES_PER_ELEM            # fused chain
+            + (e * 4 + rows * 4) * 3            # sum_dim(1), mean_dim(1), argmax(1)
+            + (e * 4 + cols * 4)                # sum_dim(0)
+            + e * 4 + 4)                        # full sum
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("elemwise_chain_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.path = None
+        self.gpu = gpu_index
+        if shutil.which("nvidia-smi"):
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- our arm
+def chain_tape():
+    from burn_b200.device import TapeBuilder
+    tb = TapeBuilder()
+    tb.op("MUL_F", ("in", 0), ("in", 1))
+    tb.op("ADD_F", "acc", ("in", 2), tmp=0)
+    tb.op("DIV_F", ("tmp", 0), ("f", 1.4142135623730951))   # gelu as the 5 primitives burn-fusion
+    tb.op("ERF_F", "acc")                                     # records (activation.rs:69-76)
+    tb.op("ADD_F", "acc", ("f", 1.0))
+    tb.op("MUL_F", ("tmp", 0), "acc")
+    tb.op("DIV_F", "acc", ("f", 2.0))
+    tb.op("SELECT", "acc", ("f", 0.0), ("in", 3), out=0)       # mask_fill(., m, 0)
+    return tb.build()
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from burn_b200 import _abi as abi
+    from burn_b200 import device as dv
+    from burn_b200.device import DeviceTensor
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dv.init(local_rank)
+    lib = abi.load()
+    check = abi.check
+    shape = (N_ROWS, N_COLS)
+
+    # synthetic inputs, seeded per rank, staged in PINNED host memory
+    rng = np.random.default_rng(1000 + rank)
+    host = {}
+    for name in ("a", "b", "c"):
+        ptr = C.c_void_p()
+        check(lib.b200_host_alloc(C.byref(ptr), ELEMS * 4))
+        arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=shape)
+        arr[...] = rng.uniform(-1, 1, shape).astype(np.float32)
+        host[name] = (ptr, arr)
+    mptr = C.c_void_p()
+    check(lib.b200_host_alloc(C.byref(mptr), ELEMS))
+    marr = np.ctypeslib.as_array(C.cast(mptr, C.POINTER(C.c_uint8)), shape=shape)
+    marr[...] = host["a"][1] < 0
+    # pinned result buffers
+    res_ptr = C.c_void_p()
+    res_bytes = N_ROWS * 4 * 3 + N_COLS * 4 + 4
+    check(lib.b200_host_alloc(C.byref(res_ptr), res_bytes))
+
+    da, db, dc = (DeviceTensor.empty(shape) for _ in range(3))
+    dm = DeviceTensor.empty(shape, abi.BOOL)
+    y = DeviceTensor.empty(shape)
+    s1 = DeviceTensor.empty((N_ROWS, 1))
+    s0 = DeviceTensor.empty((1, N_COLS))
+    m1 = DeviceTensor.empty((N_ROWS, 1))
+    am = DeviceTensor.empty((N_ROWS, 1), abi.I32)
+    tot = DeviceTensor.empty((1,))
+    tape = chain_tape()
+
+    def h2d():
+        check(lib.b200_memcpy_h2d(da.data_ptr(), host["a"][0], ELEMS * 4, None))
+        check(lib.b200_memcpy_h2d(db.data_ptr(), host["b"][0], ELEMS * 4, None))
+        check(lib.b200_memcpy_h2d(dc.data_ptr(), host["c"][0], ELEMS * 4, None))
+        check(lib.b200_memcpy_h2d(dm.data_ptr(), mptr, ELEMS, None))
+
+    def d2h():
+        off = 0
+        for t, n in ((s1, N_ROWS * 4), (m1, N_ROWS * 4), (am, N_ROWS * 4), (s0, N_COLS * 4), (tot, 4)):
+            check(lib.b200_memcpy_d2h(res_ptr.value + off, t.data_ptr(), n, None))
+            off += n
+
+    ev = [C.c_void_p() for _ in range(4)]
+    for e in ev:
+        check(lib.b200_event_create(C.byref(e)))
+    chain_ev = []  # (start, stop) events around the dominant kernel, per timed step
+
+    def step(time_chain=None):
+        if time_chain is not None:
+            check(lib.b200_event_record(time_chain[0], None))
+        dv.launch_elemwise(tape, [da, db, dc, dm], [y], shape)
+        if time_chain is not None:
+            check(lib.b200_event_record(time_chain[1], None))
+        dv.launch_reduce(abi.RED_SUM, 1, shape, [y], [s1])
+        dv.launch_reduce(abi.RED_SUM, 0, shape, [y], [s0])
+        dv.launch_reduce(abi.RED_MEAN, 1, shape, [y], [m1])
+        dv.launch_reduce(abi.RED_ARGMAX, 1, shape, [y], [am])
+        dv.launch_reduce_full(abi.RED_SUM, y, tot)
+
+    def barrier():
+        check(lib.b200_device_sync())
+        if world > 1:
+            dist.barrier()
+        check(lib.b200_device_sync())
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident (kernel) timing
+    h2d()
+    for _ in range(args.warmup):
+        step()
+    for _ in range(args.steps):
+        a, b = C.c_void_p(), C.c_void_p()
+        check(lib.b200_event_create(C.byref(a)))
+        check(lib.b200_event_create(C.byref(b)))
+        chain_ev.append((a, b))
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    lib.b200_launch_count_reset()
+    check(lib.b200_event_record(ev[0], None))
+    for i in range(args.steps):
+        step(chain_ev[i])
+    check(lib.b200_event_record(ev[1], None))
+    barrier()
+    launches = int(lib.b200_launch_count())
+    ms = C.c_float()
+    check(lib.b200_event_elapsed_ms(ev[0], ev[1], C.byref(ms)))
+    total_ms = max_over_ranks(ms.value)
+    clocks = sampler.stop() if sampler else None
+    chain_ms = []
+    for a, b in chain_ev:
+        check(lib.b200_event_elapsed_ms(a, b, C.byref(ms)))
+        chain_ms.append(ms.value)
+
+    # ---- end-to-end timing: pinned host → device, step, results → host, every step
+    for _ in range(min(args.warmup, 3)):
+        h2d(); step(); d2h()
+    barrier()
+    check(lib.b200_event_record(ev[2], None))
+    for _ in range(args.steps):
+        h2d(); step(); d2h()
+    check(lib.b200_event_record(ev[3], None))
+    barrier()
+    check(lib.b200_event_elapsed_ms(ev[2], ev[3], C.byref(ms)))
+    e2e_ms = max_over_ranks(ms.value)
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on the box's host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_run(steps=1, warmup=0, rows=N_ROWS, arrays=(host["a"][1], host["b"][1], host["c"][1], marr))
+
+    if rank == 0:
+        sb = step_bytes(N_ROWS, N_COLS)
+        ms_per_step = total_ms / args.steps
+        value = world * sb / (ms_per_step * 1e-3) / 1e9
+        peak, peak_src = measured_peak()
+        chain_avg_ms = float(np.mean(chain_ms))
+        achieved = ELEMS * CHAIN_BYTES_PER_ELEM / (chain_avg_ms * 1e-3) / 1e9
+        h2d_bytes = ELEMS * 4 * 3 + ELEMS
+        line = {
+            "metric": "fused elemwise/reduce GB/s vs HBM",
+            "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "configs[1]: fused chain mask_fill(gelu(a*b+c),m,0) + sum_dim(1) + sum_dim(0) + "
+                            "mean_dim(1) + argmax(1) + sum on [8192,8192] f32, per GPU",
+                "algorithmic_bytes_per_step": sb,
+                "l2": "inputs (1.14 GB per step) exceed the 126 MB L2; no explicit flush",
+                "parallelism": f"replicas x{world} (independent shards, no data-path collective)",
+            },
+            "e2e": {"value": round(world * sb / (e2e_ms / args.steps * 1e-3) / 1e9, 2), "unit": "GB/s",
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": res_bytes,
+                    "ms_per_step": round(e2e_ms / args.steps, 3),
+                    "note": "pinned host buffers -> C ABI memcpy_h2d -> 6 launches -> memcpy_d2h of all reduction results"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "elemwise_tape_kernel_v4 (fused chain)",
+                         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "peak_source": peak_src,
+                         "traffic": ncu_traffic(), "avg_launch_ms": round(chain_avg_ms, 4),
+                         "share_of_step": round(chain_avg_ms / ms_per_step, 3)},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- reference arm
+def cpu_reference_run(steps: int, warmup: int, rows: int, arrays=None):
+    """Times the burn-ndarray restatement (oracle/) on the host: op-by-op, unfused, single
+    thread — ndarray's elementwise and reduce ops are single-threaded
+    (crates/burn-ndarray/src/ops/base.rs)."""
+    from oracle import oracle
+    oracle.build()
+    if arrays is None:
+        rng = np.random.default_rng(1000)
+        a = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
+        b = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
+        c = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
+        m = (a < 0).astype(np.uint8)
+    else:
+        a, b, c, m = (np.ascontiguousarray(x[:rows]) for x in arrays)
+
+    def one():
+        y = oracle.bench_chain_unfused(a, b, c, m)
+        oracle.float_sum_dim(y, 1)
+        oracle.float_sum_dim(y, 0)
+        oracle.float_mean_dim(y, 1)
+        oracle.float_argmax(y, 1)
+        oracle.float_sum(y)
+
+    for _ in range(warmup):
+        one()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return {"value": round(step_bytes(rows, N_COLS) / sec / 1e9, 3), "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"{steps} step(s) of the same workload on [{rows}, {N_COLS}] f32 "
+                      f"({sec:.2f} s/step), oracle/ndarray_oracle.c (gcc -O2), unfused op-by-op",
+            "host_cores_available": os.cpu_count()}
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    rows = N_ROWS if total <= 12 else max(256, (N_ROWS * 12 // total) // 256 * 256)
+    from oracle import oracle
+    oracle.build()
+    rng = np.random.default_rng(1000)
+    a = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
+    b = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
+    c = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
+    m = (a < 0).astype(np.uint8)
+
+    def one():
+        y = oracle.bench_chain_unfused(a, b, c, m)
+        oracle.float_sum_dim(y, 1)
+        oracle.float_sum_dim(y, 0)
+        oracle.float_mean_dim(y, 1)
+        oracle.float_argmax(y, 1)
+        oracle.float_sum(y)
+
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    sec = (time.perf_counter() - t0) / args.steps
+    sb = step_bytes(rows, N_COLS)
+    value = round(sb / sec / 1e9, 3)
+    sample = (f"each step = the configs[1] workload on a [{rows}, {N_COLS}] f32 sample "
+              f"({sb} algorithmic bytes), burn-ndarray restatement oracle/ndarray_oracle.c, unfused, 1 thread")
+    line = {
+        "impl": "reference", "metric": "fused elemwise/reduce GB/s vs HBM", "value": value, "unit": "GB/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] on the CPU restatement of burn-ndarray (the Rust reference cannot be "
+                               "built here: no cargo, un-vendored crates)", "sample_rows": rows},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

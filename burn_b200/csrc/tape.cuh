@@ -96,31 +96,31 @@ __device__ __forceinline__ float tanh_oracle(float x) { return (float)tanh((doub
 //   0.5 <= |x| < 4 : 28 table intervals of width 1/8: H_i + (d*Q_i(d) + L_i), d = |x| - c_i exact
 //   |x| >= 4       : +-1 (erfc(4) < half an ulp of 1)
 __device__ __forceinline__ float erf_f32(float x) {
+  // Branch-free: both regions are evaluated and selected, so the 16 independent
+  // evaluations a thread performs interleave freely.
   const float ax = fabsf(x);
-  float r;
-  if (ax < 0.5f) {
-    const float t = ax * ax;
-    float q = B200_ERF_Q4;
-    q = __fmaf_rn(q, t, B200_ERF_Q3);
-    q = __fmaf_rn(q, t, B200_ERF_Q2);
-    q = __fmaf_rn(q, t, B200_ERF_Q1);
-    q = __fmaf_rn(q, t, B200_ERF_Q0);
-    const float e = __fmaf_rn(t, q, B200_ERF_K_LO);
-    r = __fmaf_rn(ax, B200_ERF_K_HI, __fmul_rn(ax, e));
-  } else if (ax < 4.0f) {
-    const int i = __float2int_rz(__fmul_rn(__fsub_rn(ax, 0.5f), 8.0f));
-    const float c = __fmaf_rn((float)i, 0.125f, 0.5625f);
-    const float d = __fsub_rn(ax, c);
-    const float4 r0 = __ldg(&kErfB[2 * i]), r1 = __ldg(&kErfB[2 * i + 1]);
-    float q = r1.z;
-    q = __fmaf_rn(q, d, r1.y);
-    q = __fmaf_rn(q, d, r1.x);
-    q = __fmaf_rn(q, d, r0.w);
-    q = __fmaf_rn(q, d, r0.z);
-    r = __fadd_rn(r0.x, __fmaf_rn(d, q, r0.y));
-  } else {
-    r = (ax != ax) ? ax : 1.0f;
-  }
+  // region A
+  const float t = __fmul_rn(ax, ax);
+  float qa = B200_ERF_Q4;
+  qa = __fmaf_rn(qa, t, B200_ERF_Q3);
+  qa = __fmaf_rn(qa, t, B200_ERF_Q2);
+  qa = __fmaf_rn(qa, t, B200_ERF_Q1);
+  qa = __fmaf_rn(qa, t, B200_ERF_Q0);
+  const float e = __fmaf_rn(t, qa, B200_ERF_K_LO);
+  const float ra = __fmaf_rn(ax, B200_ERF_K_HI, __fmul_rn(ax, e));
+  // region B (index clamped so the table read is always in range; NaN -> row 0 -> NaN)
+  const int i = min(max(__float2int_rz(__fmul_rn(__fsub_rn(ax, 0.5f), 8.0f)), 0), 27);
+  const float c = __fmaf_rn((float)i, 0.125f, 0.5625f);
+  const float d = __fsub_rn(ax, c);
+  const float4 r0 = __ldg(&kErfB[2 * i]), r1 = __ldg(&kErfB[2 * i + 1]);
+  float qb = r1.z;
+  qb = __fmaf_rn(qb, d, r1.y);
+  qb = __fmaf_rn(qb, d, r1.x);
+  qb = __fmaf_rn(qb, d, r0.w);
+  qb = __fmaf_rn(qb, d, r0.z);
+  const float rb = __fadd_rn(r0.x, __fmaf_rn(d, qb, r0.y));
+  float r = ax < 0.5f ? ra : rb;
+  r = ax >= 4.0f ? 1.0f : r;
   return copysignf(r, x);
 }
 
@@ -143,12 +143,19 @@ __device__ __forceinline__ float sign_f(float x) {
 // sequence gives the correctly rounded quotient when nothing under/overflows; the
 // guarded range falls back to the IEEE division.  (Host only emits kOpDivScalar
 // for normal y whose significand is not all ones.)
-__device__ __forceinline__ float div_scalar_exact(float x, float y, float rinv) {
+__device__ __forceinline__ float div_scalar_fast(float x, float y, float rinv) {
   const float q = __fmul_rn(x, rinv);
   const float r = __fmaf_rn(-y, q, x);
-  const float q2 = __fmaf_rn(r, rinv, q);
+  return __fmaf_rn(r, rinv, q);
+}
+// True when Markstein's sequence is exact for x (no intermediate under/overflow);
+// zero is fine (0/y = 0).
+__device__ __forceinline__ bool div_scalar_safe(float x) {
   const float ax = fabsf(x);
-  return (ax > 1e-25f && ax < 1e25f) ? q2 : __fdiv_rn(x, y);
+  return (ax > 1e-25f && ax < 1e25f) || ax == 0.0f;
+}
+__device__ __forceinline__ float div_scalar_exact(float x, float y, float rinv) {
+  return div_scalar_safe(x) ? div_scalar_fast(x, y, rinv) : __fdiv_rn(x, y);
 }
 
 static __device__ __noinline__ float pow_f(float a, float b) { return powf(a, b); }
@@ -556,7 +563,16 @@ __device__ __forceinline__ void run_tape(const TapeParams &p, const SlotFile<VEC
       case kOpDivScalar: {
         const float ys = f_of(b[0][0]);
         const float rinv = __frcp_rn(ys);
-        B200_UN(div_scalar_exact(x, ys, rinv))
+        bool safe = true;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) safe &= div_scalar_safe(f_of(acc[u][j]));
+        if (safe) {
+          B200_UN(div_scalar_fast(x, ys, rinv))
+        } else {
+          B200_UN(__fdiv_rn(x, ys))
+        }
         break;
       }
       case kOpMulAdd:
@@ -572,15 +588,31 @@ __device__ __forceinline__ void run_tape(const TapeParams &p, const SlotFile<VEC
         // step rounded exactly as the five separate ops would be
         // (crates/burn-backend/src/backend/ops/activation.rs:69-76)
         const float s2 = 1.41421353816986083984375f;  // f32(SQRT_2)
-        const float rinv = __frcp_rn(s2);
+        const float rinv = 0.707106769084930419921875f;  // RN(1 / f32(SQRT_2))
+        bool safe = true;
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) {
-            const float x = f_of(b[u][j]);
-            const float e = erf_f32(div_scalar_exact(x, s2, rinv));
-            acc[u][j] = u_of(__fmul_rn(__fmul_rn(x, __fadd_rn(e, 1.0f)), 0.5f));
-          }
+          for (int j = 0; j < VEC; ++j) safe &= div_scalar_safe(f_of(b[u][j]));
+        if (safe) {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              const float x = f_of(b[u][j]);
+              const float e = erf_f32(div_scalar_fast(x, s2, rinv));
+              acc[u][j] = u_of(__fmul_rn(__fmul_rn(x, __fadd_rn(e, 1.0f)), 0.5f));
+            }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              const float x = f_of(b[u][j]);
+              const float e = erf_f32(__fdiv_rn(x, s2));
+              acc[u][j] = u_of(__fmul_rn(__fmul_rn(x, __fadd_rn(e, 1.0f)), 0.5f));
+            }
+        }
         break;
       }
       case B200_OP_REM_F: B200_BIN(rem_floor(x, y)) break;
