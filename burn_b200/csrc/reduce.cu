@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include "tape_host.cuh"
+#include "reduce_fast.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -507,6 +508,124 @@ static bool is_int_dtype(int32_t dt) {
   return dt == B200_I32 || dt == B200_I64 || dt == B200_BOOL || dt == B200_U8;
 }
 
+// ----------------------------------------------------------------- fast-path dispatch
+template <int K>
+static int32_t launch_fast(bool col, const fast::RowParams &rp, const fast::ColParams &cp, bool warp_rows,
+                           unsigned grid, cudaStream_t stream) {
+  if (!col) {
+    if (warp_rows) fast::reduce_row_warp_fast_kernel<K><<<grid, fast::kBlock, 0, stream>>>(rp);
+    else fast::reduce_row_fast_kernel<K><<<grid, fast::kBlock, 0, stream>>>(rp);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, cp.splits, 1);
+  cfg.blockDim = dim3(32, 8, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = cp.splits;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, fast::reduce_col_fast_kernel<K>, cp));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// Returns 1 when the reduction was launched on a fast path, 0 when the caller must
+// use the general tape path, < 0 on error.
+static int32_t try_fast_reduce(int32_t kind, int64_t outer, int64_t R, int64_t inner, const b200_tensor &in,
+                               const b200_tensor &out, cudaStream_t stream) {
+  int K;
+  switch (kind) {
+    case B200_RED_SUM: case B200_RED_MEAN: K = fast::kSum; break;
+    case B200_RED_MAX: K = fast::kMax; break;
+    case B200_RED_MIN: K = fast::kMin; break;
+    case B200_RED_ARGMAX: K = fast::kArgMax; break;
+    case B200_RED_ARGMIN: K = fast::kArgMin; break;
+    default: return 0;
+  }
+  if (in.dtype != B200_F32 || !is_contiguous(in) || !is_contiguous(out)) return 0;
+  if (((uintptr_t)in.ptr) % 16 != 0 || R == 0) return 0;
+  const bool is_arg = K >= fast::kArgMax;
+  if (is_arg ? !(out.dtype == B200_I32 || out.dtype == B200_I64)
+             : !(out.dtype == B200_F32 || out.dtype == B200_F16 || out.dtype == B200_BF16))
+    return 0;
+  const bool col = inner > 1;
+  if (col ? (inner % 4 != 0) : (R % 4 != 0)) return 0;
+  const int sms = sm_count();
+  fast::RowParams rp = {};
+  fast::ColParams cp = {};
+  void *ws = nullptr;
+  unsigned grid = 1;
+  bool warp_rows = false;
+  if (!col) {
+    rp.x = reinterpret_cast<const float *>(in.ptr);
+    rp.out = out.ptr;
+    rp.out_dtype = out.dtype;
+    rp.n_rows = (uint32_t)outer;
+    rp.r4 = (uint32_t)(R / 4);
+    rp.mean = kind == B200_RED_MEAN;
+    rp.div = (float)R;
+    rp.splits = 1;
+    rp.per_split = rp.r4;
+    warp_rows = rp.r4 <= 1024 && rp.n_rows >= (uint32_t)(sms * fast::kWarpsPerBlock);
+    if (warp_rows) {
+      grid = std::min<uint32_t>((rp.n_rows + fast::kWarpsPerBlock - 1) / fast::kWarpsPerBlock, (uint32_t)sms * 8u);
+    } else {
+      const uint32_t tile = fast::kBlock * 4;
+      const uint32_t target = (uint32_t)sms * 8u;
+      uint32_t splits = 1;
+      if (rp.n_rows < target && rp.r4 > tile * 2u)
+        splits = std::min<uint32_t>((target + rp.n_rows - 1) / rp.n_rows, (rp.r4 + tile - 1) / tile);
+      splits = std::max(1u, std::min(splits, 2048u));
+      uint32_t per = (rp.r4 + splits - 1) / splits;
+      per = ((per + tile - 1) / tile) * tile;
+      splits = (rp.r4 + per - 1) / per;
+      rp.splits = splits;
+      rp.per_split = per;
+      if (splits > 1) {
+        const size_t pbytes = sizeof(fast::VI) * (size_t)rp.n_rows * splits;
+        const size_t tbytes = sizeof(uint32_t) * (size_t)rp.n_rows;
+        B200_CUDA(cudaMallocAsync(&ws, pbytes + tbytes, stream));
+        rp.partials = reinterpret_cast<fast::VI *>(ws);
+        rp.tickets = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(ws) + pbytes);
+        B200_CUDA(cudaMemsetAsync(rp.tickets, 0, tbytes, stream));
+      }
+      grid = (unsigned)std::min<uint64_t>((uint64_t)rp.n_rows * splits, (uint64_t)sms * 8u);
+    }
+  } else {
+    cp.x = reinterpret_cast<const float *>(in.ptr);
+    cp.out = out.ptr;
+    cp.out_dtype = out.dtype;
+    cp.outer = (uint32_t)outer;
+    cp.R = (uint32_t)R;
+    cp.inner4 = (uint32_t)(inner / 4);
+    cp.mean = kind == B200_RED_MEAN;
+    cp.div = (float)R;
+    const uint32_t tiles = cp.outer * ((cp.inner4 + 31) / 32);
+    uint32_t splits = 1;
+    while (splits < 8 && tiles * splits < (uint32_t)sms * 6u && cp.R / (splits * 2) >= 64u) splits *= 2;
+    cp.splits = splits;
+    cp.rows_per_split = (cp.R + splits - 1) / splits;
+    grid = tiles;
+  }
+  int32_t st;
+  switch (K) {
+    case fast::kSum: st = launch_fast<fast::kSum>(col, rp, cp, warp_rows, grid, stream); break;
+    case fast::kMax: st = launch_fast<fast::kMax>(col, rp, cp, warp_rows, grid, stream); break;
+    case fast::kMin: st = launch_fast<fast::kMin>(col, rp, cp, warp_rows, grid, stream); break;
+    case fast::kArgMax: st = launch_fast<fast::kArgMax>(col, rp, cp, warp_rows, grid, stream); break;
+    default: st = launch_fast<fast::kArgMin>(col, rp, cp, warp_rows, grid, stream); break;
+  }
+  if (ws) cudaFreeAsync(ws, stream);
+  return st == B200_OK ? 1 : st;
+}
+
+
 // Core entry: the input shape is `shape` (rank dims); dims [ax_begin, ax_end) are
 // reduced together (ax_end - ax_begin == 1 for an axis reduce; the whole range
 // for a full reduce, which requires it to be all dims).
@@ -526,6 +645,16 @@ static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_
   const bool is_arg = kind == B200_RED_ARGMAX || kind == B200_RED_ARGMIN;
   if (is_arg) B200_REQUIRE(R > 0, B200_ERR_SHAPE, "Cannot compute arg over an empty axis");
   if (outer * inner == 0) return B200_OK;
+
+  if (!read && !write && n_inputs == 1 && n_outputs == 1) {
+    b200_tensor in_flat = inputs[0];
+    bool shapes_match = in_flat.rank == rank;
+    for (int d = 0; shapes_match && d < rank; ++d) shapes_match = in_flat.shape[d] == shape[d];
+    if (shapes_match) {
+      const int32_t fs = try_fast_reduce(kind, outer, R, inner, in_flat, outputs[0], resolve_stream(s));
+      if (fs != 0) return fs < 0 ? fs : B200_OK;
+    }
+  }
 
   ReducePlan plan;
   ReduceParams &P = plan.P;

@@ -1,0 +1,305 @@
+// Fast paths of path (b): plain f32 reductions of a contiguous tensor with no
+// fused tape — float_sum / float_sum_dim / float_mean_dim / float_max_dim /
+// float_argmax on materialised tensors, by far the most common calls
+// (crates/burn-cubecl/src/kernel/reduce/base.rs:108-150).  Everything is
+// specialised at compile time (kind, mapping), loads are 128-bit with four
+// independent requests in flight per thread, and the combine tree is
+// deterministic.  Semantics are those of reduce.cu (keepdim, first-index ties,
+// first-NaN-wins, NaN-propagating max/min).
+//
+// Roofline: HBM; algorithmic bytes = input bytes + output bytes.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "tape.cuh"
+
+namespace b200 {
+namespace fast {
+
+namespace cgf = cooperative_groups;
+
+constexpr int kBlock = 256;
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+enum Kind : int { kSum = 0, kMax = 1, kMin = 2, kArgMax = 3, kArgMin = 4 };
+
+struct VI {
+  float v;
+  int32_t i;
+};
+
+template <int K>
+__device__ __forceinline__ VI identity() {
+  VI a;
+  a.i = 0x7fffffff;
+  a.v = (K == kSum) ? 0.0f : ((K == kMax || K == kArgMax) ? -INFINITY : INFINITY);
+  return a;
+}
+
+// Folds element (x, idx) into a (sequential use: idx increases, but the rule is
+// written to be order-independent so it also serves the tree combine).
+template <int K>
+__device__ __forceinline__ VI combine(VI a, VI b) {
+  if constexpr (K == kSum) {
+    a.v = __fadd_rn(a.v, b.v);
+    return a;
+  } else if constexpr (K == kMax || K == kMin) {
+    const bool an = a.v != a.v, bn = b.v != b.v;
+    float r = (K == kMax) ? fmaxf(a.v, b.v) : fminf(a.v, b.v);
+    r = an ? a.v : (bn ? b.v : r);
+    a.v = r;
+    return a;
+  } else {
+    const bool an = a.v != a.v, bn = b.v != b.v;
+    bool better = (K == kArgMax) ? (b.v > a.v) : (b.v < a.v);
+    better = better || (b.v == a.v && b.i < a.i);
+    const bool take_b = (an || bn) ? (bn && (!an || b.i < a.i)) : better;
+    return take_b ? b : a;
+  }
+}
+
+// Sequential fold: elements reach a thread in increasing index order, so a strict
+// comparison keeps the first extreme, and "!(x <= best) && best == best" is both
+// "x beats best" and "the first NaN wins and sticks" in two predicate instructions.
+// Callers seed a.i with the index of the thread's first element (value = identity),
+// so an all -inf (+inf) lane still reports its first index.
+template <int K>
+__device__ __forceinline__ VI fold(VI a, float x, int32_t idx) {
+  if constexpr (K == kSum) {
+    a.v = __fadd_rn(a.v, x);
+  } else {
+    const bool beats = (K == kMax || K == kArgMax) ? !(x <= a.v) : !(x >= a.v);
+    const bool take = beats && (a.v == a.v);
+    a.v = take ? x : a.v;
+    if constexpr (K >= kArgMax) a.i = take ? idx : a.i;
+  }
+  return a;
+}
+
+template <int K>
+__device__ __forceinline__ VI warp_reduce(VI a) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    VI b;
+    b.v = __shfl_xor_sync(0xffffffffu, a.v, m);
+    b.i = (K >= kArgMax) ? __shfl_xor_sync(0xffffffffu, a.i, m) : 0;
+    a = combine<K>(a, b);
+  }
+  return a;
+}
+
+template <int K>
+__device__ __forceinline__ VI block_reduce(VI a, VI *scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a = warp_reduce<K>(a);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = a;
+  __syncthreads();
+  VI r = (lane < kWarpsPerBlock) ? scratch[lane] : identity<K>();
+  return warp_reduce<K>(r);
+}
+
+template <int K>
+__device__ __forceinline__ void store_result(void *out, int32_t out_dtype, int64_t idx, VI a, bool mean, float div) {
+  if constexpr (K >= kArgMax) {
+    if (out_dtype == B200_I64) reinterpret_cast<long long *>(out)[idx] = (long long)a.i;
+    else reinterpret_cast<int32_t *>(out)[idx] = a.i;
+  } else {
+    float v = a.v;
+    if (mean) v = __fdiv_rn(v, div);
+    store_one(out, out_dtype, idx, u_of(v));
+  }
+}
+
+struct RowParams {
+  const float *x;
+  void *out;
+  int32_t out_dtype;
+  uint32_t n_rows;
+  uint32_t r4;          // row length in float4
+  uint32_t splits;      // CTAs per row
+  uint32_t per_split;   // float4 per split (multiple of kBlock*4)
+  VI *partials;
+  uint32_t *tickets;
+  int32_t mean;
+  float div;
+};
+
+// One CTA per (row, split); four 128-bit loads in flight per thread.
+template <int K>
+__global__ void __launch_bounds__(kBlock) reduce_row_fast_kernel(const RowParams P) {
+  __shared__ VI scratch[kWarpsPerBlock];
+  __shared__ uint32_t s_last;
+  const uint32_t n_work = P.n_rows * P.splits;
+  for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const uint32_t row = w / P.splits, split = w - row * P.splits;
+    const float4 *p = reinterpret_cast<const float4 *>(P.x) + (size_t)row * P.r4;
+    const uint32_t begin = split * P.per_split, end = min(P.r4, begin + P.per_split);
+    VI a = identity<K>();
+    if (begin + threadIdx.x < end) a.i = (int32_t)((begin + threadIdx.x) * 4);
+    for (uint32_t base = begin + threadIdx.x; base < end; base += kBlock * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = base + k * kBlock;
+        v[k] = i < end ? __ldcs(p + i) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = base + k * kBlock;
+        if (i < end) {
+          a = fold<K>(a, v[k].x, (int32_t)(i * 4));
+          a = fold<K>(a, v[k].y, (int32_t)(i * 4 + 1));
+          a = fold<K>(a, v[k].z, (int32_t)(i * 4 + 2));
+          a = fold<K>(a, v[k].w, (int32_t)(i * 4 + 3));
+        }
+      }
+    }
+    a = block_reduce<K>(a, scratch);
+    if (P.splits == 1) {
+      if (threadIdx.x == 0) store_result<K>(P.out, P.out_dtype, row, a, P.mean, P.div);
+    } else {
+      if (threadIdx.x == 0) {
+        P.partials[(size_t)row * P.splits + split] = a;
+        __threadfence();
+        s_last = (atomicAdd(&P.tickets[row], 1u) == P.splits - 1) ? 1u : 0u;
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        VI b = identity<K>();
+        for (uint32_t s = threadIdx.x; s < P.splits; s += kBlock) {
+          const float2 raw = __ldcg(reinterpret_cast<const float2 *>(&P.partials[(size_t)row * P.splits + s]));
+          VI e;
+          e.v = raw.x;
+          e.i = __float_as_int(raw.y);
+          b = combine<K>(b, e);
+        }
+        b = block_reduce<K>(b, scratch);
+        if (threadIdx.x == 0) {
+          store_result<K>(P.out, P.out_dtype, row, b, P.mean, P.div);
+          P.tickets[row] = 0u;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// One warp per short row (R <= 4096 elements): no shared memory, no barriers.
+template <int K>
+__global__ void __launch_bounds__(kBlock) reduce_row_warp_fast_kernel(const RowParams P) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t row = blockIdx.x * kWarpsPerBlock + warp; row < P.n_rows; row += gridDim.x * kWarpsPerBlock) {
+    const float4 *p = reinterpret_cast<const float4 *>(P.x) + (size_t)row * P.r4;
+    VI a = identity<K>();
+    if ((uint32_t)lane < P.r4) a.i = lane * 4;
+    for (uint32_t base = lane; base < P.r4; base += 32 * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = base + k * 32;
+        v[k] = i < P.r4 ? __ldcs(p + i) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = base + k * 32;
+        if (i < P.r4) {
+          a = fold<K>(a, v[k].x, (int32_t)(i * 4));
+          a = fold<K>(a, v[k].y, (int32_t)(i * 4 + 1));
+          a = fold<K>(a, v[k].z, (int32_t)(i * 4 + 2));
+          a = fold<K>(a, v[k].w, (int32_t)(i * 4 + 3));
+        }
+      }
+    }
+    a = warp_reduce<K>(a);
+    if (lane == 0) store_result<K>(P.out, P.out_dtype, row, a, P.mean, P.div);
+  }
+}
+
+struct ColParams {
+  const float *x;
+  void *out;
+  int32_t out_dtype;
+  uint32_t outer, R, inner4;   // inner in float4
+  uint32_t splits, rows_per_split;
+  int32_t mean;
+  float div;
+};
+
+// blockDim = (32, 8): 32 column-vectors (128 columns, 512 B per row) x 8 row
+// groups; gridDim = (column tiles, splits) with cluster (1, splits, 1) — the
+// cluster's partial columns are combined through distributed shared memory.
+template <int K>
+__global__ void __launch_bounds__(kBlock) reduce_col_fast_kernel(const ColParams P) {
+  constexpr int TX = 32, TY = 8;
+  __shared__ VI part[TY][TX][4];
+  __shared__ VI cta_result[TX][4];
+  const uint32_t tiles_per_outer = (P.inner4 + TX - 1) / TX;
+  const uint32_t o = blockIdx.x / tiles_per_outer;
+  const uint32_t c4 = (blockIdx.x - o * tiles_per_outer) * TX + threadIdx.x;
+  const bool col_ok = c4 < P.inner4;
+  const uint32_t r_begin = blockIdx.y * P.rows_per_split;
+  const uint32_t r_end = min(P.R, r_begin + P.rows_per_split);
+  const float4 *p = reinterpret_cast<const float4 *>(P.x) + (size_t)o * P.R * P.inner4 + c4;
+
+  VI a[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    a[j] = identity<K>();
+    if (r_begin + threadIdx.y < r_end) a[j].i = (int32_t)(r_begin + threadIdx.y);
+  }
+  if (col_ok) {
+    for (uint32_t base = r_begin + threadIdx.y; base < r_end; base += TY * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t r = base + k * TY;
+        v[k] = r < r_end ? __ldcs(p + (size_t)r * P.inner4) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t r = base + k * TY;
+        if (r < r_end) {
+          a[0] = fold<K>(a[0], v[k].x, (int32_t)r);
+          a[1] = fold<K>(a[1], v[k].y, (int32_t)r);
+          a[2] = fold<K>(a[2], v[k].z, (int32_t)r);
+          a[3] = fold<K>(a[3], v[k].w, (int32_t)r);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) part[threadIdx.y][threadIdx.x][j] = a[j];
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      VI b = part[0][threadIdx.x][j];
+      for (int y = 1; y < TY; ++y) b = combine<K>(b, part[y][threadIdx.x][j]);
+      a[j] = b;
+      cta_result[threadIdx.x][j] = b;
+    }
+  }
+  if (P.splits > 1) {
+    cgf::cluster_group cluster = cgf::this_cluster();
+    cluster.sync();
+    if (cluster.block_rank() == 0 && threadIdx.y == 0) {
+      for (uint32_t rk = 1; rk < P.splits; ++rk) {
+        const VI *remote = cluster.map_shared_rank(&cta_result[0][0], rk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = combine<K>(a[j], remote[threadIdx.x * 4 + j]);
+      }
+    }
+    cluster.sync();
+    if (cluster.block_rank() != 0) return;
+  }
+  if (threadIdx.y == 0 && col_ok) {
+    const int64_t base = ((int64_t)o * P.inner4 + c4) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) store_result<K>(P.out, P.out_dtype, base + j, a[j], P.mean, P.div);
+  }
+}
+
+}  // namespace fast
+}  // namespace b200

@@ -1,0 +1,188 @@
+"""GPU parity: gather / scatter_add / select / select_add / copy-cast / arange / random.
+
+Protocol of crates/burn-backend-tests/tests/cubecl/{gather,scatter,select,select_assign}.rs
+and the golden values of tests/tensor/float/ops/{gather_scatter,select}.rs.  Indexing results
+are bit-exact; scatter_add / select_add keep the oracle's sequential accumulation order
+(crates/burn-ndarray/src/ops/base.rs:140-183), so float sums are bit-exact too.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from burn_b200 import _abi as abi
+from burn_b200 import device as dv
+from burn_b200.device import DeviceTensor
+from oracle import oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def lib():
+    return abi.load()
+
+
+def gather(dim, t, idx):
+    out = DeviceTensor.empty(idx.shape, t.dtype)
+    a, b, c = t.desc(), idx.desc(), out.desc()
+    abi.check(lib().b200_launch_gather(dim, C.byref(a), C.byref(b), C.byref(c), None))
+    return out.numpy()
+
+
+def scatter_add(dim, t, idx, v):
+    a, b, c = t.desc(), idx.desc(), v.desc()
+    abi.check(lib().b200_launch_scatter_add(dim, C.byref(a), C.byref(b), C.byref(c), None))
+    return t.numpy()
+
+
+def select(dim, t, idx):
+    shape = list(t.shape)
+    shape[dim] = idx.shape[0]
+    out = DeviceTensor.empty(shape, t.dtype)
+    a, b, c = t.desc(), idx.desc(), out.desc()
+    abi.check(lib().b200_launch_select(dim, C.byref(a), C.byref(b), C.byref(c), None))
+    return out.numpy()
+
+
+def select_add(dim, t, idx, v):
+    a, b, c = t.desc(), idx.desc(), v.desc()
+    abi.check(lib().b200_launch_select_add(dim, C.byref(a), C.byref(b), C.byref(c), None))
+    return t.numpy()
+
+
+def test_gather_reference_goldens(dev):
+    # crates/burn-backend-tests/tests/tensor/float/ops/gather_scatter.rs (should_gather_1d_dim0 / 2d)
+    t = H.up(np.array([0.0, 1.0, 2.0], dtype=np.float32))
+    idx = H.up(np.array([1, 1, 0, 1, 2], dtype=np.int64))
+    H.assert_exact(gather(0, t, idx), np.array([1.0, 1.0, 0.0, 1.0, 2.0], dtype=np.float32))
+    t2 = H.up(np.array([[0.0, 1.0, 2.0], [3.0, 4.0, 5.0]], dtype=np.float32))
+    i0 = H.up(np.array([[0, 1, 0], [1, 0, 1]], dtype=np.int64))
+    H.assert_exact(gather(0, t2, i0), np.array([[0.0, 4.0, 2.0], [3.0, 1.0, 5.0]], dtype=np.float32))
+    i1 = H.up(np.array([[2, 1, 0, 0], [2, 0, 1, 2]], dtype=np.int64))
+    H.assert_exact(gather(1, t2, i1), np.array([[2.0, 1.0, 0.0, 0.0], [5.0, 3.0, 4.0, 5.0]], dtype=np.float32))
+
+
+@pytest.mark.parametrize("shape,dim", [((7, 33), 1), ((7, 33), 0), ((4, 6, 20), 1), ((128, 1000), 1)])
+@pytest.mark.parametrize("itype", [np.int32, np.int64])
+def test_gather_random_vs_oracle(dev, shape, dim, itype):
+    rng = np.random.default_rng(1)
+    t = rng.uniform(-1, 1, shape).astype(np.float32)
+    ishape = list(shape)
+    ishape[dim] = 5
+    idx = rng.integers(0, shape[dim], size=ishape).astype(itype)
+    H.assert_exact(gather(dim, H.up(t), H.up(idx)), oracle.float_gather(dim, t, idx))
+
+
+def test_cross_entropy_gather_shape(dev):
+    # CE loss: log-probs [N, V] gathered by targets [N, 1] (crates/burn-nn/src/loss/cross_entropy.rs:171-197)
+    rng = np.random.default_rng(2)
+    lp = rng.uniform(-10, 0, (512, 5000)).astype(np.float32)
+    tg = rng.integers(0, 5000, size=(512, 1)).astype(np.int64)
+    H.assert_exact(gather(1, H.up(lp), H.up(tg)), oracle.float_gather(1, lp, tg))
+
+
+def test_scatter_add_reference_goldens(dev):
+    # gather_scatter.rs should_scatter_1d / 2d_dim0
+    t = H.up(np.zeros(3, dtype=np.float32))
+    H.assert_exact(scatter_add(0, t, H.up(np.array([1, 0, 2], dtype=np.int64)),
+                               H.up(np.array([5.0, 4.0, 3.0], dtype=np.float32))),
+                   np.array([4.0, 5.0, 3.0], dtype=np.float32))
+    t = H.up(np.zeros((2, 3), dtype=np.float32))
+    v = H.up(np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]], dtype=np.float32))
+    i = H.up(np.array([[1, 0, 1], [1, 1, 0]], dtype=np.int64))
+    H.assert_exact(scatter_add(0, t, i, v), np.array([[0.0, 2.0, 6.0], [5.0, 5.0, 3.0]], dtype=np.float32))
+
+
+@pytest.mark.parametrize("shape,dim,n", [((50, 8), 0, 300), ((6, 40), 1, 100), ((3, 64, 5), 1, 200)])
+def test_scatter_add_bit_exact_with_collisions(dev, shape, dim, n):
+    rng = np.random.default_rng(3)
+    t = rng.uniform(-1, 1, shape).astype(np.float32)
+    ishape = list(shape)
+    ishape[dim] = n
+    idx = rng.integers(0, shape[dim], size=ishape).astype(np.int64)
+    v = rng.uniform(-1, 1, ishape).astype(np.float32)
+    H.assert_exact(scatter_add(dim, H.up(t), H.up(idx), H.up(v)), oracle.float_scatter_add(dim, t, idx, v))
+
+
+def test_select_and_embedding_forward(dev):
+    # select.rs goldens + embedding forward = select(weight [V, d], ids) (ops/modules/base.rs:140-160)
+    t = np.array([[0.0, 1.0, 2.0], [3.0, 4.0, 5.0]], dtype=np.float32)
+    H.assert_exact(select(0, H.up(t), H.up(np.array([1, 0], dtype=np.int64))), t[[1, 0]])
+    H.assert_exact(select(1, H.up(t), H.up(np.array([1, 1, 0, 1, 2], dtype=np.int64))), t[:, [1, 1, 0, 1, 2]])
+    rng = np.random.default_rng(4)
+    w = rng.standard_normal((1000, 64)).astype(np.float32)
+    ids = rng.integers(0, 1000, size=(777,)).astype(np.int32)
+    H.assert_exact(select(0, H.up(w), H.up(ids)), oracle.float_select(w, 0, ids))
+
+
+def test_select_add_embedding_backward_bit_exact(dev):
+    # embedding backward = zeros[V, d].select_add(0, ids, grad) (ops/modules/base.rs:161-180)
+    rng = np.random.default_rng(5)
+    V, d, n = 300, 48, 2000
+    ids = rng.integers(0, V, size=(n,)).astype(np.int64)
+    g = rng.standard_normal((n, d)).astype(np.float32)
+    got = select_add(0, H.up(np.zeros((V, d), dtype=np.float32)), H.up(ids), H.up(g))
+    H.assert_exact(got, oracle.float_select_add(np.zeros((V, d), dtype=np.float32), 0, ids, g))
+    # select.rs should_select_add_2d_dim1-style case
+    t = np.array([[0.0, 1.0, 2.0], [3.0, 4.0, 5.0]], dtype=np.float32)
+    v = np.array([[1.0, 2.0, 3.0, 4.0, 5.0], [6.0, 7.0, 8.0, 9.0, 10.0]], dtype=np.float32)
+    i = np.array([1, 1, 0, 1, 2], dtype=np.int64)
+    H.assert_exact(select_add(1, H.up(t), H.up(i), H.up(v)), oracle.float_select_add(t, 1, i, v))
+
+
+def test_copy_of_strided_views_and_casts(dev):
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-100, 100, (6, 10, 12)).astype(np.float32)
+    t = H.up(x)
+    H.assert_exact(t.permute([2, 0, 1]).contiguous().numpy(), x.transpose(2, 0, 1))
+    H.assert_exact(t.swap_dims(0, 2).contiguous().numpy(), x.swapaxes(0, 2))
+    H.assert_exact(t.slice([(1, 5), (2, 9), (3, 11)]).contiguous().numpy(), x[1:5, 2:9, 3:11])
+    H.assert_exact(H.up(x[:1]).expand((4, 10, 12)).contiguous().numpy(), np.broadcast_to(x[:1], (4, 10, 12)))
+    out = DeviceTensor.empty(x.shape, abi.I32)
+    s, d = t.desc(), out.desc()
+    abi.check(lib().b200_launch_copy(C.byref(s), C.byref(d), None))
+    H.assert_exact(out.numpy(), x.astype(np.int32))
+    outh = DeviceTensor.empty(x.shape, abi.F16)
+    d = outh.desc()
+    abi.check(lib().b200_launch_copy(C.byref(s), C.byref(d), None))
+    H.assert_exact(outh.numpy(), x.astype(np.float16))
+
+
+def test_arange(dev):
+    out = DeviceTensor.empty((1000,), abi.I64)
+    d = out.desc()
+    abi.check(lib().b200_launch_arange(C.byref(d), 5, 3, None))
+    H.assert_exact(out.numpy(), np.arange(1000, dtype=np.int64) * 3 + 5)
+
+
+def test_random_distributions(dev):
+    # statistical checks only, like tests/cubecl/{uniform,normal,bernoulli}.rs
+    n = 1 << 20
+    out = DeviceTensor.empty((n,))
+    d = out.desc()
+    abi.check(lib().b200_launch_random(C.byref(d), 0, -2.0, 3.0, 42, 0, None))
+    u = out.numpy()
+    assert u.min() >= -2.0 and u.max() < 3.0
+    assert abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 25 / 12) < 0.02
+    abi.check(lib().b200_launch_random(C.byref(d), 1, 1.0, 2.0, 43, 0, None))
+    g = out.numpy()
+    assert abs(g.mean() - 1.0) < 0.01 and abs(g.std() - 2.0) < 0.01
+    abi.check(lib().b200_launch_random(C.byref(d), 2, 0.25, 0.0, 44, 0, None))
+    b = out.numpy()
+    assert set(np.unique(b)) <= {0.0, 1.0} and abs(b.mean() - 0.25) < 0.005
+    # same seed → same stream; different offset → different values
+    abi.check(lib().b200_launch_random(C.byref(d), 0, 0.0, 1.0, 7, 0, None))
+    r1 = out.numpy()
+    abi.check(lib().b200_launch_random(C.byref(d), 0, 0.0, 1.0, 7, 0, None))
+    assert np.array_equal(r1, out.numpy())
+    abi.check(lib().b200_launch_random(C.byref(d), 0, 0.0, 1.0, 7, n, None))
+    assert not np.array_equal(r1, out.numpy())
+
+
+def test_gather_shape_mismatch_is_an_error(dev):
+    t = H.up(np.zeros((2, 3), dtype=np.float32))
+    idx = H.up(np.zeros((3, 3), dtype=np.int64))
+    out = DeviceTensor.empty((3, 3))
+    a, b, c = t.desc(), idx.desc(), out.desc()
+    assert lib().b200_launch_gather(1, C.byref(a), C.byref(b), C.byref(c), None) == abi.ERR_SHAPE

@@ -82,6 +82,16 @@ def test_argmax_ties_take_first_and_nan_wins(dev):
         H.assert_exact(reduce_axis(abi.RED_ARGMIN, x, axis, abi.I32), oracle.float_argmin(x, axis), f"argmin {axis}")
 
 
+def test_arg_on_constant_infinite_rows(dev):
+    # all -inf / +inf lanes: the first index must be reported (the oracle folds from (arr[0], 0))
+    x = np.full((300, 4096), -np.inf, dtype=np.float32)
+    x[5, 100] = 1.0
+    for axis in (0, 1):
+        H.assert_exact(reduce_axis(abi.RED_ARGMAX, x, axis, abi.I32), oracle.float_argmax(x, axis))
+        H.assert_exact(reduce_axis(abi.RED_ARGMIN, -x, axis, abi.I32), oracle.float_argmin(-x, axis))
+        H.assert_exact(reduce_axis(abi.RED_MAX, x, axis), oracle.float_max_dim(x, axis))
+
+
 def test_max_min_dim_exact(dev):
     x = rnd((33, 130, 12), seed=2)
     x[1, 5, 3] = np.nan
