@@ -1,0 +1,274 @@
+"""Eager op layer over the C ABI, named after the reference's backend traits.
+
+Each function is the B200 counterpart of the `FloatTensorOps` / `ActivationOps` entry point of
+the same name (crates/burn-backend/src/backend/ops/tensor.rs, ops/activation.rs): same argument
+meaning, keepdim reductions, broadcast rules, and errors raised where the reference panics.
+Composite activations are launched as ONE fused tape of the primitive ops the reference's
+default implementations issue (activation.rs:37-76,250-276) — i.e. what burn-fusion's
+ElementWise / Reduce fusers hand to `Optimization::execute`.
+
+All arithmetic runs in libburn_b200.so; nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _abi as abi
+from . import device as dv
+from ._abi import check
+from .device import DeviceTensor, TapeBuilder
+
+SQRT_2 = 1.4142135623730951
+
+
+class ShapeError(ValueError):
+    """Raised where the reference panics on incompatible shapes / dims."""
+
+
+def _bshape(a: Sequence[int], b: Sequence[int]):
+    if len(a) != len(b):
+        raise ShapeError(f"rank mismatch: {tuple(a)} vs {tuple(b)}")
+    out = []
+    for x, y in zip(a, b):
+        if x != y and x != 1 and y != 1:
+            raise ShapeError(f"shapes {tuple(a)} and {tuple(b)} are not broadcastable")
+        out.append(max(x, y))
+    return tuple(out)
+
+
+def _launch(tb: TapeBuilder, inputs, shape, out_dtype=abi.F32) -> DeviceTensor:
+    out = DeviceTensor.empty(shape, out_dtype)
+    if out.numel:
+        dv.launch_elemwise(tb.build(), inputs, [out], shape)
+    return out
+
+
+def _binary(opname: str, lhs: DeviceTensor, rhs: DeviceTensor, out_dtype=abi.F32) -> DeviceTensor:
+    shape = _bshape(lhs.shape, rhs.shape)
+    tb = TapeBuilder().op(opname, ("in", 0), ("in", 1), out=0)
+    return _launch(tb, [lhs.expand(shape), rhs.expand(shape)], shape, out_dtype)
+
+
+def _scalar(opname: str, lhs: DeviceTensor, s, out_dtype=abi.F32, kind="f") -> DeviceTensor:
+    tb = TapeBuilder().op(opname, ("in", 0), (kind, s), out=0)
+    return _launch(tb, [lhs], lhs.shape, out_dtype)
+
+
+def _unary(opname: str, x: DeviceTensor, out_dtype=abi.F32) -> DeviceTensor:
+    return _launch(TapeBuilder().op(opname, ("in", 0), out=0), [x], x.shape, out_dtype)
+
+
+# ---- FloatTensorOps: arithmetic (tensor.rs:183-329)
+def float_add(a, b): return _binary("ADD_F", a, b)
+def float_sub(a, b): return _binary("SUB_F", a, b)
+def float_mul(a, b): return _binary("MUL_F", a, b)
+def float_div(a, b): return _binary("DIV_F", a, b)
+def float_remainder(a, b): return _binary("REM_F", a, b)
+def float_powf(a, b): return _binary("POW_F", a, b)
+def float_add_scalar(a, s): return _scalar("ADD_F", a, s)
+def float_sub_scalar(a, s): return _scalar("SUB_F", a, s)
+def float_mul_scalar(a, s): return _scalar("MUL_F", a, s)
+def float_div_scalar(a, s): return _scalar("DIV_F", a, s)
+def float_remainder_scalar(a, s): return _scalar("REM_F", a, s)
+def float_powf_scalar(a, s): return _scalar("POW_F", a, s)
+
+# ---- unary math (tensor.rs:1024-1442)
+def float_exp(a): return _unary("EXP_F", a)
+def float_log(a): return _unary("LOG_F", a)
+def float_log1p(a): return _unary("LOG1P_F", a)
+def float_sqrt(a): return _unary("SQRT_F", a)
+def float_abs(a): return _unary("ABS_F", a)
+def float_neg(a): return _unary("NEG_F", a)
+def float_recip(a): return _unary("RECIP_F", a)
+def float_tanh(a): return _unary("TANH_F", a)
+def float_erf(a): return _unary("ERF_F", a)
+def float_sin(a): return _unary("SIN_F", a)
+def float_cos(a): return _unary("COS_F", a)
+def float_floor(a): return _unary("FLOOR_F", a)
+def float_ceil(a): return _unary("CEIL_F", a)
+def float_round(a): return _unary("ROUND_F", a)
+def float_trunc(a): return _unary("TRUNC_F", a)
+def float_sign(a): return _unary("SIGN_F", a)
+
+
+def float_clamp(a, lo, hi):
+    return _launch(TapeBuilder().op("CLAMP_F", ("in", 0), ("f", lo), ("f", hi), out=0), [a], a.shape)
+
+
+# ---- comparisons → bool (tensor.rs:675-850)
+def float_equal(a, b): return _binary("EQ_F", a, b, abi.BOOL)
+def float_greater(a, b): return _binary("GT_F", a, b, abi.BOOL)
+def float_greater_equal(a, b): return _binary("GE_F", a, b, abi.BOOL)
+def float_lower(a, b): return _binary("LT_F", a, b, abi.BOOL)
+def float_lower_equal(a, b): return _binary("LE_F", a, b, abi.BOOL)
+def float_equal_elem(a, s): return _scalar("EQ_F", a, s, abi.BOOL)
+def float_greater_elem(a, s): return _scalar("GT_F", a, s, abi.BOOL)
+def float_greater_equal_elem(a, s): return _scalar("GE_F", a, s, abi.BOOL)
+def float_lower_elem(a, s): return _scalar("LT_F", a, s, abi.BOOL)
+def float_lower_equal_elem(a, s): return _scalar("LE_F", a, s, abi.BOOL)
+
+
+# ---- masks (tensor.rs:609-630)
+def float_mask_fill(x: DeviceTensor, mask: DeviceTensor, value: float) -> DeviceTensor:
+    shape = _bshape(x.shape, mask.shape)
+    tb = TapeBuilder().op("SELECT", ("in", 0), ("f", value), ("in", 1), out=0)
+    return _launch(tb, [x.expand(shape), mask.expand(shape)], shape)
+
+
+def float_mask_where(x: DeviceTensor, mask: DeviceTensor, source: DeviceTensor) -> DeviceTensor:
+    shape = _bshape(_bshape(x.shape, mask.shape), source.shape)
+    tb = TapeBuilder().op("SELECT", ("in", 0), ("in", 1), ("in", 2), out=0)
+    return _launch(tb, [x.expand(shape), source.expand(shape), mask.expand(shape)], shape)
+
+
+# ---- casts (tensor.rs:135,1013)
+def float_into_int(x: DeviceTensor, dtype=abi.I32) -> DeviceTensor:
+    return _unary("F2I", x, dtype)
+
+
+def float_cast(x: DeviceTensor, dtype: int) -> DeviceTensor:
+    return _unary("MOV", x, dtype)
+
+
+# ---- reductions (tensor.rs:883-949,1484-1636)
+def _check_dim(x: DeviceTensor, dim: int) -> int:
+    if dim < 0:
+        dim += x.ndim
+    if not 0 <= dim < x.ndim:
+        raise ShapeError(f"dim {dim} out of range for rank {x.ndim}")
+    return dim
+
+
+def _reduce(kind: int, x: DeviceTensor, dim: int, out_dtype=abi.F32) -> DeviceTensor:
+    dim = _check_dim(x, dim)
+    shape = list(x.shape)
+    shape[dim] = 1
+    out = DeviceTensor.empty(shape, out_dtype)
+    if out.numel:
+        dv.launch_reduce(kind, dim, x.shape, [x], [out])
+    return out
+
+
+def float_sum_dim(x, dim): return _reduce(abi.RED_SUM, x, dim)
+def float_mean_dim(x, dim): return _reduce(abi.RED_MEAN, x, dim)
+def float_prod_dim(x, dim): return _reduce(abi.RED_PROD, x, dim)
+def float_max_dim(x, dim): return _reduce(abi.RED_MAX, x, dim)
+def float_min_dim(x, dim): return _reduce(abi.RED_MIN, x, dim)
+def float_argmax(x, dim, out_dtype=abi.I32): return _reduce(abi.RED_ARGMAX, x, dim, out_dtype)
+def float_argmin(x, dim, out_dtype=abi.I32): return _reduce(abi.RED_ARGMIN, x, dim, out_dtype)
+
+
+def _reduce_full(kind: int, x: DeviceTensor) -> DeviceTensor:
+    out = DeviceTensor.empty((1,))
+    dv.launch_reduce_full(kind, x, out)
+    return out
+
+
+def float_sum(x): return _reduce_full(abi.RED_SUM, x)
+def float_mean(x): return _reduce_full(abi.RED_MEAN, x)
+def float_max(x): return _reduce_full(abi.RED_MAX, x)
+def float_min(x): return _reduce_full(abi.RED_MIN, x)
+
+
+# ---- matmul (tensor.rs:341)
+def float_matmul(lhs: DeviceTensor, rhs: DeviceTensor, precision: int = abi.MM_F32X3, epilogue=None,
+                 epi_inputs: Sequence[DeviceTensor] = ()) -> DeviceTensor:
+    if lhs.ndim != rhs.ndim or lhs.ndim < 2:
+        raise ShapeError("matmul operands must have the same rank >= 2")
+    if lhs.shape[-1] != rhs.shape[-2]:
+        raise ShapeError(f"matmul inner dims differ: {lhs.shape} x {rhs.shape}")
+    batch = _bshape(lhs.shape[:-2], rhs.shape[:-2])
+    out = DeviceTensor.empty(tuple(batch) + (lhs.shape[-2], rhs.shape[-1]))
+    a, b, c = lhs.desc(), rhs.desc(), out.desc()
+    ws_bytes = C.c_uint64()
+    check(abi.load().b200_matmul_workspace_bytes(C.byref(a), C.byref(b), precision, C.byref(ws_bytes)))
+    ws = dv.Storage(ws_bytes.value) if ws_bytes.value else None
+    epi, n_epi = dv._descs(epi_inputs)
+    check(abi.load().b200_launch_matmul(C.byref(a), C.byref(b), C.byref(c), precision,
+                                        C.byref(epilogue) if epilogue is not None else None, epi, n_epi,
+                                        ws.ptr if ws else None, ws_bytes.value, None))
+    return out
+
+
+# ---- indexing (tensor.rs:435-543)
+def float_gather(dim: int, x: DeviceTensor, indices: DeviceTensor) -> DeviceTensor:
+    out = DeviceTensor.empty(indices.shape, x.dtype)
+    a, b, c = x.desc(), indices.desc(), out.desc()
+    check(abi.load().b200_launch_gather(dim, C.byref(a), C.byref(b), C.byref(c), None))
+    return out
+
+
+def float_scatter_add(dim: int, x: DeviceTensor, indices: DeviceTensor, value: DeviceTensor) -> DeviceTensor:
+    out = x.contiguous()  # the reference returns a new tensor unless it owns `x`
+    a, b, c = out.desc(), indices.desc(), value.desc()
+    check(abi.load().b200_launch_scatter_add(dim, C.byref(a), C.byref(b), C.byref(c), None))
+    return out
+
+
+def float_select(x: DeviceTensor, dim: int, indices: DeviceTensor) -> DeviceTensor:
+    dim = _check_dim(x, dim)
+    shape = list(x.shape)
+    shape[dim] = indices.shape[0]
+    out = DeviceTensor.empty(shape, x.dtype)
+    a, b, c = x.desc(), indices.desc(), out.desc()
+    check(abi.load().b200_launch_select(dim, C.byref(a), C.byref(b), C.byref(c), None))
+    return out
+
+
+def float_select_add(x: DeviceTensor, dim: int, indices: DeviceTensor, value: DeviceTensor) -> DeviceTensor:
+    dim = _check_dim(x, dim)
+    out = x.contiguous()
+    a, b, c = out.desc(), indices.desc(), value.desc()
+    check(abi.load().b200_launch_select_add(dim, C.byref(a), C.byref(b), C.byref(c), None))
+    return out
+
+
+# ---- ActivationOps defaults, fused (activation.rs:37-76,139-160,250-276)
+def relu(x: DeviceTensor) -> DeviceTensor:
+    tb = (TapeBuilder().op("LE_F", ("in", 0), ("f", 0.0), tmp=0)
+          .op("SELECT", ("in", 0), ("f", 0.0), ("tmp", 0), out=0))
+    return _launch(tb, [x], x.shape)
+
+
+def gelu(x: DeviceTensor) -> DeviceTensor:
+    tb = (TapeBuilder().op("DIV_F", ("in", 0), ("f", SQRT_2)).op("ERF_F", "acc").op("ADD_F", "acc", ("f", 1.0))
+          .op("MUL_F", ("in", 0), "acc").op("DIV_F", "acc", ("f", 2.0), out=0))
+    return _launch(tb, [x], x.shape)
+
+
+def sigmoid(x: DeviceTensor) -> DeviceTensor:
+    return _unary("SIGMOID_F", x)
+
+
+def softmax(x: DeviceTensor, dim: int) -> DeviceTensor:
+    """max_dim → sub → exp → sum_dim → div: two reduce launches with fused read/write tapes."""
+    dim = _check_dim(x, dim)
+    m = float_max_dim(x, dim)
+    # e = exp(x - max) written once, while its row sum is reduced by the same launch?  The reduce
+    # entry point has no elementwise outputs, so: fused exp(x-max) → sum, then one fused divide.
+    shape = x.shape
+    red = list(shape)
+    red[dim] = 1
+    s = DeviceTensor.empty(red)
+    rd = TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("EXP_F", "acc")
+    dv.launch_reduce(abi.RED_SUM, dim, shape, [x, m.expand(shape)], [s], read=rd.build())
+    tb = (TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("EXP_F", "acc")
+          .op("DIV_F", "acc", ("in", 2), out=0))
+    return _launch(tb, [x, m.expand(shape), s.expand(shape)], shape)
+
+
+def log_softmax(x: DeviceTensor, dim: int) -> DeviceTensor:
+    dim = _check_dim(x, dim)
+    m = float_max_dim(x, dim)
+    shape = x.shape
+    red = list(shape)
+    red[dim] = 1
+    lse = DeviceTensor.empty(red)
+    rd = TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("EXP_F", "acc")
+    wr = TapeBuilder().op("LOG_F", ("in", 0), out=0)
+    dv.launch_reduce(abi.RED_SUM, dim, shape, [x, m.expand(shape)], [lse], read=rd.build(), write=wr.build())
+    tb = TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("SUB_F", "acc", ("in", 2), out=0)
+    return _launch(tb, [x, m.expand(shape), lse.expand(shape)], shape)

@@ -1,0 +1,13 @@
+"""GPU: the reference's golden vectors run through the CUDA library (C ABI) — the same fixtures
+tests/test_oracle_golden.py pins the oracle with, with the tolerance each reference test uses."""
+import pytest
+
+from tests import golden_runner as G
+
+pytestmark = pytest.mark.gpu
+CASES = G.load_cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_device_reproduces_reference_golden(dev, case):
+    G.check(case, G.run_device(case))
