@@ -3,14 +3,6 @@
 #include "common.cuh"
 using namespace b200;
 
-extern "C" int32_t b200_matmul_workspace_bytes(const b200_tensor *, const b200_tensor *, int32_t, uint64_t *bytes) {
-  if (bytes) *bytes = 0;
-  return fail(B200_ERR_UNSUPPORTED, "b200_launch_matmul is not implemented yet");
-}
-extern "C" int32_t b200_launch_matmul(const b200_tensor *, const b200_tensor *, const b200_tensor *, int32_t,
-                                      const b200_tape *, const b200_tensor *, int32_t, void *, uint64_t, b200_stream) {
-  return fail(B200_ERR_UNSUPPORTED, "b200_launch_matmul is not implemented yet");
-}
 extern "C" int32_t b200_launch_softmax(const b200_tensor *, const b200_tensor *, int32_t, b200_stream) {
   return fail(B200_ERR_UNSUPPORTED, "b200_launch_softmax is not implemented yet");
 }
