@@ -1,0 +1,184 @@
+"""ctypes face of the C++ host fusion layer (include/burn_b200_host.h, burn_b200/host/fusion.cpp).
+
+`FusionStream` plays the role of `Fusion<B>`'s per-device stream: ops are recorded lazily as
+OperationIr-like entries, the ElementWise / Matmul / Reduce fusers carve the queue into blocks and
+every block runs as one kernel when the stream is drained (`read`, `sync`).  `LazyTensor.drop()`
+is `OperationIr::Drop` — dropping an intermediate before the drain is what lets it live in
+registers only, exactly as with burn-fusion's refcounted `FusionTensor`
+(crates/burn-fusion/src/tensor.rs:108-156).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _abi as abi
+from ._abi import check
+
+BLOCK_ELEMWISE, BLOCK_REDUCE, BLOCK_MATMUL, BLOCK_EAGER = range(4)
+
+
+class BlockInfo(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_ops", C.c_int32), ("n_inputs", C.c_int32), ("n_outputs", C.c_int32),
+                ("n_tape_ops", C.c_int32), ("launches", C.c_int32)]
+
+
+_vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
+HOST_SIGNATURES = {
+    "b200h_stream_create": (_i32, [C.POINTER(_vp), _i32]),
+    "b200h_stream_destroy": (_i32, [_vp]),
+    "b200h_from_host": (_i64, [_vp, _vp, _i32, _i32, C.POINTER(_i64)]),
+    "b200h_read": (_i32, [_vp, _i64, _vp, C.c_uint64]),
+    "b200h_shape": (_i32, [_vp, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64)]),
+    "b200h_sync": (_i32, [_vp]),
+    "b200h_binary": (_i64, [_vp, _i32, _i64, _i64]),
+    "b200h_scalar": (_i64, [_vp, _i32, _i64, C.c_double]),
+    "b200h_unary": (_i64, [_vp, _i32, _i64]),
+    "b200h_mask_fill": (_i64, [_vp, _i64, _i64, C.c_double]),
+    "b200h_mask_where": (_i64, [_vp, _i64, _i64, _i64]),
+    "b200h_reduce_dim": (_i64, [_vp, _i32, _i64, _i32]),
+    "b200h_matmul": (_i64, [_vp, _i64, _i64, _i32]),
+    "b200h_swap_dims": (_i64, [_vp, _i64, _i32, _i32]),
+    "b200h_drop": (_i32, [_vp, _i64]),
+    "b200h_block_count": (_i32, [_vp]),
+    "b200h_block_get": (_i32, [_vp, _i32, C.POINTER(BlockInfo)]),
+    "b200h_block_clear": (_i32, [_vp]),
+}
+
+_NP = {abi.F32: np.float32, abi.I32: np.int32, abi.I64: np.int64, abi.BOOL: np.uint8, abi.U8: np.uint8,
+       abi.F16: np.float16}
+_bound = False
+
+
+def _lib():
+    global _bound
+    lib = abi.load()
+    if not _bound:
+        for name, (res, args) in HOST_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _bound = True
+    return lib
+
+
+def _id(v: int) -> int:
+    if v < 0:
+        raise abi.B200Error(-1, abi.load().b200_last_error().decode("utf-8", "replace"))
+    return v
+
+
+class LazyTensor:
+    def __init__(self, stream: "FusionStream", tid: int):
+        self.stream, self.id, self._dropped = stream, tid, False
+
+    # ---- metadata
+    def _meta(self):
+        dt, rk = C.c_int32(), C.c_int32()
+        shape = (C.c_int64 * abi.MAX_RANK)()
+        check(_lib().b200h_shape(self.stream.h, self.id, C.byref(dt), C.byref(rk), shape))
+        return dt.value, tuple(shape[i] for i in range(rk.value))
+
+    @property
+    def shape(self):
+        return self._meta()[1]
+
+    @property
+    def dtype(self):
+        return self._meta()[0]
+
+    # ---- ownership
+    def drop(self) -> None:
+        if not self._dropped:
+            self._dropped = True
+            check(_lib().b200h_drop(self.stream.h, self.id))
+
+    # ---- readback (drains the stream)
+    def numpy(self) -> np.ndarray:
+        dt, shape = self._meta()
+        out = np.empty(shape, dtype=_NP[dt])
+        check(_lib().b200h_read(self.stream.h, self.id, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out.astype(bool) if dt == abi.BOOL else out
+
+    # ---- ops named after the reference Tensor API
+    def _bin(self, op, other): return LazyTensor(self.stream, _id(_lib().b200h_binary(self.stream.h, abi.OP[op], self.id, other.id)))
+    def _sc(self, op, s): return LazyTensor(self.stream, _id(_lib().b200h_scalar(self.stream.h, abi.OP[op], self.id, float(s))))
+    def _un(self, op): return LazyTensor(self.stream, _id(_lib().b200h_unary(self.stream.h, abi.OP[op], self.id)))
+
+    def add(self, o): return self._bin("ADD_F", o)
+    def sub(self, o): return self._bin("SUB_F", o)
+    def mul(self, o): return self._bin("MUL_F", o)
+    def div(self, o): return self._bin("DIV_F", o)
+    def add_scalar(self, s): return self._sc("ADD_F", s)
+    def sub_scalar(self, s): return self._sc("SUB_F", s)
+    def mul_scalar(self, s): return self._sc("MUL_F", s)
+    def div_scalar(self, s): return self._sc("DIV_F", s)
+    def lower_equal_elem(self, s): return self._sc("LE_F", s)
+    def lower_elem(self, s): return self._sc("LT_F", s)
+    def greater_elem(self, s): return self._sc("GT_F", s)
+    def exp(self): return self._un("EXP_F")
+    def log(self): return self._un("LOG_F")
+    def erf(self): return self._un("ERF_F")
+    def sqrt(self): return self._un("SQRT_F")
+    def tanh(self): return self._un("TANH_F")
+    def mask_fill(self, mask, value): return LazyTensor(self.stream, _id(_lib().b200h_mask_fill(self.stream.h, self.id, mask.id, float(value))))
+    def mask_where(self, mask, src): return LazyTensor(self.stream, _id(_lib().b200h_mask_where(self.stream.h, self.id, mask.id, src.id)))
+    def _red(self, kind, dim): return LazyTensor(self.stream, _id(_lib().b200h_reduce_dim(self.stream.h, kind, self.id, dim)))
+    def sum_dim(self, dim): return self._red(abi.RED_SUM, dim)
+    def mean_dim(self, dim): return self._red(abi.RED_MEAN, dim)
+    def max_dim(self, dim): return self._red(abi.RED_MAX, dim)
+    def argmax(self, dim): return self._red(abi.RED_ARGMAX, dim)
+    def matmul(self, o, precision=abi.MM_F32X3): return LazyTensor(self.stream, _id(_lib().b200h_matmul(self.stream.h, self.id, o.id, precision)))
+    def swap_dims(self, d0, d1): return LazyTensor(self.stream, _id(_lib().b200h_swap_dims(self.stream.h, self.id, d0, d1)))
+
+
+class FusionStream:
+    def __init__(self, plan_only: bool = False):
+        self.h = C.c_void_p()
+        check(_lib().b200h_stream_create(C.byref(self.h), 1 if plan_only else 0))
+        self.plan_only = plan_only
+
+    def close(self):
+        if self.h:
+            _lib().b200h_stream_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def tensor(self, a) -> LazyTensor:
+        a = np.ascontiguousarray(a)
+        dt = {np.dtype(np.float32): abi.F32, np.dtype(np.int32): abi.I32, np.dtype(np.int64): abi.I64,
+              np.dtype(np.bool_): abi.BOOL, np.dtype(np.uint8): abi.U8}[a.dtype]
+        if a.dtype == np.bool_:
+            a = a.astype(np.uint8)
+        shape = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+        return LazyTensor(self, _id(_lib().b200h_from_host(self.h, a.ctypes.data_as(C.c_void_p), dt, a.ndim, shape)))
+
+    def placeholder(self, shape: Sequence[int], dtype=abi.F32) -> LazyTensor:
+        """A tensor with no host data (plan-only streams)."""
+        sh = (C.c_int64 * len(shape))(*shape)
+        return LazyTensor(self, _id(_lib().b200h_from_host(self.h, None, dtype, len(shape), sh)))
+
+    def sync(self):
+        check(_lib().b200h_sync(self.h))
+
+    def blocks(self):
+        out = []
+        for i in range(_lib().b200h_block_count(self.h)):
+            b = BlockInfo()
+            check(_lib().b200h_block_get(self.h, i, C.byref(b)))
+            out.append(b)
+        return out
+
+    def clear_blocks(self):
+        check(_lib().b200h_block_clear(self.h))
+
+
+def gelu(x: LazyTensor) -> LazyTensor:
+    """ActivationOps::gelu default: the five primitive ops, each intermediate dropped after use
+    (crates/burn-backend/src/backend/ops/activation.rs:69-76)."""
+    t = x.div_scalar(1.4142135623730951)
+    e = t.erf(); t.drop()
+    p = e.add_scalar(1.0); e.drop()
+    m = x.mul(p); p.drop()
+    y = m.div_scalar(2.0); m.drop()
+    return y

@@ -33,6 +33,17 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert name in names, f"{name} bound in _abi.py but not declared in the header"
 
 
+def test_host_layer_symbols_are_exported():
+    from burn_b200 import fusion
+    host_header = (ROOT / "include" / "burn_b200_host.h").read_text()
+    names = set(re.findall(r"^(?:int32_t|b200h_id)\s*(b200h_[a-z0-9_]+)\s*\(", host_header, re.M))
+    assert len(names) >= 18
+    lib = abi.load()
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in burn_b200_host.h but not exported"
+        assert name in fusion.HOST_SIGNATURES
+
+
 def test_opcode_table_matches_header():
     enum_body = HEADER[HEADER.index("B200_OP_MOV = 0"):HEADER.index("B200_OP_COUNT")]
     header_ops = re.findall(r"B200_OP_([A-Z0-9_]+)", enum_body)
