@@ -175,6 +175,110 @@ elemwise_tape_kernel_v1(const __grid_constant__ TapeParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// TMA bulk-copy variant (linear layouts): the whole CTA tile of every input is one contiguous
+// run of global memory, so ONE thread issues ONE `cp.async.bulk` per input per tile (SASS
+// UBLKCP) with mbarrier completion, instead of 16 per-thread LDGSTS + address arithmetic per
+// input.  The bytes land exactly in the thread-private slot layout: thread t's u-th vector sits
+// at element (u*BLOCK + t)*4 of the tile.  8/16-bit inputs land packed and are expanded in
+// place between two CTA barriers.
+__device__ __forceinline__ uint32_t ew_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int U, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+elemwise_tape_kernel_bulk(const __grid_constant__ TapeParams p, uint32_t flags) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  SlotFile<4, U, BLOCK> slots;
+  slots.smem = smem;
+  slots.tid = threadIdx.x;
+  constexpr uint32_t kTileVecs = BLOCK * U;
+  const uint32_t n_tiles = (p.n_vec + kTileVecs - 1) / kTileVecs;
+  const int tmp_base = p.n_in;
+  const bool needs_expand = flags & 2u;
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ew_smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (p.n_scalars > 0) init_scalars<4, U, BLOCK>(p, slots, tmp_base + p.n_tmp);
+  __syncthreads();
+
+  uint32_t parity = 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t vec0 = tile * kTileVecs;
+    const uint32_t tile_vecs = min(kTileVecs, p.n_vec - vec0);
+    if (threadIdx.x == 0) {
+      // generic-proxy accesses of the previous tile → async-proxy writes of this one
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      uint32_t total = 0;
+      for (int k = 0; k < p.n_in; ++k) total += tile_vecs * 4u * (uint32_t)p.in[k].async_es;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ew_smem_u32(&mbar)), "r"(total) : "memory");
+      for (int k = 0; k < p.n_in; ++k) {
+        const uint32_t es = (uint32_t)p.in[k].async_es;
+        const char *g = reinterpret_cast<const char *>(p.in[k].ptr) + (size_t)vec0 * 4u * es;
+        const uint32_t dst = ew_smem_u32(smem) + (uint32_t)(k * U * BLOCK) * 16u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(g), "r"(tile_vecs * 4u * es), "r"(ew_smem_u32(&mbar)) : "memory");
+      }
+    }
+    // wait for the tile
+    asm volatile(
+        "{\n.reg .pred p;\nBULK_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BULK_DONE;\nbra BULK_WAIT;\nBULK_DONE:\n}\n" ::"r"(ew_smem_u32(&mbar)), "r"(parity) : "memory");
+    parity ^= 1;
+
+    const uint32_t v0 = vec0 + threadIdx.x;
+    if (needs_expand) {
+      // packed 8/16-bit inputs: read own raw words, barrier, rewrite as 16-byte lane words
+      for (int k = 0; k < p.n_in; ++k) {
+        const OperandDesc &d = p.in[k];
+        if (d.async_es == 4) continue;
+        uint32_t raw[U][2];
+        const uint8_t *base = reinterpret_cast<const uint8_t *>(smem) + (size_t)(k * U * BLOCK) * 16;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t e = (uint32_t)(u * BLOCK + threadIdx.x);
+          if (d.async_es == 1) {
+            raw[u][0] = *reinterpret_cast<const uint32_t *>(base + e * 4);
+            raw[u][1] = 0;
+          } else {
+            const uint2 w = *reinterpret_cast<const uint2 *>(base + e * 8);
+            raw[u][0] = w.x;
+            raw[u][1] = w.y;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          uint32_t r[4] = {raw[u][0], raw[u][1], 0, 0};
+          expand_raw(d.dtype, r);
+          slots.put(k, u, r);
+        }
+      }
+    }
+
+    uint32_t acc[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[u][j] = 0;
+    run_tape<4, U, BLOCK>(
+        p, slots, acc,
+        [&](int o, const uint32_t(&val)[U][4]) {
+          const OperandDesc &d = p.out[o];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t v = v0 + u * BLOCK;
+            if (v < p.n_vec) store_operand<4, kRankLinear>(p, d, v, coords3<4, kRankLinear>(p, v), val[u]);
+          }
+        },
+        0, tmp_base);
+    __syncthreads();  // every thread is done with the slots before the next tile overwrites them
+  }
+}
+
 template <typename Kern, typename... Args>
 static int32_t launch_persistent(Kern kern, int block, size_t smem, uint64_t n_tiles, cudaStream_t stream,
                                  Args... args) {
@@ -202,10 +306,27 @@ static int32_t launch_v4(const CompiledTape &ct, TapeParams &p, int rm, cudaStre
       if (d.async_es != 4) flags |= 2u;
     }
   }
-  // ring depth: keep >= ~16 x 16 B in flight per thread, bounded by shared memory so
-  // that at least 2-3 CTAs stay resident per SM
+  // TMA bulk path: linear layout, every input streams as one contiguous run per tile
+  // (with a single input the per-thread path is as fast and needs no CTA barrier)
+  bool bulk = rm == kRankLinear && ct.n_in >= 2 && !(flags & 1u) && !getenv("B200_EW_NO_BULK");
+  for (int k = 0; k < ct.n_in && bulk; ++k) {
+    const OperandDesc &d = p.in[k];
+    if (d.s3[2] != 1 || ((uintptr_t)d.ptr) % 16 != 0 || ((uint64_t)p.n_vec * 4u * (uint32_t)d.async_es) % 16 != 0)
+      bulk = false;
+  }
+  if (bulk) {
+    const size_t smem_b = std::max<size_t>(slot_file_bytes(ct.n_in + ct.n_tmp, (int)ct.scalars.size(), 4, U, BLOCK), 16);
+    if ((int)smem_b <= max_smem_optin()) {
+      int32_t stb = finalize_tape(ct, U, BLOCK, 1, p);
+      if (stb != B200_OK) return stb;
+      const uint64_t tiles_b = ((uint64_t)p.n_vec + BLOCK * U - 1) / (BLOCK * U);
+      return launch_persistent(elemwise_tape_kernel_bulk<U, BLOCK>, BLOCK, smem_b, tiles_b, stream, p, flags);
+    }
+  }
+  // per-thread cp.async path.  Ring depth 1 measured best on B200 (occupancy beats the ring:
+  // chain 293 us at 1 stage vs 365 us at 2); B200_EW_STAGES overrides for tuning.
   int stages = 1;
-  if (n_async > 0) stages = std::max(2, std::min(4, 16 / (n_async * U) + 1));
+  if (const char *ev = getenv("B200_EW_STAGES")) stages = std::max(1, std::min(4, atoi(ev)));
   const size_t smem_cap = 100 * 1024;
   auto bytes_for = [&](int s) { return slot_file_bytes(s * ct.n_in + ct.n_tmp, (int)ct.scalars.size(), 4, U, BLOCK); };
   while (stages > 1 && bytes_for(stages) > smem_cap) --stages;

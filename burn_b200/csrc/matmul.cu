@@ -265,10 +265,11 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: 32 bytes along the swizzled row per MMA; MN-major: UMMA_K rows of 128 B
-            // SBO = byte stride between swizzle atoms along MN, LBO = along K
-            const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), 1024, BK * 128)
+            // MN-major (validated on hardware for bf16): LBO = stride between 128-byte MN groups
+            // (one TMA box of BK rows), SBO = stride between 8-row K atoms
+            const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
                                      : make_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), 1024, BK * 128)
+            const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
                                      : make_desc(sb + k * 32, 16, 1024);
             umma<BF16>(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
           }
@@ -431,11 +432,10 @@ struct Operand {
 
 static bool tma_ok(const Operand &o, int64_t mn, int64_t k) {
   const int64_t align = 16 / o.es;
-  // MN-major operands: the MN-major UMMA descriptor path (SWIZZLE_128B_BASE32B for 32-bit
-  // types) is not validated on hardware yet — such operands are repacked K-major by the
-  // pre-pass instead (one extra read+write of the operand).
-  if (o.mn_major) return false;
-  if (((uintptr_t)o.ptr) % 16 != 0) return false;
+  // 16-bit MN-major operands are consumed in place (MN-major UMMA descriptors, validated on
+  // hardware).  32-bit MN-major operands would need the SWIZZLE_128B_BASE32B canonical layout,
+  // which this kernel does not implement: they are repacked K-major by the pre-pass.
+  if (o.mn_major && o.es == 4) return false;
   const int64_t inner = o.mn_major ? o.s_mn : o.s_k, outer = o.mn_major ? o.s_k : o.s_mn;
   if (inner != 1) return false;
   if ((o.mn_major ? k : mn) > 1 && (outer % align != 0 || outer < (o.mn_major ? mn : k))) return false;

@@ -589,6 +589,12 @@ __device__ __forceinline__ void run_tape(const TapeParams &p, const SlotFile<VEC
         // (crates/burn-backend/src/backend/ops/activation.rs:69-76)
         const float s2 = 1.41421353816986083984375f;  // f32(SQRT_2)
         const float rinv = 0.707106769084930419921875f;  // RN(1 / f32(SQRT_2))
+        if (!(flags & kFlagHasB)) {  // x is the accumulator itself
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) b[u][j] = acc[u][j];
+        }
         bool safe = true;
 #pragma unroll
         for (int u = 0; u < U; ++u)

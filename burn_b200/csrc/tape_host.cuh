@@ -141,7 +141,25 @@ static inline int32_t compile_tape(const b200_tape *tape, int n_in, int n_out, C
                           ((o3.a == pop.a && o3.b == B200_ARG_ACC) || (o3.b == pop.a && o3.a == B200_ARG_ACC));
       const bool div_ok = o4.op == B200_OP_DIV_F && o4.a == B200_ARG_ACC && scalar_is(o4.b, 0x40000000u);
       if (erf_ok && add_ok && mul_ok && div_ok) {
-        emit(kOpGelu, a, none, o4.dst_temp == B200_DST_NONE ? -1 : o4.dst_temp,
+        // X was just produced by the previous op and is not read again: keep it in ACC
+        // instead of a round trip through a temp slot.
+        SymArg src = a;
+        if (a.kind == 2 && !ct.ops.empty() && ct.ops.back().dst_tmp == a.idx) {
+          bool read_later = false;
+          for (int j = i + 5; j < tape->n_ops && !read_later; ++j) {
+            const b200_tape_op &oj = tape->ops[j];
+            const int arj = op_arity(oj.op);
+            const uint8_t args[3] = {oj.a, oj.b, oj.c};
+            for (int k = 0; k < arj; ++k)
+              if ((args[k] >> 6) == 2 && (args[k] & 63) == a.idx) read_later = true;
+            if (oj.dst_temp == a.idx) break;  // overwritten before any further read
+          }
+          if (!read_later) {
+            ct.ops.back().dst_tmp = -1;
+            src = none;
+          }
+        }
+        emit(kOpGelu, src, none, o4.dst_temp == B200_DST_NONE ? -1 : o4.dst_temp,
              o4.dst_out == B200_DST_NONE ? -1 : o4.dst_out);
         i += 4;
         continue;
@@ -201,7 +219,16 @@ static inline int32_t compile_tape(const b200_tape *tape, int n_in, int n_out, C
     }
     emit(op, b, c, dt, dout);
   }
-  ct.n_tmp = n_tmp + (used_scratch ? 1 : 0);
+  // temps actually referenced after lowering (peepholes may have removed some)
+  int used_tmp = 0;
+  for (const SymOp &o : ct.ops) {
+    if (o.dst_tmp >= 0) used_tmp = std::max(used_tmp, o.dst_tmp + 1);
+    if (o.b.kind == 2) used_tmp = std::max(used_tmp, o.b.idx + 1);
+    if (o.c.kind == 2) used_tmp = std::max(used_tmp, o.c.idx + 1);
+  }
+  (void)n_tmp;
+  (void)used_scratch;
+  ct.n_tmp = used_tmp;
   B200_REQUIRE((int)ct.ops.size() <= kMaxIOps, B200_ERR_UNSUPPORTED,
                "tape compiles to %zu internal ops (limit %d)", ct.ops.size(), kMaxIOps);
   return B200_OK;
