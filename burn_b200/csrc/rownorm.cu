@@ -1,0 +1,310 @@
+// Row-resident softmax / log_softmax / layer_norm along the last axis — the single-pass
+// counterpart of the reference's ReduceBroadcasted optimization
+// (crates/burn-cubecl-fusion/src/optim/reduce_broadcasted/unit.rs:65), which fuses the chains
+//   softmax     = max_dim, sub, exp, sum_dim, div            (crates/burn-backend/src/backend/ops/activation.rs:250-256)
+//   log_softmax = max_dim, sub, exp, sum_dim, log, sub       (activation.rs:271-276)
+//   layer_norm  = mean_dim, sub, mul, mean_dim, add_scalar, sqrt, div, mul, add
+//                                                            (crates/burn-backend/src/backend/ops/modules/base.rs:846-877)
+// into one kernel.  Each element goes through exactly the f32 operations of the op-by-op chain
+// (IEEE sub/div/sqrt, expf/logf); only the order of the row sums differs from the oracle
+// (<= 1e-5 relative, like every reduction here).
+//
+// One row stays on chip between the passes: a warp keeps a row of up to 2048 elements in
+// registers (128-bit loads, shuffle trees); longer rows (up to ~57 K f32, e.g. a 50 257-entry
+// vocabulary) are staged once in shared memory by a whole CTA.  HBM traffic = one read + one
+// write of the tensor.  Roofline: HBM; algorithmic bytes = 8 B / element.
+#include "common.cuh"
+
+namespace b200 {
+namespace rn {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+
+enum Mode : int { kSoftmax = 0, kLogSoftmax = 1, kLayerNorm = 2 };
+
+struct Params {
+  const float *x;
+  float *y;
+  const float *gamma;  // layer_norm scale (may be null)
+  const float *beta;   // layer_norm shift (may be null)
+  int64_t x_row_stride, y_row_stride;
+  uint32_t rows, R;
+  float eps;
+  float inv_unused;
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+// NaN-propagating max like the oracle's max_dim (first NaN wins → NaN)
+__device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
+
+// ---- a warp owns a row; V float4 per lane live in registers
+template <int MODE, int V>
+__global__ void __launch_bounds__(kBlock) row_warp_kernel(const Params P) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t r4 = P.R >> 2;
+  for (uint32_t row = blockIdx.x * kWarps + warp; row < P.rows; row += gridDim.x * kWarps) {
+    const float4 *xr = reinterpret_cast<const float4 *>(P.x + (int64_t)row * P.x_row_stride);
+    float4 *yr = reinterpret_cast<float4 *>(P.y + (int64_t)row * P.y_row_stride);
+    float4 v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const uint32_t i = lane + k * 32;
+      v[k] = i < r4 ? __ldcs(xr + i) : make_float4(0, 0, 0, 0);
+    }
+    if constexpr (MODE == kLayerNorm) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < V; ++k)
+        if (lane + k * 32 < r4) s = __fadd_rn(s, __fadd_rn(__fadd_rn(v[k].x, v[k].y), __fadd_rn(v[k].z, v[k].w)));
+      const float mean = __fdiv_rn(warp_sum(s), (float)P.R);
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        v[k].x = __fsub_rn(v[k].x, mean); v[k].y = __fsub_rn(v[k].y, mean);
+        v[k].z = __fsub_rn(v[k].z, mean); v[k].w = __fsub_rn(v[k].w, mean);
+        if (lane + k * 32 < r4)
+          q = __fadd_rn(q, __fadd_rn(__fadd_rn(__fmul_rn(v[k].x, v[k].x), __fmul_rn(v[k].y, v[k].y)),
+                                     __fadd_rn(__fmul_rn(v[k].z, v[k].z), __fmul_rn(v[k].w, v[k].w))));
+      }
+      const float var = __fdiv_rn(warp_sum(q), (float)P.R);
+      const float denom = __fsqrt_rn(__fadd_rn(var, P.eps));
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const uint32_t i = lane + k * 32;
+        if (i >= r4) continue;
+        float4 o;
+        o.x = __fdiv_rn(v[k].x, denom); o.y = __fdiv_rn(v[k].y, denom);
+        o.z = __fdiv_rn(v[k].z, denom); o.w = __fdiv_rn(v[k].w, denom);
+        if (P.gamma) {
+          const float4 g = __ldg(reinterpret_cast<const float4 *>(P.gamma) + i);
+          o.x = __fmul_rn(o.x, g.x); o.y = __fmul_rn(o.y, g.y); o.z = __fmul_rn(o.z, g.z); o.w = __fmul_rn(o.w, g.w);
+        }
+        if (P.beta) {
+          const float4 b = __ldg(reinterpret_cast<const float4 *>(P.beta) + i);
+          o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
+        }
+        __stcs(yr + i, o);
+      }
+    } else {
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < V; ++k)
+        if (lane + k * 32 < r4) m = nan_max(m, nan_max(nan_max(v[k].x, v[k].y), nan_max(v[k].z, v[k].w)));
+      {  // NaN-aware warp max
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) m = nan_max(m, __shfl_xor_sync(0xffffffffu, m, s));
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        v[k].x = __fsub_rn(v[k].x, m); v[k].y = __fsub_rn(v[k].y, m);
+        v[k].z = __fsub_rn(v[k].z, m); v[k].w = __fsub_rn(v[k].w, m);
+        float4 e;
+        e.x = expf(v[k].x); e.y = expf(v[k].y); e.z = expf(v[k].z); e.w = expf(v[k].w);
+        if (lane + k * 32 < r4) s = __fadd_rn(s, __fadd_rn(__fadd_rn(e.x, e.y), __fadd_rn(e.z, e.w)));
+        if constexpr (MODE == kSoftmax) v[k] = e;
+      }
+      s = warp_sum(s);
+      const float ls = logf(s);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const uint32_t i = lane + k * 32;
+        if (i >= r4) continue;
+        float4 o;
+        if constexpr (MODE == kSoftmax) {
+          o.x = __fdiv_rn(v[k].x, s); o.y = __fdiv_rn(v[k].y, s); o.z = __fdiv_rn(v[k].z, s); o.w = __fdiv_rn(v[k].w, s);
+        } else {
+          o.x = __fsub_rn(v[k].x, ls); o.y = __fsub_rn(v[k].y, ls); o.z = __fsub_rn(v[k].z, ls); o.w = __fsub_rn(v[k].w, ls);
+        }
+        __stcs(yr + i, o);
+      }
+    }
+  }
+}
+
+// ---- a CTA owns a row staged in shared memory (any R that fits, scalar accesses allowed)
+__device__ __forceinline__ float block_reduce_sum(float v, float *scratch) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = (threadIdx.x & 31) < kWarps ? scratch[threadIdx.x & 31] : 0.f;
+  return warp_sum(r);
+}
+__device__ __forceinline__ float block_reduce_max(float v, float *scratch) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) v = nan_max(v, __shfl_xor_sync(0xffffffffu, v, s));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = (threadIdx.x & 31) < kWarps ? scratch[threadIdx.x & 31] : -INFINITY;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) r = nan_max(r, __shfl_xor_sync(0xffffffffu, r, s));
+  return r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) row_cta_kernel(const Params P) {
+  extern __shared__ float rowbuf[];
+  __shared__ float scratch[kWarps];
+  for (uint32_t row = blockIdx.x; row < P.rows; row += gridDim.x) {
+    const float *xr = P.x + (int64_t)row * P.x_row_stride;
+    float *yr = P.y + (int64_t)row * P.y_row_stride;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) rowbuf[i] = __ldcs(xr + i);
+    __syncthreads();
+    if constexpr (MODE == kLayerNorm) {
+      float s = 0.f;
+      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) s = __fadd_rn(s, rowbuf[i]);
+      const float mean = __fdiv_rn(block_reduce_sum(s, scratch), (float)P.R);
+      float q = 0.f;
+      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) {
+        const float c = __fsub_rn(rowbuf[i], mean);
+        rowbuf[i] = c;
+        q = __fadd_rn(q, __fmul_rn(c, c));
+      }
+      const float var = __fdiv_rn(block_reduce_sum(q, scratch), (float)P.R);
+      const float denom = __fsqrt_rn(__fadd_rn(var, P.eps));
+      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) {
+        float o = __fdiv_rn(rowbuf[i], denom);
+        if (P.gamma) o = __fmul_rn(o, __ldg(P.gamma + i));
+        if (P.beta) o = __fadd_rn(o, __ldg(P.beta + i));
+        __stcs(yr + i, o);
+      }
+    } else {
+      float m = -INFINITY;
+      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) m = nan_max(m, rowbuf[i]);
+      m = block_reduce_max(m, scratch);
+      float s = 0.f;
+      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) {
+        const float sh = __fsub_rn(rowbuf[i], m);
+        const float e = expf(sh);
+        s = __fadd_rn(s, e);
+        rowbuf[i] = MODE == kSoftmax ? e : sh;
+      }
+      s = block_reduce_sum(s, scratch);
+      const float ls = logf(s);
+      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock)
+        __stcs(yr + i, MODE == kSoftmax ? __fdiv_rn(rowbuf[i], s) : __fsub_rn(rowbuf[i], ls));
+    }
+  }
+}
+
+// Collapses [..., R] into (rows, row stride); requires a unit inner stride and leading dims that
+// are jointly strided.
+static int32_t rows_view(const b200_tensor &t, uint32_t &rows, uint32_t &R, int64_t &row_stride, const char *what) {
+  B200_REQUIRE(t.rank >= 1 && t.rank <= B200_MAX_RANK, B200_ERR_INVALID, "%s: bad rank %d", what, t.rank);
+  B200_REQUIRE(t.dtype == B200_F32, B200_ERR_UNSUPPORTED, "%s: only f32 is implemented", what);
+  const int last = t.rank - 1;
+  B200_REQUIRE(t.shape[last] == 1 || t.strides[last] == 1, B200_ERR_UNSUPPORTED, "%s: the normalised axis must be contiguous", what);
+  int64_t n_rows = 1, stride = t.shape[last];
+  bool first = true;
+  for (int d = last - 1; d >= 0; --d) {
+    if (t.shape[d] == 1) continue;
+    if (first) { stride = t.strides[d]; first = false; }
+    B200_REQUIRE(t.strides[d] == stride * n_rows, B200_ERR_UNSUPPORTED, "%s: leading dims must be jointly strided", what);
+    n_rows *= t.shape[d];
+  }
+  B200_REQUIRE(n_rows < (1ll << 31) && t.shape[last] < (1ll << 31), B200_ERR_UNSUPPORTED, "%s: too large", what);
+  rows = (uint32_t)n_rows;
+  R = (uint32_t)t.shape[last];
+  row_stride = stride;
+  return B200_OK;
+}
+
+template <int MODE>
+static int32_t launch_rows(const Params &P, cudaStream_t stream) {
+  if (P.rows == 0 || P.R == 0) return B200_OK;
+  const bool vec_ok = P.R % 4 == 0 && ((uintptr_t)P.x) % 16 == 0 && ((uintptr_t)P.y) % 16 == 0 &&
+                      P.x_row_stride % 4 == 0 && P.y_row_stride % 4 == 0 &&
+                      (!P.gamma || ((uintptr_t)P.gamma) % 16 == 0) && (!P.beta || ((uintptr_t)P.beta) % 16 == 0);
+  const int sms = sm_count();
+  if (vec_ok && P.R <= 2048) {
+    const uint32_t r4 = P.R / 4;
+    const unsigned grid = (unsigned)std::min<uint32_t>((P.rows + kWarps - 1) / kWarps, (uint32_t)sms * 8u);
+    if (r4 <= 32) row_warp_kernel<MODE, 1><<<grid, kBlock, 0, stream>>>(P);
+    else if (r4 <= 64) row_warp_kernel<MODE, 2><<<grid, kBlock, 0, stream>>>(P);
+    else if (r4 <= 128) row_warp_kernel<MODE, 4><<<grid, kBlock, 0, stream>>>(P);
+    else if (r4 <= 256) row_warp_kernel<MODE, 8><<<grid, kBlock, 0, stream>>>(P);
+    else row_warp_kernel<MODE, 16><<<grid, kBlock, 0, stream>>>(P);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
+  const size_t smem = (size_t)P.R * 4;
+  B200_REQUIRE((int)smem + 1024 <= max_smem_optin(), B200_ERR_UNSUPPORTED,
+               "row of %u f32 does not fit in shared memory; use the op chain", P.R);
+  auto kern = row_cta_kernel<MODE>;
+  if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+  const unsigned grid = (unsigned)std::min<uint32_t>(P.rows, (uint32_t)(sms * std::max(per_sm, 1)));
+  kern<<<grid, kBlock, smem, stream>>>(P);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+}  // namespace rn
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int32_t b200_launch_softmax(const b200_tensor *input, const b200_tensor *out, int32_t log_softmax,
+                                       b200_stream s) {
+  B200_REQUIRE(input && out && input->ptr && out->ptr, B200_ERR_INVALID, "null argument");
+  B200_REQUIRE(input->rank == out->rank, B200_ERR_SHAPE, "softmax rank mismatch");
+  for (int d = 0; d < input->rank; ++d)
+    B200_REQUIRE(input->shape[d] == out->shape[d], B200_ERR_SHAPE, "softmax shape mismatch at dim %d", d);
+  rn::Params P;
+  memset(&P, 0, sizeof(P));
+  uint32_t rows2, R2;
+  int32_t st = rn::rows_view(*input, P.rows, P.R, P.x_row_stride, "softmax input");
+  if (st != B200_OK) return st;
+  st = rn::rows_view(*out, rows2, R2, P.y_row_stride, "softmax output");
+  if (st != B200_OK) return st;
+  P.x = reinterpret_cast<const float *>(input->ptr);
+  P.y = reinterpret_cast<float *>(out->ptr);
+  return log_softmax ? rn::launch_rows<rn::kLogSoftmax>(P, resolve_stream(s))
+                     : rn::launch_rows<rn::kSoftmax>(P, resolve_stream(s));
+}
+
+extern "C" int32_t b200_launch_layer_norm(const b200_tensor *input, const b200_tensor *gamma, const b200_tensor *beta,
+                                          double eps, const b200_tensor *out, b200_stream s) {
+  B200_REQUIRE(input && out && input->ptr && out->ptr, B200_ERR_INVALID, "null argument");
+  B200_REQUIRE(input->rank == out->rank, B200_ERR_SHAPE, "layer_norm rank mismatch");
+  for (int d = 0; d < input->rank; ++d)
+    B200_REQUIRE(input->shape[d] == out->shape[d], B200_ERR_SHAPE, "layer_norm shape mismatch at dim %d", d);
+  rn::Params P;
+  memset(&P, 0, sizeof(P));
+  uint32_t rows2, R2;
+  int32_t st = rn::rows_view(*input, P.rows, P.R, P.x_row_stride, "layer_norm input");
+  if (st != B200_OK) return st;
+  st = rn::rows_view(*out, rows2, R2, P.y_row_stride, "layer_norm output");
+  if (st != B200_OK) return st;
+  auto vec1d = [&](const b200_tensor *t, const float *&dst, const char *what) -> int32_t {
+    dst = nullptr;
+    if (!t) return B200_OK;
+    B200_REQUIRE(t->dtype == B200_F32 && t->ptr, B200_ERR_UNSUPPORTED, "%s must be f32", what);
+    int64_t n = 1;
+    for (int d = 0; d < t->rank; ++d) n *= t->shape[d];
+    B200_REQUIRE(n == (int64_t)P.R && (t->shape[t->rank - 1] == 1 || t->strides[t->rank - 1] == 1), B200_ERR_SHAPE,
+                 "%s must hold d_model = %u contiguous values", what, P.R);
+    dst = reinterpret_cast<const float *>(t->ptr);
+    return B200_OK;
+  };
+  if ((st = vec1d(gamma, P.gamma, "gamma")) != B200_OK) return st;
+  if ((st = vec1d(beta, P.beta, "beta")) != B200_OK) return st;
+  P.x = reinterpret_cast<const float *>(input->ptr);
+  P.y = reinterpret_cast<float *>(out->ptr);
+  P.eps = (float)eps;
+  return rn::launch_rows<rn::kLayerNorm>(P, resolve_stream(s));
+}

@@ -272,3 +272,23 @@ def log_softmax(x: DeviceTensor, dim: int) -> DeviceTensor:
     dv.launch_reduce(abi.RED_SUM, dim, shape, [x, m.expand(shape)], [lse], read=rd.build(), write=wr.build())
     tb = TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("SUB_F", "acc", ("in", 2), out=0)
     return _launch(tb, [x, m.expand(shape), lse.expand(shape)], shape)
+
+
+# ---- row-resident fused kernels (ReduceBroadcasted analogue)
+def softmax_rows(x: DeviceTensor, log: bool = False) -> DeviceTensor:
+    """softmax / log_softmax along the LAST axis in one kernel (b200_launch_softmax)."""
+    out = DeviceTensor.empty(x.shape)
+    a, b = x.desc(), out.desc()
+    check(abi.load().b200_launch_softmax(C.byref(a), C.byref(b), 1 if log else 0, None))
+    return out
+
+
+def layer_norm(x: DeviceTensor, gamma: DeviceTensor | None, beta: DeviceTensor | None, eps: float) -> DeviceTensor:
+    """ModuleOps::layer_norm over the last axis in one kernel (b200_launch_layer_norm)."""
+    out = DeviceTensor.empty(x.shape)
+    a, o = x.desc(), out.desc()
+    g = gamma.desc() if gamma is not None else None
+    b = beta.desc() if beta is not None else None
+    check(abi.load().b200_launch_layer_norm(C.byref(a), C.byref(g) if g is not None else None,
+                                            C.byref(b) if b is not None else None, float(eps), C.byref(o), None))
+    return out

@@ -1,0 +1,73 @@
+"""GPU parity: row-resident softmax / log_softmax / layer_norm (the ReduceBroadcasted analogue,
+crates/burn-cubecl-fusion/src/optim/reduce_broadcasted/) vs the oracle's op-by-op chains
+(activation.rs:250-276, ops/modules/base.rs:846-877) and vs our own unfused op chain.
+Tolerance: 1e-5 relative (row sums are reassociated), tiny absolute floor for softmax tails."""
+import numpy as np
+import pytest
+
+from burn_b200 import ops
+from burn_b200.device import DeviceTensor
+from oracle import oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(shape, seed, lo=-3.0, hi=3.0):
+    return np.random.default_rng(seed).uniform(lo, hi, shape).astype(np.float32)
+
+
+SHAPES = [(7, 4), (64, 128), (33, 256), (16, 8, 512), (4, 2, 3, 1024), (9, 2048), (5, 4096), (3, 50257), (2, 1000)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_softmax_and_log_softmax_rows(dev, shape):
+    x = rnd(shape, 1)
+    last = len(shape) - 1
+    H.assert_close(ops.softmax_rows(H.up(x)).numpy(), oracle.softmax(x, last), 1e-5, 1e-10, "softmax")
+    H.assert_close(ops.softmax_rows(H.up(x), log=True).numpy(), oracle.log_softmax(x, last), 1e-5, 1e-6, "log_softmax")
+
+
+def test_softmax_reference_goldens(dev):
+    # crates/burn-backend-tests/tests/tensor/float/activation/softmax.rs:6,42
+    x = np.array([[1.0, 7.0], [13.0, -3.0]], dtype=np.float32)
+    H.assert_close(ops.softmax_rows(H.up(x)).numpy(),
+                   np.array([[2.472623e-03, 9.975274e-01], [1.0, 1.125352e-07]], dtype=np.float32), 5e-3, 1e-5)
+    x = np.array([[-1.0, 0.0, 1.0, 2.0], [0.5, 0.5, 0.5, 0.5]], dtype=np.float32)
+    H.assert_close(ops.softmax_rows(H.up(x)).numpy(),
+                   np.array([[0.03205860, 0.08714432, 0.23688284, 0.64391422], [0.25] * 4], dtype=np.float32), 5e-3, 1e-5)
+
+
+def test_fused_softmax_equals_unfused_chain(dev):
+    x = rnd((8, 16, 64, 64), 2)          # attention scores shape
+    a = ops.softmax_rows(H.up(x)).numpy()
+    b = ops.softmax(H.up(x), 3).numpy()  # max_dim / sub / exp / sum_dim / div through tapes + reduces
+    H.assert_close(a, b, 1e-5, 1e-10)
+    assert np.allclose(a.sum(axis=-1), 1.0, atol=1e-5)
+
+
+def test_attention_mask_rows(dev):
+    x = rnd((4, 8, 32, 32), 3)
+    x[:, :, :, 20:] = -1.0e9              # mask_fill(-1e9) as MHA does (mha.rs:282-285)
+    got = ops.softmax_rows(H.up(x)).numpy()
+    assert np.all(got[..., 20:] == 0.0)
+    H.assert_close(got, oracle.softmax(x, 3), 1e-5, 1e-10)
+
+
+@pytest.mark.parametrize("shape", [(64, 512), (4, 256, 512), (8, 1024), (3, 5000), (10, 36)])
+def test_layer_norm_rows(dev, shape):
+    x = rnd(shape, 4)
+    d = shape[-1]
+    g, b = rnd((d,), 5, 0.5, 1.5), rnd((d,), 6, -0.5, 0.5)
+    got = ops.layer_norm(H.up(x), H.up(g), H.up(b), 1e-5).numpy()
+    H.assert_close(got, oracle.layer_norm(x, g, b, 1e-5), 1e-5, 2e-6, "layer_norm")
+    got = ops.layer_norm(H.up(x), None, None, 1e-5).numpy()
+    H.assert_close(got, oracle.layer_norm(x, None, None, 1e-5), 1e-5, 2e-6, "layer_norm no affine")
+
+
+def test_non_contiguous_last_axis_is_rejected(dev):
+    from burn_b200 import _abi as abi
+    t = H.up(rnd((8, 16), 7)).swap_dims(0, 1)
+    with pytest.raises(abi.B200Error) as e:
+        ops.softmax_rows(t)
+    assert e.value.status == abi.ERR_UNSUPPORTED
