@@ -380,19 +380,30 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
 // ------------------------------------------------------------------ operand preparation kernels
 // 3xTF32 split: writes [hi | hi | lo] (which = 0, operand A) or [hi | lo | hi] (which = 1,
 // operand B) along K' = 3K as a K-major matrix [rows, 3K] from a strided [rows, K] view.
-__global__ void split3_kernel(const float *src, int64_t s_row, int64_t s_k, int64_t s_batch, float *dst, int rows, int K,
+struct SplitBatch {
+  int32_t bsz[kMaxBatchDims];
+  int64_t s_b[kMaxBatchDims];
+};
+__global__ void split3_kernel(const float *src, int64_t s_row, int64_t s_k, SplitBatch sb, float *dst, int rows, int K,
                               int K3pad, int which, int64_t n_total) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % K);
     const int64_t t = i / K;
     const int r = (int)(t % rows);
     const int64_t bt = t / rows;
-    const float x = src[bt * s_batch + (int64_t)r * s_row + (int64_t)k * s_k];
+    int64_t rest = bt, boff = 0;
+#pragma unroll
+    for (int d = kMaxBatchDims - 1; d >= 0; --d) {
+      const int64_t c = rest % sb.bsz[d];
+      rest /= sb.bsz[d];
+      boff += c * sb.s_b[d];
+    }
+    const float x = src[boff + (int64_t)r * s_row + (int64_t)k * s_k];
     uint32_t hi_b, lo_b;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi_b) : "f"(x));
     const float hi = __uint_as_float(hi_b);
-    const float rest = x - hi;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_b) : "f"(rest));
+    const float rest_f = x - hi;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_b) : "f"(rest_f));
     const float lo = __uint_as_float(lo_b);
     float *row = dst + (bt * rows + r) * (int64_t)K3pad;
     row[k] = hi;
@@ -636,22 +647,14 @@ extern "C" int32_t b200_launch_matmul(const b200_tensor *a, const b200_tensor *b
       B200_REQUIRE(t->dtype == B200_F32, B200_ERR_UNSUPPORTED, "F32X3 needs f32 operands");
       const int64_t K3p = (int64_t)align_up(3 * pl.K, 4);
       B200_CUDA(cudaMemsetAsync(ws, 0, need, stream));
-      // the split kernel walks a [own_batch, mn, K] view; batch dims must collapse to one stride
-      int64_t sb = 0;
-      bool ok = true;
-      {
-        int64_t expect = -1;
-        for (int d = mm::kMaxBatchDims - 1; d >= 0; --d) {
-          if (o.bsz[d] <= 1) continue;
-          if (expect < 0) { sb = o.s_b[d]; expect = o.s_b[d] * o.bsz[d]; }
-          else if (o.s_b[d] == expect) expect *= o.bsz[d];
-          else ok = false;
-        }
+      mm::SplitBatch sbatch;
+      for (int d = 0; d < mm::kMaxBatchDims; ++d) {
+        sbatch.bsz[d] = std::max(o.bsz[d], 1);
+        sbatch.s_b[d] = o.bsz[d] > 1 ? o.s_b[d] : 0;
       }
-      B200_REQUIRE(ok, B200_ERR_UNSUPPORTED, "F32X3 operand batch dims must be jointly strided");
       const int64_t total = own_batch * mn * pl.K;
       const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
-      mm::split3_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float *>(t->ptr), o.s_mn, o.s_k, sb,
+      mm::split3_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float *>(t->ptr), o.s_mn, o.s_k, sbatch,
                                                    reinterpret_cast<float *>(ws), (int)mn, (int)pl.K, (int)K3p,
                                                    is_a ? 0 : 1, total);
       B200_LAUNCH_CHECK();

@@ -1,0 +1,440 @@
+"""Training-step workload generator for BASELINE configs 4/5 (transformer encoder / decoder LM).
+
+NOT part of the kernel product: this module plays the role of the reference's *callers* of the
+hot path — burn-nn modules, burn-autodiff's reverse tape and burn-optim's Adam — so that the
+fused elementwise / reduce / matmul kernels and the NCCL all-reduce can be measured on the op
+streams those crates issue.  It mirrors, op for op:
+  Linear                 crates/burn-backend/src/backend/ops/modules/linear.rs:17-128
+  LayerNorm              crates/burn-backend/src/backend/ops/modules/base.rs:846-877
+  MultiHeadAttention     crates/burn-nn/src/modules/attention/mha.rs:212-311
+  PositionWiseFeedForward crates/burn-nn/src/modules/transformer/pwff.rs:105-111
+  TransformerEncoderLayer crates/burn-nn/src/modules/transformer/encoder.rs:245-303 (post-norm default)
+  matmul backward        crates/burn-autodiff/src/ops/tensor.rs:560-616 (grad·rhsᵀ, lhsᵀ·grad)
+  cross-entropy          crates/burn-nn/src/loss/cross_entropy.rs:171-197 (log_softmax, gather, mean)
+  Adam                   crates/burn-optim/src/optim/adam.rs:149-210
+All tensor math runs in libburn_b200.so through burn_b200.ops; this file only sequences launches.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Sequence
+
+import numpy as np
+
+from . import _abi as abi
+from . import device as dv
+from . import ops
+from .device import DeviceTensor, TapeBuilder
+
+
+# ------------------------------------------------------------------ reverse tape (burn-autodiff)
+class Var:
+    """A tensor on the autodiff tape."""
+    __slots__ = ("v", "g", "requires_grad", "name")
+
+    def __init__(self, v: DeviceTensor, requires_grad: bool = False, name: str = ""):
+        self.v, self.g, self.requires_grad, self.name = v, None, requires_grad, name
+
+
+class Tape:
+    def __init__(self, precision: int = abi.MM_TF32):
+        self.steps: list[Callable[[], None]] = []
+        self.precision = precision
+
+    def add(self, fn: Callable[[], None]) -> None:
+        self.steps.append(fn)
+
+    def backward(self) -> None:
+        for fn in reversed(self.steps):
+            fn()
+        self.steps.clear()
+
+
+def accumulate(var: Var, g: DeviceTensor) -> None:
+    if not var.requires_grad:
+        return
+    var.g = g if var.g is None else ops.float_add(var.g, g)
+
+
+def _run(tb: TapeBuilder, inputs, shape, n_out=1):
+    outs = [DeviceTensor.empty(shape) for _ in range(n_out)]
+    dv.launch_elemwise(tb.build(), inputs, outs, shape)
+    return outs[0] if n_out == 1 else outs
+
+
+# ------------------------------------------------------------------ ops with backward
+def matmul(tape: Tape, a: Var, b: Var, out: DeviceTensor | None = None, epilogue=None, epi_inputs=()) -> Var:
+    y = Var(_mm(a.v, b.v, tape.precision, out, epilogue, epi_inputs), a.requires_grad or b.requires_grad)
+
+    def bw():
+        if y.g is None:
+            return
+        nd = a.v.ndim
+        if a.requires_grad:
+            accumulate(a, _reduce_to(_mm(y.g, b.v.swap_dims(nd - 2, nd - 1), tape.precision), a.v.shape))
+        if b.requires_grad:
+            accumulate(b, _reduce_to(_mm(a.v.swap_dims(nd - 2, nd - 1), y.g, tape.precision), b.v.shape))
+    tape.add(bw)
+    return y
+
+
+def _mm(a: DeviceTensor, b: DeviceTensor, precision, out=None, epilogue=None, epi_inputs=()):
+    if out is None:
+        return ops.float_matmul(a, b, precision, epilogue, epi_inputs)
+    ad, bd, cd = a.desc(), b.desc(), out.desc()
+    lib = abi.load()
+    wsb = C.c_uint64()
+    abi.check(lib.b200_matmul_workspace_bytes(C.byref(ad), C.byref(bd), precision, C.byref(wsb)))
+    ws = dv.Storage(wsb.value) if wsb.value else None
+    epi, n_epi = dv._descs(epi_inputs)
+    abi.check(lib.b200_launch_matmul(C.byref(ad), C.byref(bd), C.byref(cd), precision,
+                                     C.byref(epilogue) if epilogue is not None else None, epi, n_epi,
+                                     ws.ptr if ws else None, wsb.value, None))
+    return out
+
+
+def _reduce_to(g: DeviceTensor, shape) -> DeviceTensor:
+    """Sums broadcast batch dims back to `shape` (autodiff's broadcast backward = SumDim chains)."""
+    for d, (gs, s) in enumerate(zip(g.shape, shape)):
+        if gs != s:
+            g = ops.float_sum_dim(g, d)
+    return g
+
+
+def linear(tape: Tape, x: Var, w: Var, b: Var | None, gelu_after: bool = False) -> Var:
+    """x[..., d_in] · W[d_in, d_out] + b, batch folded into M (linear.rs:26-41).  The bias add is
+    the GEMM's fuse-on-write epilogue (MatmulOptimization)."""
+    lead = x.v.shape[:-1]
+    m = int(np.prod(lead))
+    x2 = x.v.reshape((m, x.v.shape[-1]))
+    epi = epi_in = None
+    fuse_bias = b is not None and w.v.shape[1] % 4 == 0     # the fused epilogue needs N % 4 == 0
+    if fuse_bias:
+        epi = TapeBuilder().op("ADD_F", ("in", 0), ("in", 1), out=0).build()
+        epi_in = [b.v.reshape((1, b.v.shape[-1]))]
+    y2 = ops.float_matmul(x2, w.v, tape.precision, epi, epi_in or ())
+    if b is not None and not fuse_bias:
+        y2 = ops.float_add(y2, b.v.reshape((1, b.v.shape[-1])))
+    y = Var(y2.reshape(tuple(lead) + (w.v.shape[1],)), True)
+
+    def bw():
+        if y.g is None:
+            return
+        g2 = y.g.reshape((m, w.v.shape[1]))
+        if x.requires_grad:
+            accumulate(x, ops.float_matmul(g2, w.v.swap_dims(0, 1), tape.precision).reshape(x.v.shape))
+        if w.requires_grad:
+            accumulate(w, ops.float_matmul(x2.swap_dims(0, 1), g2, tape.precision))
+        if b is not None and b.requires_grad:
+            accumulate(b, ops.float_sum_dim(g2, 0).reshape(b.v.shape))   # linear_bias_backward: column reduce
+    tape.add(bw)
+    return y
+
+
+def add(tape: Tape, a: Var, b: Var) -> Var:
+    y = Var(ops.float_add(a.v, b.v), True)
+
+    def bw():
+        if y.g is not None:
+            accumulate(a, y.g)
+            accumulate(b, y.g)
+    tape.add(bw)
+    return y
+
+
+def gelu(tape: Tape, x: Var) -> Var:
+    y = Var(ops.gelu(x.v), True)
+
+    def bw():
+        if y.g is None or not x.requires_grad:
+            return
+        # d/dx [x(1+erf(x/√2))/2] = (1+erf(x/√2))/2 + x·exp(-x²/2)/√(2π)  — the chain rule through the
+        # five primitive ops, as one fused tape over (x, dy)
+        tb = TapeBuilder()
+        tb.op("MUL_F", ("in", 0), ("in", 0))
+        tb.op("MUL_F", "acc", ("f", -0.5))
+        tb.op("EXP_F", "acc")
+        tb.op("MUL_F", "acc", ("in", 0))
+        tb.op("MUL_F", "acc", ("f", 0.3989422804014327), tmp=0)
+        tb.op("DIV_F", ("in", 0), ("f", 1.4142135623730951))
+        tb.op("ERF_F", "acc")
+        tb.op("ADD_F", "acc", ("f", 1.0))
+        tb.op("MUL_F", "acc", ("f", 0.5))
+        tb.op("ADD_F", "acc", ("tmp", 0))
+        tb.op("MUL_F", "acc", ("in", 1), out=0)
+        accumulate(x, _run(tb, [x.v, y.g], x.v.shape))
+    tape.add(bw)
+    return y
+
+
+def layer_norm(tape: Tape, x: Var, gamma: Var, beta: Var, eps: float = 1e-5) -> Var:
+    y = Var(ops.layer_norm(x.v, gamma.v, beta.v, eps), True)
+
+    def bw():
+        if y.g is None:
+            return
+        shape = x.v.shape
+        last = len(shape) - 1
+        d = shape[-1]
+        red = tuple(shape[:-1]) + (1,)
+        bshape = (1,) * last + (d,)
+        # statistics recomputed with fused reduces (read tapes), x̂ never materialised twice
+        mean = ops.float_mean_dim(x.v, last)
+        var = DeviceTensor.empty(red)
+        rd = TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("MUL_F", "acc", "acc")
+        dv.launch_reduce(abi.RED_MEAN, last, shape, [x.v, mean.expand(shape)], [var], read=rd.build())
+        rstd = _run(TapeBuilder().op("ADD_F", ("in", 0), ("f", eps)).op("SQRT_F", "acc").op("RECIP_F", "acc", out=0),
+                    [var], red)
+        xhat = _run(TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("MUL_F", "acc", ("in", 2), out=0),
+                    [x.v, mean.expand(shape), rstd.expand(shape)], shape)
+        rows = int(np.prod(shape[:-1]))
+        if gamma.requires_grad:
+            prod = ops.float_mul(y.g, xhat)
+            accumulate(gamma, ops.float_sum_dim(prod.reshape((rows, d)), 0).reshape(gamma.v.shape))
+        if beta.requires_grad:
+            accumulate(beta, ops.float_sum_dim(y.g.reshape((rows, d)), 0).reshape(beta.v.shape))
+        if x.requires_grad:
+            gg = gamma.v.reshape(bshape).expand(shape)
+            m1, m2 = DeviceTensor.empty(red), DeviceTensor.empty(red)
+            dv.launch_reduce(abi.RED_MEAN, last, shape, [y.g, gg], [m1],
+                             read=TapeBuilder().op("MUL_F", ("in", 0), ("in", 1)).build())
+            dv.launch_reduce(abi.RED_MEAN, last, shape, [y.g, gg, xhat], [m2],
+                             read=TapeBuilder().op("MUL_F", ("in", 0), ("in", 1)).op("MUL_F", "acc", ("in", 2)).build())
+            tb = TapeBuilder()
+            tb.op("MUL_F", ("in", 0), ("in", 1))            # g = dy*gamma
+            tb.op("SUB_F", "acc", ("in", 2), tmp=0)         # g - mean(g)
+            tb.op("MUL_F", ("in", 3), ("in", 4))            # x̂ * mean(g x̂)
+            tb.op("SUB_F", ("tmp", 0), "acc")
+            tb.op("MUL_F", "acc", ("in", 5), out=0)         # * rstd
+            accumulate(x, _run(tb, [y.g, gg, m1.expand(shape), xhat, m2.expand(shape), rstd.expand(shape)], shape))
+    tape.add(bw)
+    return y
+
+
+def attention(tape: Tape, q: Var, k: Var, v: Var, n_heads: int, mask: DeviceTensor | None) -> Var:
+    """softmax(q·kᵀ/√dk [mask_fill -1e9]) · v on [B,S,d] projections viewed as [B,H,S,dk] (mha.rs:212-311).
+    Heads are strided views; q·kᵀ scales in the GEMM epilogue; the context GEMM writes straight into the
+    [B,S,H,dk] layout (no swap_dims copy)."""
+    B, S, d = q.v.shape
+    dk = d // n_heads
+    def heads(t):
+        return t.reshape((B, S, n_heads, dk)).swap_dims(1, 2)
+    qh, kh, vh = heads(q.v), heads(k.v), heads(v.v)
+    scale = TapeBuilder().op("DIV_F", ("in", 0), ("f", math.sqrt(dk)), out=0).build()
+    scores = ops.float_matmul(qh, kh.swap_dims(2, 3), tape.precision, scale)
+    if mask is not None:
+        scores = ops.float_mask_fill(scores, mask.expand(scores.shape), -1.0e9)
+    w = ops.softmax_rows(scores)
+    ctx_buf = DeviceTensor.empty((B, S, n_heads, dk))
+    _mm(w, vh, tape.precision, out=ctx_buf.swap_dims(1, 2))
+    y = Var(ctx_buf.reshape((B, S, d)), True)
+
+    def bw():
+        if y.g is None:
+            return
+        gh = y.g.reshape((B, S, n_heads, dk)).swap_dims(1, 2)          # [B,H,S,dk] view
+        # dV = Pᵀ·g ; dP = g·Vᵀ
+        dv_buf = DeviceTensor.empty((B, S, n_heads, dk))
+        _mm(w.swap_dims(2, 3), gh, tape.precision, out=dv_buf.swap_dims(1, 2))
+        dp = ops.float_matmul(gh, vh.swap_dims(2, 3), tape.precision)
+        # softmax backward: dS = (dP - sum(dP∘P, -1)) ∘ P, then the 1/√dk of the scores
+        shape = w.shape
+        red = tuple(shape[:-1]) + (1,)
+        dot = DeviceTensor.empty(red)
+        dv.launch_reduce(abi.RED_SUM, 3, shape, [dp, w], [dot],
+                         read=TapeBuilder().op("MUL_F", ("in", 0), ("in", 1)).build())
+        tb = (TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("MUL_F", "acc", ("in", 2))
+              .op("DIV_F", "acc", ("f", math.sqrt(dk)), out=0))
+        ds = _run(tb, [dp, dot.expand(shape), w], shape)
+        if mask is not None:
+            ds = ops.float_mask_fill(ds, mask.expand(shape), 0.0)
+        dq_buf, dk_buf = DeviceTensor.empty((B, S, n_heads, dk)), DeviceTensor.empty((B, S, n_heads, dk))
+        _mm(ds, kh, tape.precision, out=dq_buf.swap_dims(1, 2))
+        _mm(ds.swap_dims(2, 3), qh, tape.precision, out=dk_buf.swap_dims(1, 2))
+        accumulate(q, dq_buf.reshape((B, S, d)))
+        accumulate(k, dk_buf.reshape((B, S, d)))
+        accumulate(v, dv_buf.reshape((B, S, d)))
+    tape.add(bw)
+    return y
+
+
+def embedding(tape: Tape, weight: Var, ids: DeviceTensor) -> Var:
+    """select(weight, 0, ids) / embedding_backward = zeros.select_add (ops/modules/base.rs:140-180)."""
+    flat = ids.reshape((ids.numel,))
+    y = Var(ops.float_select(weight.v, 0, flat).reshape(tuple(ids.shape) + (weight.v.shape[1],)), True)
+
+    def bw():
+        if y.g is None or not weight.requires_grad:
+            return
+        z = DeviceTensor.empty(weight.v.shape)
+        abi.check(abi.load().b200_memset(z.data_ptr(), 0, z.numel * 4, None))
+        a, b, c = z.desc(), flat.desc(), y.g.reshape((flat.numel, weight.v.shape[1])).desc()
+        abi.check(abi.load().b200_launch_select_add(0, C.byref(a), C.byref(b), C.byref(c), None))
+        accumulate(weight, z)
+    tape.add(bw)
+    return y
+
+
+def cross_entropy(tape: Tape, logits: Var, targets: DeviceTensor) -> Var:
+    """mean(-log_softmax(logits)[target])  (cross_entropy.rs:171-197); logits [N, V], targets i32 [N]."""
+    n, vsz = logits.v.shape
+    logp = ops.softmax_rows(logits.v, log=True)
+    picked = ops.float_gather(1, logp, targets.reshape((n, 1)))
+    loss = ops.float_mul_scalar(ops.float_mean(picked), -1.0)
+    y = Var(loss, True)
+
+    def bw():
+        # d logits = (softmax - onehot) / N   (upstream gradient of the scalar loss is 1)
+        cols = DeviceTensor.empty((1, vsz), abi.I32)
+        d = cols.desc()
+        abi.check(abi.load().b200_launch_arange(C.byref(d), 0, 1, None))
+        tb = TapeBuilder()
+        tb.op("EQ_I", ("in", 1), ("in", 2))
+        tb.op("B2F", "acc", tmp=0)
+        tb.op("EXP_F", ("in", 0))
+        tb.op("SUB_F", "acc", ("tmp", 0))
+        tb.op("MUL_F", "acc", ("f", 1.0 / n), out=0)
+        g = _run(tb, [logp, cols.expand((n, vsz)), targets.reshape((n, 1)).expand((n, vsz))], (n, vsz))
+        accumulate(logits, g)
+    tape.add(bw)
+    return y
+
+
+def mean_square(tape: Tape, x: Var) -> Var:
+    sq = ops.float_mul(x.v, x.v)
+    y = Var(ops.float_mean(sq), True)
+
+    def bw():
+        accumulate(x, ops.float_mul_scalar(x.v, 2.0 / x.v.numel))
+    tape.add(bw)
+    return y
+
+
+# ------------------------------------------------------------------ modules (burn-nn)
+class Param(Var):
+    def __init__(self, a: np.ndarray, name: str):
+        super().__init__(DeviceTensor.from_numpy(np.ascontiguousarray(a, dtype=np.float32)), True, name)
+        self.m = self.s = None  # Adam moments
+
+
+def _uniform(rng, shape, fan_in):
+    k = 1.0 / math.sqrt(fan_in)     # Initializer::KaimingUniform{gain 1/√3, fan_out_only false} bound
+    return rng.uniform(-k, k, shape).astype(np.float32)
+
+
+class EncoderLayer:
+    def __init__(self, rng, d_model, d_ff, n_heads, idx):
+        self.h = n_heads
+        p = lambda a, n: Param(a, f"layer{idx}.{n}")
+        self.wq, self.bq = p(_uniform(rng, (d_model, d_model), d_model), "wq"), p(_uniform(rng, (d_model,), d_model), "bq")
+        self.wk, self.bk = p(_uniform(rng, (d_model, d_model), d_model), "wk"), p(_uniform(rng, (d_model,), d_model), "bk")
+        self.wv, self.bv = p(_uniform(rng, (d_model, d_model), d_model), "wv"), p(_uniform(rng, (d_model,), d_model), "bv")
+        self.wo, self.bo = p(_uniform(rng, (d_model, d_model), d_model), "wo"), p(_uniform(rng, (d_model,), d_model), "bo")
+        self.w1, self.b1 = p(_uniform(rng, (d_model, d_ff), d_model), "w1"), p(_uniform(rng, (d_ff,), d_model), "b1")
+        self.w2, self.b2 = p(_uniform(rng, (d_ff, d_model), d_ff), "w2"), p(_uniform(rng, (d_model,), d_ff), "b2")
+        self.g1, self.be1 = p(np.ones(d_model), "ln1.gamma"), p(np.zeros(d_model), "ln1.beta")
+        self.g2, self.be2 = p(np.ones(d_model), "ln2.gamma"), p(np.zeros(d_model), "ln2.beta")
+
+    def params(self):
+        return [self.wq, self.bq, self.wk, self.bk, self.wv, self.bv, self.wo, self.bo, self.w1, self.b1,
+                self.w2, self.b2, self.g1, self.be1, self.g2, self.be2]
+
+    def forward(self, tape: Tape, x: Var, mask) -> Var:
+        q, k, v = linear(tape, x, self.wq, self.bq), linear(tape, x, self.wk, self.bk), linear(tape, x, self.wv, self.bv)
+        ctx = attention(tape, q, k, v, self.h, mask)
+        x = add(tape, x, linear(tape, ctx, self.wo, self.bo))
+        x = layer_norm(tape, x, self.g1, self.be1)                 # post-norm (norm_first = false)
+        hdn = gelu(tape, linear(tape, x, self.w1, self.b1))
+        x = add(tape, x, linear(tape, hdn, self.w2, self.b2))
+        return layer_norm(tape, x, self.g2, self.be2)
+
+
+class Encoder:
+    """TransformerEncoderConfig::new(d_model, d_ff, n_heads, n_layers), dropout 0."""
+
+    def __init__(self, seed, d_model, d_ff, n_heads, n_layers):
+        rng = np.random.default_rng(seed)
+        self.layers = [EncoderLayer(rng, d_model, d_ff, n_heads, i) for i in range(n_layers)]
+
+    def params(self):
+        return [p for l in self.layers for p in l.params()]
+
+    def forward(self, tape, x, mask=None):
+        for l in self.layers:
+            x = l.forward(tape, x, mask)
+        return x
+
+
+class LanguageModel:
+    """examples/text-generation model: token + positional embedding → encoder (causal mask) → vocab head
+    (examples/text-generation/src/model.rs:53-100)."""
+
+    def __init__(self, seed, vocab, max_seq, d_model, d_ff, n_heads, n_layers):
+        rng = np.random.default_rng(seed)
+        self.tok = Param(rng.standard_normal((vocab, d_model)).astype(np.float32), "embedding_token")
+        self.pos = Param(rng.standard_normal((max_seq, d_model)).astype(np.float32), "embedding_pos")
+        self.enc = Encoder(seed + 1, d_model, d_ff, n_heads, n_layers)
+        self.wout = Param(_uniform(rng, (d_model, vocab), d_model), "output.w")
+        self.bout = Param(_uniform(rng, (vocab,), d_model), "output.b")
+
+    def params(self):
+        return [self.tok, self.pos] + self.enc.params() + [self.wout, self.bout]
+
+    def loss(self, tape, tokens: DeviceTensor, targets: DeviceTensor, pos_ids: DeviceTensor, causal: DeviceTensor):
+        B, S = tokens.shape
+        x = add(tape, embedding(tape, self.tok, tokens), embedding(tape, self.pos, pos_ids))
+        h = self.enc.forward(tape, x, causal)
+        logits = linear(tape, h, self.wout, self.bout)
+        return cross_entropy(tape, _reshape(tape, logits, (B * S, logits.v.shape[-1])), targets.reshape((B * S,)))
+
+
+def _reshape(tape: Tape, x: Var, shape) -> Var:
+    y = Var(x.v.reshape(shape), True)
+
+    def bw():
+        if y.g is not None:
+            accumulate(x, y.g.reshape(x.v.shape))
+    tape.add(bw)
+    return y
+
+
+# ------------------------------------------------------------------ Adam (burn-optim adam.rs:149-210)
+class Adam:
+    def __init__(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-5):
+        self.lr, self.b1, self.b2, self.eps, self.t = lr, beta1, beta2, eps, 0
+
+    def step(self, params: Sequence[Param]) -> None:
+        self.t += 1
+        c1 = 1.0 - self.b1 ** self.t
+        c2 = 1.0 - self.b2 ** self.t
+        for p in params:
+            if p.g is None:
+                continue
+            if p.m is None:
+                p.m, p.s = DeviceTensor.empty(p.v.shape), DeviceTensor.empty(p.v.shape)
+                lib = abi.load()
+                abi.check(lib.b200_memset(p.m.data_ptr(), 0, p.m.numel * 4, None))
+                abi.check(lib.b200_memset(p.s.data_ptr(), 0, p.s.numel * 4, None))
+            # one fused kernel, three in-place outputs: m, v, p
+            tb = TapeBuilder()
+            tb.op("MUL_F", ("in", 3), ("f", 1.0 - self.b1), tmp=0)            # (1-β1) g
+            tb.op("MUL_F", ("in", 1), ("f", self.b1))
+            tb.op("ADD_F", "acc", ("tmp", 0), tmp=1, out=1)                    # m'
+            tb.op("MUL_F", ("in", 3), ("in", 3))
+            tb.op("MUL_F", "acc", ("f", 1.0 - self.b2), tmp=0)                 # (1-β2) g²
+            tb.op("MUL_F", ("in", 2), ("f", self.b2))
+            tb.op("ADD_F", "acc", ("tmp", 0), out=2)                           # v'
+            tb.op("DIV_F", "acc", ("f", c2))
+            tb.op("SQRT_F", "acc")
+            tb.op("ADD_F", "acc", ("f", self.eps), tmp=0)                      # √(v̂)+ε
+            tb.op("DIV_F", ("tmp", 1), ("f", c1))
+            tb.op("DIV_F", "acc", ("tmp", 0))
+            tb.op("MUL_F", "acc", ("f", self.lr), tmp=0)
+            tb.op("SUB_F", ("in", 0), ("tmp", 0), out=0)                       # p' = p - lr·m̂/(√v̂+ε)
+            dv.launch_elemwise(tb.build(), [p.v, p.m, p.s, p.g], [p.v, p.m, p.s], p.v.shape)
+
+    @staticmethod
+    def zero_grad(params):
+        for p in params:
+            p.g = None
