@@ -129,6 +129,11 @@ SIGNATURES = {
     "b200_event_destroy": (_i32, [_vp]),
     "b200_event_record": (_i32, [_vp, _vp]),
     "b200_event_elapsed_ms": (_i32, [_vp, _vp, C.POINTER(C.c_float)]),
+    "b200_graph_begin": (_i32, [_vp]),
+    "b200_graph_end": (_i32, [_vp, C.POINTER(C.c_void_p)]),
+    "b200_graph_launch": (_i32, [_vp, _vp]),
+    "b200_graph_destroy": (_i32, [_vp]),
+    "b200_graph_node_count": (_i32, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "b200_launch_count": (_u64, []),
     "b200_launch_count_reset": (None, []),
 }

@@ -131,14 +131,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// Shared-memory matrix descriptor (sm_100 format, version 1, SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (sm_100 format, version 1).  layout: 2 = SWIZZLE_128B (16-byte
+// swizzle atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms — what MN-major 32-bit operands need;
+// the TMA side is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -267,9 +270,12 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
             // K-major: 32 bytes along the swizzled row per MMA; MN-major: UMMA_K rows of 128 B
             // MN-major (validated on hardware for bf16): LBO = stride between 128-byte MN groups
             // (one TMA box of BK rows), SBO = stride between 8-row K atoms
-            const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
+            // (one TMA box of BK rows), SBO = stride between K atoms: 8 rows of 128 B for 16-bit
+            // operands, 4 rows for 32-bit ones (32-byte swizzle atoms)
+            constexpr uint32_t kMnSbo = BF16 ? 1024 : 512, kMnLayout = BF16 ? 2 : 1;
+            const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), BK * 128, kMnSbo, kMnLayout)
                                      : make_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
+            const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), BK * 128, kMnSbo, kMnLayout)
                                      : make_desc(sb + k * 32, 16, 1024);
             umma<BF16>(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
           }
@@ -443,10 +449,11 @@ struct Operand {
 
 static bool tma_ok(const Operand &o, int64_t mn, int64_t k) {
   const int64_t align = 16 / o.es;
-  // 16-bit MN-major operands are consumed in place (MN-major UMMA descriptors, validated on
-  // hardware).  32-bit MN-major operands would need the SWIZZLE_128B_BASE32B canonical layout,
-  // which this kernel does not implement: they are repacked K-major by the pre-pass.
-  if (o.mn_major && o.es == 4) return false;
+  // MN-major operands are consumed in place through MN-major UMMA descriptors: 16-bit ones with the
+  // plain SWIZZLE_128B layout, 32-bit ones with SWIZZLE_128B_BASE32B (TMA: SWIZZLE_128B_ATOM_32B).
+  // B200_MM_REPACK_TF32_MN=1 forces the old K-major repack pre-pass for 32-bit operands (debug).
+  static const bool repack32 = std::getenv("B200_MM_REPACK_TF32_MN") != nullptr;
+  if (o.mn_major && o.es == 4 && repack32) return false;
   const int64_t inner = o.mn_major ? o.s_mn : o.s_k, outer = o.mn_major ? o.s_k : o.s_mn;
   if (inner != 1) return false;
   if ((o.mn_major ? k : mn) > 1 && (outer % align != 0 || outer < (o.mn_major ? mn : k))) return false;
@@ -476,8 +483,9 @@ static int32_t make_tmap(CUtensorMap *map, const Operand &o, int64_t mn, int64_t
     strides[1 + d] = (cuuint64_t)sb * o.es;
   }
   const CUtensorMapDataType dt = o.es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUresult r = enc(map, dt, 5, o.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = (o.mn_major && o.es == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(map, dt, 5, o.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
   return B200_OK;
 }

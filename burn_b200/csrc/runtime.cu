@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -184,6 +185,73 @@ int32_t b200_event_elapsed_ms(b200_event start, b200_event stop, float *ms) {
   B200_REQUIRE(ms, B200_ERR_INVALID, "ms is null");
   B200_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
   B200_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------- CUDA graphs
+struct B200Graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t kernel_nodes = 0, total_nodes = 0;
+};
+
+int32_t b200_graph_begin(b200_stream s) {
+  // relaxed: other host threads (and host-only driver calls such as tensor-map encoding) stay legal
+  B200_CUDA(cudaStreamBeginCapture(resolve_stream(s), cudaStreamCaptureModeRelaxed));
+  return B200_OK;
+}
+
+int32_t b200_graph_end(b200_stream s, b200_graph *out) {
+  B200_REQUIRE(out, B200_ERR_INVALID, "out is null");
+  B200Graph *g = new B200Graph();
+  cudaError_t e = cudaStreamEndCapture(resolve_stream(s), &g->graph);
+  if (e != cudaSuccess || !g->graph) {
+    delete g;
+    return fail(B200_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  }
+  size_t n = 0;
+  B200_CUDA(cudaGraphGetNodes(g->graph, nullptr, &n));
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n) B200_CUDA(cudaGraphGetNodes(g->graph, nodes.data(), &n));
+  g->total_nodes = n;
+  for (size_t i = 0; i < n; ++i) {
+    cudaGraphNodeType t;
+    B200_CUDA(cudaGraphNodeGetType(nodes[i], &t));
+    if (t == cudaGraphNodeTypeKernel) ++g->kernel_nodes;
+  }
+  // allocations still live at the end of one replay are released at the start of the next
+  e = cudaGraphInstantiateWithFlags(&g->exec, g->graph, cudaGraphInstantiateFlagAutoFreeOnLaunch);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(g->graph);
+    delete g;
+    return fail(B200_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  }
+  *out = (b200_graph)g;
+  return B200_OK;
+}
+
+int32_t b200_graph_launch(b200_graph gh, b200_stream s) {
+  B200Graph *g = (B200Graph *)gh;
+  B200_REQUIRE(g && g->exec, B200_ERR_INVALID, "graph is null");
+  B200_CUDA(cudaGraphLaunch(g->exec, resolve_stream(s)));
+  g_launches.fetch_add(g->kernel_nodes);
+  return B200_OK;
+}
+
+int32_t b200_graph_destroy(b200_graph gh) {
+  B200Graph *g = (B200Graph *)gh;
+  if (!g) return B200_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+  return B200_OK;
+}
+
+int32_t b200_graph_node_count(b200_graph gh, uint64_t *kernel_nodes, uint64_t *total_nodes) {
+  B200Graph *g = (B200Graph *)gh;
+  B200_REQUIRE(g, B200_ERR_INVALID, "graph is null");
+  if (kernel_nodes) *kernel_nodes = g->kernel_nodes;
+  if (total_nodes) *total_nodes = g->total_nodes;
   return B200_OK;
 }
 

@@ -43,6 +43,49 @@ def sync(stream=None) -> None:
     check(_lib().b200_stream_sync(stream))
 
 
+class Graph:
+    """A captured launch sequence (b200_graph_*): `with Graph.capture() as g: ...` records every
+    launch / alloc / free issued on the default stream; `g.launch()` replays it."""
+
+    def __init__(self):
+        self.handle = C.c_void_p()
+        self.kernel_nodes = self.total_nodes = 0
+        self._stream = None
+
+    @classmethod
+    def capture(cls, stream=None) -> "Graph":
+        g = cls()
+        g._stream = stream
+        return g
+
+    def __enter__(self):
+        import gc
+        gc.collect()            # no stray pre-capture buffers may be freed inside the capture
+        check(_lib().b200_graph_begin(self._stream))
+        return self
+
+    def __exit__(self, et, ev, tb):
+        import gc
+        gc.collect()            # buffers allocated inside the capture are freed inside it
+        st = _lib().b200_graph_end(self._stream, C.byref(self.handle))
+        if et is None:
+            check(st)
+            k, t = C.c_uint64(), C.c_uint64()
+            check(_lib().b200_graph_node_count(self.handle, C.byref(k), C.byref(t)))
+            self.kernel_nodes, self.total_nodes = k.value, t.value
+        return False
+
+    def launch(self, stream=None) -> None:
+        check(_lib().b200_graph_launch(self.handle, stream))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                abi.load().b200_graph_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class Storage:
     """Refcounted device allocation (freed stream-ordered when the last view dies)."""
 

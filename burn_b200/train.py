@@ -55,6 +55,9 @@ def accumulate(var: Var, g: DeviceTensor) -> None:
     if not var.requires_grad:
         return
     var.g = g if var.g is None else ops.float_add(var.g, g)
+    hook = getattr(var, "on_grad", None)
+    if hook is not None:
+        hook(var)
 
 
 def _run(tb: TapeBuilder, inputs, shape, n_out=1):
@@ -313,9 +316,12 @@ def mean_square(tape: Tape, x: Var) -> Var:
 
 # ------------------------------------------------------------------ modules (burn-nn)
 class Param(Var):
+    __slots__ = ("m", "s", "on_grad")
+
     def __init__(self, a: np.ndarray, name: str):
         super().__init__(DeviceTensor.from_numpy(np.ascontiguousarray(a, dtype=np.float32)), True, name)
         self.m = self.s = None  # Adam moments
+        self.on_grad = None     # called once the gradient is final (each parameter is used once per step)
 
 
 def _uniform(rng, shape, fan_in):
@@ -383,10 +389,21 @@ class LanguageModel:
 
     def loss(self, tape, tokens: DeviceTensor, targets: DeviceTensor, pos_ids: DeviceTensor, causal: DeviceTensor):
         B, S = tokens.shape
-        x = add(tape, embedding(tape, self.tok, tokens), embedding(tape, self.pos, pos_ids))
+        x = add(tape, embedding(tape, self.pos, pos_ids), embedding(tape, self.tok, tokens))
+        x = scale(tape, x, 0.5)                                   # (pos + tok) / 2, model.rs:66
         h = self.enc.forward(tape, x, causal)
         logits = linear(tape, h, self.wout, self.bout)
         return cross_entropy(tape, _reshape(tape, logits, (B * S, logits.v.shape[-1])), targets.reshape((B * S,)))
+
+
+def scale(tape: Tape, x: Var, c: float) -> Var:
+    y = Var(ops.float_mul_scalar(x.v, c), True)
+
+    def bw():
+        if y.g is not None:
+            accumulate(x, ops.float_mul_scalar(y.g, c))
+    tape.add(bw)
+    return y
 
 
 def _reshape(tape: Tape, x: Var, shape) -> Var:
@@ -403,11 +420,22 @@ def _reshape(tape: Tape, x: Var, shape) -> Var:
 class Adam:
     def __init__(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-5):
         self.lr, self.b1, self.b2, self.eps, self.t = lr, beta1, beta2, eps, 0
+        self.coef = None        # device [2]: 1-β1^t, 1-β2^t — inputs, not immediates, so a graph replays
+
+    def advance(self) -> None:
+        """Host side of a step: bump t and upload the two bias-correction scalars (8 bytes)."""
+        self.t += 1
+        if self.coef is None:
+            self.coef = DeviceTensor.empty((2,))
+        c = np.array([1.0 - self.b1 ** self.t, 1.0 - self.b2 ** self.t], dtype=np.float32)
+        abi.check(abi.load().b200_memcpy_h2d(self.coef.data_ptr(), c.ctypes.data, 8, None))  # pageable: staged synchronously
 
     def step(self, params: Sequence[Param]) -> None:
-        self.t += 1
-        c1 = 1.0 - self.b1 ** self.t
-        c2 = 1.0 - self.b2 ** self.t
+        self.advance()
+        self.apply(params)
+
+    def apply(self, params: Sequence[Param]) -> None:
+        """The device side: one fused launch per parameter (capturable)."""
         for p in params:
             if p.g is None:
                 continue
@@ -425,16 +453,51 @@ class Adam:
             tb.op("MUL_F", "acc", ("f", 1.0 - self.b2), tmp=0)                 # (1-β2) g²
             tb.op("MUL_F", ("in", 2), ("f", self.b2))
             tb.op("ADD_F", "acc", ("tmp", 0), out=2)                           # v'
-            tb.op("DIV_F", "acc", ("f", c2))
+            tb.op("DIV_F", "acc", ("in", 5))                                   # v̂ = v'/(1-β2^t)
             tb.op("SQRT_F", "acc")
             tb.op("ADD_F", "acc", ("f", self.eps), tmp=0)                      # √(v̂)+ε
-            tb.op("DIV_F", ("tmp", 1), ("f", c1))
+            tb.op("DIV_F", ("tmp", 1), ("in", 4))                              # m̂ = m'/(1-β1^t)
             tb.op("DIV_F", "acc", ("tmp", 0))
             tb.op("MUL_F", "acc", ("f", self.lr), tmp=0)
             tb.op("SUB_F", ("in", 0), ("tmp", 0), out=0)                       # p' = p - lr·m̂/(√v̂+ε)
-            dv.launch_elemwise(tb.build(), [p.v, p.m, p.s, p.g], [p.v, p.m, p.s], p.v.shape)
+            c1 = self.coef.slice([(0, 1)]).reshape((1,) * p.v.ndim).expand(p.v.shape)
+            c2 = self.coef.slice([(1, 2)]).reshape((1,) * p.v.ndim).expand(p.v.shape)
+            dv.launch_elemwise(tb.build(), [p.v, p.m, p.s, p.g, c1, c2], [p.v, p.m, p.s], p.v.shape)
 
     @staticmethod
     def zero_grad(params):
         for p in params:
             p.g = None
+
+
+# ------------------------------------------------------------------ DDP gradient sync (burn-train ddp)
+class GradSync:
+    """All-reduce(Mean) of every parameter gradient as soon as it is final, overlapped with the rest
+    of backward on the collective stream, fenced before the optimizer (SURVEY.md §3.4;
+    crates/burn-cubecl/src/ops/distributed.rs:17-50 issues one collective per parameter — here
+    small gradients are grouped into buckets of `bucket_bytes` per NCCL group call)."""
+
+    def __init__(self, comm, params: Sequence[Param], bucket_bytes: int = 32 << 20):
+        self.comm, self.bucket_bytes = comm, bucket_bytes
+        self.pending: list[DeviceTensor] = []
+        self.pending_bytes = 0
+        self.calls = 0
+        for p in params:
+            p.on_grad = self.ready
+
+    def ready(self, p: Param) -> None:
+        self.pending.append(p.g)
+        self.pending_bytes += p.g.numel * 4
+        if self.pending_bytes >= self.bucket_bytes:
+            self.flush()
+
+    def flush(self) -> None:
+        if self.pending:
+            self.comm.all_reduce_bucket(self.pending, mean=True)
+            self.calls += 1
+            self.pending, self.pending_bytes = [], 0
+
+    def wait(self) -> None:
+        """sync_collective: the optimizer's launches wait for every outstanding all-reduce."""
+        self.flush()
+        self.comm.sync()

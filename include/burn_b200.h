@@ -95,6 +95,22 @@ int32_t b200_event_destroy(b200_event e);
 int32_t b200_event_record(b200_event e, b200_stream s);
 int32_t b200_event_elapsed_ms(b200_event start, b200_event stop, float *ms); /* syncs on stop */
 
+/* CUDA-graph capture of a launch sequence (the replacement
+ * for re-walking burn-fusion's ExecutionPlan store every step,
+ * crates/burn-fusion/src/stream/store/base.rs — a training step whose shapes do
+ * not change is captured once and replayed with one driver call).  Everything
+ * issued on `s` between begin and end — kernels, b200_alloc/b200_free (become
+ * graph memory nodes), memsets, d2d copies, and collectives forked onto the comm
+ * stream and joined back by b200_collective_sync — is recorded, not executed.
+ * Buffers allocated before the capture keep their addresses across replays;
+ * buffers allocated inside it must also be freed inside it. */
+typedef void *b200_graph;
+int32_t b200_graph_begin(b200_stream s);
+int32_t b200_graph_end(b200_stream s, b200_graph *out);
+int32_t b200_graph_launch(b200_graph g, b200_stream s);
+int32_t b200_graph_destroy(b200_graph g);
+int32_t b200_graph_node_count(b200_graph g, uint64_t *kernel_nodes, uint64_t *total_nodes);
+
 /* Stream-ordered caching allocator (cudaMallocAsync pool, never trimmed until
  * b200_memory_cleanup).  Replaces cubecl's memory pools behind
  * CubeTensor::handle; b200_retain/b200_free give the refcount semantics of

@@ -89,7 +89,7 @@ def test_language_model_loss_and_grads_with_causal_mask(dev):
     tape.backward()
     # reference
     tt, tp = t64(lm.tok), t64(lm.pos)
-    x = tt[torch.tensor(tok, dtype=torch.long)] + tp[torch.tensor(pos, dtype=torch.long)]
+    x = (tt[torch.tensor(tok, dtype=torch.long)] + tp[torch.tensor(pos, dtype=torch.long)]) / 2
     P = {n: t64(p) for n, p in zip(NAMES, lm.enc.layers[0].params())}
     hdn = torch_layer(x, P, h, torch.tensor(causal))
     two, tbo = t64(lm.wout), t64(lm.bout)

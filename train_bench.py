@@ -1,0 +1,239 @@
+#!/usr/bin/env python
+"""train_bench.py — the second half of BASELINE.json's metric: transformer train tokens/s at
+1/2/4/8 B200 (configs[3] and configs[4]), measured on the op streams burn-nn / burn-autodiff /
+burn-optim issue (burn_b200/train.py) through the burn_b200 C ABI.
+
+  python train_bench.py --config lm --steps 10 --warmup 3 [--mm tf32|bf16|f32x3] [--eager]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+      --master-port P train_bench.py --config lm ...
+
+One step = upload this rank's token batch from pinned host memory, forward, loss, backward with
+every parameter gradient all-reduced (Mean) over NCCL as soon as it is final (N > 1), Adam on every
+parameter, loss read back to the host.  The device work is captured ONCE into a CUDA graph
+(b200_graph_*) and replayed; `--eager` replays the Python launch sequence instead.  Weak scaling:
+the per-GPU batch is fixed, tokens/s is the whole-job aggregate, time is max over ranks on the device.
+bench.py imports `run()` and attaches its result to the bench line under "train".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# configs[3]: burn-nn TransformerEncoder d_model 512, 6 layers, 8 heads, seq 256, batch 64 (d_ff 2048: 4·d_model)
+# configs[4]: text-generation-style LM d_model 1024, 12 layers, seq 1024 (16 heads, d_ff 4096; vocab = GPT-2's
+#             50257 + [START]/[END]/[PAD] = 50260, examples/text-generation/src/data/tokenizer.rs:27-31);
+#             per-GPU batch 8 → 8192 tokens per GPU per step (SURVEY.md §8 sizes "T5")
+CONFIGS = {
+    "encoder": dict(kind="encoder", d=512, ff=2048, h=8, L=6, S=256, B=64),
+    "lm": dict(kind="lm", d=1024, ff=4096, h=16, L=12, S=1024, B=8, vocab=50260),
+    "lm-tiny": dict(kind="lm", d=64, ff=128, h=4, L=2, S=32, B=2, vocab=96),
+    "encoder-tiny": dict(kind="encoder", d=64, ff=128, h=4, L=2, S=16, B=4),
+}
+
+
+def model_flops(cfg) -> float:
+    """fwd+bwd FLOPs per step per GPU: 6·(GEMM params)·tokens + 12·L·B·S²·d for attention."""
+    d, ff, L, S, B = cfg["d"], cfg["ff"], cfg["L"], cfg["S"], cfg["B"]
+    tokens = B * S
+    p = L * (4 * d * d + 2 * d * ff)
+    if cfg["kind"] == "lm":
+        p += d * cfg["vocab"]
+    return 6.0 * p * tokens + 12.0 * L * B * S * S * d
+
+
+def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_rank: int,
+        mm: str = "tf32", use_graph: bool = True, bucket_mb: int = 32, init_device: bool = True):
+    import torch
+    import torch.distributed as dist
+    from burn_b200 import _abi as abi
+    from burn_b200 import device as dv
+    from burn_b200 import train as T
+    from burn_b200.device import DeviceTensor
+    from burn_b200.distributed import Communicator
+
+    cfg = CONFIGS[cfg_name]
+    prec = {"tf32": abi.MM_TF32, "bf16": abi.MM_BF16, "f32x3": abi.MM_F32X3}[mm]
+    if init_device:
+        torch.cuda.set_device(local_rank)
+        dv.init(local_rank)
+    lib = abi.load()
+    check = abi.check
+    B, S, d = cfg["B"], cfg["S"], cfg["d"]
+
+    # ---- model (same seed on every rank = identical replicas), optimizer, gradient sync
+    if cfg["kind"] == "lm":
+        model = T.LanguageModel(11, cfg["vocab"], S, d, cfg["ff"], cfg["h"], cfg["L"])
+    else:
+        model = T.Encoder(11, d, cfg["ff"], cfg["h"], cfg["L"])
+    params = model.params()
+    n_params = sum(p.v.numel for p in params)
+    opt = T.Adam(lr=1e-4)
+    comm = sync = None
+    if world > 1:
+        comm = Communicator(rank, world, device=torch.device("cuda", local_rank))
+        sync = T.GradSync(comm, params, bucket_bytes=bucket_mb << 20)
+
+    # ---- this rank's synthetic batch, pinned on the host, persistent device buffers
+    rng = np.random.default_rng(5000 + rank)
+
+    def pinned(shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        check(lib.b200_host_alloc(C.byref(ptr), n))
+        ctype = {np.int32: C.c_int32, np.float32: C.c_float}[dtype]
+        return ptr, np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=shape), n
+
+    loss_dev = DeviceTensor.empty((1,))
+    loss_ptr, loss_host, _ = pinned((1,), np.float32)
+    if cfg["kind"] == "lm":
+        tok_ptr, tok_host, tok_bytes = pinned((B, S), np.int32)
+        tgt_ptr, tgt_host, _ = pinned((B, S), np.int32)
+        tok_host[...] = rng.integers(0, cfg["vocab"], (B, S))
+        tgt_host[...] = np.roll(tok_host, -1, axis=1)                    # next-token targets
+        tok_dev, tgt_dev = DeviceTensor.empty((B, S), abi.I32), DeviceTensor.empty((B, S), abi.I32)
+        pos_dev = DeviceTensor.from_numpy(np.tile(np.arange(S, dtype=np.int32), (B, 1)))
+        causal = DeviceTensor.from_numpy(np.triu(np.ones((S, S), dtype=bool), k=1)[None, None])
+        h2d_bytes = 2 * tok_bytes
+
+        def h2d():
+            check(lib.b200_memcpy_h2d(tok_dev.data_ptr(), tok_ptr, tok_bytes, None))
+            check(lib.b200_memcpy_h2d(tgt_dev.data_ptr(), tgt_ptr, tok_bytes, None))
+    else:
+        x_ptr, x_host, x_bytes = pinned((B, S, d), np.float32)
+        x_host[...] = rng.standard_normal((B, S, d)).astype(np.float32)
+        x_dev = DeviceTensor.empty((B, S, d))
+        h2d_bytes = x_bytes
+
+        def h2d():
+            check(lib.b200_memcpy_h2d(x_dev.data_ptr(), x_ptr, x_bytes, None))
+
+    def device_step():
+        """forward → loss → backward (+ overlapped all-reduce) → Adam; every buffer it allocates dies here."""
+        tape = T.Tape(prec)
+        if cfg["kind"] == "lm":
+            loss = model.loss(tape, tok_dev, tgt_dev, pos_dev, causal)
+        else:
+            loss = T.mean_square(tape, model.forward(tape, T.Var(x_dev, False)))
+        check(lib.b200_memcpy_d2d(loss_dev.data_ptr(), loss.v.data_ptr(), 4, None))
+        del loss
+        tape.backward()
+        if sync is not None:
+            sync.wait()
+        opt.apply(params)
+        T.Adam.zero_grad(params)
+
+    def d2h():
+        check(lib.b200_memcpy_d2h(loss_ptr, loss_dev.data_ptr(), 4, None))
+
+    def barrier():
+        check(lib.b200_device_sync())
+        if world > 1:
+            dist.barrier()
+        check(lib.b200_device_sync())
+
+    # ---- one eager step (creates the Adam moments, sets kernel attributes), then capture
+    losses = []
+    h2d(); opt.advance(); device_step(); d2h()
+    check(lib.b200_device_sync())
+    losses.append(float(loss_host[0]))
+    graph = None
+    if use_graph:
+        with dv.Graph.capture() as graph:
+            device_step()
+
+    def step():
+        h2d()
+        opt.advance()
+        if graph is not None:
+            graph.launch()
+        else:
+            device_step()
+        d2h()
+
+    for _ in range(warmup):
+        step()
+        check(lib.b200_device_sync())
+        losses.append(float(loss_host[0]))
+    ev0, ev1 = C.c_void_p(), C.c_void_p()
+    check(lib.b200_event_create(C.byref(ev0)))
+    check(lib.b200_event_create(C.byref(ev1)))
+    barrier()
+    lib.b200_launch_count_reset()
+    check(lib.b200_event_record(ev0, None))
+    for _ in range(steps):
+        step()
+    check(lib.b200_event_record(ev1, None))
+    barrier()
+    launches = int(lib.b200_launch_count())
+    ms = C.c_float()
+    check(lib.b200_event_elapsed_ms(ev0, ev1, C.byref(ms)))
+    total_ms = ms.value
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    losses.append(float(loss_host[0]))
+    ms_per_step = total_ms / steps
+    tokens = B * S * world
+    flops = model_flops(cfg) * world
+    out = {
+        "metric": "transformer train tokens/s", "value": round(tokens / (ms_per_step * 1e-3), 1), "unit": "tokens/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms_per_step, 3),
+        "scaling": "weak", "dtype": {"tf32": "f32 storage, tf32 tensor-core GEMMs", "bf16": "f32 storage, bf16 GEMM operands, f32 accumulate",
+                                      "f32x3": "f32 storage, 3xTF32 split GEMMs"}[mm],
+        "config": {"workload": f"configs[{3 if cfg['kind'] == 'encoder' else 4}] " + (
+            f"TransformerEncoder d_model {d}, {cfg['L']} layers, {cfg['h']} heads, seq {S}, batch {B}/GPU, fwd+bwd+Adam"
+            if cfg["kind"] == "encoder" else
+            f"decoder LM d_model {d}, {cfg['L']} layers, {cfg['h']} heads, d_ff {cfg['ff']}, vocab {cfg['vocab']}, seq {S}, "
+            f"batch {B}/GPU, fwd+bwd+NCCL grad all-reduce+Adam"),
+            "params": n_params, "tokens_per_step": tokens,
+            "parallelism": f"dp{world}" + (f", {sync.calls // max(1, steps + warmup + (2 if use_graph else 1))} NCCL group calls/step, "
+                                            f"{bucket_mb} MiB buckets" if sync else ""),
+            "launch": "cuda graph replay" if graph is not None else "eager (python launch loop)"},
+        "model_tflops_per_s": round(flops / (ms_per_step * 1e-3) / 1e12, 1),
+        "gpu_launches": launches, "kernels_per_step": launches // max(steps, 1),
+        "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+        "loss_first": round(losses[0], 5), "loss_last": round(losses[-1], 5),
+    }
+    if comm is not None:
+        comm.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="lm", choices=sorted(CONFIGS))
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mm", default="tf32", choices=["tf32", "bf16", "f32x3"])
+    ap.add_argument("--eager", action="store_true")
+    ap.add_argument("--bucket-mb", type=int, default=32)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    out = run(args.config, args.steps, args.warmup, rank, world, local_rank, args.mm, not args.eager, args.bucket_mb)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
