@@ -78,10 +78,16 @@ class Graph:
     def launch(self, stream=None) -> None:
         check(_lib().b200_graph_launch(self.handle, stream))
 
+    def destroy(self) -> None:
+        """Must run before b200_comm_destroy of any communicator whose collectives were captured:
+        ncclCommDestroy waits for every graph that still references the communicator."""
+        if self.handle:
+            check(_lib().b200_graph_destroy(self.handle))
+            self.handle = C.c_void_p()
+
     def __del__(self):
         try:
-            if self.handle:
-                abi.load().b200_graph_destroy(self.handle)
+            self.destroy()
         except Exception:
             pass
 

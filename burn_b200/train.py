@@ -473,31 +473,49 @@ class Adam:
 # ------------------------------------------------------------------ DDP gradient sync (burn-train ddp)
 class GradSync:
     """All-reduce(Mean) of every parameter gradient as soon as it is final, overlapped with the rest
-    of backward on the collective stream, fenced before the optimizer (SURVEY.md §3.4;
-    crates/burn-cubecl/src/ops/distributed.rs:17-50 issues one collective per parameter — here
-    small gradients are grouped into buckets of `bucket_bytes` per NCCL group call)."""
+    of backward on the collective stream, fenced before the optimizer.  The
+    reference issues one collective per parameter (crates/burn-cubecl/src/ops/distributed.rs:17-50:
+    218 tensors in config 5); here gradients are packed into persistent flat buckets of about
+    `bucket_bytes` in backward order — one ncclAllReduce per bucket, fired when its last member
+    arrives — and `p.g` becomes a view of the bucket, which the optimizer reads in place.  Persistent
+    bucket storage also keeps the collective's addresses fixed across CUDA-graph replays."""
 
     def __init__(self, comm, params: Sequence[Param], bucket_bytes: int = 32 << 20):
-        self.comm, self.bucket_bytes = comm, bucket_bytes
-        self.pending: list[DeviceTensor] = []
-        self.pending_bytes = 0
+        self.comm = comm
         self.calls = 0
+        self.buckets: list[dict] = []
+        self.slot: dict[int, tuple[dict, DeviceTensor]] = {}
+        members, size = [], 0
+        order = list(reversed(list(params)))              # the order backward finalises gradients in
+        for i, p in enumerate(order):
+            members.append(p)
+            size += (p.v.numel + 3) // 4 * 4              # 16-byte aligned slots
+            if size * 4 >= bucket_bytes or i == len(order) - 1:
+                flat = DeviceTensor.empty((size,))
+                b = {"flat": flat, "n": len(members), "arrived": 0}
+                off = 0
+                for q in members:
+                    self.slot[id(q)] = (b, flat.slice([(off, off + q.v.numel)]).reshape(q.v.shape))
+                    off += (q.v.numel + 3) // 4 * 4
+                self.buckets.append(b)
+                members, size = [], 0
         for p in params:
             p.on_grad = self.ready
 
     def ready(self, p: Param) -> None:
-        self.pending.append(p.g)
-        self.pending_bytes += p.g.numel * 4
-        if self.pending_bytes >= self.bucket_bytes:
-            self.flush()
-
-    def flush(self) -> None:
-        if self.pending:
-            self.comm.all_reduce_bucket(self.pending, mean=True)
+        b, view = self.slot[id(p)]
+        src = p.g if p.g.is_contiguous() else p.g.contiguous()
+        abi.check(abi.load().b200_memcpy_d2d(view.data_ptr(), src.data_ptr(), view.numel * 4, None))
+        p.g = view
+        b["arrived"] += 1
+        if b["arrived"] == b["n"]:
+            self.comm.all_reduce(b["flat"], mean=True)
             self.calls += 1
-            self.pending, self.pending_bytes = [], 0
+            b["arrived"] = 0
 
     def wait(self) -> None:
         """sync_collective: the optimizer's launches wait for every outstanding all-reduce."""
-        self.flush()
+        for b in self.buckets:
+            if b["arrived"]:
+                raise RuntimeError("a gradient bucket is incomplete: some parameter received no gradient")
         self.comm.sync()

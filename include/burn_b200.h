@@ -103,7 +103,9 @@ int32_t b200_event_elapsed_ms(b200_event start, b200_event stop, float *ms); /* 
  * graph memory nodes), memsets, d2d copies, and collectives forked onto the comm
  * stream and joined back by b200_collective_sync — is recorded, not executed.
  * Buffers allocated before the capture keep their addresses across replays;
- * buffers allocated inside it must also be freed inside it. */
+ * buffers allocated inside it must also be freed inside it.  A graph that
+ * captured collectives must be destroyed before b200_comm_destroy (NCCL waits
+ * for every graph that references the communicator). */
 typedef void *b200_graph;
 int32_t b200_graph_begin(b200_stream s);
 int32_t b200_graph_end(b200_stream s, b200_graph *out);

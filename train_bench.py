@@ -196,14 +196,17 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
             f"decoder LM d_model {d}, {cfg['L']} layers, {cfg['h']} heads, d_ff {cfg['ff']}, vocab {cfg['vocab']}, seq {S}, "
             f"batch {B}/GPU, fwd+bwd+NCCL grad all-reduce+Adam"),
             "params": n_params, "tokens_per_step": tokens,
-            "parallelism": f"dp{world}" + (f", {sync.calls // max(1, steps + warmup + (2 if use_graph else 1))} NCCL group calls/step, "
-                                            f"{bucket_mb} MiB buckets" if sync else ""),
+            "parallelism": f"dp{world}" + (f", {len(sync.buckets)} ncclAllReduce(avg) per step on ~{bucket_mb} MiB flat buckets, "
+                                            f"overlapped with backward on the collective stream" if sync else ""),
             "launch": "cuda graph replay" if graph is not None else "eager (python launch loop)"},
         "model_tflops_per_s": round(flops / (ms_per_step * 1e-3) / 1e12, 1),
         "gpu_launches": launches, "kernels_per_step": launches // max(steps, 1),
         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
         "loss_first": round(losses[0], 5), "loss_last": round(losses[-1], 5),
     }
+    if graph is not None:
+        check(lib.b200_device_sync())
+        graph.destroy()             # before the communicator: NCCL waits for graphs that captured it
     if comm is not None:
         comm.close()
     return out
