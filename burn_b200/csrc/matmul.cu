@@ -32,6 +32,8 @@ constexpr int kThreads = 192;
 constexpr int kAccStages = 2;
 constexpr int kMaxBatchDims = 3;
 constexpr int kEpiBlock = 128, kEpiU = 4;  // epilogue tape geometry: 16 columns per dispatch
+constexpr int kMaxFastSteps = 6;
+constexpr int kOutStageBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x [32 rows x 128 B]
 
 struct Params {
   CUtensorMap tma_a, tma_b;
@@ -44,6 +46,17 @@ struct Params {
   int32_t tiles_m, tiles_n, k_blocks, stages;
   int32_t has_epilogue;
   int32_t c_dtype;
+  // fast epilogue (epi_fast != 0): the tape is a straight chain acc = OP(acc, operand) evaluated
+  // on the 32 accumulator columns a lane holds, staged through swizzled smem and written with TMA
+  CUtensorMap tma_c;
+  int32_t epi_fast, n_steps;
+  struct Step {
+    int32_t op;
+    int32_t b_kind, b_idx;   // 0 none, 1 input (TapeParams.in[idx]), 3 scalar (bits in b_bits)
+    uint32_t b_bits;
+    int32_t c_kind, c_idx;
+    uint32_t c_bits;
+  } steps[kMaxFastSteps];
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -115,6 +128,75 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t 
         : "memory");
   }
 }
+// ---- CTA-pair (cta_group::2) variants.  The shared::cluster address of a CTA-local object carries the
+// CTA rank in bit 24; clearing it addresses the same object in the pair's leader (even-ranked) CTA.
+constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// arrive on the LEADER CTA's copy of `bar` (no-op mask when executed by the leader itself)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask)
+               : "memory");
+}
+// TMA load into this CTA's smem whose bytes are accounted on the leader CTA's mbarrier
+__device__ __forceinline__ void tma_load_5d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                                 int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// commit: arrive on `bar` in BOTH CTAs of the pair when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  if constexpr (BF16) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -122,6 +204,120 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One operand of a fast-epilogue step for the 32 columns [n0, n0+32) of row m.
+__device__ __forceinline__ void epi_fetch(const TapeParams &T, int kind, int idx, uint32_t bits, int batch_lin, int m,
+                                          int n0, bool row_ok, int N, uint32_t (&o)[32]) {
+  if (kind != 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = bits;
+    return;
+  }
+  const OperandDesc &d = T.in[idx];
+  const int64_t base = (int64_t)batch_lin * d.s3[0] + (int64_t)m * d.s3[1];
+  if (d.s3[2] == 0) {
+    const uint32_t v = row_ok ? load_one(d.ptr, d.dtype, base) : 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = v;
+    return;
+  }
+  const int64_t off = base + (int64_t)n0 * d.s3[2];
+  if (d.mode == kModeVec && d.dtype == B200_F32) {
+    const uint4 *p4 = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(d.ptr) + off);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row_ok && n0 + q * 4 < N) v = __ldg(p4 + q);
+      o[q * 4] = v.x; o[q * 4 + 1] = v.y; o[q * 4 + 2] = v.z; o[q * 4 + 3] = v.w;
+    }
+  } else if (d.mode == kModeVec && (d.dtype == B200_BOOL || d.dtype == B200_U8)) {
+    const uint32_t *p1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(d.ptr) + off);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t w = (row_ok && n0 + q * 4 < N) ? __ldg(p1 + q) : 0u;
+      o[q * 4] = w & 0xFFu; o[q * 4 + 1] = (w >> 8) & 0xFFu; o[q * 4 + 2] = (w >> 16) & 0xFFu; o[q * 4 + 3] = w >> 24;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = (row_ok && n0 + j < N) ? load_one(d.ptr, d.dtype, off + (int64_t)j * d.s3[2]) : 0u;
+  }
+}
+
+// Applies the fast-epilogue chain to a lane's 32 accumulator columns.  Every op rounds exactly as
+// the tape interpreter's (tape.cuh run_tape) — same intrinsics, same erf — so fused == unfused.
+__device__ __forceinline__ void epi_apply(const Params &P, const TapeParams &T, int batch_lin, int m, int n0, bool row_ok,
+                                          uint32_t (&r)[32]) {
+  for (int s = 0; s < P.n_steps; ++s) {
+    const Params::Step &st = P.steps[s];
+    uint32_t b[32];
+    if (st.b_kind) epi_fetch(T, st.b_kind, st.b_idx, st.b_bits, batch_lin, m, n0, row_ok, P.N, b);
+#define B200_EPI_BIN(expr)                                \
+  _Pragma("unroll") for (int j = 0; j < 32; ++j) {        \
+    const float x = f_of(r[j]), y = f_of(b[j]);           \
+    r[j] = u_of(expr);                                    \
+  }
+    switch (st.op) {
+      case B200_OP_ADD_F: B200_EPI_BIN(__fadd_rn(x, y)) break;
+      case B200_OP_SUB_F: B200_EPI_BIN(__fsub_rn(x, y)) break;
+      case B200_OP_MUL_F: B200_EPI_BIN(__fmul_rn(x, y)) break;
+      case B200_OP_DIV_F: B200_EPI_BIN(__fdiv_rn(x, y)) break;
+      case B200_OP_MIN_F: B200_EPI_BIN((x != x || y != y) ? __int_as_float(0x7fc00000) : fminf(x, y)) break;
+      case B200_OP_MAX_F: B200_EPI_BIN((x != x || y != y) ? __int_as_float(0x7fc00000) : fmaxf(x, y)) break;
+      case kOpDivScalar: {
+        const float rinv = __frcp_rn(f_of(b[0]));   // b is the scalar divisor, broadcast
+        B200_EPI_BIN((div_scalar_safe(x) ? div_scalar_fast(x, y, rinv) : __fdiv_rn(x, y)))
+        break;
+      }
+      case kOpMulAdd: {
+        uint32_t c[32];
+        epi_fetch(T, st.c_kind, st.c_idx, st.c_bits, batch_lin, m, n0, row_ok, P.N, c);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = u_of(__fadd_rn(__fmul_rn(f_of(r[j]), f_of(b[j])), f_of(c[j])));
+        break;
+      }
+      case kOpGelu: {
+        const float s2 = 1.41421353816986083984375f, rinv = 0.707106769084930419921875f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = f_of(r[j]);
+          const float q = div_scalar_safe(x) ? div_scalar_fast(x, s2, rinv) : __fdiv_rn(x, s2);
+          r[j] = u_of(__fmul_rn(__fmul_rn(x, __fadd_rn(erf_f32(q), 1.0f)), 0.5f));
+        }
+        break;
+      }
+      case B200_OP_SELECT: {  // acc = C ? B : acc
+        uint32_t c[32];
+        epi_fetch(T, st.c_kind, st.c_idx, st.c_bits, batch_lin, m, n0, row_ok, P.N, c);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = c[j] ? b[j] : r[j];
+        break;
+      }
+      default: break;
+    }
+#undef B200_EPI_BIN
+  }
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -147,9 +343,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 
 // ------------------------------------------------------------------ kernel
 // ES = operand element size (4: tf32, 2: bf16).  A_MN / B_MN: operand is MN-major in memory.
-template <int ES, bool A_MN, bool B_MN>
+// CTAS = 1: one CTA per 128x128 tile.  CTAS = 2: a CTA pair (cluster of 2, cta_group::2) per 256x256
+// tile — each CTA stages its own 128 rows of A and 128 of the 256 B rows (same 32 KB per stage for
+// twice the math: halves the L2→smem bytes per flop, which is what caps the single-CTA kernel at
+// ~50% of the tensor peak), the leader CTA issues M=256,N=256 MMAs that read both CTAs' smem and
+// write each CTA's half of the accumulator into its own TMEM; each CTA runs its own epilogue.
+template <int ES, bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ TapeParams T) {
+  constexpr bool PAIR = CTAS == 2;
+  constexpr int TN = PAIR ? 256 : BN;     // accumulator columns per tile (per CTA)
   constexpr int BK = 128 / ES;            // K elements per stage (one 128-byte swizzle row)
   constexpr int UMMA_K = 32 / ES;         // K per tcgen05.mma
   constexpr uint32_t kATile = BM * BK * ES, kBTile = BN * BK * ES;  // 16 KB each
@@ -159,7 +362,8 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *tiles = smem;
-  uint64_t *full = reinterpret_cast<uint64_t *>(tiles + (size_t)P.stages * kStageBytes);
+  uint8_t *out_stage = tiles + (size_t)P.stages * kStageBytes;   // 1024-aligned; kOutStageBytes when epi_fast
+  uint64_t *full = reinterpret_cast<uint64_t *>(out_stage + (P.epi_fast ? kOutStageBytes : 0));
   uint64_t *empty = full + P.stages;
   uint64_t *acc_full = empty + P.stages;
   uint64_t *acc_empty = acc_full + kAccStages;
@@ -169,30 +373,38 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_batch = P.batch[0] * P.batch[1] * P.batch[2];
-  const int n_tiles = P.tiles_m * P.tiles_n * n_batch;
+  const int n_tiles = P.tiles_m * P.tiles_n * n_batch;          // tiles of (128*CTAS) x TN
+  const int cta_rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // tile-loop start
+  const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;    // tile-loop stride
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.tma_a);
     tma_prefetch_desc(&P.tma_b);
+    if (P.epi_fast) tma_prefetch_desc(&P.tma_c);
     for (int s = 0; s < P.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[s], 4 * CTAS);  // one arrive per epilogue warp (of both CTAs in a pair)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kAccStages * BN);
-  if (P.has_epilogue && warp >= 2) {
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, kAccStages * TN);
+    else tmem_alloc(tmem_slot, kAccStages * TN);
+  }
+  if (P.has_epilogue && !P.epi_fast && warp >= 2) {
     SlotFile<4, kEpiU, kEpiBlock> slots;
     slots.smem = epi_smem;
     slots.tid = threadIdx.x - 64;
     init_scalars<4, kEpiU, kEpiBlock>(T, slots, T.n_in + T.n_tmp);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before anything lands on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -212,36 +424,43 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      auto load = [&](void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3, int c4) {
+        if constexpr (PAIR) tma_load_5d_pair(dst, map, bar, c0, c1, c2, c3, c4);
+        else tma_load_5d(dst, map, bar, c0, c1, c2, c3, c4);
+      };
+      for (int tile = worker; tile < n_tiles; tile += n_workers) {
         int m_blk, n_blk, b[kMaxBatchDims];
         tile_coords(tile, m_blk, n_blk, b);
         const int ab0 = b[0] * P.a_bflag[0], ab1 = b[1] * P.a_bflag[1], ab2 = b[2] * P.a_bflag[2];
         const int bb0 = b[0] * P.b_bflag[0], bb1 = b[1] * P.b_bflag[1], bb2 = b[2] * P.b_bflag[2];
+        const int m0 = (m_blk * CTAS + cta_rank) * BM;           // this CTA's 128 rows of A
+        const int n0 = n_blk * TN + cta_rank * BN;               // this CTA's 128 rows of B
         for (int kb = 0; kb < P.k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t *sa = tiles + (size_t)stage * kStageBytes;
           uint8_t *sb = sa + kATile;
-          mbar_expect_tx(&full[stage], kStageBytes);
+          // a pair accounts both CTAs' bytes on the leader's barrier
+          if (cta_rank == 0) mbar_expect_tx(&full[stage], kStageBytes * CTAS);
           if constexpr (!A_MN) {
-            tma_load_5d(sa, &P.tma_a, &full[stage], kb * BK, m_blk * BM, ab2, ab1, ab0);
+            load(sa, &P.tma_a, &full[stage], kb * BK, m0, ab2, ab1, ab0);
           } else {
 #pragma unroll
             for (int g = 0; g < BM / BK; ++g)  // BK == elements per 128-byte MN group
-              tma_load_5d(sa + g * (BK * 128), &P.tma_a, &full[stage], m_blk * BM + g * BK, kb * BK, ab2, ab1, ab0);
+              load(sa + g * (BK * 128), &P.tma_a, &full[stage], m0 + g * BK, kb * BK, ab2, ab1, ab0);
           }
           if constexpr (!B_MN) {
-            tma_load_5d(sb, &P.tma_b, &full[stage], kb * BK, n_blk * BN, bb2, bb1, bb0);
+            load(sb, &P.tma_b, &full[stage], kb * BK, n0, bb2, bb1, bb0);
           } else {
 #pragma unroll
             for (int g = 0; g < BN / BK; ++g)
-              tma_load_5d(sb + g * (BK * 128), &P.tma_b, &full[stage], n_blk * BN + g * BK, kb * BK, bb2, bb1, bb0);
+              load(sb + g * (BK * 128), &P.tma_b, &full[stage], n0 + g * BK, kb * BK, bb2, bb1, bb0);
           }
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && cta_rank == 0) {
+    // ===================== MMA issuer (the leader CTA of a pair) =====================
     // instruction descriptor: D = F32, A/B = TF32 or BF16, majors, N, M
     uint32_t idesc = 0;
     idesc |= 1u << 4;                              // c_format = F32
@@ -249,18 +468,20 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
     idesc |= (BF16 ? 1u : 2u) << 10;               // b_format
     idesc |= (A_MN ? 1u : 0u) << 15;               // a_major
     idesc |= (B_MN ? 1u : 0u) << 16;               // b_major
-    idesc |= (uint32_t)(BN >> 3) << 17;            // n_dim
-    idesc |= (uint32_t)(BM >> 4) << 24;            // m_dim
+    idesc |= (uint32_t)(TN >> 3) << 17;            // n_dim
+    idesc |= (uint32_t)((BM * CTAS) >> 4) << 24;   // m_dim
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+    for (int tile = worker; tile < n_tiles; tile += n_workers) {
+      if constexpr (PAIR) mbar_wait_cluster(&acc_empty[acc], acc_phase ^ 1);
+      else mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TN);
       for (int kb = 0; kb < P.k_blocks; ++kb) {
-        mbar_wait(&full[stage], phase);
+        if constexpr (PAIR) mbar_wait_cluster(&full[stage], phase);
+        else mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(tiles + (size_t)stage * kStageBytes);
@@ -277,42 +498,86 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
                                      : make_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), BK * 128, kMnSbo, kMnLayout)
                                      : make_desc(sb + k * 32, 16, 1024);
-            umma<BF16>(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
+            if constexpr (PAIR) umma_pair<BF16>(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
+            else umma<BF16>(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
           }
         }
         __syncwarp();
-        if (lane == 0) umma_commit(&empty[stage]);  // frees the smem stage when these MMAs retire
+        if (lane == 0) {                            // frees the smem stage (in both CTAs) when these MMAs retire
+          if constexpr (PAIR) umma_commit_pair(&empty[stage]);
+          else umma_commit(&empty[stage]);
+        }
         if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
-      if (lane == 0) umma_commit(&acc_full[acc]);   // accumulator complete → epilogue
+      if (lane == 0) {                              // accumulator complete → epilogue (of both CTAs)
+        if constexpr (PAIR) umma_commit_pair(&acc_full[acc]);
+        else umma_commit(&acc_full[acc]);
+      }
       __syncwarp();
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row_in_tile = quarter * 32 + lane;
     SlotFile<4, kEpiU, kEpiBlock> slots;
     slots.smem = epi_smem;
     slots.tid = threadIdx.x - 64;
-    int acc = 0;
+    int acc = 0, sbuf = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < n_tiles; tile += n_workers) {
       int m_blk, n_blk, b[kMaxBatchDims];
       tile_coords(tile, m_blk, n_blk, b);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const int m = m_blk * BM + row_in_tile;
+      const int m = (m_blk * CTAS + cta_rank) * BM + row_in_tile;
       const int64_t c_batch = b[0] * P.c_batch_stride[0] + b[1] * P.c_batch_stride[1] + b[2] * P.c_batch_stride[2];
       float *crow = P.c + c_batch + (int64_t)m * P.ldc;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TN);
       const int batch_lin = (b[0] * P.batch[1] + b[1]) * P.batch[2] + b[2];
+      if (P.epi_fast) {
+        // 32 columns per pass: TMEM → registers → op chain → 128B-swizzled smem → TMA store (full
+        // 128-byte lines, rows/columns past M/N clipped by the tensor map)
+        const int m_warp = (m_blk * CTAS + cta_rank) * BM + quarter * 32;
+        uint8_t *wbuf = out_stage + (warp - 2) * 8192;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          const int n0 = n_blk * TN + c0;
+          if (n0 >= P.N || m_warp >= P.M) break;
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+          if (P.n_steps) epi_apply(P, T, batch_lin, m, n0, m < P.M, r);
+          uint8_t *buf = wbuf + sbuf * 4096;
+          sbuf ^= 1;
+          if (lane == 0) bulk_wait_read<1>();          // the store that last read this buffer is done with it
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4 *>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&P.tma_c, buf, n0, m_warp, b[2], b[1], b[0]);
+            bulk_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_leader(&acc_empty[acc]);
+          else mbar_arrive(&acc_empty[acc]);
+        }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
         tmem_ld_wait();
-        const int n0 = n_blk * BN + c0;
+        const int n0 = n_blk * TN + c0;
         if (m >= P.M || n0 >= P.N) continue;
         if (!P.has_epilogue) {
           if (n0 + 16 <= P.N && (reinterpret_cast<uintptr_t>(crow + n0) & 15) == 0) {
@@ -370,16 +635,23 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_leader(&acc_empty[acc]);
+        else mbar_arrive(&acc_empty[acc]);
+      }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
 
+  if (P.epi_fast && warp >= 2 && lane == 0) bulk_wait_all();   // this lane's TMA stores have landed
+  __syncwarp();                             // the elected producer / issuer lane rejoins its warp
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // neither CTA may exit (or free TMEM) while its peer still uses it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kAccStages * BN);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kAccStages * TN);
+    else tmem_dealloc(tmem_base, kAccStages * TN);
   }
 }
 
@@ -490,6 +762,90 @@ static int32_t make_tmap(CUtensorMap *map, const Operand &o, int64_t mn, int64_t
   return B200_OK;
 }
 
+// Output tensor map for the fast epilogue's TMA stores: [32 columns x 32 rows] boxes, 128B swizzle.
+static bool tma_c_ok(const b200_tensor *c, int r, const int64_t *c_sb, const int32_t *batch, int64_t M) {
+  if (c->dtype != B200_F32 || ((uintptr_t)c->ptr & 15)) return false;
+  if (c->strides[r - 1] != 1 && c->shape[r - 1] != 1) return false;
+  if (M > 1 && (c->strides[r - 2] % 4 != 0 || c->strides[r - 2] < c->shape[r - 1])) return false;
+  for (int d = 0; d < mm::kMaxBatchDims; ++d)
+    if (batch[d] > 1 && (c_sb[d] % 4 != 0 || c_sb[d] <= 0)) return false;
+  return true;
+}
+
+static int32_t make_tmap_c(CUtensorMap *map, void *ptr, int64_t M, int64_t N, int64_t ldc, const int64_t *c_sb,
+                           const int32_t *batch) {
+  EncodeTiledFn enc = encode_fn();
+  B200_REQUIRE(enc, B200_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable from the driver");
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5] = {32, 32, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+  dims[0] = (cuuint64_t)N;
+  dims[1] = (cuuint64_t)M;
+  strides[0] = (cuuint64_t)std::max<int64_t>(ldc, 4) * 4;
+  for (int d = 0; d < mm::kMaxBatchDims; ++d) {
+    const int src = mm::kMaxBatchDims - 1 - d;
+    dims[2 + d] = (cuuint64_t)std::max(batch[src], 1);
+    strides[1 + d] = (cuuint64_t)(batch[src] > 1 ? c_sb[src] : 4) * 4;
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed with %d", (int)r);
+  return B200_OK;
+}
+
+// Recognises an epilogue tape that is one straight chain acc = OP(acc, operand) ending in the single
+// output, with no temporaries — bias add, scaling, mask fill, gelu/relu and their compositions.
+static bool match_fast_epilogue(const CompiledTape &ct, const b200_tensor *epi_inputs, mm::Params &P) {
+  const size_t n = ct.ops.size();
+  if (n < 1 || n - 1 > (size_t)mm::kMaxFastSteps) return false;
+  const SymOp &first = ct.ops[0];
+  if (first.op != kOpLoad || first.b.kind != 1 || first.b.idx != 0 || first.dst_tmp >= 0) return false;
+  if (n == 1) return first.dst_out == 0;
+  if (first.dst_out >= 0) return false;
+  auto arg_ok = [&](const SymArg &a, bool allow_bool) {
+    if (a.kind == 3) return a.idx >= 0 && (size_t)a.idx < ct.scalars.size();
+    if (a.kind != 1 || a.idx < 1) return false;
+    const int dt = epi_inputs[a.idx - 1].dtype;
+    return dt == B200_F32 || (allow_bool && (dt == B200_BOOL || dt == B200_U8));
+  };
+  P.n_steps = 0;
+  for (size_t i = 1; i < n; ++i) {
+    const SymOp &o = ct.ops[i];
+    if (o.dst_tmp >= 0) return false;
+    if ((i + 1 == n) != (o.dst_out == 0) || (i + 1 != n && o.dst_out >= 0)) return false;
+    mm::Params::Step st;
+    memset(&st, 0, sizeof(st));
+    st.op = o.op;
+    switch (o.op) {
+      case B200_OP_ADD_F: case B200_OP_SUB_F: case B200_OP_MUL_F: case B200_OP_DIV_F:
+      case B200_OP_MIN_F: case B200_OP_MAX_F:
+        if (!arg_ok(o.b, false)) return false;
+        break;
+      case kOpDivScalar:
+        if (o.b.kind != 3 || !arg_ok(o.b, false)) return false;
+        break;
+      case kOpMulAdd:
+        if (!arg_ok(o.b, false) || !arg_ok(o.c, false)) return false;
+        break;
+      case kOpGelu:
+        if (o.b.kind != 0) return false;   // gelu of the accumulator only
+        break;
+      case B200_OP_SELECT:
+        if (!arg_ok(o.b, false) || !arg_ok(o.c, true)) return false;
+        break;
+      default: return false;
+    }
+    auto put = [&](const SymArg &a, int32_t &kind, int32_t &idx, uint32_t &bits) {
+      kind = a.kind == 1 ? 1 : (a.kind == 3 ? 3 : 0);
+      idx = a.kind == 1 ? a.idx : 0;
+      bits = a.kind == 3 ? ct.scalars[a.idx] : 0u;
+    };
+    put(o.b, st.b_kind, st.b_idx, st.b_bits);
+    put(o.c, st.c_kind, st.c_idx, st.c_bits);
+    P.steps[P.n_steps++] = st;
+  }
+  return true;
+}
+
 struct MatmulPlan {
   int rank, nb;
   int64_t M, N, K;
@@ -575,17 +931,44 @@ static size_t operand_ws_bytes(const b200_tensor *t, bool is_a, int precision, c
   return align_up((size_t)own_batch * mn * align_up(k, 4) * 4, 256);
 }
 
-template <int ES, bool A_MN, bool B_MN>
-static int32_t launch_gemm(const mm::Params &P, const TapeParams &T, size_t epi_bytes, cudaStream_t stream) {
-  auto kern = mm::gemm_tcgen05_kernel<ES, A_MN, B_MN>;
+template <int ES, bool A_MN, bool B_MN, int CTAS>
+static int32_t launch_gemm_n(const mm::Params &P, const TapeParams &T, size_t epi_bytes, cudaStream_t stream) {
+  auto kern = mm::gemm_tcgen05_kernel<ES, A_MN, B_MN, CTAS>;
   const size_t stage_bytes = 32 * 1024;
-  const size_t smem = 1024 + (size_t)P.stages * stage_bytes + 256 + epi_bytes + 64;
+  const size_t smem = 1024 + (size_t)P.stages * stage_bytes + (P.epi_fast ? mm::kOutStageBytes : 0) + 256 + epi_bytes + 64;
   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_tiles = P.tiles_m * P.tiles_n * P.batch[0] * P.batch[1] * P.batch[2];
-  const unsigned grid = (unsigned)std::max(1, std::min(n_tiles, sm_count()));
-  kern<<<grid, mm::kThreads, smem, stream>>>(P, T);
+  if (CTAS == 1) {
+    const unsigned grid = (unsigned)std::max(1, std::min(n_tiles, sm_count()));
+    kern<<<grid, mm::kThreads, smem, stream>>>(P, T);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2u * (unsigned)std::max(1, std::min(n_tiles, sm_count() / 2)));
+    cfg.blockDim = dim3(mm::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, P, T));
+  }
   B200_LAUNCH_CHECK();
   return B200_OK;
+}
+
+template <int ES, bool A_MN, bool B_MN>
+static int32_t launch_gemm(mm::Params &P, const TapeParams &T, size_t epi_bytes, cudaStream_t stream, bool pair) {
+  if (pair) {
+    P.tiles_m = (P.M + 2 * mm::BM - 1) / (2 * mm::BM);
+    P.tiles_n = (P.N + 255) / 256;
+    return launch_gemm_n<ES, A_MN, B_MN, 2>(P, T, epi_bytes, stream);
+  }
+  return launch_gemm_n<ES, A_MN, B_MN, 1>(P, T, epi_bytes, stream);
 }
 
 }  // namespace b200
@@ -744,12 +1127,18 @@ extern "C" int32_t b200_launch_matmul(const b200_tensor *a, const b200_tensor *b
   TapeParams T;
   memset(&T, 0, sizeof(T));
   size_t epi_bytes = 0;
+  // the fast epilogue (TMA stores of full 128-byte lines) needs a 16-byte-aligned f32 output
+  // with 16-byte-multiple row and batch strides; B200_MM_LEGACY_EPILOGUE=1 disables it (debug)
+  static const bool legacy_epi = std::getenv("B200_MM_LEGACY_EPILOGUE") != nullptr;
+  bool fast = !legacy_epi && tma_c_ok(c, r, pl.c_sb, pl.batch, pl.M);
   if (epilogue) {
     B200_REQUIRE(n_epi_inputs >= 0 && n_epi_inputs + 1 <= B200_MAX_TAPE_INPUTS, B200_ERR_INVALID, "too many epilogue inputs");
     B200_REQUIRE(pl.N % 4 == 0, B200_ERR_UNSUPPORTED, "a fused matmul epilogue needs N %% 4 == 0 (got N = %lld)", (long long)pl.N);
     CompiledTape ct;
     st = compile_tape(epilogue, n_epi_inputs + 1, 1, ct);
     if (st != B200_OK) return st;
+    fast = fast && match_fast_epilogue(ct, epi_inputs, P);
+    if (!fast) P.n_steps = 0;
     st = finalize_tape(ct, mm::kEpiU, mm::kEpiBlock, 1, T);
     if (st != B200_OK) return st;
     // describe operands at the collapsed output shape [batch, M, N]
@@ -784,21 +1173,36 @@ extern "C" int32_t b200_launch_matmul(const b200_tensor *a, const b200_tensor *b
     st = as3(*c, T.out[0], "matmul output", 0);
     if (st != B200_OK) return st;
     T.rank = 3;
-    P.has_epilogue = 1;
-    epi_bytes = slot_file_bytes(T.n_in + T.n_tmp, T.n_scalars, 4, mm::kEpiU, mm::kEpiBlock) + 16;
+    P.has_epilogue = fast ? 0 : 1;
+    if (!fast) epi_bytes = slot_file_bytes(T.n_in + T.n_tmp, T.n_scalars, 4, mm::kEpiU, mm::kEpiBlock) + 16;
   }
-  const size_t budget = (size_t)max_smem_optin() - 2048 - epi_bytes;
+  if (fast) {
+    st = make_tmap_c(&P.tma_c, c->ptr, pl.M, pl.N, P.ldc, pl.c_sb, pl.batch);
+    if (st != B200_OK) return st;
+    P.epi_fast = 1;
+    epi_bytes = 0;
+  }
+  const size_t budget = (size_t)max_smem_optin() - 2048 - epi_bytes - (fast ? mm::kOutStageBytes : 0);
   P.stages = (int32_t)std::max<size_t>(2, std::min<size_t>(6, budget / (32 * 1024)));
 
+  // CTA pairs (256x256 tiles) whenever the output is wide and tall enough to fill them;
+  // B200_MM_NO_PAIR=1 keeps the single-CTA 128x128 kernel (debug / comparison)
+  static const bool no_pair = std::getenv("B200_MM_NO_PAIR") != nullptr;
+  // when they need no more waves than the single-CTA kernel would (a pair runs its tile at twice
+  // the per-SM rate, so equal waves = half the time; tiny problems keep the cheaper launch)
+  const int64_t t128 = (int64_t)P.tiles_m * P.tiles_n * n_batch;
+  const int64_t t256 = ((pl.M + 255) / 256) * ((pl.N + 255) / 256) * n_batch;
+  const int64_t sms = sm_count(), waves1 = (t128 + sms - 1) / sms, waves2 = (t256 + sms / 2 - 1) / (sms / 2);
+  const bool pair = !no_pair && pl.M > 128 && pl.N > 128 && (t256 >= sms / 2 || waves2 < waves1);
   const bool amn = oa.mn_major, bmn = ob.mn_major;
   if (es == 4) {
-    if (!amn && !bmn) return launch_gemm<4, false, false>(P, T, epi_bytes, stream);
-    if (!amn && bmn) return launch_gemm<4, false, true>(P, T, epi_bytes, stream);
-    if (amn && !bmn) return launch_gemm<4, true, false>(P, T, epi_bytes, stream);
-    return launch_gemm<4, true, true>(P, T, epi_bytes, stream);
+    if (!amn && !bmn) return launch_gemm<4, false, false>(P, T, epi_bytes, stream, pair);
+    if (!amn && bmn) return launch_gemm<4, false, true>(P, T, epi_bytes, stream, pair);
+    if (amn && !bmn) return launch_gemm<4, true, false>(P, T, epi_bytes, stream, pair);
+    return launch_gemm<4, true, true>(P, T, epi_bytes, stream, pair);
   }
-  if (!amn && !bmn) return launch_gemm<2, false, false>(P, T, epi_bytes, stream);
-  if (!amn && bmn) return launch_gemm<2, false, true>(P, T, epi_bytes, stream);
-  if (amn && !bmn) return launch_gemm<2, true, false>(P, T, epi_bytes, stream);
-  return launch_gemm<2, true, true>(P, T, epi_bytes, stream);
+  if (!amn && !bmn) return launch_gemm<2, false, false>(P, T, epi_bytes, stream, pair);
+  if (!amn && bmn) return launch_gemm<2, false, true>(P, T, epi_bytes, stream, pair);
+  if (amn && !bmn) return launch_gemm<2, true, false>(P, T, epi_bytes, stream, pair);
+  return launch_gemm<2, true, true>(P, T, epi_bytes, stream, pair);
 }

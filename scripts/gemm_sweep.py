@@ -1,0 +1,67 @@
+"""GEMM throughput + spot-check sweep (configs[2] shapes).  usage: gemm_sweep.py [quick]"""
+import os, sys, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from burn_b200 import _abi as abi, device as dv
+from burn_b200.device import DeviceTensor
+from tests import helpers as H
+dv.init(0); lib = abi.load()
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+
+def timed(fn, iters):
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    abi.check(lib.b200_event_create(C.byref(e0))); abi.check(lib.b200_event_create(C.byref(e1)))
+    for _ in range(3): fn()
+    dv.sync()
+    abi.check(lib.b200_event_record(e0, None))
+    for _ in range(iters): fn()
+    abi.check(lib.b200_event_record(e1, None))
+    ms = C.c_float(); abi.check(lib.b200_event_elapsed_ms(e0, e1, C.byref(ms)))
+    return ms.value / iters
+
+def case(batch, m, n, k, prec, layout="NT", check=True):
+    rng = np.random.default_rng(m + n + k)
+    bs = (batch,) if batch > 1 else ()
+    a = rng.uniform(-0.5, 0.5, bs + (m, k)).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, bs + (k, n)).astype(np.float32)
+    bf = prec == abi.MM_BF16
+    mk = (lambda x: DeviceTensor.from_bf16_of(x)) if bf else H.up
+    nd = len(bs) + 2
+    da = mk(a) if layout[0] == "N" else mk(np.ascontiguousarray(np.swapaxes(a, -1, -2))).swap_dims(nd - 2, nd - 1)
+    db = mk(b) if layout[1] == "N" else mk(np.ascontiguousarray(np.swapaxes(b, -1, -2))).swap_dims(nd - 2, nd - 1)
+    out = DeviceTensor.empty(bs + (m, n))
+    ad, bd, cd = da.desc(), db.desc(), out.desc()
+    wsb = C.c_uint64()
+    abi.check(lib.b200_matmul_workspace_bytes(C.byref(ad), C.byref(bd), prec, C.byref(wsb)))
+    ws = dv.Storage(wsb.value) if wsb.value else None
+    fn = lambda: abi.check(lib.b200_launch_matmul(C.byref(ad), C.byref(bd), C.byref(cd), prec, None, None, 0,
+                                                  ws.ptr if ws else None, wsb.value, None))
+    ms = timed(fn, 5 if quick else 20)
+    err = -1.0
+    if check:
+        got = out.numpy()
+        rows = rng.integers(0, m, 16)
+        sl = (0,) * len(bs)
+        ref = a[sl][rows].astype(np.float64) @ b[sl].astype(np.float64)
+        bound = np.abs(a[sl][rows]).astype(np.float64) @ np.abs(b[sl]).astype(np.float64)
+        err = float(np.max(np.abs(got[sl][rows] - ref) / bound))
+        sl2 = (batch - 1,) * len(bs)
+        ref2 = a[sl2][rows].astype(np.float64) @ b[sl2].astype(np.float64)
+        err = max(err, float(np.max(np.abs(got[sl2][rows] - ref2) / (np.abs(a[sl2][rows]).astype(np.float64) @ np.abs(b[sl2]).astype(np.float64)))))
+    tf = 2.0 * batch * m * n * k / (ms * 1e-3) / 1e12
+    name = {abi.MM_TF32: "tf32", abi.MM_BF16: "bf16", abi.MM_F32X3: "f32x3"}[prec]
+    print(f"{name:5s} {layout} b{batch:<3d} {m:6d}x{n:6d}x{k:6d}  {ms:9.4f} ms  {tf:8.1f} TF/s  relerr {err:.2e}", flush=True)
+
+shapes = [(1, 256, 256, 256), (1, 384, 640, 200), (1, 1024, 1024, 1024), (1, 4096, 4096, 4096), (1, 8192, 8192, 8192)]
+if not quick:
+    shapes += [(1, 2048, 2048, 2048), (1, 16384, 16384, 16384), (64, 2048, 2048, 2048), (1, 8192, 1024, 1024), (1, 8192, 4096, 1024), (1, 8192, 1024, 4096), (1, 1024, 4096, 8192)]
+for prec in (abi.MM_BF16, abi.MM_TF32):
+    for (bt, m, n, k) in shapes:
+        if m * k * 4 > 2.2e9: check = False
+        else: check = True
+        case(bt, m, n, k, prec, "NT", check and m <= 8192)
+for lay in ("NN", "TN", "TT"):
+    case(1, 4096, 4096, 4096, abi.MM_TF32, lay)
+    case(1, 4096, 4096, 4096, abi.MM_BF16, lay)
+if not quick:
+    case(1, 4096, 4096, 4096, abi.MM_F32X3, "NN")

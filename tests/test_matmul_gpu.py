@@ -39,7 +39,9 @@ def check(got, a, b, precision, what=""):
 
 
 SHAPES = [(128, 128, 128), (256, 384, 512), (1, 1, 1), (5, 3, 7), (130, 70, 33), (64, 200, 1000), (1000, 40, 96),
-          (129, 257, 31)]
+          (129, 257, 31),
+          # tall/wide enough for the CTA-pair (cta_group::2, 256x256 tile) kernel, with ragged edges
+          (1536, 1280, 96), (1300, 1100, 330), (2048, 1024, 64)]
 
 
 @pytest.mark.parametrize("m,n,k", SHAPES)
@@ -134,6 +136,28 @@ def test_fused_bias_gelu_epilogue(dev, precision):
     want = oracle.gelu(oracle.float_add(plain, bias))
     # same GEMM result in, same op chain: only the erf 1-ulp allowance applies
     H.assert_close(got, want, H.REL_ELEMWISE, H.ABS_GELU, "fused epilogue == unfused chain")
+
+
+@pytest.mark.parametrize("precision", [abi.MM_F32X3, abi.MM_TF32, abi.MM_BF16])
+def test_cta_pair_kernel_layouts_batches_and_epilogue(dev, precision):
+    """Shapes that select the CTA-pair kernel: every operand orientation, a broadcast batch, and the
+    fused bias+gelu epilogue on a ragged [.., 1100, 1300] output."""
+    m, n, k = 1100, 1300, 200
+    a, b = rnd((m, k), 31), rnd((k, n), 32)
+    da_t = H.up(np.ascontiguousarray(a.T)).swap_dims(0, 1)
+    db_t = H.up(np.ascontiguousarray(b.T)).swap_dims(0, 1)
+    for da, db, what in ((H.up(a), H.up(b), "NN"), (H.up(a), db_t, "NT"), (da_t, H.up(b), "TN"), (da_t, db_t, "TT")):
+        check(ops.float_matmul(da, db, precision).numpy(), a, b, precision, what)
+    a3, b3 = rnd((3, 1, 520, 72), 33), rnd((1, 2, 72, 1032), 34)
+    check(ops.float_matmul(H.up(a3), H.up(b3), precision).numpy(), a3, b3, precision, "broadcast batch")
+    n4 = 1300
+    bias = rnd((1, n4), 35)
+    tb = TapeBuilder().op("ADD_F", ("in", 0), ("in", 1), tmp=0)
+    H.gelu_tape(tb, ("tmp", 0), out=0)
+    got = ops.float_matmul(H.up(a), H.up(b), precision, epilogue=tb.build(), epi_inputs=[H.up(bias)]).numpy()
+    plain = ops.float_matmul(H.up(a), H.up(b), precision).numpy()
+    # erf's 1-ulp allowance scales with |x|/2 in gelu; pre-activations reach |x| ~ 5 here (ABS_GELU covers |x| <= 4)
+    H.assert_close(got, oracle.gelu(oracle.float_add(plain, bias)), H.REL_ELEMWISE, 2e-7, "pair epilogue")
 
 
 def test_inner_dim_mismatch_is_an_error(dev):
