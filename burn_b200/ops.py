@@ -292,3 +292,30 @@ def layer_norm(x: DeviceTensor, gamma: DeviceTensor | None, beta: DeviceTensor |
     check(abi.load().b200_launch_layer_norm(C.byref(a), C.byref(g) if g is not None else None,
                                             C.byref(b) if b is not None else None, float(eps), C.byref(o), None))
     return out
+
+
+def softmax_backward(y: DeviceTensor, dy: DeviceTensor, mask: DeviceTensor | None = None, div: float = 1.0) -> DeviceTensor:
+    """dx = (dy - sum(dy*y, -1)) * y / div, 0 where `mask` (b200_launch_softmax_backward)."""
+    out = DeviceTensor.empty(y.shape)
+    a, g, o = y.desc(), dy.desc(), out.desc()
+    m = mask.desc() if mask is not None else None
+    check(abi.load().b200_launch_softmax_backward(C.byref(a), C.byref(g), C.byref(m) if m is not None else None,
+                                                  float(div), C.byref(o), None))
+    return out
+
+
+def layer_norm_backward(x: DeviceTensor, dy: DeviceTensor, gamma: DeviceTensor | None, eps: float):
+    """(dx, dgamma, dbeta) of layer_norm over the last axis: one row-resident kernel plus the
+    deterministic column reduce of its per-CTA partials (b200_launch_layer_norm_backward)."""
+    lib = abi.load()
+    d = x.shape[-1]
+    dx = DeviceTensor.empty(x.shape)
+    a, g, o = x.desc(), dy.desc(), dx.desc()
+    n = C.c_int32()
+    check(lib.b200_layer_norm_backward_partials(C.byref(a), C.byref(n)))
+    pg, pb = DeviceTensor.empty((n.value, d)), DeviceTensor.empty((n.value, d))
+    pgd, pbd = pg.desc(), pb.desc()
+    gm = gamma.desc() if gamma is not None else None
+    check(lib.b200_launch_layer_norm_backward(C.byref(a), C.byref(g), C.byref(gm) if gm is not None else None,
+                                              float(eps), C.byref(o), C.byref(pgd), C.byref(pbd), None))
+    return dx, float_sum_dim(pg, 0).reshape((d,)), float_sum_dim(pb, 0).reshape((d,))

@@ -177,40 +177,15 @@ def layer_norm(tape: Tape, x: Var, gamma: Var, beta: Var, eps: float = 1e-5) -> 
     def bw():
         if y.g is None:
             return
-        shape = x.v.shape
-        last = len(shape) - 1
-        d = shape[-1]
-        red = tuple(shape[:-1]) + (1,)
-        bshape = (1,) * last + (d,)
-        # statistics recomputed with fused reduces (read tapes), x̂ never materialised twice
-        mean = ops.float_mean_dim(x.v, last)
-        var = DeviceTensor.empty(red)
-        rd = TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("MUL_F", "acc", "acc")
-        dv.launch_reduce(abi.RED_MEAN, last, shape, [x.v, mean.expand(shape)], [var], read=rd.build())
-        rstd = _run(TapeBuilder().op("ADD_F", ("in", 0), ("f", eps)).op("SQRT_F", "acc").op("RECIP_F", "acc", out=0),
-                    [var], red)
-        xhat = _run(TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("MUL_F", "acc", ("in", 2), out=0),
-                    [x.v, mean.expand(shape), rstd.expand(shape)], shape)
-        rows = int(np.prod(shape[:-1]))
+        # one row-resident kernel: statistics recomputed on chip, dx written once, dgamma/dbeta as
+        # per-CTA partials finished by a column reduce
+        dx, dgamma, dbeta = ops.layer_norm_backward(x.v, y.g, gamma.v, eps)
         if gamma.requires_grad:
-            prod = ops.float_mul(y.g, xhat)
-            accumulate(gamma, ops.float_sum_dim(prod.reshape((rows, d)), 0).reshape(gamma.v.shape))
+            accumulate(gamma, dgamma.reshape(gamma.v.shape))
         if beta.requires_grad:
-            accumulate(beta, ops.float_sum_dim(y.g.reshape((rows, d)), 0).reshape(beta.v.shape))
+            accumulate(beta, dbeta.reshape(beta.v.shape))
         if x.requires_grad:
-            gg = gamma.v.reshape(bshape).expand(shape)
-            m1, m2 = DeviceTensor.empty(red), DeviceTensor.empty(red)
-            dv.launch_reduce(abi.RED_MEAN, last, shape, [y.g, gg], [m1],
-                             read=TapeBuilder().op("MUL_F", ("in", 0), ("in", 1)).build())
-            dv.launch_reduce(abi.RED_MEAN, last, shape, [y.g, gg, xhat], [m2],
-                             read=TapeBuilder().op("MUL_F", ("in", 0), ("in", 1)).op("MUL_F", "acc", ("in", 2)).build())
-            tb = TapeBuilder()
-            tb.op("MUL_F", ("in", 0), ("in", 1))            # g = dy*gamma
-            tb.op("SUB_F", "acc", ("in", 2), tmp=0)         # g - mean(g)
-            tb.op("MUL_F", ("in", 3), ("in", 4))            # x̂ * mean(g x̂)
-            tb.op("SUB_F", ("tmp", 0), "acc")
-            tb.op("MUL_F", "acc", ("in", 5), out=0)         # * rstd
-            accumulate(x, _run(tb, [y.g, gg, m1.expand(shape), xhat, m2.expand(shape), rstd.expand(shape)], shape))
+            accumulate(x, dx)
     tape.add(bw)
     return y
 
@@ -224,10 +199,11 @@ def attention(tape: Tape, q: Var, k: Var, v: Var, n_heads: int, mask: DeviceTens
     def heads(t):
         return t.reshape((B, S, n_heads, dk)).swap_dims(1, 2)
     qh, kh, vh = heads(q.v), heads(k.v), heads(v.v)
-    scale = TapeBuilder().op("DIV_F", ("in", 0), ("f", math.sqrt(dk)), out=0).build()
-    scores = ops.float_matmul(qh, kh.swap_dims(2, 3), tape.precision, scale)
+    # scores = mask_fill(q·kᵀ/√dk, mask, -1e9): scaling and mask fill are the GEMM's fused epilogue
+    epi = TapeBuilder().op("DIV_F", ("in", 0), ("f", math.sqrt(dk)), out=0 if mask is None else None)
     if mask is not None:
-        scores = ops.float_mask_fill(scores, mask.expand(scores.shape), -1.0e9)
+        epi.op("SELECT", "acc", ("f", -1.0e9), ("in", 1), out=0)
+    scores = ops.float_matmul(qh, kh.swap_dims(2, 3), tape.precision, epi.build(), () if mask is None else (mask,))
     w = ops.softmax_rows(scores)
     ctx_buf = DeviceTensor.empty((B, S, n_heads, dk))
     _mm(w, vh, tape.precision, out=ctx_buf.swap_dims(1, 2))
@@ -241,17 +217,9 @@ def attention(tape: Tape, q: Var, k: Var, v: Var, n_heads: int, mask: DeviceTens
         dv_buf = DeviceTensor.empty((B, S, n_heads, dk))
         _mm(w.swap_dims(2, 3), gh, tape.precision, out=dv_buf.swap_dims(1, 2))
         dp = ops.float_matmul(gh, vh.swap_dims(2, 3), tape.precision)
-        # softmax backward: dS = (dP - sum(dP∘P, -1)) ∘ P, then the 1/√dk of the scores
-        shape = w.shape
-        red = tuple(shape[:-1]) + (1,)
-        dot = DeviceTensor.empty(red)
-        dv.launch_reduce(abi.RED_SUM, 3, shape, [dp, w], [dot],
-                         read=TapeBuilder().op("MUL_F", ("in", 0), ("in", 1)).build())
-        tb = (TapeBuilder().op("SUB_F", ("in", 0), ("in", 1)).op("MUL_F", "acc", ("in", 2))
-              .op("DIV_F", "acc", ("f", math.sqrt(dk)), out=0))
-        ds = _run(tb, [dp, dot.expand(shape), w], shape)
-        if mask is not None:
-            ds = ops.float_mask_fill(ds, mask.expand(shape), 0.0)
+        # softmax backward dS = (dP - sum(dP∘P, -1)) ∘ P, the 1/√dk of the scores and the mask_fill
+        # backward (0 where masked) in one row-resident kernel
+        ds = ops.softmax_backward(w, dp, mask, math.sqrt(dk))
         dq_buf, dk_buf = DeviceTensor.empty((B, S, n_heads, dk)), DeviceTensor.empty((B, S, n_heads, dk))
         _mm(ds, kh, tape.precision, out=dq_buf.swap_dims(1, 2))
         _mm(ds.swap_dims(2, 3), qh, tape.precision, out=dk_buf.swap_dims(1, 2))

@@ -332,6 +332,26 @@ int32_t b200_launch_softmax(const b200_tensor *input, const b200_tensor *out,
 int32_t b200_launch_layer_norm(const b200_tensor *input, const b200_tensor *gamma,
                                const b200_tensor *beta, double eps,
                                const b200_tensor *out, b200_stream s);
+/* Backward of the two row chains in one pass each (what burn-autodiff's reverse
+ * walk over those op chains computes, crates/burn-autodiff/src/ops/tensor.rs —
+ * div/exp/sub/sum_dim/mean_dim backward steps).
+ * softmax: dx = (dy - sum(dy*y)) * y / div, and 0 where `mask` (bool, broadcast
+ * over the leading dims; may be NULL) is set — `div` and `mask` fold in the
+ * score scaling and mask_fill backward of MultiHeadAttention
+ * (crates/burn-nn/src/modules/attention/mha.rs:253-311). */
+int32_t b200_launch_softmax_backward(const b200_tensor *y, const b200_tensor *dy,
+                                     const b200_tensor *mask, double div,
+                                     const b200_tensor *dx, b200_stream s);
+/* layer_norm: dx for the input, plus per-CTA partial rows of dgamma = sum(dy*xhat)
+ * and dbeta = sum(dy) as [n_partials, d_model] tensors the caller column-sums with
+ * b200_launch_reduce (deterministic; no atomics).  n_partials comes from
+ * b200_layer_norm_backward_partials.  gamma may be NULL. */
+int32_t b200_layer_norm_backward_partials(const b200_tensor *input, int32_t *n_partials);
+int32_t b200_launch_layer_norm_backward(const b200_tensor *input, const b200_tensor *dy,
+                                        const b200_tensor *gamma, double eps,
+                                        const b200_tensor *dx,
+                                        const b200_tensor *partial_gamma,
+                                        const b200_tensor *partial_beta, b200_stream s);
 
 /* ------------------------------------------------ collectives */
 /* DistributedOps::{all_reduce, sync_collective}

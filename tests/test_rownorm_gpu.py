@@ -71,3 +71,53 @@ def test_non_contiguous_last_axis_is_rejected(dev):
     with pytest.raises(abi.B200Error) as e:
         ops.softmax_rows(t)
     assert e.value.status == abi.ERR_UNSUPPORTED
+
+
+# ---- backward row kernels (b200_launch_softmax_backward / b200_launch_layer_norm_backward)
+BWD_SHAPES = [(7, 4), (33, 256), (2, 3, 8, 1024), (5, 2048), (3, 1000), (2, 4100), (1, 1, 6, 6)]
+
+
+@pytest.mark.parametrize("shape", BWD_SHAPES)
+@pytest.mark.parametrize("masked", [False, True])
+def test_softmax_backward_rows(dev, shape, masked):
+    """dx = (dy - sum(dy*y)) * y / div, 0 where masked — against the same formula in float64."""
+    x, dy = rnd(shape, 3), rnd(shape, 4, -1.0, 1.0)
+    y = oracle.softmax(x, len(shape) - 1)
+    mask = None
+    dmask = None
+    if masked:
+        mshape = (1,) * (len(shape) - 2) + tuple(shape[-2:])          # broadcast over the leading dims
+        mask = np.random.default_rng(5).random(mshape) < 0.3
+        dmask = H.up(mask)
+    div = 8.0 if masked else 1.7
+    got = ops.softmax_backward(H.up(y), H.up(dy), dmask, div).numpy()
+    y64, dy64 = y.astype(np.float64), dy.astype(np.float64)
+    want = (dy64 - (dy64 * y64).sum(-1, keepdims=True)) * y64 / div
+    if masked:
+        want = np.where(np.broadcast_to(mask, shape), 0.0, want)
+        assert np.all(got[np.broadcast_to(mask, shape)] == 0.0)
+    scale = np.abs(want).max() + 1e-30
+    assert np.abs(got - want).max() <= 1e-5 * scale, f"max err {np.abs(got - want).max():.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(7, 4), (64, 128), (16, 8, 512), (300, 1024), (9, 2048), (3, 1000), (2, 4100)])
+@pytest.mark.parametrize("with_gamma", [True, False])
+def test_layer_norm_backward_rows(dev, shape, with_gamma):
+    d = shape[-1]
+    x, dy = rnd(shape, 6), rnd(shape, 7, -1.0, 1.0)
+    gamma = rnd((d,), 8, 0.5, 1.5) if with_gamma else None
+    eps = 1e-5
+    dx, dgamma, dbeta = ops.layer_norm_backward(H.up(x), H.up(dy), H.up(gamma) if with_gamma else None, eps)
+    x64, dy64 = x.astype(np.float64), dy.astype(np.float64)
+    mean = x64.mean(-1, keepdims=True)
+    var = ((x64 - mean) ** 2).mean(-1, keepdims=True)
+    rstd = 1.0 / np.sqrt(var + eps)
+    xh = (x64 - mean) * rstd
+    g = dy64 * (gamma.astype(np.float64) if with_gamma else 1.0)
+    want_dx = (g - g.mean(-1, keepdims=True) - xh * (g * xh).mean(-1, keepdims=True)) * rstd
+    want_dg = (dy64 * xh).reshape(-1, d).sum(0)
+    want_db = dy64.reshape(-1, d).sum(0)
+    for got, want, what in ((dx.numpy(), want_dx, "dx"), (dgamma.numpy(), want_dg, "dgamma"), (dbeta.numpy(), want_db, "dbeta")):
+        scale = np.abs(want).max() + 1e-30
+        err = np.abs(got - want).max()
+        assert err <= 2e-5 * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
