@@ -520,7 +520,7 @@ static int32_t launch_fast(bool col, const fast::RowParams &rp, const fast::ColP
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, cp.splits, 1);
-  cfg.blockDim = dim3(32, 8, 1);
+  cfg.blockDim = dim3(cp.tx, fast::kBlock / cp.tx, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -530,7 +530,9 @@ static int32_t launch_fast(bool col, const fast::RowParams &rp, const fast::ColP
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, fast::reduce_col_fast_kernel<K>, cp));
+  if (cp.tx == 32) B200_CUDA(cudaLaunchKernelEx(&cfg, fast::reduce_col_fast_kernel<K, 32>, cp));
+  else if (cp.tx == 16) B200_CUDA(cudaLaunchKernelEx(&cfg, fast::reduce_col_fast_kernel<K, 16>, cp));
+  else B200_CUDA(cudaLaunchKernelEx(&cfg, fast::reduce_col_fast_kernel<K, 8>, cp));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -606,7 +608,10 @@ static int32_t try_fast_reduce(int32_t kind, int64_t outer, int64_t R, int64_t i
     cp.inner4 = (uint32_t)(inner / 4);
     cp.mean = kind == B200_RED_MEAN;
     cp.div = (float)R;
-    const uint32_t tiles = cp.outer * ((cp.inner4 + 31) / 32);
+    uint32_t tx = 32;
+    while (tx > 8 && cp.outer * ((cp.inner4 + tx - 1) / tx) * 8u < (uint32_t)sms * 2u && cp.R >= 1024u) tx /= 2;
+    cp.tx = tx;
+    const uint32_t tiles = cp.outer * ((cp.inner4 + tx - 1) / tx);
     uint32_t splits = 1;
     while (splits < 8 && tiles * splits < (uint32_t)sms * 6u && cp.R / (splits * 2) >= 64u) splits *= 2;
     cp.splits = splits;

@@ -225,14 +225,17 @@ struct ColParams {
   uint32_t splits, rows_per_split;
   int32_t mean;
   float div;
+  uint32_t tx;                 // column-vectors per CTA (32, 16 or 8)
 };
 
 // blockDim = (32, 8): 32 column-vectors (128 columns, 512 B per row) x 8 row
 // groups; gridDim = (column tiles, splits) with cluster (1, splits, 1) — the
 // cluster's partial columns are combined through distributed shared memory.
-template <int K>
+// TX narrows to 16 / 8 column-vectors (TY = 16 / 32 row groups) when 128-column tiles would
+// leave most SMs without a CTA (tall, narrow inputs such as a [8192, 1024] bias gradient).
+template <int K, int TX>
 __global__ void __launch_bounds__(kBlock) reduce_col_fast_kernel(const ColParams P) {
-  constexpr int TX = 32, TY = 8;
+  constexpr int TY = kBlock / TX;
   __shared__ VI part[TY][TX][4];
   __shared__ VI cta_result[TX][4];
   const uint32_t tiles_per_outer = (P.inner4 + TX - 1) / TX;

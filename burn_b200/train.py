@@ -128,7 +128,11 @@ def linear(tape: Tape, x: Var, w: Var, b: Var | None, gelu_after: bool = False) 
         if x.requires_grad:
             accumulate(x, ops.float_matmul(g2, w.v.swap_dims(0, 1), tape.precision).reshape(x.v.shape))
         if w.requires_grad:
-            accumulate(w, ops.float_matmul(x2.swap_dims(0, 1), g2, tape.precision))
+            slot = getattr(w, "grad_slot", None)
+            if slot is not None and w.g is None:      # the GEMM writes the bucket slot directly
+                accumulate(w, _mm(x2.swap_dims(0, 1), g2, tape.precision, out=slot))
+            else:
+                accumulate(w, ops.float_matmul(x2.swap_dims(0, 1), g2, tape.precision))
         if b is not None and b.requires_grad:
             accumulate(b, ops.float_sum_dim(g2, 0).reshape(b.v.shape))   # linear_bias_backward: column reduce
     tape.add(bw)
@@ -238,7 +242,8 @@ def embedding(tape: Tape, weight: Var, ids: DeviceTensor) -> Var:
     def bw():
         if y.g is None or not weight.requires_grad:
             return
-        z = DeviceTensor.empty(weight.v.shape)
+        slot = getattr(weight, "grad_slot", None)
+        z = slot if slot is not None and weight.g is None else DeviceTensor.empty(weight.v.shape)
         abi.check(abi.load().b200_memset(z.data_ptr(), 0, z.numel * 4, None))
         a, b, c = z.desc(), flat.desc(), y.g.reshape((flat.numel, weight.v.shape[1])).desc()
         abi.check(abi.load().b200_launch_select_add(0, C.byref(a), C.byref(b), C.byref(c), None))
@@ -284,12 +289,13 @@ def mean_square(tape: Tape, x: Var) -> Var:
 
 # ------------------------------------------------------------------ modules (burn-nn)
 class Param(Var):
-    __slots__ = ("m", "s", "on_grad")
+    __slots__ = ("m", "s", "on_grad", "grad_slot")
 
     def __init__(self, a: np.ndarray, name: str):
         super().__init__(DeviceTensor.from_numpy(np.ascontiguousarray(a, dtype=np.float32)), True, name)
         self.m = self.s = None  # Adam moments
         self.on_grad = None     # called once the gradient is final (each parameter is used once per step)
+        self.grad_slot = None   # where the gradient should be written (a view of a flat bucket), if any
 
 
 def _uniform(rng, shape, fan_in):
@@ -412,25 +418,33 @@ class Adam:
                 lib = abi.load()
                 abi.check(lib.b200_memset(p.m.data_ptr(), 0, p.m.numel * 4, None))
                 abi.check(lib.b200_memset(p.s.data_ptr(), 0, p.s.numel * 4, None))
-            # one fused kernel, three in-place outputs: m, v, p
-            tb = TapeBuilder()
-            tb.op("MUL_F", ("in", 3), ("f", 1.0 - self.b1), tmp=0)            # (1-β1) g
-            tb.op("MUL_F", ("in", 1), ("f", self.b1))
-            tb.op("ADD_F", "acc", ("tmp", 0), tmp=1, out=1)                    # m'
-            tb.op("MUL_F", ("in", 3), ("in", 3))
-            tb.op("MUL_F", "acc", ("f", 1.0 - self.b2), tmp=0)                 # (1-β2) g²
-            tb.op("MUL_F", ("in", 2), ("f", self.b2))
-            tb.op("ADD_F", "acc", ("tmp", 0), out=2)                           # v'
-            tb.op("DIV_F", "acc", ("in", 5))                                   # v̂ = v'/(1-β2^t)
-            tb.op("SQRT_F", "acc")
-            tb.op("ADD_F", "acc", ("f", self.eps), tmp=0)                      # √(v̂)+ε
-            tb.op("DIV_F", ("tmp", 1), ("in", 4))                              # m̂ = m'/(1-β1^t)
-            tb.op("DIV_F", "acc", ("tmp", 0))
-            tb.op("MUL_F", "acc", ("f", self.lr), tmp=0)
-            tb.op("SUB_F", ("in", 0), ("tmp", 0), out=0)                       # p' = p - lr·m̂/(√v̂+ε)
-            c1 = self.coef.slice([(0, 1)]).reshape((1,) * p.v.ndim).expand(p.v.shape)
-            c2 = self.coef.slice([(1, 2)]).reshape((1,) * p.v.ndim).expand(p.v.shape)
-            dv.launch_elemwise(tb.build(), [p.v, p.m, p.s, p.g, c1, c2], [p.v, p.m, p.s], p.v.shape)
+            self.update(p.v, p.m, p.s, p.g)
+
+    def apply_arena(self, arena: "ParamArena") -> None:
+        """Multi-tensor Adam: one fused launch per flat bucket instead of one per parameter."""
+        for b in arena.buckets:
+            self.update(b["p"], b["m"], b["s"], b["g"])
+
+    def update(self, pv: DeviceTensor, pm: DeviceTensor, ps: DeviceTensor, pg: DeviceTensor) -> None:
+        """One fused kernel, three in-place outputs (m, v, p) — adam.rs:149-210, op for op."""
+        tb = TapeBuilder()
+        tb.op("MUL_F", ("in", 3), ("f", 1.0 - self.b1), tmp=0)            # (1-β1) g
+        tb.op("MUL_F", ("in", 1), ("f", self.b1))
+        tb.op("ADD_F", "acc", ("tmp", 0), tmp=1, out=1)                    # m'
+        tb.op("MUL_F", ("in", 3), ("in", 3))
+        tb.op("MUL_F", "acc", ("f", 1.0 - self.b2), tmp=0)                 # (1-β2) g²
+        tb.op("MUL_F", ("in", 2), ("f", self.b2))
+        tb.op("ADD_F", "acc", ("tmp", 0), out=2)                           # v'
+        tb.op("DIV_F", "acc", ("in", 5))                                   # v̂ = v'/(1-β2^t)
+        tb.op("SQRT_F", "acc")
+        tb.op("ADD_F", "acc", ("f", self.eps), tmp=0)                      # √(v̂)+ε
+        tb.op("DIV_F", ("tmp", 1), ("in", 4))                              # m̂ = m'/(1-β1^t)
+        tb.op("DIV_F", "acc", ("tmp", 0))
+        tb.op("MUL_F", "acc", ("f", self.lr), tmp=0)
+        tb.op("SUB_F", ("in", 0), ("tmp", 0), out=0)                       # p' = p - lr·m̂/(√v̂+ε)
+        c1 = self.coef.slice([(0, 1)]).reshape((1,) * pv.ndim).expand(pv.shape)
+        c2 = self.coef.slice([(1, 2)]).reshape((1,) * pv.ndim).expand(pv.shape)
+        dv.launch_elemwise(tb.build(), [pv, pm, ps, pg, c1, c2], [pv, pm, ps], pv.shape)
 
     @staticmethod
     def zero_grad(params):
@@ -438,47 +452,58 @@ class Adam:
             p.g = None
 
 
-# ------------------------------------------------------------------ DDP gradient sync (burn-train ddp)
-class GradSync:
-    """All-reduce(Mean) of every parameter gradient as soon as it is final, overlapped with the rest
-    of backward on the collective stream, fenced before the optimizer.  The
-    reference issues one collective per parameter (crates/burn-cubecl/src/ops/distributed.rs:17-50:
-    218 tensors in config 5); here gradients are packed into persistent flat buckets of about
-    `bucket_bytes` in backward order — one ncclAllReduce per bucket, fired when its last member
-    arrives — and `p.g` becomes a view of the bucket, which the optimizer reads in place.  Persistent
-    bucket storage also keeps the collective's addresses fixed across CUDA-graph replays."""
+# ------------------------------------------------------------------ flat parameter arena + DDP gradient sync
+class ParamArena:
+    """Packs parameters, Adam moments and gradients into persistent flat buckets of about
+    `bucket_bytes`, in the order backward finalises gradients.
 
-    def __init__(self, comm, params: Sequence[Param], bucket_bytes: int = 32 << 20):
+      * gradients: weight-gradient GEMMs and the embedding scatter write their bucket slot directly,
+        other gradients are copied in; `p.g` becomes a view of the bucket.
+      * DDP (comm given): one ncclAllReduce(avg) per bucket, fired when its last member arrives and
+        overlapped with the rest of backward on the collective stream, fenced before the optimizer
+        (SURVEY.md §3.4).  The reference issues one collective per parameter
+        (crates/burn-cubecl/src/ops/distributed.rs:17-50: 218 tensors in config 5).
+      * optimizer: Adam runs as one fused launch per bucket over the flat p/m/v/g arrays
+        (multi-tensor Adam) instead of one launch per parameter.
+    Persistent storage keeps every address fixed across CUDA-graph replays."""
+
+    def __init__(self, params: Sequence[Param], comm=None, bucket_bytes: int = 32 << 20):
         self.comm = comm
-        self.calls = 0
         self.buckets: list[dict] = []
-        self.slot: dict[int, tuple[dict, DeviceTensor]] = {}
+        self.slot: dict[int, dict] = {}
+        lib = abi.load()
         members, size = [], 0
-        order = list(reversed(list(params)))              # the order backward finalises gradients in
+        order = list(reversed(list(params)))
         for i, p in enumerate(order):
             members.append(p)
             size += (p.v.numel + 3) // 4 * 4              # 16-byte aligned slots
             if size * 4 >= bucket_bytes or i == len(order) - 1:
-                flat = DeviceTensor.empty((size,))
-                b = {"flat": flat, "n": len(members), "arrived": 0}
+                flats = {k: DeviceTensor.empty((size,)) for k in ("p", "m", "s", "g")}
+                for t in flats.values():
+                    abi.check(lib.b200_memset(t.data_ptr(), 0, size * 4, None))
+                b = dict(flats, n=len(members), arrived=0)
                 off = 0
                 for q in members:
-                    self.slot[id(q)] = (b, flat.slice([(off, off + q.v.numel)]).reshape(q.v.shape))
+                    view = {k: flats[k].slice([(off, off + q.v.numel)]).reshape(q.v.shape) for k in flats}
+                    abi.check(lib.b200_memcpy_d2d(view["p"].data_ptr(), q.v.data_ptr(), q.v.numel * 4, None))
+                    q.v, q.m, q.s, q.grad_slot = view["p"], view["m"], view["s"], view["g"]
+                    q.on_grad = self.ready
+                    self.slot[id(q)] = b
                     off += (q.v.numel + 3) // 4 * 4
                 self.buckets.append(b)
                 members, size = [], 0
-        for p in params:
-            p.on_grad = self.ready
+        dv.sync()
 
     def ready(self, p: Param) -> None:
-        b, view = self.slot[id(p)]
-        src = p.g if p.g.is_contiguous() else p.g.contiguous()
-        abi.check(abi.load().b200_memcpy_d2d(view.data_ptr(), src.data_ptr(), view.numel * 4, None))
-        p.g = view
+        b = self.slot[id(p)]
+        if p.g.data_ptr() != p.grad_slot.data_ptr():
+            src = p.g if p.g.is_contiguous() else p.g.contiguous()
+            abi.check(abi.load().b200_memcpy_d2d(p.grad_slot.data_ptr(), src.data_ptr(), src.numel * 4, None))
+            p.g = p.grad_slot
         b["arrived"] += 1
         if b["arrived"] == b["n"]:
-            self.comm.all_reduce(b["flat"], mean=True)
-            self.calls += 1
+            if self.comm is not None:
+                self.comm.all_reduce(b["g"], mean=True)
             b["arrived"] = 0
 
     def wait(self) -> None:
@@ -486,4 +511,5 @@ class GradSync:
         for b in self.buckets:
             if b["arrived"]:
                 raise RuntimeError("a gradient bucket is incomplete: some parameter received no gradient")
-        self.comm.sync()
+        if self.comm is not None:
+            self.comm.sync()

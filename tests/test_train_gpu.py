@@ -129,3 +129,32 @@ def test_tf32_and_bf16_training_losses_stay_close_to_f32x3(dev):
     ref = losses[abi.MM_F32X3]
     assert abs(losses[abi.MM_TF32] - ref) <= 2e-3 * abs(ref)
     assert abs(losses[abi.MM_BF16] - ref) <= 2e-2 * abs(ref)
+
+
+def test_param_arena_matches_per_parameter_adam_bit_for_bit(dev):
+    """Flat buckets (direct-to-bucket gradients + multi-tensor Adam) change where tensors live,
+    not a single rounding: parameters after two steps equal the per-parameter path exactly."""
+    d, ff, h, L, B, S = 32, 64, 4, 1, 2, 8
+    x = np.random.default_rng(9).standard_normal((B, S, d)).astype(np.float32)
+    results = []
+    for use_arena in (False, True):
+        enc = T.Encoder(12, d, ff, h, L)
+        params = enc.params()
+        opt = T.Adam(lr=1e-2)
+        arena = T.ParamArena(params, None, bucket_bytes=8 << 10) if use_arena else None
+        for _ in range(2):
+            tape = T.Tape(abi.MM_F32X3)
+            T.mean_square(tape, enc.forward(tape, T.Var(H.up(x), False)))
+            tape.backward()
+            opt.advance()
+            if use_arena:
+                arena.wait()
+                opt.apply_arena(arena)
+            else:
+                opt.apply(params)
+            T.Adam.zero_grad(params)
+        results.append([p.v.numpy() for p in params])
+        if use_arena:
+            assert len(arena.buckets) > 1
+    for a, b in zip(*results):
+        assert np.array_equal(a, b)

@@ -77,10 +77,11 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
     params = model.params()
     n_params = sum(p.v.numel for p in params)
     opt = T.Adam(lr=1e-4)
-    comm = sync = None
+    comm = None
     if world > 1:
         comm = Communicator(rank, world, device=torch.device("cuda", local_rank))
-        sync = T.GradSync(comm, params, bucket_bytes=bucket_mb << 20)
+    # flat p/m/v/g buckets: direct-to-bucket gradients, one all-reduce and one Adam launch per bucket
+    arena = T.ParamArena(params, comm, bucket_bytes=bucket_mb << 20)
 
     # ---- this rank's synthetic batch, pinned on the host, persistent device buffers
     rng = np.random.default_rng(5000 + rank)
@@ -126,9 +127,8 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
         check(lib.b200_memcpy_d2d(loss_dev.data_ptr(), loss.v.data_ptr(), 4, None))
         del loss
         tape.backward()
-        if sync is not None:
-            sync.wait()
-        opt.apply(params)
+        arena.wait()
+        opt.apply_arena(arena)
         T.Adam.zero_grad(params)
 
     def d2h():
@@ -196,8 +196,9 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
             f"decoder LM d_model {d}, {cfg['L']} layers, {cfg['h']} heads, d_ff {cfg['ff']}, vocab {cfg['vocab']}, seq {S}, "
             f"batch {B}/GPU, fwd+bwd+NCCL grad all-reduce+Adam"),
             "params": n_params, "tokens_per_step": tokens,
-            "parallelism": f"dp{world}" + (f", {len(sync.buckets)} ncclAllReduce(avg) per step on ~{bucket_mb} MiB flat buckets, "
-                                            f"overlapped with backward on the collective stream" if sync else ""),
+            "parallelism": f"dp{world}" + (f", {len(arena.buckets)} ncclAllReduce(avg) per step on ~{bucket_mb} MiB flat buckets, "
+                                            f"overlapped with backward on the collective stream" if comm else "")
+                           + f"; multi-tensor Adam: {len(arena.buckets)} launches",
             "launch": "cuda graph replay" if graph is not None else "eager (python launch loop)"},
         "model_tflops_per_s": round(flops / (ms_per_step * 1e-3) / 1e12, 1),
         "gpu_launches": launches, "kernels_per_step": launches // max(steps, 1),
