@@ -166,6 +166,42 @@ __global__ void select_add_kernel(IdxTensor t, IdxTensor idx, IdxTensor v, int d
   }
 }
 
+// select_add on rows of a 2-D f32 table (embedding backward): t[idx[i], :] += v[i, :].
+// A warp owns a chunk of target rows x 128 columns.  It scans the indices 32 at a time (one
+// coalesced load), ballots the ones that land in its chunk and applies them in increasing i —
+// the same per-element order as the sequential reference loop (crates/burn-ndarray/src/ops/base.rs
+// select_assign), so the sums are bit-identical and need no atomics — while every index is read
+// once per warp instead of once per thread.
+__global__ void __launch_bounds__(256) select_add_rows_kernel(float *t, int64_t t_stride, const void *idx, int32_t idx_dtype,
+                                                              int64_t idx_stride, const float *v, int64_t v_stride,
+                                                              int64_t n, int64_t rows_t, int cols4, int col_groups,
+                                                              int chunks, int64_t rows_per_chunk) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp; w < (int64_t)col_groups * chunks; w += n_warps) {
+    const int cg = (int)(w % col_groups);
+    const int64_t lo = (w / col_groups) * rows_per_chunk, hi = min(rows_t, lo + rows_per_chunk);
+    const int c4 = cg * 32 + lane;
+    const bool col_ok = c4 < cols4;
+    for (int64_t base = 0; base < n; base += 32) {
+      const int64_t i = base + lane;
+      const int64_t k = i < n ? load_index(idx, idx_dtype, i * idx_stride) : -1;
+      unsigned hits = __ballot_sync(0xffffffffu, k >= lo && k < hi);
+      while (hits) {
+        const int b = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int64_t kb = __shfl_sync(0xffffffffu, k, b);
+        if (col_ok) {
+          float4 *dst = reinterpret_cast<float4 *>(t + kb * t_stride) + c4;
+          const float4 a = *dst, x = __ldg(reinterpret_cast<const float4 *>(v + (base + b) * v_stride) + c4);
+          *dst = make_float4(__fadd_rn(a.x, x.x), __fadd_rn(a.y, x.y), __fadd_rn(a.z, x.z), __fadd_rn(a.w, x.w));
+        }
+      }
+    }
+  }
+}
+
 __global__ void arange_kernel(void *out, int32_t dtype, int64_t n, int64_t start, int64_t step) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -366,6 +402,25 @@ extern "C" int32_t b200_launch_select_add(int32_t dim, const b200_tensor *tensor
     }
   }
   if (lanes == 0 || indices->shape[0] == 0) return B200_OK;
+  // embedding-backward shape: rows of a 2-D f32 table with aligned, unit-stride columns
+  if (tensor->rank == 2 && dim == 0 && tensor->dtype == B200_F32 && tensor->shape[1] % 4 == 0 &&
+      tensor->strides[1] == 1 && value->strides[1] == 1 && tensor->strides[0] % 4 == 0 && value->strides[0] % 4 == 0 &&
+      ((uintptr_t)tensor->ptr % 16) == 0 && ((uintptr_t)value->ptr % 16) == 0 && tensor->shape[0] > 0) {
+    const int cols4 = (int)(tensor->shape[1] / 4), col_groups = (cols4 + 31) / 32;
+    const int64_t rows_t = tensor->shape[0];
+    const int64_t want_warps = (int64_t)sm_count() * 16;
+    const int chunks_r = (int)std::max<int64_t>(1, std::min<int64_t>(rows_t, want_warps / col_groups));
+    const int64_t rpc_r = (rows_t + chunks_r - 1) / chunks_r;
+    const int chunks_eff = (int)((rows_t + rpc_r - 1) / rpc_r);
+    const int64_t warps = (int64_t)col_groups * chunks_eff;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, (warps + 7) / 8);
+    select_add_rows_kernel<<<grid, 256, 0, resolve_stream(s)>>>(
+        reinterpret_cast<float *>(tensor->ptr), tensor->strides[0], indices->ptr, indices->dtype, indices->strides[0],
+        reinterpret_cast<const float *>(value->ptr), value->strides[0], indices->shape[0], rows_t, cols4, col_groups,
+        chunks_eff, rpc_r);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   int chunks;
   int64_t rpc;
   pick_chunks(lanes, tensor->shape[dim], chunks, rpc);

@@ -31,7 +31,7 @@ struct Params {
   int64_t x_row_stride, y_row_stride;
   uint32_t rows, R;
   float eps;
-  float inv_unused;
+  int32_t vec;   // CTA kernel: rows are 16-byte aligned and R % 4 == 0
 };
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -155,13 +155,19 @@ __device__ __forceinline__ float block_reduce_max(float v, float *scratch) {
 
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) row_cta_kernel(const Params P) {
-  extern __shared__ float rowbuf[];
+  extern __shared__ __align__(16) float rowbuf[];
   __shared__ float scratch[kWarps];
   for (uint32_t row = blockIdx.x; row < P.rows; row += gridDim.x) {
     const float *xr = P.x + (int64_t)row * P.x_row_stride;
     float *yr = P.y + (int64_t)row * P.y_row_stride;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) rowbuf[i] = __ldcs(xr + i);
+    if (P.vec) {   // 128-bit loads when the row is 16-byte aligned and R % 4 == 0
+      const float4 *x4 = reinterpret_cast<const float4 *>(xr);
+      float4 *b4 = reinterpret_cast<float4 *>(rowbuf);
+      for (uint32_t i = threadIdx.x; i < (P.R >> 2); i += kBlock) b4[i] = __ldcs(x4 + i);
+    } else {
+      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) rowbuf[i] = __ldcs(xr + i);
+    }
     __syncthreads();
     if constexpr (MODE == kLayerNorm) {
       float s = 0.f;
@@ -194,8 +200,19 @@ __global__ void __launch_bounds__(kBlock) row_cta_kernel(const Params P) {
       }
       s = block_reduce_sum(s, scratch);
       const float ls = logf(s);
-      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock)
-        __stcs(yr + i, MODE == kSoftmax ? __fdiv_rn(rowbuf[i], s) : __fsub_rn(rowbuf[i], ls));
+      if (P.vec) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(rowbuf);
+        float4 *y4 = reinterpret_cast<float4 *>(yr);
+        for (uint32_t i = threadIdx.x; i < (P.R >> 2); i += kBlock) {
+          float4 o = b4[i];
+          if (MODE == kSoftmax) { o.x = __fdiv_rn(o.x, s); o.y = __fdiv_rn(o.y, s); o.z = __fdiv_rn(o.z, s); o.w = __fdiv_rn(o.w, s); }
+          else { o.x = __fsub_rn(o.x, ls); o.y = __fsub_rn(o.y, ls); o.z = __fsub_rn(o.z, ls); o.w = __fsub_rn(o.w, ls); }
+          __stcs(y4 + i, o);
+        }
+      } else {
+        for (uint32_t i = threadIdx.x; i < P.R; i += kBlock)
+          __stcs(yr + i, MODE == kSoftmax ? __fdiv_rn(rowbuf[i], s) : __fsub_rn(rowbuf[i], ls));
+      }
     }
   }
 }
@@ -243,12 +260,14 @@ static int32_t launch_rows(const Params &P, cudaStream_t stream) {
   const size_t smem = (size_t)P.R * 4;
   B200_REQUIRE((int)smem + 1024 <= max_smem_optin(), B200_ERR_UNSUPPORTED,
                "row of %u f32 does not fit in shared memory; use the op chain", P.R);
+  Params Q = P;
+  Q.vec = vec_ok ? 1 : 0;
   auto kern = row_cta_kernel<MODE>;
   if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
   const unsigned grid = (unsigned)std::min<uint32_t>(P.rows, (uint32_t)(sms * std::max(per_sm, 1)));
-  kern<<<grid, kBlock, smem, stream>>>(P);
+  kern<<<grid, kBlock, smem, stream>>>(Q);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -392,16 +392,26 @@ def _reshape(tape: Tape, x: Var, shape) -> Var:
 
 # ------------------------------------------------------------------ Adam (burn-optim adam.rs:149-210)
 class Adam:
+    """AdamConfig::new() defaults except lr (crates/burn-optim/src/optim/adam.rs:31-50): β1 0.9, β2 0.999, ε 1e-5.
+    The update is the op sequence of AdaptiveMomentum::transform + Adam::step (adam.rs:149-210, :80-84):
+        m' = m·β1 + g·(1-β1);  v' = v·β2 + g²·(1-β2)
+        u  = (m'·cf) / (√v' + ε_t),  cf = √(1-β2^t)/(1-β1^t),  ε_t = ε·√(1-β2^t);   p' = p - u·lr"""
+
     def __init__(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-5):
         self.lr, self.b1, self.b2, self.eps, self.t = lr, beta1, beta2, eps, 0
-        self.coef = None        # device [2]: 1-β1^t, 1-β2^t — inputs, not immediates, so a graph replays
+        self.coef = None        # device [2]: cf, ε_t — inputs, not immediates, so a captured graph replays
+
+    def coefficients(self, t: int):
+        f = np.float32
+        bc2s = np.sqrt(f(1.0) - f(self.b2) ** t, dtype=np.float32)
+        return f(bc2s / (f(1.0) - f(self.b1) ** t)), f(f(self.eps) * bc2s)
 
     def advance(self) -> None:
-        """Host side of a step: bump t and upload the two bias-correction scalars (8 bytes)."""
+        """Host side of a step: bump t and upload the two time-dependent scalars (8 bytes)."""
         self.t += 1
         if self.coef is None:
             self.coef = DeviceTensor.empty((2,))
-        c = np.array([1.0 - self.b1 ** self.t, 1.0 - self.b2 ** self.t], dtype=np.float32)
+        c = np.array(self.coefficients(self.t), dtype=np.float32)
         abi.check(abi.load().b200_memcpy_h2d(self.coef.data_ptr(), c.ctypes.data, 8, None))  # pageable: staged synchronously
 
     def step(self, params: Sequence[Param]) -> None:
@@ -409,7 +419,7 @@ class Adam:
         self.apply(params)
 
     def apply(self, params: Sequence[Param]) -> None:
-        """The device side: one fused launch per parameter (capturable)."""
+        """One fused elementwise-tape launch per parameter (the op stream burn-fusion would fuse)."""
         for p in params:
             if p.g is None:
                 continue
@@ -418,30 +428,34 @@ class Adam:
                 lib = abi.load()
                 abi.check(lib.b200_memset(p.m.data_ptr(), 0, p.m.numel * 4, None))
                 abi.check(lib.b200_memset(p.s.data_ptr(), 0, p.s.numel * 4, None))
-            self.update(p.v, p.m, p.s, p.g)
+            self.update_tape(p.v, p.m, p.s, p.g)
 
     def apply_arena(self, arena: "ParamArena") -> None:
-        """Multi-tensor Adam: one fused launch per flat bucket instead of one per parameter."""
+        """Multi-tensor Adam: one b200_launch_adam per flat bucket instead of one launch per parameter."""
+        lib = abi.load()
+        c = self.coef.desc()
         for b in arena.buckets:
-            self.update(b["p"], b["m"], b["s"], b["g"])
+            p, m, s, g = b["p"].desc(), b["m"].desc(), b["s"].desc(), b["g"].desc()
+            abi.check(lib.b200_launch_adam(C.byref(p), C.byref(m), C.byref(s), C.byref(g), C.byref(c),
+                                           float(self.lr), float(self.b1), float(self.b2), None))
 
-    def update(self, pv: DeviceTensor, pm: DeviceTensor, ps: DeviceTensor, pg: DeviceTensor) -> None:
-        """One fused kernel, three in-place outputs (m, v, p) — adam.rs:149-210, op for op."""
+    def update_tape(self, pv: DeviceTensor, pm: DeviceTensor, ps: DeviceTensor, pg: DeviceTensor) -> None:
+        f = np.float32
+        omb1, omb2 = float(f(1.0) - f(self.b1)), float(f(1.0) - f(self.b2))
         tb = TapeBuilder()
-        tb.op("MUL_F", ("in", 3), ("f", 1.0 - self.b1), tmp=0)            # (1-β1) g
+        tb.op("MUL_F", ("in", 3), ("f", omb1), tmp=0)                      # g·(1-β1)
         tb.op("MUL_F", ("in", 1), ("f", self.b1))
         tb.op("ADD_F", "acc", ("tmp", 0), tmp=1, out=1)                    # m'
         tb.op("MUL_F", ("in", 3), ("in", 3))
-        tb.op("MUL_F", "acc", ("f", 1.0 - self.b2), tmp=0)                 # (1-β2) g²
+        tb.op("MUL_F", "acc", ("f", omb2), tmp=0)                          # g²·(1-β2)
         tb.op("MUL_F", ("in", 2), ("f", self.b2))
         tb.op("ADD_F", "acc", ("tmp", 0), out=2)                           # v'
-        tb.op("DIV_F", "acc", ("in", 5))                                   # v̂ = v'/(1-β2^t)
         tb.op("SQRT_F", "acc")
-        tb.op("ADD_F", "acc", ("f", self.eps), tmp=0)                      # √(v̂)+ε
-        tb.op("DIV_F", ("tmp", 1), ("in", 4))                              # m̂ = m'/(1-β1^t)
+        tb.op("ADD_F", "acc", ("in", 5), tmp=0)                            # √v' + ε_t
+        tb.op("MUL_F", ("tmp", 1), ("in", 4))                              # m'·cf
         tb.op("DIV_F", "acc", ("tmp", 0))
-        tb.op("MUL_F", "acc", ("f", self.lr), tmp=0)
-        tb.op("SUB_F", ("in", 0), ("tmp", 0), out=0)                       # p' = p - lr·m̂/(√v̂+ε)
+        tb.op("MUL_F", "acc", ("f", self.lr), tmp=0)                       # ·lr
+        tb.op("SUB_F", ("in", 0), ("tmp", 0), out=0)                       # p' = p - delta
         c1 = self.coef.slice([(0, 1)]).reshape((1,) * pv.ndim).expand(pv.shape)
         c2 = self.coef.slice([(1, 2)]).reshape((1,) * pv.ndim).expand(pv.shape)
         dv.launch_elemwise(tb.build(), [pv, pm, ps, pg, c1, c2], [pv, pm, ps], pv.shape)

@@ -353,6 +353,17 @@ int32_t b200_launch_layer_norm_backward(const b200_tensor *input, const b200_ten
                                         const b200_tensor *partial_gamma,
                                         const b200_tensor *partial_beta, b200_stream s);
 
+/* ------------------------------------------------ optimizer */
+/* Multi-tensor Adam over one flat buffer, in place: the op sequence of
+ * AdaptiveMomentum::transform + Adam::step
+ * (crates/burn-optim/src/optim/adam.rs:149-210, :80-84) in one pass.
+ * coef = device [2] f32 {sqrt(1-b2^t)/(1-b1^t), eps*sqrt(1-b2^t)}: the
+ * time-dependent scalars live in device memory so a captured step replays. */
+int32_t b200_launch_adam(const b200_tensor *param, const b200_tensor *moment1,
+                         const b200_tensor *moment2, const b200_tensor *grad,
+                         const b200_tensor *coef, double lr, double beta1,
+                         double beta2, b200_stream s);
+
 /* ------------------------------------------------ collectives */
 /* DistributedOps::{all_reduce, sync_collective}
  * (crates/burn-backend/src/backend/distributed/ops.rs:116-131; reference impl

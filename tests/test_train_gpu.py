@@ -101,6 +101,7 @@ def test_language_model_loss_and_grads_with_causal_mask(dev):
 
 
 def test_adam_step_matches_formula(dev):
+    """AdaptiveMomentum::transform + Adam::step (adam.rs:149-210, :80-84) in float64."""
     rng = np.random.default_rng(5)
     w, g = rng.standard_normal((33, 20)).astype(np.float32), rng.standard_normal((33, 20)).astype(np.float32)
     p = T.Param(w, "w")
@@ -113,7 +114,8 @@ def test_adam_step_matches_formula(dev):
         opt.step([p])
         m = 0.9 * m + 0.1 * g
         s = 0.999 * s + 0.001 * g.astype(np.float64) ** 2
-        ref = ref - 1e-2 * (m / (1 - 0.9 ** t)) / (np.sqrt(s / (1 - 0.999 ** t)) + 1e-5)
+        bc2s = np.sqrt(1 - 0.999 ** t)
+        ref = ref - 1e-2 * (m * (bc2s / (1 - 0.9 ** t))) / (np.sqrt(s) + 1e-5 * bc2s)
     assert np.allclose(p.v.numpy(), ref, rtol=2e-5, atol=1e-6)
 
 
