@@ -254,6 +254,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     check(lib.b200_event_elapsed_ms(ev[2], ev[3], C.byref(ms)))
     e2e_ms = max_over_ranks(ms.value)
 
+    # ---- second half of the metric: transformer train tokens/s (configs[4], DDP over NCCL when N > 1)
+    train = None
+    if not args.no_train:
+        for t in (da, db, dc, dm, y):
+            t.storage = None            # release the 1.3 GB of elementwise buffers first
+        try:
+            import train_bench
+            train = train_bench.run("lm", steps=args.train_steps, warmup=3, rank=rank, world=world,
+                                    local_rank=local_rank, mm="tf32", use_graph=True, init_device=False)
+        except Exception as e:  # the headline metric above stands on its own
+            train = {"error": repr(e)[:300]}
+
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the box's host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -284,7 +296,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "ms_per_step": round(e2e_ms / args.steps, 3),
                     "note": "pinned host buffers -> C ABI memcpy_h2d -> 6 launches -> memcpy_d2h of all reduction results"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "elemwise_tape_kernel_v4 (fused chain)",
+            "roofline": {"bound": "hbm", "kernel": "elemwise_tape_kernel_bulk (fused chain: 4 inputs, 8 ops, 1 output)",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "peak_source": peak_src,
                          "traffic": ncu_traffic(), "avg_launch_ms": round(chain_avg_ms, 4),
@@ -293,6 +305,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if train is not None:
+            line["train"] = train
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -388,6 +402,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the transformer-training measurement")
+    ap.add_argument("--train-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
