@@ -367,6 +367,10 @@ static int32_t launch_v1(const CompiledTape &ct, TapeParams &p, int rm, cudaStre
 
 using namespace b200;
 
+namespace b200 {
+int32_t jit_try_elemwise(const CompiledTape &ct, const TapeParams &p, int vec, int rank_mode_, cudaStream_t stream);
+}
+
 extern "C" int32_t b200_launch_elemwise(const b200_tape *tape, const b200_tensor *inputs,
                                         int32_t n_inputs, const b200_tensor *outputs,
                                         int32_t n_outputs, int32_t rank,
@@ -417,5 +421,8 @@ extern "C" int32_t b200_launch_elemwise(const b200_tape *tape, const b200_tensor
   p.n_vec = (uint32_t)(numel / vec);
 
   cudaStream_t stream = resolve_stream(s);
+  // large linear launches: NVRTC-specialised kernel (jit.cu); everything else: the interpreter
+  const int32_t jst = jit_try_elemwise(ct, p, vec, rm, stream);
+  if (jst != 0) return jst < 0 ? jst : B200_OK;
   return vec == 4 ? launch_v4(ct, p, rm, stream) : launch_v1(ct, p, rm, stream);
 }

@@ -1,0 +1,189 @@
+// NVRTC specialisation of hot elementwise tapes ("consider NVRTC specialisation as a
+// second mode").  The reference JIT-compiles every fused trace (CubeCL → CUDA C++ → NVRTC,
+// crates/burn-cubecl-fusion/src/engine/codegen/kernel.rs); here the op-tape interpreter stays the
+// general path and large, linear launches get a kernel generated from the compiled tape: straight-
+// line code over U=2 vectors of 4 elements per thread, operands in registers (no slot file, no
+// dispatch), 128-bit streaming loads/stores.  Each op is `eval_op<OPC>` from tape_eval.cuh — the
+// interpreter's arithmetic with the opcode folded at compile time — so results are bit-identical.
+// Kernels are cached by generated source; libnvrtc is dlopen()ed, and when it is missing or a
+// compile fails the launch simply stays on the interpreter (still a GPU path).
+// B200_TAPE_JIT=0 disables, B200_TAPE_JIT_MIN_VEC overrides the size threshold.
+#include <dlfcn.h>
+
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "tape_host.cuh"
+#include "tape_eval.cuh"
+#include "jit_embed.inc"
+
+namespace b200 {
+namespace jit {
+
+typedef struct _nvrtcProgram *nvrtcProgram;
+struct Nvrtc {
+  void *h = nullptr;
+  int (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+  int (*CompileProgram)(nvrtcProgram, int, const char *const *) = nullptr;
+  int (*GetCUBINSize)(nvrtcProgram, size_t *) = nullptr;
+  int (*GetCUBIN)(nvrtcProgram, char *) = nullptr;
+  int (*GetProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
+  int (*GetProgramLog)(nvrtcProgram, char *) = nullptr;
+  int (*DestroyProgram)(nvrtcProgram *) = nullptr;
+  bool ok = false, tried = false;
+};
+static Nvrtc g_rtc;
+static std::mutex g_mu;
+static std::unordered_map<std::string, cudaKernel_t> g_cache;   // nullptr = compile failed, do not retry
+
+static bool load_nvrtc() {
+  if (g_rtc.tried) return g_rtc.ok;
+  g_rtc.tried = true;
+  for (const char *name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
+    g_rtc.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+    if (g_rtc.h) break;
+  }
+  if (!g_rtc.h) {
+    fprintf(stderr, "[burn_b200] libnvrtc not found: elementwise tapes stay on the interpreter\n");
+    return false;
+  }
+#define B200_RTC_SYM(field, sym)                                            \
+  *(void **)(&g_rtc.field) = dlsym(g_rtc.h, sym);                           \
+  if (!g_rtc.field) { fprintf(stderr, "[burn_b200] libnvrtc lacks %s\n", sym); return false; }
+  B200_RTC_SYM(CreateProgram, "nvrtcCreateProgram")
+  B200_RTC_SYM(CompileProgram, "nvrtcCompileProgram")
+  B200_RTC_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+  B200_RTC_SYM(GetCUBIN, "nvrtcGetCUBIN")
+  B200_RTC_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+  B200_RTC_SYM(GetProgramLog, "nvrtcGetProgramLog")
+  B200_RTC_SYM(DestroyProgram, "nvrtcDestroyProgram")
+#undef B200_RTC_SYM
+  g_rtc.ok = true;
+  return true;
+}
+
+static bool dtype_in_ok(int32_t dt) { return dt == B200_F32 || dt == B200_I32 || dt == B200_BOOL || dt == B200_U8 || dt == B200_BF16; }
+static bool dtype_out_ok(int32_t dt) { return dt == B200_F32 || dt == B200_I32 || dt == B200_BOOL || dt == B200_U8; }
+
+// Generates the kernel source for a compiled tape over linear operands.
+static std::string generate(const CompiledTape &ct, const TapeParams &p) {
+  std::string s;
+  s += "#include \"burn_b200.h\"\n#include \"tape_eval.cuh\"\nusing namespace b200;\n";
+  s += "extern \"C\" __global__ void __launch_bounds__(256) b200_jit_kernel(const JitParams P) {\n";
+  s += "  constexpr int U = 2;\n  const uint32_t stride = gridDim.x * 256u;\n";
+  for (size_t k = 0; k < ct.scalars.size(); ++k) s += "  const uint32_t S" + std::to_string(k) + " = P.scalars[" + std::to_string(k) + "];\n";
+  for (int i = 0; i < ct.n_in; ++i)
+    if (p.in[i].mode == kModeBcast)
+      s += "  const uint32_t B" + std::to_string(i) + " = jit_ld1<" + std::to_string(p.in[i].dtype) + ">(P.in[" + std::to_string(i) + "]);\n";
+  s += "  for (uint32_t v0 = blockIdx.x * 256u + threadIdx.x; v0 < P.n_vec; v0 += U * stride) {\n";
+  for (int i = 0; i < ct.n_in; ++i)
+    if (p.in[i].mode == kModeVec) s += "    uint32_t I" + std::to_string(i) + "[U][4];\n";
+  s += "#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const uint32_t v = v0 + u * stride;\n      if (v < P.n_vec) {\n";
+  for (int i = 0; i < ct.n_in; ++i)
+    if (p.in[i].mode == kModeVec)
+      s += "        jit_ld4<" + std::to_string(p.in[i].dtype) + ">(P.in[" + std::to_string(i) + "], v, I" + std::to_string(i) + "[u]);\n";
+  s += "      }\n    }\n";
+  s += "#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const uint32_t v = v0 + u * stride;\n      if (v < P.n_vec) {\n";
+  for (int o = 0; o < ct.n_out; ++o) s += "        uint32_t O" + std::to_string(o) + "[4];\n";
+  s += "#pragma unroll\n        for (int j = 0; j < 4; ++j) {\n          uint32_t a = 0u;\n";
+  for (int t = 0; t < ct.n_tmp; ++t) s += "          uint32_t T" + std::to_string(t) + " = 0u;\n";
+  auto arg = [&](const SymArg &x, bool acc_if_none) -> std::string {
+    switch (x.kind) {
+      case 1: return p.in[x.idx].mode == kModeBcast ? "B" + std::to_string(x.idx) : "I" + std::to_string(x.idx) + "[u][j]";
+      case 2: return "T" + std::to_string(x.idx);
+      case 3: return "S" + std::to_string(x.idx);
+      default: return acc_if_none ? "a" : "0u";
+    }
+  };
+  for (const SymOp &o : ct.ops) {
+    s += "          a = eval_op<" + std::to_string(o.op) + ">(a, " + arg(o.b, o.op == kOpGelu) + ", " + arg(o.c, false) + ");\n";
+    if (o.dst_tmp >= 0) s += "          T" + std::to_string(o.dst_tmp) + " = a;\n";
+    if (o.dst_out >= 0) s += "          O" + std::to_string(o.dst_out) + "[j] = a;\n";
+  }
+  s += "        }\n";
+  for (int o = 0; o < ct.n_out; ++o)
+    s += "        jit_st4<" + std::to_string(p.out[o].dtype) + ">(P.out[" + std::to_string(o) + "], v, O" + std::to_string(o) + ");\n";
+  s += "      }\n    }\n  }\n}\n";
+  return s;
+}
+
+static cudaKernel_t compile(const std::string &src) {
+  nvrtcProgram prog = nullptr;
+  const char *hdr_src[] = {kJitSrc_burn_b200_h, kJitSrc_tape_eval_cuh, kJitSrc_tape_math_cuh, kJitSrc_erf_table_inc,
+                           kJitSrc_stdint_h, kJitSrc_stdint_h};
+  const char *hdr_name[] = {"burn_b200.h", "tape_eval.cuh", "tape_math.cuh", "erf_table.inc", "stdint.h", "stddef.h"};
+  if (g_rtc.CreateProgram(&prog, src.c_str(), "b200_jit.cu", 6, hdr_src, hdr_name) != 0) return nullptr;
+  // -default-device: burn_b200.h's host prototypes are only declarations here
+  const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-diag-suppress=177"};
+  const int rc = g_rtc.CompileProgram(prog, 5, opts);
+  cudaKernel_t kern = nullptr;
+  if (rc != 0) {
+    size_t n = 0;
+    g_rtc.GetProgramLogSize(prog, &n);
+    std::string log(n + 1, '\0');
+    if (n) g_rtc.GetProgramLog(prog, &log[0]);
+    fprintf(stderr, "[burn_b200] NVRTC failed (%d); this tape stays on the interpreter:\n%.2000s\n", rc, log.c_str());
+  } else {
+    size_t n = 0;
+    if (g_rtc.GetCUBINSize(prog, &n) == 0 && n) {
+      std::string cubin(n, '\0');
+      if (g_rtc.GetCUBIN(prog, &cubin[0]) == 0) {
+        cudaLibrary_t lib = nullptr;
+        if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess) {
+          if (cudaLibraryGetKernel(&kern, lib, "b200_jit_kernel") != cudaSuccess) kern = nullptr;
+        }
+        if (!kern) {
+          fprintf(stderr, "[burn_b200] loading a specialised kernel failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        }
+      }
+    }
+  }
+  g_rtc.DestroyProgram(&prog);
+  return kern;
+}
+
+}  // namespace jit
+
+// Returns 1 when the launch ran on a specialised kernel, 0 when the caller should use the interpreter.
+int32_t jit_try_elemwise(const CompiledTape &ct, const TapeParams &p, int vec, int rank_mode_, cudaStream_t stream) {
+  static const bool enabled = [] { const char *e = std::getenv("B200_TAPE_JIT"); return !(e && e[0] == '0'); }();
+  static const uint32_t min_vec = [] {
+    const char *e = std::getenv("B200_TAPE_JIT_MIN_VEC");
+    return e ? (uint32_t)strtoul(e, nullptr, 10) : (1u << 18);
+  }();
+  if (!enabled || vec != 4 || rank_mode_ != kRankLinear || p.n_vec < min_vec) return 0;
+  for (int i = 0; i < ct.n_in; ++i) {
+    const OperandDesc &d = p.in[i];
+    if (!jit::dtype_in_ok(d.dtype)) return 0;
+    if (!(d.mode == kModeBcast || (d.mode == kModeVec && d.s3[2] == 1))) return 0;
+  }
+  for (int o = 0; o < ct.n_out; ++o)
+    if (!jit::dtype_out_ok(p.out[o].dtype) || p.out[o].mode != kModeVec || p.out[o].s3[2] != 1) return 0;
+
+  cudaKernel_t kern = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(jit::g_mu);
+    if (!jit::load_nvrtc()) return 0;
+    const std::string src = jit::generate(ct, p);
+    auto it = jit::g_cache.find(src);
+    if (it == jit::g_cache.end()) it = jit::g_cache.emplace(src, jit::compile(src)).first;
+    kern = it->second;
+  }
+  if (!kern) return 0;
+  JitParams P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < ct.n_in; ++i) P.in[i] = p.in[i].ptr;
+  for (int o = 0; o < ct.n_out; ++o) P.out[o] = p.out[o].ptr;
+  for (size_t k = 0; k < ct.scalars.size(); ++k) P.scalars[k] = ct.scalars[k];
+  P.n_vec = p.n_vec;
+  const uint32_t per_block = 256u * 2u;
+  const unsigned grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((p.n_vec + per_block - 1) / per_block, (uint32_t)sm_count() * 8u));
+  void *args[] = {&P};
+  B200_CUDA(cudaLaunchKernel((const void *)kern, dim3(grid), dim3(256), args, 0, stream));
+  count_launch(1);
+  return 1;
+}
+
+}  // namespace b200

@@ -22,7 +22,7 @@
 // overhead per op for 4*U elements of work per thread.
 #pragma once
 #include "common.cuh"
-#include "erf_table.inc"
+#include "tape_math.cuh"
 
 namespace b200 {
 
@@ -33,16 +33,6 @@ enum LoadMode : int32_t {
   kModeVec = 0,     // VEC consecutive elements, aligned vector access
   kModeBcast = 1,   // innermost stride 0: one element broadcast to all lanes
   kModeGather = 2   // VEC element accesses at offset + j*inner_stride
-};
-
-// Internal opcodes = public opcodes + a few compiler-generated ones.
-enum : int {
-  kOpLoad = B200_OP_COUNT,  // acc = B
-  kOpSave,                  // no-op carrying a dst_temp (acc saved to a temp)
-  kOpDivScalar,             // acc = acc / B, B a scalar: exact Markstein sequence
-  kOpMulAdd,                // acc = RN(RN(acc * B) + C)   (two roundings, never an FMA)
-  kOpGelu,                  // acc = gelu(B): the reference's 5-op chain executed in one dispatch
-  kIOpCount
 };
 
 // 64-bit internal op: {op:8, dst_tmp:8, dst_out:8, flags:8, b_addr:16, c_addr:16}
@@ -78,103 +68,6 @@ struct TapeParams {
   int32_t n_iops, n_in, n_out, n_tmp, n_scalars, rank;
   uint32_t n_vec;  // number of VEC-wide vectors (numel / VEC)
 };
-
-// ----------------------------------------------------------------- scalar math
-__device__ __forceinline__ float f_of(uint32_t u) { return __uint_as_float(u); }
-__device__ __forceinline__ uint32_t u_of(float f) { return __float_as_uint(f); }
-
-// tanh evaluated the way the oracle does: f64 libm, rounded to f32
-// (crates/burn-ndarray/src/ops/tensor.rs:620-626).
-__device__ __forceinline__ float tanh_oracle(float x) { return (float)tanh((double)x); }
-
-// erf.  The oracle computes libm::erf in f64 and rounds to f32
-// (crates/burn-ndarray/src/ops/tensor.rs:714-720); FP64 runs at half rate on B200
-// and would cap a fused gelu chain below the HBM roofline, so this is an f32
-// routine designed (scripts/fit_erf.py) to land within 1 ulp of that correctly
-// rounded value — equal to it for ~99% of inputs:
-//   |x| < 0.5      : x*K_hi + x*(K_lo + t*Q(t)), t = x^2 (single final rounding)
-//   0.5 <= |x| < 4 : 28 table intervals of width 1/8: H_i + (d*Q_i(d) + L_i), d = |x| - c_i exact
-//   |x| >= 4       : +-1 (erfc(4) < half an ulp of 1)
-__device__ __forceinline__ float erf_f32(float x) {
-  // Branch-free: both regions are evaluated and selected, so the 16 independent
-  // evaluations a thread performs interleave freely.
-  const float ax = fabsf(x);
-  // region A
-  const float t = __fmul_rn(ax, ax);
-  float qa = B200_ERF_Q4;
-  qa = __fmaf_rn(qa, t, B200_ERF_Q3);
-  qa = __fmaf_rn(qa, t, B200_ERF_Q2);
-  qa = __fmaf_rn(qa, t, B200_ERF_Q1);
-  qa = __fmaf_rn(qa, t, B200_ERF_Q0);
-  const float e = __fmaf_rn(t, qa, B200_ERF_K_LO);
-  const float ra = __fmaf_rn(ax, B200_ERF_K_HI, __fmul_rn(ax, e));
-  // region B (index clamped so the table read is always in range; NaN -> row 0 -> NaN)
-  const int i = min(max(__float2int_rz(__fmul_rn(__fsub_rn(ax, 0.5f), 8.0f)), 0), 27);
-  const float c = __fmaf_rn((float)i, 0.125f, 0.5625f);
-  const float d = __fsub_rn(ax, c);
-  const float4 r0 = __ldg(&kErfB[2 * i]), r1 = __ldg(&kErfB[2 * i + 1]);
-  float qb = r1.z;
-  qb = __fmaf_rn(qb, d, r1.y);
-  qb = __fmaf_rn(qb, d, r1.x);
-  qb = __fmaf_rn(qb, d, r0.w);
-  qb = __fmaf_rn(qb, d, r0.z);
-  const float rb = __fadd_rn(r0.x, __fmaf_rn(d, qb, r0.y));
-  float r = ax < 0.5f ? ra : rb;
-  r = ax >= 4.0f ? 1.0f : r;
-  return copysignf(r, x);
-}
-
-// Python-style float modulo used by the reference for `remainder`
-// (crates/burn-ndarray/src/ops/base.rs — `((x % rhs) + rhs) % rhs`).
-__device__ __forceinline__ float rem_floor(float x, float y) {
-  return fmodf(fmodf(x, y) + y, y);
-}
-
-__device__ __forceinline__ int32_t irem_floor(int32_t x, int32_t y) {
-  if (y == 0) return 0;
-  return ((x % y) + y) % y;
-}
-
-__device__ __forceinline__ float sign_f(float x) {
-  return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : x);  // NaN stays NaN
-}
-
-// x / y for a launch-constant y with correctly rounded rinv = RN(1/y): Markstein's
-// sequence gives the correctly rounded quotient when nothing under/overflows; the
-// guarded range falls back to the IEEE division.  (Host only emits kOpDivScalar
-// for normal y whose significand is not all ones.)
-__device__ __forceinline__ float div_scalar_fast(float x, float y, float rinv) {
-  const float q = __fmul_rn(x, rinv);
-  const float r = __fmaf_rn(-y, q, x);
-  return __fmaf_rn(r, rinv, q);
-}
-// True when Markstein's sequence is exact for x (no intermediate under/overflow);
-// zero is fine (0/y = 0).
-__device__ __forceinline__ bool div_scalar_safe(float x) {
-  const float ax = fabsf(x);
-  return (ax > 1e-25f && ax < 1e25f) || ax == 0.0f;
-}
-__device__ __forceinline__ float div_scalar_exact(float x, float y, float rinv) {
-  return div_scalar_safe(x) ? div_scalar_fast(x, y, rinv) : __fdiv_rn(x, y);
-}
-
-static __device__ __noinline__ float pow_f(float a, float b) { return powf(a, b); }
-static __device__ __noinline__ float slow_unary(int op, float x) {
-  switch (op) {
-    case B200_OP_SIN_F: return (float)sin((double)x);
-    case B200_OP_COS_F: return (float)cos((double)x);
-    case B200_OP_TAN_F: return (float)tan((double)x);
-    case B200_OP_SINH_F: return (float)sinh((double)x);
-    case B200_OP_COSH_F: return (float)cosh((double)x);
-    case B200_OP_ASIN_F: return (float)asin((double)x);
-    case B200_OP_ACOS_F: return (float)acos((double)x);
-    case B200_OP_ATAN_F: return (float)atan((double)x);
-    case B200_OP_ASINH_F: return (float)asinh((double)x);
-    case B200_OP_ACOSH_F: return (float)acosh((double)x);
-    case B200_OP_ATANH_F: return (float)atanh((double)x);
-    default: return x;
-  }
-}
 
 // ----------------------------------------------------------------- typed vector IO
 // Loads VEC consecutive elements of `dtype` starting at element offset `off`

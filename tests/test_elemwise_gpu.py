@@ -264,3 +264,15 @@ def test_full_size_chain_properties(dev):
     H.assert_close(got[blk], want, H.REL_ELEMWISE, 0.0, "sampled block")
     again = H.run_tape(bench_chain_tape(), [da, db, dc, dm], (n, n))
     assert np.array_equal(got, again)
+
+
+def test_division_by_scalar_keeps_the_sign_of_zero(dev):
+    """x / c runs as Markstein's exact sequence; -0.0 / 3 must stay -0.0 like IEEE division (oracle: ndarray `/`)."""
+    x = np.zeros(64, dtype=np.float32)
+    x[::2] = -0.0
+    x[5] = 7.5
+    from burn_b200 import ops
+    for c in (3.0, -3.0, 1.4142135623730951):
+        got = ops.float_div_scalar(H.up(x), c).numpy()
+        want = x / np.float32(c)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), c

@@ -1,0 +1,82 @@
+"""GPU: NVRTC-specialised elementwise kernels (burn_b200/csrc/jit.cu) against the op-tape interpreter.
+Large linear launches are compiled from the tape; the same launch with B200_TAPE_JIT_MIN_VEC raised
+runs on the interpreter.  Both must agree bit for bit (same eval code, opcode folded at compile time)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import sys, hashlib
+import numpy as np
+sys.path.insert(0, %r)
+from burn_b200 import _abi as abi, device as dv, ops
+from burn_b200.device import DeviceTensor, TapeBuilder
+from tests import helpers as H
+dv.init(0)
+n = (1 << 20) + 4 * 37          # > the JIT threshold, ragged against the 512-vector block
+rng = np.random.default_rng(0)
+a = rng.uniform(-3, 3, n).astype(np.float32); b = rng.uniform(-3, 3, n).astype(np.float32)
+c = rng.uniform(0.1, 3, n).astype(np.float32); m = rng.random(n) < 0.3
+ia = rng.integers(-100, 100, n).astype(np.int32); ib = rng.integers(1, 17, n).astype(np.int32)
+a[:8] = [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-30, -1e30, 4.5]
+da, db, dc, dm, dia, dib = (H.up(x) for x in (a, b, c, m, ia, ib))
+case = [0]
+def run(tb, ins, n_out=1, dts=(abi.F32,)):
+    outs = [DeviceTensor.empty((n,), dts[i]) for i in range(n_out)]
+    tape = tb.build()
+    dv.launch_elemwise(tape, ins, outs, (n,))
+    h = hashlib.sha256()
+    for o in outs:
+        h.update(o.numpy().tobytes())
+    names = "+".join(k for o in tb.ops for k, v in abi.OP.items() if v == o[0])
+    print("CASE", case[0], names, h.hexdigest()[:16])
+    case[0] += 1
+# the bench chain
+tb = TapeBuilder(); tb.op("MUL_F", ("in", 0), ("in", 1)); tb.op("ADD_F", "acc", ("in", 2), tmp=0)
+H.gelu_tape(tb, ("tmp", 0)); tb.op("SELECT", "acc", ("f", 0.0), ("in", 3), out=0)
+run(tb, [da, db, dc, dm])
+# every float unary / binary op, comparisons, int ops, casts, scalar division, two outputs
+for name in ["NEG_F", "ABS_F", "EXP_F", "LOG_F", "LOG1P_F", "SQRT_F", "RECIP_F", "TANH_F", "ERF_F", "FLOOR_F", "CEIL_F",
+             "ROUND_F", "TRUNC_F", "SIGN_F", "SIGMOID_F", "SIN_F", "COS_F", "ATAN_F"]:
+    run(TapeBuilder().op(name, ("in", 0), out=0), [dc if name in ("LOG_F", "SQRT_F") else da])
+for name in ["ADD_F", "SUB_F", "MUL_F", "DIV_F", "REM_F", "POW_F", "MIN_F", "MAX_F", "ATAN2_F"]:
+    run(TapeBuilder().op(name, ("in", 0), ("in", 1), out=0), [dc if name == "POW_F" else da, db])
+for name in ["EQ_F", "NE_F", "LT_F", "LE_F", "GT_F", "GE_F"]:
+    run(TapeBuilder().op(name, ("in", 0), ("in", 1), out=0), [da, db], dts=(abi.BOOL,))
+for name in ["ADD_I", "SUB_I", "MUL_I", "DIV_I", "REM_I", "MIN_I", "MAX_I", "AND_I", "OR_I", "XOR_I", "SHL_I", "SHR_I"]:
+    run(TapeBuilder().op(name, ("in", 0), ("in", 1), out=0), [dia, dib], dts=(abi.I32,))
+run(TapeBuilder().op("DIV_F", ("in", 0), ("f", 3.0), out=0), [da])
+run(TapeBuilder().op("DIV_F", ("in", 0), ("f", 8.0), out=0), [da])
+run(TapeBuilder().op("CLAMP_F", ("in", 0), ("f", -1.0), ("f", 1.5), out=0), [da])
+run(TapeBuilder().op("F2I", ("in", 0), out=0), [db], dts=(abi.I32,))
+run(TapeBuilder().op("I2F", ("in", 0), out=0), [dia])
+run(TapeBuilder().op("B2F", ("in", 0), out=0), [dm])
+tb = TapeBuilder(); tb.op("MUL_F", ("in", 0), ("in", 1), tmp=0, out=1); tb.op("ADD_F", ("tmp", 0), ("in", 2)); tb.op("EXP_F", "acc", out=0)
+run(tb, [da, db, H.up(np.float32([0.25]).reshape(1)).expand((n,))], n_out=2, dts=(abi.F32, abi.F32))
+print("DONE")
+'''
+
+
+def _run(env_extra):
+    env = dict(os.environ, **env_extra)
+    r = subprocess.run([sys.executable, "-c", SCRIPT % ROOT], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "DONE" in r.stdout
+    cases = {tuple(l.split()[1:3]): l.split()[3] for l in r.stdout.splitlines() if l.startswith("CASE")}
+    return cases, r.stderr
+
+
+def test_specialised_kernels_match_the_interpreter_bit_for_bit(dev):
+    jit, err = _run({"B200_TAPE_JIT": "1"})
+    assert "NVRTC failed" not in err and "libnvrtc not found" not in err, err[-2000:]
+    interp, _ = _run({"B200_TAPE_JIT": "0"})
+    assert len(jit) == len(interp) > 50
+    differing = [k for k in interp if jit.get(k) != interp[k]]
+    assert not differing, f"specialised kernel != interpreter for {differing}"
