@@ -296,7 +296,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "ms_per_step": round(e2e_ms / args.steps, 3),
                     "note": "pinned host buffers -> C ABI memcpy_h2d -> 6 launches -> memcpy_d2h of all reduction results"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "elemwise_tape_kernel_bulk (fused chain: 4 inputs, 8 ops, 1 output)",
+            "roofline": {"bound": "hbm", "kernel": "b200_jit_kernel (NVRTC-specialised fused chain: 4 inputs, 8 ops, 1 output)",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "peak_source": peak_src,
                          "traffic": ncu_traffic(), "avg_launch_ms": round(chain_avg_ms, 4),

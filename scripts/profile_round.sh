@@ -15,7 +15,7 @@ cap() {  # name, kernel regex, skip, command...
   python scripts/ncu_summary.py gpurun_out/$name.raw.csv > gpurun_out/$name.txt 2>&1
   rm -f gpurun_out/$name.ncu-rep
 }
-cap chain "elemwise_tape_kernel" 4 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train
+cap chain "b200_jit_kernel|elemwise_tape_kernel" 4 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train
 cap gemm_bf16 "gemm_tcgen05" 2 python scripts/prof_gemm.py
 cap gemm_tf32 "gemm_tcgen05" 5 python scripts/prof_gemm.py
 cap reduce_row "reduce_row_fast_kernel" 6 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train
