@@ -46,6 +46,7 @@ struct Params {
   int32_t tiles_m, tiles_n, k_blocks, stages;
   int32_t has_epilogue;
   int32_t c_dtype;
+  int32_t k_split;   // batch[0] enumerates K splits: k offset = b[0] * k_blocks * BK, partial outputs
   // fast epilogue (epi_fast != 0): the tape is a straight chain acc = OP(acc, operand) evaluated
   // on the 32 accumulator columns a lane holds, staged through swizzled smem and written with TMA
   CUtensorMap tma_c;
@@ -435,7 +436,9 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
         const int bb0 = b[0] * P.b_bflag[0], bb1 = b[1] * P.b_bflag[1], bb2 = b[2] * P.b_bflag[2];
         const int m0 = (m_blk * CTAS + cta_rank) * BM;           // this CTA's 128 rows of A
         const int n0 = n_blk * TN + cta_rank * BN;               // this CTA's 128 rows of B
-        for (int kb = 0; kb < P.k_blocks; ++kb) {
+        const int kb0 = P.k_split ? b[0] * P.k_blocks : 0;      // split-K: this tile's slice of K
+        for (int kbi = 0; kbi < P.k_blocks; ++kbi) {
+          const int kb = kb0 + kbi;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t *sa = tiles + (size_t)stage * kStageBytes;
           uint8_t *sb = sa + kATile;
@@ -901,6 +904,44 @@ static int32_t plan_matmul(const b200_tensor *a, const b200_tensor *b, const b20
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Tile configuration: CTA pairs (256x256) or single CTAs (128x128), and how many K splits.
+// Costs are in units of (one wave) x (K per split): a pair runs a 256x256 tile on two SMs at the
+// full tensor rate, a single CTA a 128x128 tile at about half of it, so a wave costs the same.
+// Split-K (partials [S, ..., M, N] in the workspace + one deterministic column reduce) fills the
+// machine when a long-K product has few output tiles — e.g. a [1024, 8192]·[8192, 1024] weight
+// gradient is 16 pair tiles for 74 pairs.
+struct GemmConfig {
+  bool pair;
+  int splits;
+};
+static GemmConfig choose_config(const MatmulPlan &pl, int es, bool allow_split) {
+  static const bool no_pair = std::getenv("B200_MM_NO_PAIR") != nullptr;
+  static const bool no_split = std::getenv("B200_MM_NO_SPLITK") != nullptr;
+  const int64_t n_batch = (int64_t)pl.batch[0] * pl.batch[1] * pl.batch[2];
+  const int64_t sms = sm_count();
+  const int64_t t128 = ((pl.M + 127) / 128) * ((pl.N + 127) / 128) * n_batch;
+  const int64_t t256 = ((pl.M + 255) / 256) * ((pl.N + 255) / 256) * n_batch;
+  const int BK = 128 / es;
+  const bool can_split = allow_split && !no_split && pl.nb <= 2 && pl.batch[0] == 1;
+  auto splits_for = [&](int64_t units, int64_t capacity) -> int64_t {
+    if (!can_split) return 1;
+    return std::max<int64_t>(1, std::min<int64_t>({(int64_t)8, capacity / std::max<int64_t>(units, 1), pl.K / (16 * BK)}));
+  };
+  const bool can_pair = !no_pair && pl.M > 128 && pl.N > 128;
+  const int64_t s1 = splits_for(t128, sms), s2 = can_pair ? splits_for(t256, sms / 2) : 1;
+  const int64_t cost1 = ((t128 * s1 + sms - 1) / sms) * ((pl.K + s1 - 1) / s1);
+  const int64_t cost2 = ((t256 * s2 + sms / 2 - 1) / (sms / 2)) * ((pl.K + s2 - 1) / s2);
+  GemmConfig c;
+  c.pair = can_pair && (t256 >= sms / 2 || cost2 < cost1);
+  c.splits = (int)(c.pair ? s2 : s1);
+  return c;
+}
+static size_t split_ws_bytes(const MatmulPlan &pl, int splits) {
+  if (splits <= 1) return 0;
+  const int64_t n_batch = (int64_t)pl.batch[0] * pl.batch[1] * pl.batch[2];
+  return align_up((size_t)splits * n_batch * pl.M * pl.N * 4, 256);
+}
+
 // Bytes of scratch one operand needs under `precision` (0 when it can be consumed in place).
 static size_t operand_ws_bytes(const b200_tensor *t, bool is_a, int precision, const MatmulPlan &pl) {
   const int r = t->rank;
@@ -983,7 +1024,9 @@ extern "C" int32_t b200_matmul_workspace_bytes(const b200_tensor *a, const b200_
   MatmulPlan pl;
   int32_t st = plan_matmul(a, b, nullptr, pl);
   if (st != B200_OK) return st;
-  *bytes = operand_ws_bytes(a, true, precision, pl) + operand_ws_bytes(b, false, precision, pl);
+  const GemmConfig cfg = choose_config(pl, precision == B200_MM_BF16 ? 2 : 4, true);
+  *bytes = operand_ws_bytes(a, true, precision, pl) + operand_ws_bytes(b, false, precision, pl) +
+           split_ws_bytes(pl, cfg.splits);
   return B200_OK;
 }
 
@@ -1013,6 +1056,11 @@ extern "C" int32_t b200_launch_matmul(const b200_tensor *a, const b200_tensor *b
   }
 
   const size_t need_a = operand_ws_bytes(a, true, precision, pl), need_b = operand_ws_bytes(b, false, precision, pl);
+  // split-K only for plain f32 outputs without an epilogue, and only when the caller's workspace has
+  // room for the partials (b200_matmul_workspace_bytes reports them)
+  GemmConfig cfg = choose_config(pl, precision == B200_MM_BF16 ? 2 : 4, !epilogue && c->dtype == B200_F32);
+  if (cfg.splits > 1 && need_a + need_b + split_ws_bytes(pl, cfg.splits) > workspace_bytes)
+    cfg = choose_config(pl, precision == B200_MM_BF16 ? 2 : 4, false);
   B200_REQUIRE(need_a + need_b <= workspace_bytes && (need_a + need_b == 0 || workspace), B200_ERR_INVALID,
                "matmul needs %zu bytes of workspace, got %llu", need_a + need_b, (unsigned long long)workspace_bytes);
 
@@ -1122,6 +1170,20 @@ extern "C" int32_t b200_launch_matmul(const b200_tensor *a, const b200_tensor *b
   const int BK = 128 / es;
   P.k_blocks = (int32_t)((K_eff + BK - 1) / BK);
   P.c_dtype = c->dtype;
+  float *partials = nullptr;
+  if (cfg.splits > 1) {
+    // split-K: batch slot 0 enumerates the K slices; each writes its own [batch.., M, N] partial
+    partials = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + need_a + need_b);
+    P.c = partials;
+    P.ldc = pl.N;
+    P.k_split = 1;
+    P.k_blocks = (P.k_blocks + cfg.splits - 1) / cfg.splits;
+    P.batch[0] = cfg.splits;
+    P.a_bflag[0] = P.b_bflag[0] = 0;
+    P.c_batch_stride[2] = pl.M * pl.N;
+    P.c_batch_stride[1] = P.c_batch_stride[2] * pl.batch[2];
+    P.c_batch_stride[0] = P.c_batch_stride[1] * pl.batch[1];
+  }
 
   // ---- epilogue tape
   TapeParams T;
@@ -1130,7 +1192,7 @@ extern "C" int32_t b200_launch_matmul(const b200_tensor *a, const b200_tensor *b
   // the fast epilogue (TMA stores of full 128-byte lines) needs a 16-byte-aligned f32 output
   // with 16-byte-multiple row and batch strides; B200_MM_LEGACY_EPILOGUE=1 disables it (debug)
   static const bool legacy_epi = std::getenv("B200_MM_LEGACY_EPILOGUE") != nullptr;
-  bool fast = !legacy_epi && tma_c_ok(c, r, pl.c_sb, pl.batch, pl.M);
+  bool fast = !legacy_epi && (partials ? pl.N % 4 == 0 : tma_c_ok(c, r, pl.c_sb, pl.batch, pl.M));
   if (epilogue) {
     B200_REQUIRE(n_epi_inputs >= 0 && n_epi_inputs + 1 <= B200_MAX_TAPE_INPUTS, B200_ERR_INVALID, "too many epilogue inputs");
     B200_REQUIRE(pl.N % 4 == 0, B200_ERR_UNSUPPORTED, "a fused matmul epilogue needs N %% 4 == 0 (got N = %lld)", (long long)pl.N);
@@ -1177,7 +1239,7 @@ extern "C" int32_t b200_launch_matmul(const b200_tensor *a, const b200_tensor *b
     if (!fast) epi_bytes = slot_file_bytes(T.n_in + T.n_tmp, T.n_scalars, 4, mm::kEpiU, mm::kEpiBlock) + 16;
   }
   if (fast) {
-    st = make_tmap_c(&P.tma_c, c->ptr, pl.M, pl.N, P.ldc, pl.c_sb, pl.batch);
+    st = make_tmap_c(&P.tma_c, P.c, pl.M, pl.N, P.ldc, P.c_batch_stride, P.batch);
     if (st != B200_OK) return st;
     P.epi_fast = 1;
     epi_bytes = 0;
@@ -1185,24 +1247,38 @@ extern "C" int32_t b200_launch_matmul(const b200_tensor *a, const b200_tensor *b
   const size_t budget = (size_t)max_smem_optin() - 2048 - epi_bytes - (fast ? mm::kOutStageBytes : 0);
   P.stages = (int32_t)std::max<size_t>(2, std::min<size_t>(6, budget / (32 * 1024)));
 
-  // CTA pairs (256x256 tiles) whenever the output is wide and tall enough to fill them;
-  // B200_MM_NO_PAIR=1 keeps the single-CTA 128x128 kernel (debug / comparison)
-  static const bool no_pair = std::getenv("B200_MM_NO_PAIR") != nullptr;
-  // when they need no more waves than the single-CTA kernel would (a pair runs its tile at twice
-  // the per-SM rate, so equal waves = half the time; tiny problems keep the cheaper launch)
-  const int64_t t128 = (int64_t)P.tiles_m * P.tiles_n * n_batch;
-  const int64_t t256 = ((pl.M + 255) / 256) * ((pl.N + 255) / 256) * n_batch;
-  const int64_t sms = sm_count(), waves1 = (t128 + sms - 1) / sms, waves2 = (t256 + sms / 2 - 1) / (sms / 2);
-  const bool pair = !no_pair && pl.M > 128 && pl.N > 128 && (t256 >= sms / 2 || waves2 < waves1);
+  const bool pair = cfg.pair;
   const bool amn = oa.mn_major, bmn = ob.mn_major;
   if (es == 4) {
-    if (!amn && !bmn) return launch_gemm<4, false, false>(P, T, epi_bytes, stream, pair);
-    if (!amn && bmn) return launch_gemm<4, false, true>(P, T, epi_bytes, stream, pair);
-    if (amn && !bmn) return launch_gemm<4, true, false>(P, T, epi_bytes, stream, pair);
-    return launch_gemm<4, true, true>(P, T, epi_bytes, stream, pair);
+    if (!amn && !bmn) st = launch_gemm<4, false, false>(P, T, epi_bytes, stream, pair);
+    else if (!amn && bmn) st = launch_gemm<4, false, true>(P, T, epi_bytes, stream, pair);
+    else if (amn && !bmn) st = launch_gemm<4, true, false>(P, T, epi_bytes, stream, pair);
+    else st = launch_gemm<4, true, true>(P, T, epi_bytes, stream, pair);
+  } else {
+    if (!amn && !bmn) st = launch_gemm<2, false, false>(P, T, epi_bytes, stream, pair);
+    else if (!amn && bmn) st = launch_gemm<2, false, true>(P, T, epi_bytes, stream, pair);
+    else if (amn && !bmn) st = launch_gemm<2, true, false>(P, T, epi_bytes, stream, pair);
+    else st = launch_gemm<2, true, true>(P, T, epi_bytes, stream, pair);
   }
-  if (!amn && !bmn) return launch_gemm<2, false, false>(P, T, epi_bytes, stream, pair);
-  if (!amn && bmn) return launch_gemm<2, false, true>(P, T, epi_bytes, stream, pair);
-  if (amn && !bmn) return launch_gemm<2, true, false>(P, T, epi_bytes, stream, pair);
-  return launch_gemm<2, true, true>(P, T, epi_bytes, stream, pair);
+  if (st != B200_OK || !partials) return st;
+  // deterministic combine of the K-split partials: C = sum over the leading axis
+  b200_tensor pin, cout;
+  memset(&pin, 0, sizeof(pin));
+  memset(&cout, 0, sizeof(cout));
+  pin.ptr = partials;
+  pin.dtype = cout.dtype = B200_F32;
+  pin.rank = cout.rank = r + 1;
+  cout.ptr = c->ptr;
+  int64_t in_shape[B200_MAX_RANK], acc = 1;
+  for (int d = r - 1; d >= 0; --d) {
+    pin.shape[d + 1] = cout.shape[d + 1] = in_shape[d + 1] = c->shape[d];
+    pin.strides[d + 1] = acc;
+    cout.strides[d + 1] = c->strides[d];
+    acc *= c->shape[d];
+  }
+  pin.shape[0] = in_shape[0] = cfg.splits;
+  pin.strides[0] = acc;
+  cout.shape[0] = 1;
+  cout.strides[0] = acc;
+  return b200_launch_reduce(B200_RED_SUM, 0, r + 1, in_shape, nullptr, &pin, 1, nullptr, nullptr, 0, &cout, 1, s);
 }

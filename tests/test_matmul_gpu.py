@@ -160,6 +160,26 @@ def test_cta_pair_kernel_layouts_batches_and_epilogue(dev, precision):
     H.assert_close(got, oracle.gelu(oracle.float_add(plain, bias)), H.REL_ELEMWISE, 2e-7, "pair epilogue")
 
 
+@pytest.mark.parametrize("precision", [abi.MM_F32X3, abi.MM_TF32, abi.MM_BF16])
+def test_split_k_long_contractions(dev, precision):
+    """Few output tiles, long K: the launcher splits K across CTAs / CTA pairs into workspace partials
+    and combines them with the deterministic column reduce (weight-gradient shapes, xᵀ·g)."""
+    for (m, n, k) in ((1024, 1024, 8192), (256, 384, 4100), (130, 70, 4096)):
+        a, b = rnd((m, k), 41), rnd((k, n), 42)
+        check(ops.float_matmul(H.up(a), H.up(b), precision).numpy(), a, b, precision, f"split-K NN {m}x{n}x{k}")
+    m, n, k = 512, 768, 4096                     # dW = xᵀ·g: both operands MN-major views
+    x, g = rnd((k, m), 43), rnd((k, n), 44)
+    got = ops.float_matmul(H.up(x).swap_dims(0, 1), H.up(g), precision).numpy()
+    check(got, np.ascontiguousarray(x.T), g, precision, "split-K TN")
+    a3, b3 = rnd((2, 200, 4096), 45), rnd((2, 4096, 300), 46)
+    check(ops.float_matmul(H.up(a3), H.up(b3), precision).numpy(), a3, b3, precision, "split-K batched")
+    # determinism: the combine has a fixed order
+    a, b = rnd((1024, 8192), 47), rnd((8192, 1024), 48)
+    r1 = ops.float_matmul(H.up(a), H.up(b), precision).numpy()
+    r2 = ops.float_matmul(H.up(a), H.up(b), precision).numpy()
+    assert np.array_equal(r1, r2)
+
+
 def test_inner_dim_mismatch_is_an_error(dev):
     with pytest.raises(ops.ShapeError):
         ops.float_matmul(H.up(rnd((4, 5), 0)), H.up(rnd((6, 7), 0)))
