@@ -28,12 +28,12 @@ namespace b200 {
 namespace mm {
 
 constexpr int BM = 128, BN = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;            // TMA warp, MMA warp, 8 epilogue warps (4 of them fast-epilogue only)
 constexpr int kAccStages = 2;
 constexpr int kMaxBatchDims = 3;
 constexpr int kEpiBlock = 128, kEpiU = 4;  // epilogue tape geometry: 16 columns per dispatch
 constexpr int kMaxFastSteps = 6;
-constexpr int kOutStageBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x [32 rows x 128 B]
+constexpr int kOutStageBytes = 8 * 4096;  // 8 epilogue warps x one [32 rows x 128 B] staging buffer
 
 struct Params {
   CUtensorMap tma_a, tma_b;
@@ -389,7 +389,7 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4 * CTAS);  // one arrive per epilogue warp (of both CTAs in a pair)
+      mbar_init(&acc_empty[s], (P.epi_fast ? 8 : 4) * CTAS);  // one arrive per working epilogue warp (of both CTAs in a pair)
     }
     fence_barrier_init();
   }
@@ -397,7 +397,7 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
     if constexpr (PAIR) tmem_alloc_pair(tmem_slot, kAccStages * TN);
     else tmem_alloc(tmem_slot, kAccStages * TN);
   }
-  if (P.has_epilogue && !P.epi_fast && warp >= 2) {
+  if (P.has_epilogue && !P.epi_fast && warp >= 2 && warp < 6) {
     SlotFile<4, kEpiU, kEpiBlock> slots;
     slots.smem = epi_smem;
     slots.tid = threadIdx.x - 64;
@@ -519,14 +519,17 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
       __syncwarp();
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp >= 2) {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+  } else if (warp >= 2 && (P.epi_fast || warp < 6)) {
+    // ===================== epilogue (warps 2..9; 6..9 only help the fast epilogue) =====================
+    // a warp may only touch TMEM lanes 32*(warp%4)..+31: warps w and w+4 share a quarter and take
+    // alternate 32-column chunks of it
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     SlotFile<4, kEpiU, kEpiBlock> slots;
     slots.smem = epi_smem;
     slots.tid = threadIdx.x - 64;
-    int acc = 0, sbuf = 0;
+    int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = worker; tile < n_tiles; tile += n_workers) {
       int m_blk, n_blk, b[kMaxBatchDims];
@@ -542,18 +545,16 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
         // 32 columns per pass: TMEM → registers → op chain → 128B-swizzled smem → TMA store (full
         // 128-byte lines, rows/columns past M/N clipped by the tensor map)
         const int m_warp = (m_blk * CTAS + cta_rank) * BM + quarter * 32;
-        uint8_t *wbuf = out_stage + (warp - 2) * 8192;
+        uint8_t *buf = out_stage + (warp - 2) * 4096;
 #pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 32) {
+        for (int c0 = half * 32; c0 < TN; c0 += 64) {
           const int n0 = n_blk * TN + c0;
           if (n0 >= P.N || m_warp >= P.M) break;
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
           tmem_ld_wait();
           if (P.n_steps) epi_apply(P, T, batch_lin, m, n0, m < P.M, r);
-          uint8_t *buf = wbuf + sbuf * 4096;
-          sbuf ^= 1;
-          if (lane == 0) bulk_wait_read<1>();          // the store that last read this buffer is done with it
+          if (lane == 0) bulk_wait_read<0>();          // the previous store has finished reading the buffer
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 8; ++q)

@@ -32,6 +32,7 @@ struct SoftmaxBwd {
   int64_t y_stride, dy_stride, dx_stride, mask_stride;
   uint32_t rows, R, mask_rows;
   float div;
+  float mul;                 // 1/div when that is exact (div a power of two): x*mul == x/div bit for bit; else 0
 };
 
 struct LayerNormBwd {
@@ -90,7 +91,9 @@ __global__ void __launch_bounds__(kBlock) softmax_bwd_warp_kernel(const SoftmaxB
       float4 o;
       o.x = __fmul_rn(__fsub_rn(g[k].x, dot), y[k].x); o.y = __fmul_rn(__fsub_rn(g[k].y, dot), y[k].y);
       o.z = __fmul_rn(__fsub_rn(g[k].z, dot), y[k].z); o.w = __fmul_rn(__fsub_rn(g[k].w, dot), y[k].w);
-      if (P.div != 1.0f) {
+      if (P.mul != 0.0f) {
+        o.x = __fmul_rn(o.x, P.mul); o.y = __fmul_rn(o.y, P.mul); o.z = __fmul_rn(o.z, P.mul); o.w = __fmul_rn(o.w, P.mul);
+      } else if (P.div != 1.0f) {
         o.x = __fdiv_rn(o.x, P.div); o.y = __fdiv_rn(o.y, P.div); o.z = __fdiv_rn(o.z, P.div); o.w = __fdiv_rn(o.w, P.div);
       }
       if (mr) {
@@ -294,6 +297,11 @@ extern "C" int32_t b200_launch_softmax_backward(const b200_tensor *y, const b200
   P.dy = reinterpret_cast<const float *>(dy->ptr);
   P.dx = reinterpret_cast<float *>(dx->ptr);
   P.div = (float)div;
+  {
+    int e = 0;
+    const float m = frexpf(fabsf(P.div), &e);           // power of two with a normal reciprocal
+    P.mul = (m == 0.5f && e > -120 && e < 120 && P.div != 1.0f) ? 1.0f / P.div : 0.0f;
+  }
   bool mask_vec = true;
   if (mask) {
     // [..., Sq, R] with every leading dim of size 1 (broadcast over the batch), or the full shape

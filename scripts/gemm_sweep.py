@@ -52,6 +52,25 @@ def case(batch, m, n, k, prec, layout="NT", check=True):
     name = {abi.MM_TF32: "tf32", abi.MM_BF16: "bf16", abi.MM_F32X3: "f32x3"}[prec]
     print(f"{name:5s} {layout} b{batch:<3d} {m:6d}x{n:6d}x{k:6d}  {ms:9.4f} ms  {tf:8.1f} TF/s  relerr {err:.2e}", flush=True)
 
+def epi_case(m, n, k, prec):
+    """configs[2]: fused bias + GELU epilogue, timed against the plain GEMM of the same shape."""
+    from burn_b200.device import TapeBuilder
+    rng = np.random.default_rng(7)
+    a = rng.uniform(-0.5, 0.5, (m, k)).astype(np.float32); b = rng.uniform(-0.5, 0.5, (n, k)).astype(np.float32)
+    bias = rng.uniform(-0.5, 0.5, (1, n)).astype(np.float32)
+    bf = prec == abi.MM_BF16
+    mk = (lambda x: DeviceTensor.from_bf16_of(x)) if bf else H.up
+    da, db, dbias = mk(a), mk(b).swap_dims(0, 1), H.up(bias)
+    out = DeviceTensor.empty((m, n))
+    tb = TapeBuilder().op("ADD_F", ("in", 0), ("in", 1), tmp=0)
+    H.gelu_tape(tb, ("tmp", 0), out=0)
+    tape = tb.build()
+    ad, bd, cd, ed = da.desc(), db.desc(), out.desc(), dbias.desc()
+    fn = lambda: abi.check(lib.b200_launch_matmul(C.byref(ad), C.byref(bd), C.byref(cd), prec, C.byref(tape), C.byref(ed), 1, None, 0, None))
+    ms = timed(fn, 5 if quick else 20)
+    name = {abi.MM_TF32: "tf32", abi.MM_BF16: "bf16"}[prec]
+    print(f"{name:5s} NT +bias+gelu epilogue {m:6d}x{n:6d}x{k:6d}  {ms:9.4f} ms  {2.0*m*n*k/(ms*1e-3)/1e12:8.1f} TF/s", flush=True)
+
 shapes = [(1, 256, 256, 256), (1, 384, 640, 200), (1, 1024, 1024, 1024), (1, 4096, 4096, 4096), (1, 8192, 8192, 8192)]
 if not quick:
     shapes += [(1, 2048, 2048, 2048), (1, 16384, 16384, 16384), (64, 2048, 2048, 2048), (1, 8192, 1024, 1024), (1, 8192, 4096, 1024), (1, 8192, 1024, 4096), (1, 1024, 4096, 8192)]
@@ -63,5 +82,10 @@ for prec in (abi.MM_BF16, abi.MM_TF32):
 for lay in ("NN", "TN", "TT"):
     case(1, 4096, 4096, 4096, abi.MM_TF32, lay)
     case(1, 4096, 4096, 4096, abi.MM_BF16, lay)
+for prec in (abi.MM_BF16, abi.MM_TF32):
+    epi_case(4096, 4096, 4096, prec)
+    if not quick:
+        epi_case(8192, 8192, 8192, prec)
 if not quick:
     case(1, 4096, 4096, 4096, abi.MM_F32X3, "NN")
+    case(1, 8192, 8192, 8192, abi.MM_F32X3, "NN", check=False)
