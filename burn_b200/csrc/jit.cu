@@ -68,16 +68,32 @@ static bool dtype_in_ok(int32_t dt) { return dt == B200_F32 || dt == B200_I32 ||
 static bool dtype_out_ok(int32_t dt) { return dt == B200_F32 || dt == B200_I32 || dt == B200_BOOL || dt == B200_U8; }
 
 // Generates the kernel source for a compiled tape over linear operands.
+struct Tuning {
+  int u, block, ctas_per_sm;
+};
+static const Tuning &tuning() {
+  static const Tuning t = [] {
+    auto env = [](const char *name, int dflt) { const char *e = std::getenv(name); return e ? atoi(e) : dflt; };
+    Tuning x{env("B200_JIT_U", 2), env("B200_JIT_BLOCK", 256), env("B200_JIT_CTAS_PER_SM", 8)};
+    if (x.u < 1 || x.u > 8) x.u = 2;
+    if (x.block != 128 && x.block != 256 && x.block != 512) x.block = 256;
+    if (x.ctas_per_sm < 1 || x.ctas_per_sm > 32) x.ctas_per_sm = 8;
+    return x;
+  }();
+  return t;
+}
+
 static std::string generate(const CompiledTape &ct, const TapeParams &p) {
   std::string s;
+  const std::string BLK = std::to_string(tuning().block) + "u";
   s += "#include \"burn_b200.h\"\n#include \"tape_eval.cuh\"\nusing namespace b200;\n";
-  s += "extern \"C\" __global__ void __launch_bounds__(256) b200_jit_kernel(const JitParams P) {\n";
-  s += "  constexpr int U = 2;\n  const uint32_t stride = gridDim.x * 256u;\n";
+  s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(tuning().block) + ") b200_jit_kernel(const JitParams P) {\n";
+  s += "  constexpr int U = " + std::to_string(tuning().u) + ";\n  const uint32_t stride = gridDim.x * " + BLK + ";\n";
   for (size_t k = 0; k < ct.scalars.size(); ++k) s += "  const uint32_t S" + std::to_string(k) + " = P.scalars[" + std::to_string(k) + "];\n";
   for (int i = 0; i < ct.n_in; ++i)
     if (p.in[i].mode == kModeBcast)
       s += "  const uint32_t B" + std::to_string(i) + " = jit_ld1<" + std::to_string(p.in[i].dtype) + ">(P.in[" + std::to_string(i) + "]);\n";
-  s += "  for (uint32_t v0 = blockIdx.x * 256u + threadIdx.x; v0 < P.n_vec; v0 += U * stride) {\n";
+  s += "  for (uint32_t v0 = blockIdx.x * " + BLK + " + threadIdx.x; v0 < P.n_vec; v0 += U * stride) {\n";
   for (int i = 0; i < ct.n_in; ++i)
     if (p.in[i].mode == kModeVec) s += "    uint32_t I" + std::to_string(i) + "[U][4];\n";
   s += "#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const uint32_t v = v0 + u * stride;\n      if (v < P.n_vec) {\n";
@@ -178,10 +194,11 @@ int32_t jit_try_elemwise(const CompiledTape &ct, const TapeParams &p, int vec, i
   for (int o = 0; o < ct.n_out; ++o) P.out[o] = p.out[o].ptr;
   for (size_t k = 0; k < ct.scalars.size(); ++k) P.scalars[k] = ct.scalars[k];
   P.n_vec = p.n_vec;
-  const uint32_t per_block = 256u * 2u;
-  const unsigned grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((p.n_vec + per_block - 1) / per_block, (uint32_t)sm_count() * 8u));
+  const uint32_t per_block = (uint32_t)(jit::tuning().block * jit::tuning().u);
+  const unsigned grid = (unsigned)std::max<uint32_t>(1u, std::min<uint32_t>((p.n_vec + per_block - 1) / per_block,
+                                                                           (uint32_t)(sm_count() * jit::tuning().ctas_per_sm)));
   void *args[] = {&P};
-  B200_CUDA(cudaLaunchKernel((const void *)kern, dim3(grid), dim3(256), args, 0, stream));
+  B200_CUDA(cudaLaunchKernel((const void *)kern, dim3(grid), dim3(jit::tuning().block), args, 0, stream));
   count_launch(1);
   return 1;
 }
