@@ -125,7 +125,7 @@ static std::string generate(const CompiledTape &ct, const TapeParams &p) {
   return s;
 }
 
-static cudaKernel_t compile(const std::string &src) {
+static cudaKernel_t compile(const std::string &src, const char *kernel_name = "b200_jit_kernel") {
   nvrtcProgram prog = nullptr;
   const char *hdr_src[] = {kJitSrc_burn_b200_h, kJitSrc_tape_eval_cuh, kJitSrc_tape_math_cuh, kJitSrc_erf_table_inc,
                            kJitSrc_stdint_h, kJitSrc_stdint_h};
@@ -148,7 +148,7 @@ static cudaKernel_t compile(const std::string &src) {
       if (g_rtc.GetCUBIN(prog, &cubin[0]) == 0) {
         cudaLibrary_t lib = nullptr;
         if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess) {
-          if (cudaLibraryGetKernel(&kern, lib, "b200_jit_kernel") != cudaSuccess) kern = nullptr;
+          if (cudaLibraryGetKernel(&kern, lib, kernel_name) != cudaSuccess) kern = nullptr;
         }
         if (!kern) {
           fprintf(stderr, "[burn_b200] loading a specialised kernel failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -160,7 +160,216 @@ static cudaKernel_t compile(const std::string &src) {
   return kern;
 }
 
+// ---- fuse-on-read reductions --------------------------------------------------------------
+// The read tape evaluated per vector, folded locally and combined per CTA; one partial (or, when a
+// row / column is not split, the final value) per CTA and lane.  Split partials are finished by the
+// plain fast reduction, so the combine order is fixed.
+struct RedParams {       // mirrored in the generated source
+  float *out;            // final output or partial buffer
+  uint32_t outer, R, inner4;     // R in elements for columns; rows use r4 = R/4 vectors
+  uint32_t r4, splits, per_split;
+  float div;             // mean divisor applied when the kernel writes final values (0 = none)
+};
+
+static std::string gen_reduce(const CompiledTape &ct, const TapeParams &p, int32_t kind, bool col) {
+  std::string s;
+  s += "#include \"burn_b200.h\"\n#include \"tape_eval.cuh\"\nusing namespace b200;\n";
+  s += "struct RedParams { float *out; uint32_t outer, R, inner4; uint32_t r4, splits, per_split; float div; };\n";
+  const bool is_sum = kind == B200_RED_SUM || kind == B200_RED_MEAN, is_max = kind == B200_RED_MAX;
+  s += std::string("#define IDENT ") + (is_sum ? "0.0f" : (is_max ? "(-INFINITY)" : "INFINITY")) + "\n";
+  if (is_sum) s += "__device__ __forceinline__ float comb(float a, float b) { return __fadd_rn(a, b); }\n";
+  else s += std::string("__device__ __forceinline__ float comb(float a, float b) { return (a != a) ? a : ((b != b) ? b : ") +
+            (is_max ? "fmaxf" : "fminf") + "(a, b)); }\n";
+  // LOAD_EVAL(g, val): the read tape on the 4 elements of vector g
+  s += "#define LOAD_EVAL(g, val) { \\\n";
+  for (int i = 0; i < ct.n_in; ++i)
+    if (p.in[i].mode == kModeVec)
+      s += "  uint32_t I" + std::to_string(i) + "[4]; jit_ld4<" + std::to_string(p.in[i].dtype) + ">(P.in[" + std::to_string(i) + "], g, I" + std::to_string(i) + "); \\\n";
+  s += "  _Pragma(\"unroll\") for (int j = 0; j < 4; ++j) { uint32_t a = 0u; \\\n";
+  for (int t = 0; t < ct.n_tmp; ++t) s += "    uint32_t T" + std::to_string(t) + " = 0u; \\\n";
+  auto arg = [&](const SymArg &x, bool acc_if_none) -> std::string {
+    switch (x.kind) {
+      case 1: return p.in[x.idx].mode == kModeBcast ? "B" + std::to_string(x.idx) : "I" + std::to_string(x.idx) + "[j]";
+      case 2: return "T" + std::to_string(x.idx);
+      case 3: return "S" + std::to_string(x.idx);
+      default: return acc_if_none ? "a" : "0u";
+    }
+  };
+  for (const SymOp &o : ct.ops) {
+    s += "    a = eval_op<" + std::to_string(o.op) + ">(a, " + arg(o.b, o.op == kOpGelu) + ", " + arg(o.c, false) + "); \\\n";
+    if (o.dst_tmp >= 0) s += "    T" + std::to_string(o.dst_tmp) + " = a; \\\n";
+  }
+  s += "    val[j] = f_of(a); } }\n";
+  auto prelude = [&]() {
+    std::string q;
+    for (size_t k = 0; k < ct.scalars.size(); ++k) q += "  const uint32_t S" + std::to_string(k) + " = P.scalars[" + std::to_string(k) + "];\n";
+    for (int i = 0; i < ct.n_in; ++i)
+      if (p.in[i].mode == kModeBcast)
+        q += "  const uint32_t B" + std::to_string(i) + " = jit_ld1<" + std::to_string(p.in[i].dtype) + ">(P.in[" + std::to_string(i) + "]);\n";
+    return q;
+  };
+  if (!col) {
+    // TPR threads per (row, split): 32 (a warp, shuffle only) or 256 (a CTA)
+    s += "template <int TPR> __device__ __forceinline__ void rows(const JitParams &P, const RedParams &Q) {\n" + prelude();
+    s += R"(  __shared__ float scratch[8];
+  const uint32_t lane_in = threadIdx.x % TPR, grp = threadIdx.x / TPR, groups = 256 / TPR;
+  const uint32_t n_work = Q.outer * Q.splits;
+  for (uint32_t w0 = blockIdx.x * groups; w0 < n_work; w0 += gridDim.x * groups) {
+    const uint32_t w = w0 + grp;
+    float acc = IDENT;
+    if (w < n_work) {
+      const uint32_t row = w / Q.splits, split = w - row * Q.splits;
+      const uint32_t begin = split * Q.per_split, end = min(Q.r4, begin + Q.per_split);
+      for (uint32_t i0 = begin + lane_in; i0 < end; i0 += 2 * TPR) {
+        float v0[4], v1[4];
+        const uint32_t i1 = i0 + TPR;
+        LOAD_EVAL(row * Q.r4 + i0, v0)
+        if (i1 < end) { LOAD_EVAL(row * Q.r4 + i1, v1) } else { v1[0] = v1[1] = v1[2] = v1[3] = IDENT; }
+        acc = comb(acc, comb(comb(v0[0], v0[1]), comb(v0[2], v0[3])));
+        acc = comb(acc, comb(comb(v1[0], v1[1]), comb(v1[2], v1[3])));
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc = comb(acc, __shfl_xor_sync(0xffffffffu, acc, m));
+    if (TPR == 256) {
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      acc = (threadIdx.x & 31) < 8 ? scratch[threadIdx.x & 31] : IDENT;
+#pragma unroll
+      for (int m = 4; m >= 1; m >>= 1) acc = comb(acc, __shfl_xor_sync(0xffffffffu, acc, m));
+    }
+    if (lane_in == 0 && w < n_work) Q.out[w] = Q.div != 0.0f ? __fdiv_rn(acc, Q.div) : acc;
+  }
+}
+extern "C" __global__ void __launch_bounds__(256) b200_jit_rows_warp(const JitParams P, const RedParams Q) { rows<32>(P, Q); }
+extern "C" __global__ void __launch_bounds__(256) b200_jit_rows_cta(const JitParams P, const RedParams Q) { rows<256>(P, Q); }
+)";
+  } else {
+    s += "extern \"C\" __global__ void __launch_bounds__(256) b200_jit_cols(const JitParams P, const RedParams Q) {\n" + prelude();
+    s += R"(  // block (32, 8): 32 column vectors x 8 row groups; grid (outer * column tiles, splits)
+  __shared__ float part[8][32][4];
+  const uint32_t tiles = (Q.inner4 + 31) / 32;
+  const uint32_t o = blockIdx.x / tiles, c4 = (blockIdx.x - o * tiles) * 32 + threadIdx.x;
+  const uint32_t r_begin = blockIdx.y * Q.per_split, r_end = min(Q.R, r_begin + Q.per_split);
+  float acc[4] = {IDENT, IDENT, IDENT, IDENT};
+  if (c4 < Q.inner4) {
+    for (uint32_t r = r_begin + threadIdx.y; r < r_end; r += 16) {
+      float v0[4], v1[4];
+      const uint32_t r1 = r + 8;
+      LOAD_EVAL((o * Q.R + r) * Q.inner4 + c4, v0)
+      if (r1 < r_end) { LOAD_EVAL((o * Q.R + r1) * Q.inner4 + c4, v1) } else { v1[0] = v1[1] = v1[2] = v1[3] = IDENT; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = comb(acc[j], comb(v0[j], v1[j]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) part[threadIdx.y][threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && c4 < Q.inner4) {
+    float4 r;
+    float *rr = reinterpret_cast<float *>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float b = part[0][threadIdx.x][j];
+      for (int y = 1; y < 8; ++y) b = comb(b, part[y][threadIdx.x][j]);
+      rr[j] = Q.div != 0.0f ? __fdiv_rn(b, Q.div) : b;
+    }
+    // partials laid out [outer][splits][inner]
+    reinterpret_cast<float4 *>(Q.out)[((size_t)o * gridDim.y + blockIdx.y) * Q.inner4 + c4] = r;
+  }
+}
+)";
+  }
+  return s;
+}
+
 }  // namespace jit
+
+int32_t fast_reduce_f32(int32_t kind, int64_t outer, int64_t R, int64_t inner, const float *in, float *out,
+                        float mean_div, cudaStream_t stream);
+
+// Fuse-on-read reduce over linear operands into a contiguous f32 output.  1 = launched, 0 = not applicable.
+int32_t jit_try_reduce(const CompiledTape &ct, const TapeParams &p, int rank_mode_, int32_t kind, int64_t outer,
+                       int64_t R, int64_t inner, float *out, cudaStream_t stream) {
+  static const bool enabled = [] { const char *e = std::getenv("B200_TAPE_JIT"); return !(e && e[0] == '0'); }();
+  static const uint32_t min_vec = [] {
+    const char *e = std::getenv("B200_TAPE_JIT_MIN_VEC");
+    return e ? (uint32_t)strtoul(e, nullptr, 10) : (1u << 18);
+  }();
+  const bool col = inner > 1;
+  if (!enabled || rank_mode_ != kRankLinear || p.n_vec < min_vec || R < 1) return 0;
+  if (col ? (inner % 4 != 0) : (R % 4 != 0)) return 0;
+  if (outer * R * inner >= (1ll << 32) || ((uintptr_t)out & 15)) return 0;
+  for (int i = 0; i < ct.n_in; ++i) {
+    const OperandDesc &d = p.in[i];
+    if (!jit::dtype_in_ok(d.dtype)) return 0;
+    if (!(d.mode == kModeBcast || (d.mode == kModeVec && d.s3[2] == 1))) return 0;
+  }
+  const int sms = sm_count();
+  jit::RedParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.outer = (uint32_t)outer;
+  Q.R = (uint32_t)R;
+  const char *kname;
+  dim3 grid, block(256);
+  uint32_t splits = 1;
+  if (!col) {
+    Q.r4 = (uint32_t)(R / 4);
+    const bool warp_rows = Q.r4 <= 1024 && outer >= (int64_t)sms * 8;
+    if (!warp_rows && outer < (int64_t)sms * 4 && Q.r4 > 4096)
+      splits = (uint32_t)std::min<int64_t>((sms * 4 + outer - 1) / outer, Q.r4 / 2048);
+    splits = std::max(1u, splits);
+    Q.per_split = ((Q.r4 + splits - 1) / splits + 511) / 512 * 512;
+    splits = (Q.r4 + Q.per_split - 1) / Q.per_split;
+    kname = warp_rows ? "b200_jit_rows_warp" : "b200_jit_rows_cta";
+    const uint64_t work = (uint64_t)outer * splits, per_cta = warp_rows ? 8 : 1;
+    grid = dim3((unsigned)std::max<uint64_t>(1, std::min<uint64_t>((work + per_cta - 1) / per_cta, (uint64_t)sms * 8)));
+  } else {
+    Q.inner4 = (uint32_t)(inner / 4);
+    const uint32_t tiles = (uint32_t)outer * ((Q.inner4 + 31) / 32);
+    while (splits < 64 && tiles * splits < (uint32_t)sms * 4u && R / (splits * 2) >= 64) splits *= 2;
+    Q.per_split = (uint32_t)((R + splits - 1) / splits);
+    splits = (uint32_t)((R + Q.per_split - 1) / Q.per_split);
+    kname = "b200_jit_cols";
+    grid = dim3(tiles, splits);
+    block = dim3(32, 8);
+  }
+  Q.splits = splits;
+  const bool mean = kind == B200_RED_MEAN;
+  Q.div = (splits == 1 && mean) ? (float)R : 0.0f;
+
+  cudaKernel_t kern = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(jit::g_mu);
+    if (!jit::load_nvrtc()) return 0;
+    const std::string src = jit::gen_reduce(ct, p, kind, col);
+    const std::string key = src + "//" + kname;
+    auto it = jit::g_cache.find(key);
+    if (it == jit::g_cache.end()) it = jit::g_cache.emplace(key, jit::compile(src, kname)).first;
+    kern = it->second;
+  }
+  if (!kern) return 0;
+  float *partials = nullptr;
+  if (splits > 1) B200_CUDA(cudaMallocAsync((void **)&partials, (size_t)outer * splits * (col ? inner : 1) * sizeof(float), stream));
+  Q.out = splits > 1 ? partials : out;
+  JitParams P;
+  memset(&P, 0, sizeof(P));
+  for (int i = 0; i < ct.n_in; ++i) P.in[i] = p.in[i].ptr;
+  for (size_t k = 0; k < ct.scalars.size(); ++k) P.scalars[k] = ct.scalars[k];
+  P.n_vec = p.n_vec;
+  void *args[] = {&P, &Q};
+  B200_CUDA(cudaLaunchKernel((const void *)kern, grid, block, args, 0, stream));
+  count_launch(1);
+  int32_t st = 1;
+  if (splits > 1) {
+    // finish: plain reduction over the split axis ([outer, splits, inner]); mean divides by the full R
+    const int32_t fs = fast_reduce_f32(kind, outer, splits, col ? inner : 1, partials, out, mean ? (float)R : 0.0f, stream);
+    cudaFreeAsync(partials, stream);
+    if (fs <= 0) st = fs < 0 ? fs : fail(B200_ERR_UNSUPPORTED, "no fast path to finish %u reduce partials", splits);
+  }
+  return st;
+}
 
 // Returns 1 when the launch ran on a specialised kernel, 0 when the caller should use the interpreter.
 int32_t jit_try_elemwise(const CompiledTape &ct, const TapeParams &p, int vec, int rank_mode_, cudaStream_t stream) {

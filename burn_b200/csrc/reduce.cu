@@ -540,7 +540,7 @@ static int32_t launch_fast(bool col, const fast::RowParams &rp, const fast::ColP
 // Returns 1 when the reduction was launched on a fast path, 0 when the caller must
 // use the general tape path, < 0 on error.
 static int32_t try_fast_reduce(int32_t kind, int64_t outer, int64_t R, int64_t inner, const b200_tensor &in,
-                               const b200_tensor &out, cudaStream_t stream) {
+                               const b200_tensor &out, cudaStream_t stream, float mean_div = 0.0f) {
   int K;
   switch (kind) {
     case B200_RED_SUM: case B200_RED_MEAN: K = fast::kSum; break;
@@ -571,7 +571,7 @@ static int32_t try_fast_reduce(int32_t kind, int64_t outer, int64_t R, int64_t i
     rp.n_rows = (uint32_t)outer;
     rp.r4 = (uint32_t)(R / 4);
     rp.mean = kind == B200_RED_MEAN;
-    rp.div = (float)R;
+    rp.div = mean_div != 0.0f ? mean_div : (float)R;
     rp.splits = 1;
     rp.per_split = rp.r4;
     warp_rows = rp.r4 <= 1024 && rp.n_rows >= (uint32_t)(sms * fast::kWarpsPerBlock);
@@ -607,7 +607,7 @@ static int32_t try_fast_reduce(int32_t kind, int64_t outer, int64_t R, int64_t i
     cp.R = (uint32_t)R;
     cp.inner4 = (uint32_t)(inner / 4);
     cp.mean = kind == B200_RED_MEAN;
-    cp.div = (float)R;
+    cp.div = mean_div != 0.0f ? mean_div : (float)R;
     uint32_t tx = 32;
     while (tx > 8 && cp.outer * ((cp.inner4 + tx - 1) / tx) * 8u < (uint32_t)sms * 2u && cp.R >= 1024u) tx /= 2;
     cp.tx = tx;
@@ -630,6 +630,25 @@ static int32_t try_fast_reduce(int32_t kind, int64_t outer, int64_t R, int64_t i
   return st == B200_OK ? 1 : st;
 }
 
+
+// Plain contiguous f32 reduction [outer, R, inner] -> [outer, inner] on the fast kernels (used by
+// jit.cu to finish split partials).  kind MEAN divides by `mean_div` instead of R when given.
+int32_t fast_reduce_f32(int32_t kind, int64_t outer, int64_t R, int64_t inner, const float *in, float *out,
+                        float mean_div, cudaStream_t stream) {
+  b200_tensor ti, to;
+  memset(&ti, 0, sizeof(ti));
+  memset(&to, 0, sizeof(to));
+  ti.ptr = const_cast<float *>(in);
+  to.ptr = out;
+  ti.dtype = to.dtype = B200_F32;
+  ti.rank = to.rank = 3;
+  ti.shape[0] = to.shape[0] = outer; ti.shape[1] = R; to.shape[1] = 1; ti.shape[2] = to.shape[2] = inner;
+  ti.strides[2] = to.strides[2] = 1; ti.strides[1] = inner; to.strides[1] = inner;
+  ti.strides[0] = R * inner; to.strides[0] = inner;
+  return try_fast_reduce(kind, outer, R, inner, ti, to, stream, mean_div);
+}
+int32_t jit_try_reduce(const CompiledTape &ct, const TapeParams &p, int rank_mode_, int32_t kind, int64_t outer,
+                       int64_t R, int64_t inner, float *out, cudaStream_t stream);
 
 // Core entry: the input shape is `shape` (rank dims); dims [ax_begin, ax_end) are
 // reduced together (ax_end - ax_begin == 1 for an axis reduce; the whole range
@@ -717,6 +736,13 @@ static int32_t reduce_impl(int32_t kind, int rank, const int64_t *shape, int ax_
 
   cudaStream_t stream = resolve_stream(s);
   const int sms = sm_count();
+  // large fuse-on-read sum/mean/max/min over linear operands into a plain f32 output: a kernel
+  // specialised from the read tape (jit.cu) does tape + local reduce; everything else: interpreter
+  if (write == &default_write && vec == 4 && !value_is_int && outputs[0].dtype == B200_F32 && is_contiguous(outputs[0]) &&
+      (kind == B200_RED_SUM || kind == B200_RED_MEAN || kind == B200_RED_MAX || kind == B200_RED_MIN)) {
+    const int32_t js = jit_try_reduce(rd_ct, P.rd, rm, kind, outer, R, inner, reinterpret_cast<float *>(outputs[0].ptr), stream);
+    if (js != 0) return js < 0 ? js : B200_OK;
+  }
   const int U = (vec == 4) ? 2 : 4;
   st = finalize_tape(rd_ct, U, kRedBlock, 1, P.rd);
   if (st != B200_OK) return st;

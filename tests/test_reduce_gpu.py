@@ -215,3 +215,27 @@ def test_full_size_reductions(dev):
     assert abs(total - ref) <= 1e-5 * np.abs(x).sum(dtype=np.float64)
     assert abs(float(r1.astype(np.float64).sum()) - ref) <= 1e-5 * np.abs(x).sum(dtype=np.float64)
     assert abs(float(r0.astype(np.float64).sum()) - ref) <= 1e-5 * np.abs(x).sum(dtype=np.float64)
+
+
+@pytest.mark.parametrize("shape,axis", [((4096, 1024), 1), ((512, 8192), 1), ((8, 262144), 1), ((2048, 2048), 0),
+                                        ((16, 4096, 64), 1), ((3, 1000, 1024), 2)])
+@pytest.mark.parametrize("kind", ["sum", "mean", "max", "min"])
+def test_large_fuse_on_read_reductions(dev, shape, axis, kind):
+    """Sizes above the specialisation threshold (NVRTC kernels from the read tape, jit.cu): rows as a warp,
+    as a CTA, split across CTAs, and columns — reduce(gelu(a*b) * 0.5, axis) against the oracle chain."""
+    a, b = rnd(shape, seed=11), rnd(shape, seed=12)
+    tb = TapeBuilder().op("MUL_F", ("in", 0), ("in", 1), tmp=0)
+    H.gelu_tape(tb, ("tmp", 0))
+    tb.op("MUL_F", "acc", ("in", 2))
+    half = DeviceTensor.from_numpy(np.float32([0.5])).reshape((1,) * len(shape)).expand(shape)   # broadcast operand
+    keep = list(shape)
+    keep[axis] = 1
+    out = DeviceTensor.empty(keep)
+    code = {"sum": abi.RED_SUM, "mean": abi.RED_MEAN, "max": abi.RED_MAX, "min": abi.RED_MIN}[kind]
+    dv.launch_reduce(code, axis, shape, [H.up(a), H.up(b), half], [out], read=tb.build())
+    y = oracle.float_mul_scalar(oracle.gelu(oracle.float_mul(a, b)), 0.5)
+    want = {"sum": oracle.float_sum_dim, "mean": oracle.float_mean_dim, "max": oracle.float_max_dim,
+            "min": oracle.float_min_dim}[kind](y, axis)
+    n = shape[axis]
+    abs_tol = {"sum": 2e-7 * n, "mean": 2e-7, "max": 2e-7, "min": 2e-7}[kind]     # erf 1-ulp allowance per element
+    H.assert_close(out.numpy(), want, H.REL_REDUCE, abs_tol, f"fused {kind} over axis {axis} of {shape}")
