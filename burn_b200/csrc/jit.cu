@@ -83,44 +83,66 @@ static const Tuning &tuning() {
   return t;
 }
 
-static std::string generate(const CompiledTape &ct, const TapeParams &p) {
+// Generates the kernel source for a compiled tape.  rank3 == false: every operand is contiguous over the
+// (collapsed, 1-D) iteration space or one broadcast element.  rank3 == true: collapsed rank <= 3 with
+// per-operand strides (broadcast rows / columns, strided views); the shape and strides are baked into
+// the source as literals so the index arithmetic strength-reduces (the kernel is shape-specialised,
+// like every kernel the reference JIT-compiles).
+static std::string generate(const CompiledTape &ct, const TapeParams &p, bool rank3) {
   std::string s;
   const std::string BLK = std::to_string(tuning().block) + "u";
+  auto N = [](long long x) { return std::to_string(x); };
   s += "#include \"burn_b200.h\"\n#include \"tape_eval.cuh\"\nusing namespace b200;\n";
-  s += "extern \"C\" __global__ void __launch_bounds__(" + std::to_string(tuning().block) + ") b200_jit_kernel(const JitParams P) {\n";
-  s += "  constexpr int U = " + std::to_string(tuning().u) + ";\n  const uint32_t stride = gridDim.x * " + BLK + ";\n";
-  for (size_t k = 0; k < ct.scalars.size(); ++k) s += "  const uint32_t S" + std::to_string(k) + " = P.scalars[" + std::to_string(k) + "];\n";
+  s += "extern \"C\" __global__ void __launch_bounds__(" + N(tuning().block) + ") b200_jit_kernel(const JitParams P) {\n";
+  s += "  constexpr int U = " + N(tuning().u) + ";\n  const uint32_t stride = gridDim.x * " + BLK + ";\n";
+  if (rank3) s += "  constexpr uint32_t SH1 = " + N(p.shape[1]) + "u, SH2V = " + N(p.shape[2] / 4) + "u;\n";
+  for (size_t k = 0; k < ct.scalars.size(); ++k) s += "  const uint32_t S" + N(k) + " = P.scalars[" + N(k) + "];\n";
+  auto row_varying = [&](const OperandDesc &d) { return rank3 && (d.s3[0] != 0 || d.s3[1] != 0); };
   for (int i = 0; i < ct.n_in; ++i)
-    if (p.in[i].mode == kModeBcast)
-      s += "  const uint32_t B" + std::to_string(i) + " = jit_ld1<" + std::to_string(p.in[i].dtype) + ">(P.in[" + std::to_string(i) + "]);\n";
+    if (p.in[i].mode == kModeBcast && !row_varying(p.in[i]))
+      s += "  const uint32_t B" + N(i) + " = jit_ld1<" + N(p.in[i].dtype) + ">(P.in[" + N(i) + "]);\n";
   s += "  for (uint32_t v0 = blockIdx.x * " + BLK + " + threadIdx.x; v0 < P.n_vec; v0 += U * stride) {\n";
-  for (int i = 0; i < ct.n_in; ++i)
-    if (p.in[i].mode == kModeVec) s += "    uint32_t I" + std::to_string(i) + "[U][4];\n";
-  s += "#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const uint32_t v = v0 + u * stride;\n      if (v < P.n_vec) {\n";
-  for (int i = 0; i < ct.n_in; ++i)
+  for (int i = 0; i < ct.n_in; ++i) {
+    if (p.in[i].mode == kModeVec) s += "    uint32_t I" + N(i) + "[U][4];\n";
+    else if (row_varying(p.in[i])) s += "    uint32_t R" + N(i) + "[U];\n";
+  }
+  // vector offset of operand d at the current coordinates
+  auto voff = [&](const OperandDesc &d) -> std::string {
+    if (!rank3) return "v";
+    return "(c0 * " + N(d.s3[0] / 4) + "u + c1 * " + N(d.s3[1] / 4) + "u + c2v)";
+  };
+  const std::string coords = rank3 ? "        const uint32_t c2v = v % SH2V, t_ = v / SH2V, c1 = t_ % SH1, c0 = t_ / SH1;\n" : "";
+  s += "#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const uint32_t v = v0 + u * stride;\n      if (v < P.n_vec) {\n" + coords;
+  for (int i = 0; i < ct.n_in; ++i) {
     if (p.in[i].mode == kModeVec)
-      s += "        jit_ld4<" + std::to_string(p.in[i].dtype) + ">(P.in[" + std::to_string(i) + "], v, I" + std::to_string(i) + "[u]);\n";
+      s += "        jit_ld4<" + N(p.in[i].dtype) + ">(P.in[" + N(i) + "], " + voff(p.in[i]) + ", I" + N(i) + "[u]);\n";
+    else if (row_varying(p.in[i]))
+      s += "        R" + N(i) + "[u] = jit_ld1_at<" + N(p.in[i].dtype) + ">(P.in[" + N(i) + "], c0 * " + N(p.in[i].s3[0]) + "u + c1 * " +
+           N(p.in[i].s3[1]) + "u);\n";
+  }
   s += "      }\n    }\n";
-  s += "#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const uint32_t v = v0 + u * stride;\n      if (v < P.n_vec) {\n";
-  for (int o = 0; o < ct.n_out; ++o) s += "        uint32_t O" + std::to_string(o) + "[4];\n";
+  s += "#pragma unroll\n    for (int u = 0; u < U; ++u) {\n      const uint32_t v = v0 + u * stride;\n      if (v < P.n_vec) {\n" + coords;
+  for (int o = 0; o < ct.n_out; ++o) s += "        uint32_t O" + N(o) + "[4];\n";
   s += "#pragma unroll\n        for (int j = 0; j < 4; ++j) {\n          uint32_t a = 0u;\n";
-  for (int t = 0; t < ct.n_tmp; ++t) s += "          uint32_t T" + std::to_string(t) + " = 0u;\n";
+  for (int t = 0; t < ct.n_tmp; ++t) s += "          uint32_t T" + N(t) + " = 0u;\n";
   auto arg = [&](const SymArg &x, bool acc_if_none) -> std::string {
     switch (x.kind) {
-      case 1: return p.in[x.idx].mode == kModeBcast ? "B" + std::to_string(x.idx) : "I" + std::to_string(x.idx) + "[u][j]";
-      case 2: return "T" + std::to_string(x.idx);
-      case 3: return "S" + std::to_string(x.idx);
+      case 1:
+        if (p.in[x.idx].mode == kModeVec) return "I" + N(x.idx) + "[u][j]";
+        return row_varying(p.in[x.idx]) ? "R" + N(x.idx) + "[u]" : "B" + N(x.idx);
+      case 2: return "T" + N(x.idx);
+      case 3: return "S" + N(x.idx);
       default: return acc_if_none ? "a" : "0u";
     }
   };
   for (const SymOp &o : ct.ops) {
-    s += "          a = eval_op<" + std::to_string(o.op) + ">(a, " + arg(o.b, o.op == kOpGelu) + ", " + arg(o.c, false) + ");\n";
-    if (o.dst_tmp >= 0) s += "          T" + std::to_string(o.dst_tmp) + " = a;\n";
-    if (o.dst_out >= 0) s += "          O" + std::to_string(o.dst_out) + "[j] = a;\n";
+    s += "          a = eval_op<" + N(o.op) + ">(a, " + arg(o.b, o.op == kOpGelu) + ", " + arg(o.c, false) + ");\n";
+    if (o.dst_tmp >= 0) s += "          T" + N(o.dst_tmp) + " = a;\n";
+    if (o.dst_out >= 0) s += "          O" + N(o.dst_out) + "[j] = a;\n";
   }
   s += "        }\n";
   for (int o = 0; o < ct.n_out; ++o)
-    s += "        jit_st4<" + std::to_string(p.out[o].dtype) + ">(P.out[" + std::to_string(o) + "], v, O" + std::to_string(o) + ");\n";
+    s += "        jit_st4<" + N(p.out[o].dtype) + ">(P.out[" + N(o) + "], " + voff(p.out[o]) + ", O" + N(o) + ");\n";
   s += "      }\n    }\n  }\n}\n";
   return s;
 }
@@ -378,20 +400,27 @@ int32_t jit_try_elemwise(const CompiledTape &ct, const TapeParams &p, int vec, i
     const char *e = std::getenv("B200_TAPE_JIT_MIN_VEC");
     return e ? (uint32_t)strtoul(e, nullptr, 10) : (1u << 18);
   }();
-  if (!enabled || vec != 4 || rank_mode_ != kRankLinear || p.n_vec < min_vec) return 0;
+  if (!enabled || vec != 4 || (rank_mode_ != kRankLinear && rank_mode_ != kRank3) || p.n_vec < min_vec) return 0;
+  const bool rank3 = rank_mode_ == kRank3;
+  auto strides_ok = [&](const OperandDesc &d, bool is_vec) {
+    if (d.s3[0] < 0 || d.s3[1] < 0) return false;
+    return !is_vec || !rank3 || (d.s3[0] % 4 == 0 && d.s3[1] % 4 == 0);
+  };
   for (int i = 0; i < ct.n_in; ++i) {
     const OperandDesc &d = p.in[i];
     if (!jit::dtype_in_ok(d.dtype)) return 0;
     if (!(d.mode == kModeBcast || (d.mode == kModeVec && d.s3[2] == 1))) return 0;
+    if (!strides_ok(d, d.mode == kModeVec)) return 0;
   }
   for (int o = 0; o < ct.n_out; ++o)
-    if (!jit::dtype_out_ok(p.out[o].dtype) || p.out[o].mode != kModeVec || p.out[o].s3[2] != 1) return 0;
+    if (!jit::dtype_out_ok(p.out[o].dtype) || p.out[o].mode != kModeVec || p.out[o].s3[2] != 1 || !strides_ok(p.out[o], true))
+      return 0;
 
   cudaKernel_t kern = nullptr;
   {
     std::lock_guard<std::mutex> lock(jit::g_mu);
     if (!jit::load_nvrtc()) return 0;
-    const std::string src = jit::generate(ct, p);
+    const std::string src = jit::generate(ct, p, rank3);
     auto it = jit::g_cache.find(src);
     if (it == jit::g_cache.end()) it = jit::g_cache.emplace(src, jit::compile(src)).first;
     kern = it->second;

@@ -131,6 +131,12 @@ __device__ __forceinline__ uint32_t jit_ld1(const void *base) {
   return (uint32_t)__ldg(reinterpret_cast<const unsigned char *>(base));
 }
 template <int DT>
+__device__ __forceinline__ uint32_t jit_ld1_at(const void *base, uint32_t off) {
+  if (DT == B200_F32 || DT == B200_I32) return __ldg(reinterpret_cast<const uint32_t *>(base) + off);
+  if (DT == B200_BF16) return (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(base) + off) << 16;
+  return (uint32_t)__ldg(reinterpret_cast<const unsigned char *>(base) + off);
+}
+template <int DT>
 __device__ __forceinline__ void jit_st4(void *base, uint32_t v, const uint32_t (&r)[4]) {
   if (DT == B200_F32 || DT == B200_I32) {
     __stcs(reinterpret_cast<uint4 *>(base) + v, make_uint4(r[0], r[1], r[2], r[3]));

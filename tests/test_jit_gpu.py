@@ -60,6 +60,24 @@ run(TapeBuilder().op("I2F", ("in", 0), out=0), [dia])
 run(TapeBuilder().op("B2F", ("in", 0), out=0), [dm])
 tb = TapeBuilder(); tb.op("MUL_F", ("in", 0), ("in", 1), tmp=0, out=1); tb.op("ADD_F", ("tmp", 0), ("in", 2)); tb.op("EXP_F", "acc", out=0)
 run(tb, [da, db, H.up(np.float32([0.25]).reshape(1)).expand((n,))], n_out=2, dts=(abi.F32, abi.F32))
+# rank-3 specialisation: row / column broadcasts, a sliced (row-strided) operand and a strided output
+R, Cc = 2048, 1024
+x2 = rng.uniform(-2, 2, (R, Cc)).astype(np.float32); rowv = rng.uniform(-2, 2, (1, Cc)).astype(np.float32)
+colv = rng.uniform(0.5, 2, (R, 1)).astype(np.float32); wide = rng.uniform(-2, 2, (R, 2 * Cc)).astype(np.float32)
+m2 = rng.random((1, Cc)) < 0.4
+dx2, drow, dcol, dwide, dm2 = (H.up(t) for t in (x2, rowv, colv, wide, m2))
+def run2(tb, ins, out=None):
+    out = out if out is not None else DeviceTensor.empty((R, Cc))
+    dv.launch_elemwise(tb.build(), ins, [out], (R, Cc))
+    names = "+".join(k for o in tb.ops for k, v in abi.OP.items() if v == o[0])
+    print("CASE", case[0], "r3:" + names, hashlib.sha256(out.numpy().tobytes()).hexdigest()[:16])
+    case[0] += 1
+tb = TapeBuilder().op("ADD_F", ("in", 0), ("in", 1)); tb.op("DIV_F", "acc", ("in", 2)); tb.op("SELECT", "acc", ("f", -1.0), ("in", 3), out=0)
+run2(tb, [dx2, drow.expand((R, Cc)), dcol.expand((R, Cc)), dm2.expand((R, Cc))])
+tb = TapeBuilder().op("MUL_F", ("in", 0), ("in", 1), tmp=0); H.gelu_tape(tb, ("tmp", 0), out=0)
+run2(tb, [dwide.slice([(0, R), (Cc, 2 * Cc)]), dx2])
+big = DeviceTensor.empty((R, 2 * Cc))
+run2(TapeBuilder().op("SUB_F", ("in", 0), ("in", 1), out=0), [dx2, dcol.expand((R, Cc))], out=big.slice([(0, R), (0, Cc)]))
 print("DONE")
 '''
 
