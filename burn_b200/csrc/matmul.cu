@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include "tape_host.cuh"
+#include "tcgen05.cuh"
 
 namespace b200 {
 namespace mm {
@@ -30,7 +31,6 @@ namespace mm {
 constexpr int BM = 128, BN = 128;
 constexpr int kThreads = 320;            // TMA warp, MMA warp, 8 epilogue warps (4 of them fast-epilogue only)
 constexpr int kAccStages = 2;
-constexpr int kMaxBatchDims = 3;
 constexpr int kEpiBlock = 128, kEpiU = 4;  // epilogue tape geometry: 16 columns per dispatch
 constexpr int kMaxFastSteps = 6;
 constexpr int kOutStageBytes = 8 * 4096;  // 8 epilogue warps x one [32 rows x 128 B] staging buffer
@@ -59,172 +59,6 @@ struct Params {
     uint32_t c_bits;
   } steps[kMaxFastSteps];
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
-                                            int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-template <bool BF16>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  if constexpr (BF16) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-        : "memory");
-  }
-}
-// ---- CTA-pair (cta_group::2) variants.  The shared::cluster address of a CTA-local object carries the
-// CTA rank in bit 24; clearing it addresses the same object in the pair's leader (even-ranked) CTA.
-constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// arrive on the LEADER CTA's copy of `bar` (no-op mask when executed by the leader itself)
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask)
-               : "memory");
-}
-// TMA load into this CTA's smem whose bytes are accounted on the leader CTA's mbarrier
-__device__ __forceinline__ void tma_load_5d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
-                                                 int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// commit: arrive on `bar` in BOTH CTAs of the pair when the MMAs issued so far retire
-__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"((uint16_t)3)
-      : "memory");
-}
-template <bool BF16>
-__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  if constexpr (BF16) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2, int c3,
-                                             int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // One operand of a fast-epilogue step for the 32 columns [n0, n0+32) of row m.
 __device__ __forceinline__ void epi_fetch(const TapeParams &T, int kind, int idx, uint32_t bits, int batch_lin, int m,
@@ -317,29 +151,6 @@ __device__ __forceinline__ void epi_apply(const Params &P, const TapeParams &T, 
     }
 #undef B200_EPI_BIN
   }
-}
-
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-// Shared-memory matrix descriptor (sm_100 format, version 1).  layout: 2 = SWIZZLE_128B (16-byte
-// swizzle atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms — what MN-major 32-bit operands need;
-// the TMA side is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout = 2) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)layout << 61;
-  return d;
 }
 
 // ------------------------------------------------------------------ kernel
@@ -697,76 +508,6 @@ __global__ void split3_kernel(const float *src, int64_t s_row, int64_t s_k, Spli
 }  // namespace mm
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// One GEMM operand as the kernel sees it: a [MN, K] matrix per batch element.
-struct Operand {
-  void *ptr;
-  int es;              // element size
-  int64_t s_mn, s_k;   // element strides
-  int64_t s_b[mm::kMaxBatchDims];
-  int32_t bsz[mm::kMaxBatchDims];  // operand's own batch extents (1 = broadcast)
-  bool mn_major;
-};
-
-static bool tma_ok(const Operand &o, int64_t mn, int64_t k) {
-  const int64_t align = 16 / o.es;
-  // MN-major operands are consumed in place through MN-major UMMA descriptors: 16-bit ones with the
-  // plain SWIZZLE_128B layout, 32-bit ones with SWIZZLE_128B_BASE32B (TMA: SWIZZLE_128B_ATOM_32B).
-  // B200_MM_REPACK_TF32_MN=1 forces the old K-major repack pre-pass for 32-bit operands (debug).
-  static const bool repack32 = std::getenv("B200_MM_REPACK_TF32_MN") != nullptr;
-  if (o.mn_major && o.es == 4 && repack32) return false;
-  const int64_t inner = o.mn_major ? o.s_mn : o.s_k, outer = o.mn_major ? o.s_k : o.s_mn;
-  if (inner != 1) return false;
-  if ((o.mn_major ? k : mn) > 1 && (outer % align != 0 || outer < (o.mn_major ? mn : k))) return false;
-  for (int d = 0; d < mm::kMaxBatchDims; ++d)
-    if (o.bsz[d] > 1 && (o.s_b[d] % align != 0 || o.s_b[d] <= 0)) return false;
-  return true;
-}
-
-static int32_t make_tmap(CUtensorMap *map, const Operand &o, int64_t mn, int64_t k) {
-  EncodeTiledFn enc = encode_fn();
-  B200_REQUIRE(enc, B200_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable from the driver");
-  const int BK = 128 / o.es;
-  cuuint64_t dims[5], strides[4];
-  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
-  const int64_t outer_stride = o.mn_major ? o.s_k : o.s_mn;
-  dims[0] = (cuuint64_t)(o.mn_major ? mn : k);
-  dims[1] = (cuuint64_t)(o.mn_major ? k : mn);
-  box[0] = (cuuint32_t)BK;                       // 128 bytes of the contiguous dimension
-  box[1] = (cuuint32_t)(o.mn_major ? BK : 128);  // MN-major: BK k-rows; K-major: 128 MN rows
-  strides[0] = (cuuint64_t)std::max<int64_t>(outer_stride, 16 / o.es) * o.es;
-  // tensor-map dims 2,3,4 = batch dims innermost-last → (b2, b1, b0)
-  for (int d = 0; d < mm::kMaxBatchDims; ++d) {
-    const int src = mm::kMaxBatchDims - 1 - d;
-    dims[2 + d] = (cuuint64_t)std::max(o.bsz[src], 1);
-    box[2 + d] = 1;
-    const int64_t sb = o.bsz[src] > 1 ? o.s_b[src] : (int64_t)(16 / o.es);
-    strides[1 + d] = (cuuint64_t)sb * o.es;
-  }
-  const CUtensorMapDataType dt = o.es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const CUtensorMapSwizzle sw = (o.mn_major && o.es == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
-  CUresult r = enc(map, dt, 5, o.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  B200_REQUIRE(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  return B200_OK;
-}
-
-// Output tensor map for the fast epilogue's TMA stores: [32 columns x 32 rows] boxes, 128B swizzle.
 static bool tma_c_ok(const b200_tensor *c, int r, const int64_t *c_sb, const int32_t *batch, int64_t M) {
   if (c->dtype != B200_F32 || ((uintptr_t)c->ptr & 15)) return false;
   if (c->strides[r - 1] != 1 && c->shape[r - 1] != 1) return false;

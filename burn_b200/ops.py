@@ -275,9 +275,10 @@ def log_softmax(x: DeviceTensor, dim: int) -> DeviceTensor:
 
 
 # ---- row-resident fused kernels (ReduceBroadcasted analogue)
-def softmax_rows(x: DeviceTensor, log: bool = False) -> DeviceTensor:
-    """softmax / log_softmax along the LAST axis in one kernel (b200_launch_softmax)."""
-    out = DeviceTensor.empty(x.shape)
+def softmax_rows(x: DeviceTensor, log: bool = False, out: DeviceTensor | None = None) -> DeviceTensor:
+    """softmax / log_softmax along the LAST axis in one kernel (b200_launch_softmax); `out` may alias `x`
+    (each row is read completely before it is written)."""
+    out = DeviceTensor.empty(x.shape) if out is None else out
     a, b = x.desc(), out.desc()
     check(abi.load().b200_launch_softmax(C.byref(a), C.byref(b), 1 if log else 0, None))
     return out
@@ -294,9 +295,10 @@ def layer_norm(x: DeviceTensor, gamma: DeviceTensor | None, beta: DeviceTensor |
     return out
 
 
-def softmax_backward(y: DeviceTensor, dy: DeviceTensor, mask: DeviceTensor | None = None, div: float = 1.0) -> DeviceTensor:
-    """dx = (dy - sum(dy*y, -1)) * y / div, 0 where `mask` (b200_launch_softmax_backward)."""
-    out = DeviceTensor.empty(y.shape)
+def softmax_backward(y: DeviceTensor, dy: DeviceTensor, mask: DeviceTensor | None = None, div: float = 1.0,
+                     out: DeviceTensor | None = None) -> DeviceTensor:
+    """dx = (dy - sum(dy*y, -1)) * y / div, 0 where `mask` (b200_launch_softmax_backward); `out` may alias `dy`."""
+    out = DeviceTensor.empty(y.shape) if out is None else out
     a, g, o = y.desc(), dy.desc(), out.desc()
     m = mask.desc() if mask is not None else None
     check(abi.load().b200_launch_softmax_backward(C.byref(a), C.byref(g), C.byref(m) if m is not None else None,
@@ -319,3 +321,23 @@ def layer_norm_backward(x: DeviceTensor, dy: DeviceTensor, gamma: DeviceTensor |
     check(lib.b200_launch_layer_norm_backward(C.byref(a), C.byref(g), C.byref(gm) if gm is not None else None,
                                               float(eps), C.byref(o), C.byref(pgd), C.byref(pbd), None))
     return dx, float_sum_dim(pg, 0).reshape((d,)), float_sum_dim(pb, 0).reshape((d,))
+
+
+def attention(q: DeviceTensor, k: DeviceTensor, v: DeviceTensor, mask: DeviceTensor | None = None, scale: float | None = None,
+              mask_value: float = float("-inf"), is_causal: bool = False, out: DeviceTensor | None = None,
+              want_weights: bool = False):
+    """ModuleOps::attention in one kernel (b200_launch_attention): softmax(q·kᵀ·scale [masked]) · v on
+    [B,H,S,64] operands (strided head views are fine).  Returns `out`, or `(out, weights)`."""
+    B, H, Sq, D = q.shape
+    Sk, Dv = k.shape[2], v.shape[3]
+    if scale is None:
+        scale = 1.0 / float(np.sqrt(D))
+    out = DeviceTensor.empty((B, H, Sq, Dv)) if out is None else out
+    w = DeviceTensor.empty((B, H, Sq, Sk)) if want_weights else None
+    qd, kd, vd, od = q.desc(), k.desc(), v.desc(), out.desc()
+    md = mask.desc() if mask is not None else None
+    wd = w.desc() if w is not None else None
+    check(abi.load().b200_launch_attention(C.byref(qd), C.byref(kd), C.byref(vd), C.byref(md) if md is not None else None,
+                                           float(scale), float(mask_value), 1 if is_causal else 0, C.byref(od),
+                                           C.byref(wd) if wd is not None else None, None))
+    return (out, w) if want_weights else out

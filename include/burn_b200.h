@@ -353,6 +353,22 @@ int32_t b200_launch_layer_norm_backward(const b200_tensor *input, const b200_ten
                                         const b200_tensor *partial_gamma,
                                         const b200_tensor *partial_beta, b200_stream s);
 
+/* ------------------------------------------------ fused attention (forward) */
+/* ModuleOps::attention (crates/burn-backend/src/backend/ops/modules/base.rs:822-830;
+ * semantics: attention_fallback, ops/modules/attention.rs:15-90):
+ *   out[B,H,Sq,Dv] = softmax(q·kᵀ·scale, masked positions = mask_value) · v
+ * mask: optional bool [B|1, H|1, Sq, Sk], nonzero = masked; is_causal additionally
+ * masks col > row + (Sk - Sq) (fully masked KV blocks are skipped).  mask_value is
+ * -inf for ModuleOps::attention, -1e9 for burn-nn's MultiHeadAttention
+ * (mha.rs:291-296).  weights (optional, [B,H,Sq,Sk]) receives the softmax output —
+ * what MultiHeadAttention keeps for its backward.  Head dim 64, f32 storage, tf32
+ * tensor-core products; other head dims return B200_ERR_UNSUPPORTED (use the chain). */
+int32_t b200_launch_attention(const b200_tensor *q, const b200_tensor *k,
+                              const b200_tensor *v, const b200_tensor *mask,
+                              double scale, double mask_value, int32_t is_causal,
+                              const b200_tensor *out, const b200_tensor *weights,
+                              b200_stream s);
+
 /* ------------------------------------------------ optimizer */
 /* Multi-tensor Adam over one flat buffer, in place: the op sequence of
  * AdaptiveMomentum::transform + Adam::step
