@@ -17,6 +17,7 @@ All tensor math runs in libburn_b200.so through burn_b200.ops; this file only se
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from typing import Callable, Sequence
 
@@ -194,23 +195,34 @@ def layer_norm(tape: Tape, x: Var, gamma: Var, beta: Var, eps: float = 1e-5) -> 
     return y
 
 
-def attention(tape: Tape, q: Var, k: Var, v: Var, n_heads: int, mask: DeviceTensor | None) -> Var:
+FUSED_ATTENTION = os.environ.get("B200_FUSED_ATTENTION", "1") != "0"
+
+
+def attention(tape: Tape, q: Var, k: Var, v: Var, n_heads: int, mask: DeviceTensor | None, causal: bool = False) -> Var:
     """softmax(q·kᵀ/√dk [mask_fill -1e9]) · v on [B,S,d] projections viewed as [B,H,S,dk] (mha.rs:212-311).
-    Heads are strided views; q·kᵀ scales in the GEMM epilogue; the context GEMM writes straight into the
-    [B,S,H,dk] layout (no swap_dims copy)."""
+    Heads are strided views and the context lands straight in the [B,S,H,dk] layout (no swap_dims copy).
+    `causal` says that `mask` is the autoregressive mask (generate_autoregressive_mask): the fused kernel
+    then builds it from indices and skips the fully masked key blocks — identical results, since a
+    -1e9 score contributes exp(-1e9 - max) = 0 exactly.
+    Forward: the fused attention kernel (head dim 64, tf32) returning the weights the backward needs;
+    otherwise scores GEMM (scaling + mask fill as its epilogue) → row softmax → context GEMM."""
     B, S, d = q.v.shape
     dk = d // n_heads
     def heads(t):
         return t.reshape((B, S, n_heads, dk)).swap_dims(1, 2)
     qh, kh, vh = heads(q.v), heads(k.v), heads(v.v)
-    # scores = mask_fill(q·kᵀ/√dk, mask, -1e9): scaling and mask fill are the GEMM's fused epilogue
-    epi = TapeBuilder().op("DIV_F", ("in", 0), ("f", math.sqrt(dk)), out=0 if mask is None else None)
-    if mask is not None:
-        epi.op("SELECT", "acc", ("f", -1.0e9), ("in", 1), out=0)
-    scores = ops.float_matmul(qh, kh.swap_dims(2, 3), tape.precision, epi.build(), () if mask is None else (mask,))
-    w = ops.softmax_rows(scores)
     ctx_buf = DeviceTensor.empty((B, S, n_heads, dk))
-    _mm(w, vh, tape.precision, out=ctx_buf.swap_dims(1, 2))
+    if FUSED_ATTENTION and dk == 64 and tape.precision == abi.MM_TF32 and S % 4 == 0:
+        _, w = ops.attention(qh, kh, vh, None if causal else mask, 1.0 / math.sqrt(dk), -1.0e9, causal and mask is not None,
+                             out=ctx_buf.swap_dims(1, 2), want_weights=True)
+    else:
+        # scores = mask_fill(q·kᵀ/√dk, mask, -1e9): scaling and mask fill are the GEMM's fused epilogue
+        epi = TapeBuilder().op("DIV_F", ("in", 0), ("f", math.sqrt(dk)), out=0 if mask is None else None)
+        if mask is not None:
+            epi.op("SELECT", "acc", ("f", -1.0e9), ("in", 1), out=0)
+        scores = ops.float_matmul(qh, kh.swap_dims(2, 3), tape.precision, epi.build(), () if mask is None else (mask,))
+        w = ops.softmax_rows(scores)
+        _mm(w, vh, tape.precision, out=ctx_buf.swap_dims(1, 2))
     y = Var(ctx_buf.reshape((B, S, d)), True)
 
     def bw():
@@ -320,9 +332,9 @@ class EncoderLayer:
         return [self.wq, self.bq, self.wk, self.bk, self.wv, self.bv, self.wo, self.bo, self.w1, self.b1,
                 self.w2, self.b2, self.g1, self.be1, self.g2, self.be2]
 
-    def forward(self, tape: Tape, x: Var, mask) -> Var:
+    def forward(self, tape: Tape, x: Var, mask, causal: bool = False) -> Var:
         q, k, v = linear(tape, x, self.wq, self.bq), linear(tape, x, self.wk, self.bk), linear(tape, x, self.wv, self.bv)
-        ctx = attention(tape, q, k, v, self.h, mask)
+        ctx = attention(tape, q, k, v, self.h, mask, causal)
         x = add(tape, x, linear(tape, ctx, self.wo, self.bo))
         x = layer_norm(tape, x, self.g1, self.be1)                 # post-norm (norm_first = false)
         hdn = gelu(tape, linear(tape, x, self.w1, self.b1))
@@ -340,9 +352,9 @@ class Encoder:
     def params(self):
         return [p for l in self.layers for p in l.params()]
 
-    def forward(self, tape, x, mask=None):
+    def forward(self, tape, x, mask=None, causal=False):
         for l in self.layers:
-            x = l.forward(tape, x, mask)
+            x = l.forward(tape, x, mask, causal)
         return x
 
 
@@ -365,7 +377,7 @@ class LanguageModel:
         B, S = tokens.shape
         x = add(tape, embedding(tape, self.pos, pos_ids), embedding(tape, self.tok, tokens))
         x = scale(tape, x, 0.5)                                   # (pos + tok) / 2, model.rs:66
-        h = self.enc.forward(tape, x, causal)
+        h = self.enc.forward(tape, x, causal, causal=True)     # the mask IS generate_autoregressive_mask
         logits = linear(tape, h, self.wout, self.bout)
         return cross_entropy(tape, _reshape(tape, logits, (B * S, logits.v.shape[-1])), targets.reshape((B * S,)))
 
