@@ -341,3 +341,16 @@ def attention(q: DeviceTensor, k: DeviceTensor, v: DeviceTensor, mask: DeviceTen
                                            float(scale), float(mask_value), 1 if is_causal else 0, C.byref(od),
                                            C.byref(wd) if wd is not None else None, None))
     return (out, w) if want_weights else out
+
+
+def attention_backward(d_out: DeviceTensor, k: DeviceTensor, v: DeviceTensor, out: DeviceTensor, weights: DeviceTensor,
+                       scale: float, is_causal: bool = False, dq: DeviceTensor | None = None):
+    """(dq, ds) of the attention core from the saved weights and context (b200_launch_attention_backward);
+    the caller finishes with dk = dsᵀ·q and dv = weightsᵀ·d_out."""
+    B, H, Sq, D = d_out.shape
+    dq = DeviceTensor.empty((B, H, Sq, D)) if dq is None else dq
+    ds = DeviceTensor.empty(weights.shape)
+    a, kd, vd, od, wd, qd, sd = (t.desc() for t in (d_out, k, v, out, weights, dq, ds))
+    check(abi.load().b200_launch_attention_backward(C.byref(a), C.byref(kd), C.byref(vd), C.byref(od), C.byref(wd), float(scale),
+                                                    1 if is_causal else 0, C.byref(qd), C.byref(sd), None))
+    return dq, ds

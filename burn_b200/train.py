@@ -225,19 +225,27 @@ def attention(tape: Tape, q: Var, k: Var, v: Var, n_heads: int, mask: DeviceTens
         _mm(w, vh, tape.precision, out=ctx_buf.swap_dims(1, 2))
     y = Var(ctx_buf.reshape((B, S, d)), True)
 
+    fused = FUSED_ATTENTION and dk == 64 and tape.precision == abi.MM_TF32 and S % 4 == 0
+    ctx_h = ctx_buf.swap_dims(1, 2)
+
     def bw():
         if y.g is None:
             return
         gh = y.g.reshape((B, S, n_heads, dk)).swap_dims(1, 2)          # [B,H,S,dk] view
-        # dV = Pᵀ·g ; dP = g·Vᵀ
+        # dV = Pᵀ·g
         dv_buf = DeviceTensor.empty((B, S, n_heads, dk))
         _mm(w.swap_dims(2, 3), gh, tape.precision, out=dv_buf.swap_dims(1, 2))
-        dp = ops.float_matmul(gh, vh.swap_dims(2, 3), tape.precision)
-        # softmax backward dS = (dP - sum(dP∘P, -1)) ∘ P, the 1/√dk of the scores and the mask_fill
-        # backward (0 where masked) in one row-resident kernel
-        ds = ops.softmax_backward(w, dp, mask, math.sqrt(dk))
         dq_buf, dk_buf = DeviceTensor.empty((B, S, n_heads, dk)), DeviceTensor.empty((B, S, n_heads, dk))
-        _mm(ds, kh, tape.precision, out=dq_buf.swap_dims(1, 2))
+        if fused:
+            # one kernel: dP = g·Vᵀ in TMEM → dS = P∘(dP − rowsum(g∘ctx))/√dk (masked positions have P = 0) → dQ = dS·K
+            _, ds = ops.attention_backward(gh, kh, vh, ctx_h, w, 1.0 / math.sqrt(dk), causal and mask is not None,
+                                           dq=dq_buf.swap_dims(1, 2))
+        else:
+            dp = ops.float_matmul(gh, vh.swap_dims(2, 3), tape.precision)
+            # softmax backward dS = (dP - sum(dP∘P, -1)) ∘ P, the 1/√dk of the scores and the mask_fill
+            # backward (0 where masked) in one row-resident kernel
+            ds = ops.softmax_backward(w, dp, mask, math.sqrt(dk))
+            _mm(ds, kh, tape.precision, out=dq_buf.swap_dims(1, 2))
         _mm(ds.swap_dims(2, 3), qh, tape.precision, out=dk_buf.swap_dims(1, 2))
         accumulate(q, dq_buf.reshape((B, S, d)))
         accumulate(k, dk_buf.reshape((B, S, d)))

@@ -369,6 +369,17 @@ int32_t b200_launch_attention(const b200_tensor *q, const b200_tensor *k,
                               const b200_tensor *out, const b200_tensor *weights,
                               b200_stream s);
 
+/* Backward of the attention core given the saved weights P and context `out`
+ * (what burn-autodiff's reverse walk over mha.rs:253-311 computes), first half in one
+ * kernel: dP = d_out·vᵀ, dS = P ∘ (dP − rowsum(d_out ∘ out)) · scale, dq = dS·k.  `ds`
+ * [B,H,Sq,Sk] is written for the two remaining products, plain float_matmul calls:
+ * dk = dSᵀ·q and dv = Pᵀ·d_out.  Masked positions need no mask (P = 0 there). */
+int32_t b200_launch_attention_backward(const b200_tensor *d_out, const b200_tensor *k,
+                                       const b200_tensor *v, const b200_tensor *out,
+                                       const b200_tensor *weights, double scale,
+                                       int32_t is_causal, const b200_tensor *dq,
+                                       const b200_tensor *ds, b200_stream s);
+
 /* ------------------------------------------------ optimizer */
 /* Multi-tensor Adam over one flat buffer, in place: the op sequence of
  * AdaptiveMomentum::transform + Adam::step

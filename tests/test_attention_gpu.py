@@ -84,3 +84,26 @@ def test_unsupported_head_dim_is_an_error(dev):
     q = H.up(rnd((1, 1, 128, 32), 8))
     with pytest.raises(Exception):
         ops.attention(q, q, q)
+
+
+@pytest.mark.parametrize("B,Hh,Sq,Sk,causal", [(1, 2, 128, 128, False), (2, 2, 200, 264, False), (1, 2, 512, 512, True), (1, 1, 1024, 1024, True)])
+def test_attention_backward_dq_ds(dev, B, Hh, Sq, Sk, causal):
+    """dS = P ∘ (dP − rowsum(dP ∘ P))·scale and dQ = dS·K from the saved weights, against float64."""
+    q, k, v = rnd((B, Hh, Sq, 64), 11, 0.5), rnd((B, Hh, Sk, 64), 12, 0.5), rnd((B, Hh, Sk, 64), 13)
+    g = rnd((B, Hh, Sq, 64), 14)
+    scale = 0.125
+    dq_, dk_, dv_ = H.up(q), H.up(k), H.up(v)
+    out, w = ops.attention(dq_, dk_, dv_, None, scale, -1.0e9, causal, want_weights=True)
+    dq, ds = ops.attention_backward(H.up(g), dk_, dv_, out, w, scale, causal)
+    _, p = reference(q, k, v, None, scale, -1.0e9, causal)
+    g64, k64, v64 = (t.astype(np.float64) for t in (g, k, v))
+    dp = np.einsum("bhqd,bhkd->bhqk", g64, v64)
+    ds_ref = p * (dp - (dp * p).sum(-1, keepdims=True)) * scale
+    dq_ref = np.einsum("bhqk,bhkd->bhqd", ds_ref, k64)
+    for got, want, what in ((ds.numpy(), ds_ref, "dS"), (dq.numpy(), dq_ref, "dQ")):
+        tol = 3e-3 * np.abs(want).max()
+        err = np.abs(got - want).max()
+        assert err <= tol, f"{what}: max err {err:.3e} > {tol:.3e}"
+    if causal:
+        cm = np.arange(Sk)[None, :] > np.arange(Sq)[:, None] + (Sk - Sq)
+        assert np.all(ds.numpy()[..., cm] == 0.0)
