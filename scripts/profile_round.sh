@@ -19,5 +19,6 @@ cap chain "b200_jit_kernel|elemwise_tape_kernel" 4 python bench.py --steps 2 --w
 cap gemm_bf16 "gemm_tcgen05" 2 python scripts/prof_gemm.py
 cap gemm_tf32 "gemm_tcgen05" 5 python scripts/prof_gemm.py
 cap reduce_row "reduce_row_fast_kernel" 6 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train
-cap softmax_bwd "softmax_bwd_warp_kernel" 2 python train_bench.py --config lm --steps 1 --warmup 0 --eager
+cap attention_fwd "attention_fwd_kernel" 2 python train_bench.py --config lm --steps 1 --warmup 0 --eager
+cap attention_bwd "attention_bwd_dq_kernel" 2 python train_bench.py --config lm --steps 1 --warmup 0 --eager
 ls -la gpurun_out | tail -20
