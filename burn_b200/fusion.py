@@ -17,7 +17,7 @@ import numpy as np
 from . import _abi as abi
 from ._abi import check
 
-BLOCK_ELEMWISE, BLOCK_REDUCE, BLOCK_MATMUL, BLOCK_EAGER = range(4)
+BLOCK_ELEMWISE, BLOCK_REDUCE, BLOCK_MATMUL, BLOCK_EAGER, BLOCK_ROWNORM = range(5)
 
 
 class BlockInfo(C.Structure):
@@ -181,4 +181,35 @@ def gelu(x: LazyTensor) -> LazyTensor:
     p = e.add_scalar(1.0); e.drop()
     m = x.mul(p); p.drop()
     y = m.div_scalar(2.0); m.drop()
+    return y
+
+
+def softmax(x: LazyTensor, dim: int) -> LazyTensor:
+    """The op chain ActivationOps::softmax records (activation.rs:250-256), intermediates dropped as
+    they go out of scope; along the last axis the ReduceBroadcasted fuser turns it into one kernel."""
+    m = x.max_dim(dim)
+    d = x.sub(m)
+    m.drop()
+    e = d.exp()
+    d.drop()
+    s = e.sum_dim(dim)
+    y = e.div(s)
+    e.drop()
+    s.drop()
+    return y
+
+
+def log_softmax(x: LazyTensor, dim: int) -> LazyTensor:
+    """ActivationOps::log_softmax (activation.rs:271-276)."""
+    m = x.max_dim(dim)
+    d = x.sub(m)
+    m.drop()
+    e = d.exp()
+    s = e.sum_dim(dim)
+    e.drop()
+    ls = s.log()
+    s.drop()
+    y = d.sub(ls)
+    d.drop()
+    ls.drop()
     return y

@@ -201,6 +201,8 @@ struct Candidate {
   int n_ops = 0;     // IR ops excluding drops
   std::vector<const Op *> read_ops, write_ops;
   const Op *core = nullptr;  // the reduce / matmul op
+  int64_t row_in = -1, row_out = -1;   // ROWNORM: the chain's input and output tensors
+  bool row_log = false;                // ROWNORM: log_softmax
   std::unordered_set<int64_t> dropped;
   TapeBuild read_tape, write_tape;
 };
@@ -256,6 +258,69 @@ struct Stream {
     }
     (void)start_shape_from;
     return best;
+  }
+
+  // ---- ReduceBroadcasted fuser: the softmax / log_softmax chains the default ActivationOps record
+  //   softmax     = max_dim, sub, exp, sum_dim, div          (activation.rs:250-256)
+  //   log_softmax = max_dim, sub, exp, sum_dim, log, sub     (activation.rs:271-276)
+  // along the last axis, every intermediate dropped inside the window → one row-resident kernel
+  // (crates/burn-cubecl-fusion/src/optim/reduce_broadcasted/ fuses the same shape of work).
+  Candidate scan_rownorm() {
+    Candidate none, c;
+    c.kind = B200H_BLOCK_ROWNORM;
+    std::vector<const Op *> ops;
+    std::vector<size_t> pos;
+    std::unordered_set<int64_t> drops;
+    size_t q = 0;
+    for (; q < queue.size() && ops.size() < 6; ++q) {
+      if (queue[q].kind == Kind::Drop) { if (ops.empty()) return none; drops.insert(queue[q].in[0]); continue; }
+      ops.push_back(&queue[q]);
+      pos.push_back(q);
+    }
+    if (ops.size() < 5) return none;
+    const Op &mx = *ops[0], &sb = *ops[1], &ex = *ops[2], &sm = *ops[3], &o4 = *ops[4];
+    const Tensor *x = get(mx.in[0]);
+    if (!x || x->dtype != B200_F32 || x->shape.empty()) return none;
+    const int last = (int)x->shape.size() - 1;
+    if (x->strides != contiguous(x->shape)) return none;
+    if (!(mx.kind == Kind::ReduceDim && mx.opcode == B200_RED_MAX && mx.dim == last)) return none;
+    if (!(sb.kind == Kind::Binary && sb.opcode == B200_OP_SUB_F && sb.in[0] == mx.in[0] && sb.in[1] == mx.out)) return none;
+    if (!(ex.kind == Kind::Unary && ex.opcode == B200_OP_EXP_F && ex.in[0] == sb.out)) return none;
+    if (!(sm.kind == Kind::ReduceDim && sm.opcode == B200_RED_SUM && sm.dim == last && sm.in[0] == ex.out)) return none;
+    std::vector<int64_t> inter = {mx.out, sb.out, ex.out, sm.out};
+    size_t n_ops;
+    if (o4.kind == Kind::Binary && o4.opcode == B200_OP_DIV_F && o4.in[0] == ex.out && o4.in[1] == sm.out) {
+      n_ops = 5;
+      c.row_out = o4.out;
+    } else if (ops.size() >= 6 && o4.kind == Kind::Unary && o4.opcode == B200_OP_LOG_F && o4.in[0] == sm.out &&
+               ops[5]->kind == Kind::Binary && ops[5]->opcode == B200_OP_SUB_F && ops[5]->in[0] == sb.out &&
+               ops[5]->in[1] == o4.out) {
+      n_ops = 6;
+      c.row_log = true;
+      c.row_out = ops[5]->out;
+      inter.push_back(o4.out);
+    } else {
+      return none;
+    }
+    // drops seen up to the last op of the chain, plus the drops that directly follow it
+    drops.clear();
+    size_t end = pos[n_ops - 1] + 1;
+    for (size_t i = 0; i < end; ++i)
+      if (queue[i].kind == Kind::Drop) drops.insert(queue[i].in[0]);
+    while (end < queue.size() && queue[end].kind == Kind::Drop &&
+           std::find(inter.begin(), inter.end(), queue[end].in[0]) != inter.end()) {
+      drops.insert(queue[end].in[0]);
+      ++end;
+    }
+    for (int64_t id : inter)
+      if (!drops.count(id)) return none;          // an intermediate is still wanted: leave it to the other fusers
+    for (int64_t id : drops)
+      if (std::find(inter.begin(), inter.end(), id) == inter.end() && id != mx.in[0]) return none;
+    c.row_in = mx.in[0];
+    c.dropped = drops;
+    c.n_ops = (int)n_ops;
+    c.consumed = (int)end;
+    return c;
   }
 
   // ---- Reduce fuser: [read block] → ReduceDim → [write block]
@@ -449,6 +514,13 @@ struct Stream {
                                 c.write_ops.empty() ? nullptr : &wt, wins.empty() ? nullptr : wins.data(),
                                 (int)wins.size(), outs.data(), (int)outs.size(), nullptr);
       }
+    } else if (c.kind == B200H_BLOCK_ROWNORM) {
+      if ((st = materialise(c.row_out)) != B200_OK) return st;
+      b200_tensor xin, yout;
+      if ((st = desc_of(c.row_in, xin)) != B200_OK || (st = desc_of(c.row_out, yout)) != B200_OK) return st;
+      info.n_inputs = 1;
+      info.n_outputs = 1;
+      if (!plan_only) st = b200_launch_softmax(&xin, &yout, c.row_log ? 1 : 0, nullptr);
     } else if (c.kind == B200H_BLOCK_MATMUL) {
       const Op &mm = *c.core;
       const int64_t out_id = c.write_ops.empty() ? mm.out : c.write_tape.outputs[0];
@@ -491,6 +563,8 @@ struct Stream {
       Candidate m = scan_matmul();
       if (r.n_ops > best.n_ops || (r.n_ops == best.n_ops && r.n_ops > 0)) best = r;
       if (m.n_ops >= best.n_ops && m.n_ops > 0) best = m;
+      Candidate rn = scan_rownorm();
+      if (rn.n_ops > best.n_ops) best = rn;
       B200_REQUIRE(best.n_ops > 0, B200_ERR_UNSUPPORTED, "no fuser accepts operation kind %d", (int)queue[0].kind);
       // ops never produce tensors that need materialising? pending outputs of dropped ids vanish
       int32_t st = execute(best);

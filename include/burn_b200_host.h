@@ -7,7 +7,10 @@
  * `OperationFuser` state machines the reference registers — ElementWise, Matmul, Reduce
  * (crates/burn-cubecl/src/fusion/registry.rs:128-146; acceptance rules
  * crates/burn-cubecl-fusion/src/engine/fuser.rs:76-190,292-710,
- * crates/burn-cubecl-fusion/src/optim/{reduce,matmul}/fuser.rs) — and executes each fused block
+ * crates/burn-cubecl-fusion/src/optim/{reduce,matmul}/fuser.rs)
+ * (plus the ReduceBroadcasted shape: the max_dim/sub/exp/sum_dim/div[/log/sub] chains of
+ * crates/burn-backend/src/backend/ops/activation.rs:250-276 → b200_launch_softmax,
+ * crates/burn-cubecl-fusion/src/optim/reduce_broadcasted/) — and executes each fused block
  * as ONE kernel through b200_launch_elemwise / b200_launch_reduce / b200_launch_matmul
  * (`Optimization::execute`, crates/burn-fusion/src/backend.rs:226-234).
  *
@@ -36,7 +39,8 @@ typedef enum {
   B200H_BLOCK_ELEMWISE = 0,
   B200H_BLOCK_REDUCE = 1,
   B200H_BLOCK_MATMUL = 2,
-  B200H_BLOCK_EAGER = 3 /* op no fuser accepts, executed on its own */
+  B200H_BLOCK_EAGER = 3, /* op no fuser accepts, executed on its own */
+  B200H_BLOCK_ROWNORM = 4 /* softmax / log_softmax chain → one row-resident kernel (ReduceBroadcasted) */
 } b200h_block_kind;
 
 /* One executed (or planned) optimization — the FusionInspector view

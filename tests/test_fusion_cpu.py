@@ -97,19 +97,39 @@ def test_read_block_value_still_alive_prevents_fuse_on_read(st):
     assert s.shape == (16, 1)
 
 
-def test_softmax_decomposes_into_two_reduce_blocks_and_one_elementwise(st):
-    # softmax = max_dim, sub, exp, sum_dim, div (activation.rs:250-256)
+def test_softmax_chain_along_the_last_axis_is_one_row_resident_block(st):
+    # softmax = max_dim, sub, exp, sum_dim, div (activation.rs:250-256) → the ReduceBroadcasted shape
+    x = st.placeholder((64, 256))
+    y = F.softmax(x, 1)
+    st.sync()
+    (blk,) = st.blocks()
+    assert blk.kind == F.BLOCK_ROWNORM and blk.n_ops == 5 and blk.n_inputs == 1 and blk.n_outputs == 1
+    assert y.shape == (64, 256)
+    st.clear_blocks()
+    z = F.log_softmax(x, 1)                              # max_dim, sub, exp, sum_dim, log, sub
+    st.sync()
+    (blk,) = st.blocks()
+    assert blk.kind == F.BLOCK_ROWNORM and blk.n_ops == 6
+    assert z.shape == (64, 256)
+
+
+def test_softmax_with_a_live_intermediate_or_another_axis_decomposes(st):
     x = st.placeholder((64, 256))
     mx = x.max_dim(1)
     sh = x.sub(mx)
     ex = sh.exp(); sh.drop()
     sm = ex.sum_dim(1)
-    y = ex.div(sm); ex.drop(); sm.drop(); mx.drop()
+    y = ex.div(sm); ex.drop(); sm.drop()                 # mx stays alive: it must be materialised
     st.sync()
     ks = kinds(st)
-    assert ks[0] == (F.BLOCK_REDUCE, 1)                 # max_dim
-    assert sum(n for _, n in ks) == 5
-    assert y.shape == (64, 256)
+    assert ks[0] == (F.BLOCK_REDUCE, 1)                  # max_dim on its own
+    assert all(k != F.BLOCK_ROWNORM for k, _ in ks) and sum(n for _, n in ks) == 5
+    assert y.shape == (64, 256) and mx.shape == (64, 1)
+    st.clear_blocks()
+    w = F.softmax(x, 0)                                  # not the last axis
+    st.sync()
+    assert all(k != F.BLOCK_ROWNORM for k, _ in kinds(st)) and sum(n for _, n in kinds(st)) == 5
+    assert w.shape == (64, 256)
 
 
 def test_matmul_with_bias_gelu_epilogue_is_one_block(st):

@@ -71,6 +71,16 @@ def test_softmax_through_the_stream(st):
     sm = ex.sum_dim(1)
     y = ex.div(sm); ex.drop(); sm.drop(); mx.drop()
     H.assert_close(y.numpy(), oracle.softmax(x, 1), H.REL_REDUCE, 1e-9)
+    (blk,) = st.blocks()                                               # the whole chain: one row-resident kernel
+    assert (blk.kind, blk.n_ops, blk.launches) == (F.BLOCK_ROWNORM, 5, 1)
+    st.clear_blocks()
+    z = F.log_softmax(st.tensor(x), 1)
+    H.assert_close(z.numpy(), oracle.log_softmax(x, 1), H.REL_REDUCE, 1e-6)
+    assert [(b.kind, b.n_ops, b.launches) for b in st.blocks()] == [(F.BLOCK_ROWNORM, 6, 1)]
+    st.clear_blocks()
+    w = F.softmax(st.tensor(x), 0)                                     # other axes: the decomposed blocks
+    H.assert_close(w.numpy(), oracle.softmax(x, 0), H.REL_REDUCE, 1e-9)
+    assert all(b.kind != F.BLOCK_ROWNORM for b in st.blocks())
     assert sum(b.launches for b in st.blocks()) == len(st.blocks())   # one launch per block
 
 
