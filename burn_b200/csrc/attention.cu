@@ -29,6 +29,7 @@ using namespace mm;
 constexpr int BQ = 128, BKV = 64, HD = 64;
 constexpr int kThreads = 192;
 constexpr uint32_t kQBytes = BQ * HD * 4, kKBytes = BKV * HD * 4, kVBytes = BKV * HD * 4, kPBytes = BQ * BKV * 4;
+constexpr uint32_t kMBytes = BQ * BKV;   // one mask tile (bytes)
 
 struct Params {
   CUtensorMap tma_q, tma_k, tma_v, tma_w;   // tma_w: weights [Sk, Sq, H, B] boxes of 32 x 128, 128B swizzle
@@ -38,6 +39,8 @@ struct Params {
   int64_t w_sb, w_sh, w_ss;
   const uint8_t *mask;           // optional bool mask, nonzero = masked
   int64_t m_sb, m_sh, m_ss;
+  CUtensorMap tma_m;             // mask tiles [64 columns x 128 rows] through TMA when its strides allow (mask_tma)
+  int32_t mask_tma, m_bcast_b, m_bcast_h;
   int32_t B, H, Sq, Sk;
   int32_t causal, q_blocks;
   float scale, mask_value;
@@ -48,13 +51,18 @@ struct Params {
   int64_t of_sb, of_sh, of_ss, do_sb, do_sh, do_ss;
 };
 
+// MASK_TMA: the bool mask arrives as TMA-loaded [128 x 64 B] tiles (kept out of the unmasked / causal
+// instantiation, whose row loop is the hot path)
+template <bool MASK_TMA>
 __global__ void __launch_bounds__(kThreads, 2) attention_fwd_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sQ = smem, *sK = sQ + kQBytes, *sV = sK + kKBytes, *sP = sV + kVBytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + kPBytes);
-  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_p = bars + 4, *bar_o = bars + 5;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6);
+  uint8_t *sM = sP + kPBytes;                      // mask tile [128 rows][64 bytes]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sM + (MASK_TMA ? kMBytes : 0));
+  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_p = bars + 4, *bar_o = bars + 5,
+           *bar_m = bars + 6;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // heavy (late, under a causal mask) query blocks first
@@ -80,6 +88,8 @@ __global__ void __launch_bounds__(kThreads, 2) attention_fwd_kernel(const __grid
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 4);
     mbar_init(bar_o, 2);      // tcgen05.commit of P·V + the issuer once the weights store has read sP
+    mbar_init(bar_m, 1);
+    if constexpr (MASK_TMA) tma_prefetch_desc(&P.tma_m);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 128);
@@ -104,7 +114,12 @@ __global__ void __launch_bounds__(kThreads, 2) attention_fwd_kernel(const __grid
       tma_load_5d(sQ + kQBytes / 2, &P.tma_q, bar_q, 32, q0, h, b, 0);
       mbar_wait(bar_q, 0);
       uint32_t ph_k = 0, ph_v = 0, ph_p = 0, ph_o = 0;
+      const int mb = P.m_bcast_b ? 0 : b, mh = P.m_bcast_h ? 0 : h;
       auto load_k = [&](int j) {
+        if constexpr (MASK_TMA) {   // the mask tile travels with K: its buffer is free once S(j-1) was consumed
+          mbar_expect_tx(bar_m, kMBytes);
+          tma_load_5d(sM, &P.tma_m, bar_m, j * BKV, q0, mh, mb, 0);
+        }
         mbar_expect_tx(bar_k, kKBytes);
         tma_load_5d(sK, &P.tma_k, bar_k, 0, j * BKV, h, b, 0);
         tma_load_5d(sK + kKBytes / 2, &P.tma_k, bar_k, 32, j * BKV, h, b, 0);
@@ -169,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_fwd_kernel(const __grid
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int causal_limit = row + (P.Sk - P.Sq);                 // columns beyond are masked when causal
     const uint8_t *mrow = P.mask ? P.mask + (int64_t)b * P.m_sb + (int64_t)h * P.m_sh + (int64_t)row * P.m_ss : nullptr;
-    uint32_t ph_s = 0, ph_o = 0;
+    uint32_t ph_s = 0, ph_o = 0, ph_m = 0;
     float m = -INFINITY, l = 0.0f;
 
     // Softmax runs in the base-2 domain: s2 = score·scale·log2(e), p = 2^(s2 - m2) / l — one FMUL and one
@@ -197,7 +212,22 @@ __global__ void __launch_bounds__(kThreads, 2) attention_fwd_kernel(const __grid
         s[c + 32] = __fmul_rn(__uint_as_float(r1[c]), scale2);
       }
       const int col0 = j * BKV;
-      if (mrow && row_ok) {
+      if constexpr (MASK_TMA) {
+        mbar_wait(bar_m, ph_m); ph_m ^= 1;
+        const uint4 *mt = reinterpret_cast<const uint4 *>(sM + r_in * BKV);
+#pragma unroll
+        for (int q = 0; q < BKV / 16; ++q) {
+          const uint4 mw = mt[q];
+          const uint32_t w4[4] = {mw.x, mw.y, mw.z, mw.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (w4[t] & 0xFFu) s[q * 16 + t * 4] = mask2;
+            if (w4[t] & 0xFF00u) s[q * 16 + t * 4 + 1] = mask2;
+            if (w4[t] & 0xFF0000u) s[q * 16 + t * 4 + 2] = mask2;
+            if (w4[t] & 0xFF000000u) s[q * 16 + t * 4 + 3] = mask2;
+          }
+        }
+      } else if (mrow && row_ok) {
         if (mask16) {
 #pragma unroll
           for (int q = 0; q < BKV / 16; ++q) {
@@ -602,6 +632,20 @@ extern "C" int32_t b200_launch_attention(const b200_tensor *q, const b200_tensor
     P.m_sb = mask->shape[0] == 1 ? 0 : mask->strides[0];
     P.m_sh = mask->shape[1] == 1 ? 0 : mask->strides[1];
     P.m_ss = mask->strides[2];
+    P.m_bcast_b = mask->shape[0] == 1;
+    P.m_bcast_h = mask->shape[1] == 1;
+    // 16-byte-multiple strides: mask tiles go through TMA (coalesced, zero-filled past the edges)
+    if (((uintptr_t)mask->ptr % 16) == 0 && P.m_ss % 16 == 0 && P.m_sb % 16 == 0 && P.m_sh % 16 == 0) {
+      EncodeTiledFn enc = encode_fn();
+      B200_REQUIRE(enc, B200_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable from the driver");
+      cuuint64_t dims[5] = {(cuuint64_t)Sk, (cuuint64_t)Sq, (cuuint64_t)(P.m_bcast_h ? 1 : H), (cuuint64_t)(P.m_bcast_b ? 1 : B), 1};
+      cuuint64_t strides[4] = {(cuuint64_t)std::max<int64_t>(P.m_ss, 16), (cuuint64_t)(P.m_bcast_h ? 16 : P.m_sh),
+                               (cuuint64_t)(P.m_bcast_b ? 16 : P.m_sb), 16};
+      cuuint32_t box[5] = {(cuuint32_t)attn::BKV, (cuuint32_t)attn::BQ, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = enc(&P.tma_m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, mask->ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) P.mask_tma = 1;
+    }
   }
   P.B = (int32_t)B; P.H = (int32_t)H; P.Sq = (int32_t)Sq; P.Sk = (int32_t)Sk;
   P.causal = is_causal ? 1 : 0;
@@ -610,9 +654,17 @@ extern "C" int32_t b200_launch_attention(const b200_tensor *q, const b200_tensor
   P.mask_value = (float)mask_value;
   const int64_t ctas = B * H * P.q_blocks;
   B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
-  const size_t smem = 1024 + attn::kQBytes + attn::kKBytes + attn::kVBytes + attn::kPBytes + 128;
-  B200_CUDA(cudaFuncSetAttribute(attn::attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn::attention_fwd_kernel<<<(unsigned)ctas, attn::kThreads, smem, resolve_stream(s)>>>(P);
+  const size_t smem = 1024 + attn::kQBytes + attn::kKBytes + attn::kVBytes + attn::kPBytes + (P.mask_tma ? attn::kMBytes : 0) + 128;
+  auto launch = [&](auto kern) -> int32_t {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two CTAs per SM need the largest shared-memory carveout
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<(unsigned)ctas, attn::kThreads, smem, resolve_stream(s)>>>(P);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  };
+  st = P.mask_tma ? launch(attn::attention_fwd_kernel<true>) : launch(attn::attention_fwd_kernel<false>);
+  if (st != B200_OK) return st;
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -695,6 +747,7 @@ extern "C" int32_t b200_launch_attention_backward(const b200_tensor *d_out, cons
   B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
   const size_t smem = 1024 + attn::kQBytes + attn::kKBytes + attn::kVBytes + attn::kPBytes + 128;
   B200_CUDA(cudaFuncSetAttribute(attn::attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B200_CUDA(cudaFuncSetAttribute(attn::attention_bwd_dq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   attn::attention_bwd_dq_kernel<<<(unsigned)ctas, attn::kThreads, smem, resolve_stream(s)>>>(P);
   B200_LAUNCH_CHECK();
   return B200_OK;
