@@ -263,8 +263,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             import train_bench
             train = train_bench.run("lm", steps=args.train_steps, warmup=3, rank=rank, world=world,
                                     local_rank=local_rank, mm="tf32", use_graph=True, init_device=False)
+            enc = train_bench.run("encoder", steps=args.train_steps, warmup=3, rank=rank, world=world,
+                                  local_rank=local_rank, mm="tf32", use_graph=True, init_device=False)
+            train["encoder_configs3"] = {k: enc[k] for k in ("value", "unit", "ms_per_step", "model_tflops_per_s", "config")}
         except Exception as e:  # the headline metric above stands on its own
-            train = {"error": repr(e)[:300]}
+            train = train if isinstance(train, dict) and "value" in train else {"error": repr(e)[:300]}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the box's host cores
     cpu = None
