@@ -272,6 +272,81 @@ static int32_t launch_rows(const Params &P, cudaStream_t stream) {
   return B200_OK;
 }
 
+// ---- softmax cross-entropy, forward value and logits gradient in one pass over a row staged in smem:
+//   picked[r] = log_softmax(x[r])[t[r]]          (what log_softmax(..).gather(1, targets) yields,
+//                                                  crates/burn-nn/src/loss/cross_entropy.rs:171-181)
+//   dx[r, i]  = (softmax(x[r])[i] - [i == t[r]]) * grad_scale      (its gradient under mean().neg())
+// dx may alias x.  HBM traffic: read the logits once, write the gradient once (8 B/elem) instead of
+// log_softmax (8) + gather + the exp/one-hot tape (8+).
+struct XentParams {
+  const float *x;
+  float *dx;
+  const void *targets;
+  float *picked;
+  int64_t x_stride, dx_stride;
+  uint32_t rows, R;
+  int32_t target_i64, vec;
+  float grad_scale;
+};
+
+__global__ void __launch_bounds__(kBlock) softmax_xent_kernel(const XentParams P) {
+  extern __shared__ __align__(16) float rowbuf[];
+  __shared__ float scratch[kWarps];
+  for (uint32_t row = blockIdx.x; row < P.rows; row += gridDim.x) {
+    const float *xr = P.x + (int64_t)row * P.x_stride;
+    float *dr = P.dx + (int64_t)row * P.dx_stride;
+    const int64_t t = P.target_i64 ? reinterpret_cast<const long long *>(P.targets)[row]
+                                   : (int64_t) reinterpret_cast<const int32_t *>(P.targets)[row];
+    __syncthreads();
+    if (P.vec) {
+      const float4 *x4 = reinterpret_cast<const float4 *>(xr);
+      float4 *b4 = reinterpret_cast<float4 *>(rowbuf);
+      for (uint32_t i = threadIdx.x; i < (P.R >> 2); i += kBlock) b4[i] = __ldcs(x4 + i);
+    } else {
+      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) rowbuf[i] = __ldcs(xr + i);
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) m = nan_max(m, rowbuf[i]);
+    m = block_reduce_max(m, scratch);
+    float s = 0.f;
+    for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) {
+      const float sh = __fsub_rn(rowbuf[i], m);
+      rowbuf[i] = sh;                      // shifted logit, as in log_softmax
+      s = __fadd_rn(s, expf(sh));
+    }
+    s = block_reduce_sum(s, scratch);
+    const float ls = logf(s);
+    if (threadIdx.x == 0 && t >= 0 && t < (int64_t)P.R) P.picked[row] = __fsub_rn(rowbuf[t], ls);
+    // gradient: exp(log_softmax) - onehot, scaled — the same values the unfused tape produces
+    if (P.vec) {
+      const float4 *b4 = reinterpret_cast<const float4 *>(rowbuf);
+      float4 *d4 = reinterpret_cast<float4 *>(dr);
+      for (uint32_t i = threadIdx.x; i < (P.R >> 2); i += kBlock) {
+        const float4 sh = b4[i];
+        float4 o;
+        o.x = expf(__fsub_rn(sh.x, ls)); o.y = expf(__fsub_rn(sh.y, ls)); o.z = expf(__fsub_rn(sh.z, ls)); o.w = expf(__fsub_rn(sh.w, ls));
+        const int64_t c = (int64_t)i * 4;
+        if (t >= c && t < c + 4) {
+          if (t == c) o.x = __fsub_rn(o.x, 1.0f);
+          else if (t == c + 1) o.y = __fsub_rn(o.y, 1.0f);
+          else if (t == c + 2) o.z = __fsub_rn(o.z, 1.0f);
+          else o.w = __fsub_rn(o.w, 1.0f);
+        }
+        o.x = __fmul_rn(o.x, P.grad_scale); o.y = __fmul_rn(o.y, P.grad_scale);
+        o.z = __fmul_rn(o.z, P.grad_scale); o.w = __fmul_rn(o.w, P.grad_scale);
+        __stcs(d4 + i, o);
+      }
+    } else {
+      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) {
+        float o = expf(__fsub_rn(rowbuf[i], ls));
+        if ((int64_t)i == t) o = __fsub_rn(o, 1.0f);
+        __stcs(dr + i, __fmul_rn(o, P.grad_scale));
+      }
+    }
+  }
+}
+
 }  // namespace rn
 }  // namespace b200
 
@@ -326,4 +401,49 @@ extern "C" int32_t b200_launch_layer_norm(const b200_tensor *input, const b200_t
   P.y = reinterpret_cast<float *>(out->ptr);
   P.eps = (float)eps;
   return rn::launch_rows<rn::kLayerNorm>(P, resolve_stream(s));
+}
+
+extern "C" int32_t b200_launch_softmax_cross_entropy(const b200_tensor *logits, const b200_tensor *targets, double grad_scale,
+                                                     const b200_tensor *picked, const b200_tensor *dlogits, b200_stream s) {
+  B200_REQUIRE(logits && targets && picked && dlogits, B200_ERR_INVALID, "null argument");
+  B200_REQUIRE(logits->rank == 2 && dlogits->rank == 2 && logits->dtype == B200_F32 && dlogits->dtype == B200_F32 &&
+                   logits->ptr && dlogits->ptr,
+               B200_ERR_UNSUPPORTED, "softmax_cross_entropy takes f32 [N, V] logits");
+  const int64_t N = logits->shape[0], V = logits->shape[1];
+  B200_REQUIRE(dlogits->shape[0] == N && dlogits->shape[1] == V, B200_ERR_SHAPE, "gradient shape mismatch");
+  B200_REQUIRE((logits->strides[1] == 1 || V == 1) && (dlogits->strides[1] == 1 || V == 1), B200_ERR_UNSUPPORTED,
+               "the class axis must be contiguous");
+  B200_REQUIRE((targets->dtype == B200_I32 || targets->dtype == B200_I64) && targets->ptr && is_contiguous(*targets),
+               B200_ERR_INVALID, "targets must be contiguous i32 / i64");
+  int64_t nt = 1, np_ = 1;
+  for (int d = 0; d < targets->rank; ++d) nt *= targets->shape[d];
+  for (int d = 0; d < picked->rank; ++d) np_ *= picked->shape[d];
+  B200_REQUIRE(nt == N && np_ == N && picked->dtype == B200_F32 && picked->ptr && is_contiguous(*picked), B200_ERR_SHAPE,
+               "targets / picked must hold N = %lld entries", (long long)N);
+  if (N == 0 || V == 0) return B200_OK;
+  B200_REQUIRE(N < (1ll << 31) && V < (1ll << 31), B200_ERR_UNSUPPORTED, "softmax_cross_entropy: too large");
+  const size_t smem = (size_t)V * 4;
+  B200_REQUIRE((int)smem + 1024 <= max_smem_optin(), B200_ERR_UNSUPPORTED,
+               "a row of %lld classes does not fit in shared memory; use the op chain", (long long)V);
+  rn::XentParams P;
+  memset(&P, 0, sizeof(P));
+  P.x = reinterpret_cast<const float *>(logits->ptr);
+  P.dx = reinterpret_cast<float *>(dlogits->ptr);
+  P.targets = targets->ptr;
+  P.picked = reinterpret_cast<float *>(picked->ptr);
+  P.x_stride = logits->strides[0];
+  P.dx_stride = dlogits->strides[0];
+  P.rows = (uint32_t)N;
+  P.R = (uint32_t)V;
+  P.target_i64 = targets->dtype == B200_I64;
+  P.vec = V % 4 == 0 && ((uintptr_t)P.x % 16) == 0 && ((uintptr_t)P.dx % 16) == 0 && P.x_stride % 4 == 0 && P.dx_stride % 4 == 0;
+  P.grad_scale = (float)grad_scale;
+  auto kern = rn::softmax_xent_kernel;
+  if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rn::kBlock, smem));
+  const unsigned grid = (unsigned)std::min<int64_t>(N, (int64_t)sm_count() * std::max(per_sm, 1));
+  kern<<<grid, rn::kBlock, smem, resolve_stream(s)>>>(P);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
 }

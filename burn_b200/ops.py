@@ -354,3 +354,14 @@ def attention_backward(d_out: DeviceTensor, k: DeviceTensor, v: DeviceTensor, ou
     check(abi.load().b200_launch_attention_backward(C.byref(a), C.byref(kd), C.byref(vd), C.byref(od), C.byref(wd), float(scale),
                                                     1 if is_causal else 0, C.byref(qd), C.byref(sd), None))
     return dq, ds
+
+
+def softmax_cross_entropy(logits: DeviceTensor, targets: DeviceTensor, grad_scale: float, inplace: bool = False):
+    """(picked, dlogits): log_softmax(logits)[target] per row and (softmax - onehot) * grad_scale, one pass
+    (b200_launch_softmax_cross_entropy).  `inplace` writes the gradient over the logits."""
+    n, _ = logits.shape
+    picked = DeviceTensor.empty((n,))
+    dl = logits if inplace else DeviceTensor.empty(logits.shape)
+    a, t, p, d = logits.desc(), targets.desc(), picked.desc(), dl.desc()
+    check(abi.load().b200_launch_softmax_cross_entropy(C.byref(a), C.byref(t), float(grad_scale), C.byref(p), C.byref(d), None))
+    return picked, dl

@@ -272,9 +272,23 @@ def embedding(tape: Tape, weight: Var, ids: DeviceTensor) -> Var:
     return y
 
 
+FUSED_XENT = os.environ.get("B200_FUSED_XENT", "1") != "0"
+
+
 def cross_entropy(tape: Tape, logits: Var, targets: DeviceTensor) -> Var:
-    """mean(-log_softmax(logits)[target])  (cross_entropy.rs:171-197); logits [N, V], targets i32 [N]."""
+    """mean(-log_softmax(logits)[target])  (cross_entropy.rs:171-197); logits [N, V], targets i32 [N].
+    Fused: one row-resident kernel yields log_softmax[target] and the logits gradient (softmax − onehot)/N
+    (written over the logits, which nothing else reads afterwards); unfused: log_softmax → gather → mean,
+    and an exp / one-hot tape in backward."""
     n, vsz = logits.v.shape
+    if FUSED_XENT and vsz * 4 + 1024 <= 227 * 1024:
+        picked, g = ops.softmax_cross_entropy(logits.v, targets.reshape((n,)), 1.0 / n, inplace=True)
+        y = Var(ops.float_mul_scalar(ops.float_mean(picked), -1.0), True)
+
+        def bw_fused():
+            accumulate(logits, g)
+        tape.add(bw_fused)
+        return y
     logp = ops.softmax_rows(logits.v, log=True)
     picked = ops.float_gather(1, logp, targets.reshape((n, 1)))
     loss = ops.float_mul_scalar(ops.float_mean(picked), -1.0)

@@ -353,6 +353,15 @@ int32_t b200_launch_layer_norm_backward(const b200_tensor *input, const b200_ten
                                         const b200_tensor *partial_gamma,
                                         const b200_tensor *partial_beta, b200_stream s);
 
+/* Cross-entropy on logits, value and gradient in one row-resident pass:
+ * picked[r] = log_softmax(logits[r])[targets[r]] (the tensor CrossEntropyLoss::forward_default
+ * reduces with mean().neg(), crates/burn-nn/src/loss/cross_entropy.rs:171-197) and
+ * dlogits = (softmax(logits) - onehot(targets)) * grad_scale, its gradient when the caller passes
+ * grad_scale = upstream / N.  dlogits may alias logits.  targets i32 / i64 [N]. */
+int32_t b200_launch_softmax_cross_entropy(const b200_tensor *logits, const b200_tensor *targets,
+                                          double grad_scale, const b200_tensor *picked,
+                                          const b200_tensor *dlogits, b200_stream s);
+
 /* ------------------------------------------------ fused attention (forward) */
 /* ModuleOps::attention (crates/burn-backend/src/backend/ops/modules/base.rs:822-830;
  * semantics: attention_fallback, ops/modules/attention.rs:15-90):

@@ -121,3 +121,24 @@ def test_layer_norm_backward_rows(dev, shape, with_gamma):
         scale = np.abs(want).max() + 1e-30
         err = np.abs(got - want).max()
         assert err <= 2e-5 * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("n,v", [(8, 16), (33, 1001), (64, 4096), (5, 50257), (4, 50260)])
+def test_softmax_cross_entropy_value_and_gradient(dev, n, v):
+    """picked = log_softmax(x)[t] and dx = (softmax(x) − onehot(t))·scale against the oracle's log_softmax
+    (the chain CrossEntropyLoss::forward_default records) — and in place over the logits."""
+    from burn_b200 import _abi as abi
+    x = rnd((n, v), 9, -4.0, 4.0)
+    t = np.random.default_rng(10).integers(0, v, n).astype(np.int32)
+    scale = 1.0 / n
+    picked, dx = ops.softmax_cross_entropy(H.up(x), H.up(t), scale)
+    logp = oracle.log_softmax(x, 1)
+    H.assert_close(picked.numpy(), logp[np.arange(n), t], 1e-5, 1e-6, "picked")
+    want = np.exp(logp.astype(np.float64))
+    want[np.arange(n), t] -= 1.0
+    want *= scale
+    got = dx.numpy()
+    assert np.abs(got - want).max() <= 1e-6 * scale + 1e-5 * np.abs(want).max()
+    dxi = H.up(x)
+    _, same = ops.softmax_cross_entropy(dxi, H.up(t.astype(np.int64)), scale, inplace=True)
+    assert same is dxi and np.array_equal(dxi.numpy(), got)
