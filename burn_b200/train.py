@@ -106,25 +106,36 @@ def _reduce_to(g: DeviceTensor, shape) -> DeviceTensor:
     return g
 
 
-def linear(tape: Tape, x: Var, w: Var, b: Var | None, gelu_after: bool = False) -> Var:
-    """x[..., d_in] · W[d_in, d_out] + b, batch folded into M (linear.rs:26-41).  The bias add is
-    the GEMM's fuse-on-write epilogue (MatmulOptimization)."""
+def linear(tape: Tape, x: Var, w: Var, b: Var | None, residual: Var | None = None) -> Var:
+    """x[..., d_in] · W[d_in, d_out] + b [+ residual], batch folded into M (linear.rs:26-41).  The bias add —
+    and the residual add of the encoder layer that follows it (encoder.rs:263-264,283) — are the GEMM's
+    fuse-on-write epilogue (MatmulOptimization): same two roundings, no extra pass over the activations."""
     lead = x.v.shape[:-1]
     m = int(np.prod(lead))
+    n_out = w.v.shape[1]
     x2 = x.v.reshape((m, x.v.shape[-1]))
     epi = epi_in = None
-    fuse_bias = b is not None and w.v.shape[1] % 4 == 0     # the fused epilogue needs N % 4 == 0
-    if fuse_bias:
-        epi = TapeBuilder().op("ADD_F", ("in", 0), ("in", 1), out=0).build()
-        epi_in = [b.v.reshape((1, b.v.shape[-1]))]
+    fuse = b is not None and n_out % 4 == 0     # the fused epilogue needs N % 4 == 0
+    if fuse:
+        tb = TapeBuilder().op("ADD_F", ("in", 0), ("in", 1), out=None if residual is not None else 0)
+        epi_in = [b.v.reshape((1, n_out))]
+        if residual is not None:
+            tb.op("ADD_F", ("in", 2), "acc", out=0)                 # x + (acc + bias), operand order of `x + y`
+            epi_in.append(residual.v.reshape((m, n_out)))
+        epi = tb.build()
     y2 = ops.float_matmul(x2, w.v, tape.precision, epi, epi_in or ())
-    if b is not None and not fuse_bias:
-        y2 = ops.float_add(y2, b.v.reshape((1, b.v.shape[-1])))
-    y = Var(y2.reshape(tuple(lead) + (w.v.shape[1],)), True)
+    if not fuse:
+        if b is not None:
+            y2 = ops.float_add(y2, b.v.reshape((1, n_out)))
+        if residual is not None:
+            y2 = ops.float_add(residual.v.reshape((m, n_out)), y2)
+    y = Var(y2.reshape(tuple(lead) + (n_out,)), True)
 
     def bw():
         if y.g is None:
             return
+        if residual is not None:
+            accumulate(residual, y.g)
         g2 = y.g.reshape((m, w.v.shape[1]))
         if x.requires_grad:
             accumulate(x, ops.float_matmul(g2, w.v.swap_dims(0, 1), tape.precision).reshape(x.v.shape))
@@ -357,10 +368,10 @@ class EncoderLayer:
     def forward(self, tape: Tape, x: Var, mask, causal: bool = False) -> Var:
         q, k, v = linear(tape, x, self.wq, self.bq), linear(tape, x, self.wk, self.bk), linear(tape, x, self.wv, self.bv)
         ctx = attention(tape, q, k, v, self.h, mask, causal)
-        x = add(tape, x, linear(tape, ctx, self.wo, self.bo))
+        x = linear(tape, ctx, self.wo, self.bo, residual=x)       # x + attention output
         x = layer_norm(tape, x, self.g1, self.be1)                 # post-norm (norm_first = false)
         hdn = gelu(tape, linear(tape, x, self.w1, self.b1))
-        x = add(tape, x, linear(tape, hdn, self.w2, self.b2))
+        x = linear(tape, hdn, self.w2, self.b2, residual=x)        # x + feed-forward output
         return layer_norm(tape, x, self.g2, self.be2)
 
 
