@@ -186,3 +186,16 @@ extern "C" int32_t b200_collective_sync(b200_comm comm, b200_stream consumer) {
   B200_CUDA(cudaStreamWaitEvent(resolve_stream(consumer), c->done, 0));
   return B200_OK;
 }
+
+extern "C" int32_t b200_collective_mark(b200_comm comm, b200_event e) {
+  B200_REQUIRE(comm && e, B200_ERR_INVALID, "null argument");
+  Comm *c = (Comm *)comm;
+  B200_CUDA(cudaEventRecord((cudaEvent_t)e, c->stream));
+  return B200_OK;
+}
+
+extern "C" int32_t b200_stream_wait_event(b200_stream s, b200_event e) {
+  B200_REQUIRE(e, B200_ERR_INVALID, "event is null");
+  B200_CUDA(cudaStreamWaitEvent(resolve_stream(s), (cudaEvent_t)e, 0));
+  return B200_OK;
+}

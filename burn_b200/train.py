@@ -479,10 +479,12 @@ class Adam:
         """Multi-tensor Adam: one b200_launch_adam per flat bucket instead of one launch per parameter."""
         lib = abi.load()
         c = self.coef.desc()
-        for b in arena.buckets:
+        for b in arena.buckets:      # backward order: early buckets update while late all-reduces still run
+            arena.fence(b)
             p, m, s, g = b["p"].desc(), b["m"].desc(), b["s"].desc(), b["g"].desc()
             abi.check(lib.b200_launch_adam(C.byref(p), C.byref(m), C.byref(s), C.byref(g), C.byref(c),
                                            float(self.lr), float(self.b1), float(self.b2), None))
+        arena.join()
 
     def update_tape(self, pv: DeviceTensor, pm: DeviceTensor, ps: DeviceTensor, pg: DeviceTensor) -> None:
         f = np.float32
@@ -540,7 +542,11 @@ class ParamArena:
                 flats = {k: DeviceTensor.empty((size,)) for k in ("p", "m", "s", "g")}
                 for t in flats.values():
                     abi.check(lib.b200_memset(t.data_ptr(), 0, size * 4, None))
-                b = dict(flats, n=len(members), arrived=0)
+                b = dict(flats, n=len(members), arrived=0, done=None)
+                if comm is not None:          # per-bucket fence: Adam on this bucket waits for its all-reduce only
+                    ev = C.c_void_p()
+                    abi.check(lib.b200_event_create(C.byref(ev)))
+                    b["done"] = ev
                 off = 0
                 for q in members:
                     view = {k: flats[k].slice([(off, off + q.v.numel)]).reshape(q.v.shape) for k in flats}
@@ -563,12 +569,22 @@ class ParamArena:
         if b["arrived"] == b["n"]:
             if self.comm is not None:
                 self.comm.all_reduce(b["g"], mean=True)
+                abi.check(abi.load().b200_collective_mark(self.comm.handle, b["done"]))
             b["arrived"] = 0
 
     def wait(self) -> None:
-        """sync_collective: the optimizer's launches wait for every outstanding all-reduce."""
+        """Every gradient has arrived (their all-reduces may still be in flight: the optimizer fences per
+        bucket, see Adam.apply_arena)."""
         for b in self.buckets:
             if b["arrived"]:
                 raise RuntimeError("a gradient bucket is incomplete: some parameter received no gradient")
+
+    def fence(self, b: dict) -> None:
+        """The compute stream waits for bucket b's all-reduce only."""
+        if self.comm is not None:
+            abi.check(abi.load().b200_stream_wait_event(None, b["done"]))
+
+    def join(self) -> None:
+        """sync_collective: the compute stream rejoins the collective stream completely."""
         if self.comm is not None:
             self.comm.sync()

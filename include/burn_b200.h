@@ -425,6 +425,11 @@ int32_t b200_all_reduce_multi(b200_comm comm, void *const *ptrs,
 /* Makes `consumer` wait for every collective issued so far
  * (DistributedOps::sync_collective). */
 int32_t b200_collective_sync(b200_comm comm, b200_stream consumer);
+/* Finer-grained fences: record `e` on the collective stream behind the collectives issued so far,
+ * and make a stream wait for an event — so the optimizer launches of one gradient bucket wait for
+ * that bucket's all-reduce only, while later buckets are still in flight. */
+int32_t b200_collective_mark(b200_comm comm, b200_event e);
+int32_t b200_stream_wait_event(b200_stream s, b200_event e);
 
 /* ------------------------------------------------ introspection */
 /* Number of kernels this library has launched since load (bench.py's

@@ -57,6 +57,7 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
     from burn_b200 import _abi as abi
     from burn_b200 import device as dv
     from burn_b200 import train as T
+    from burn_b200 import ops
     from burn_b200.device import DeviceTensor
     from burn_b200.distributed import Communicator
 
@@ -182,6 +183,15 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     losses.append(float(loss_host[0]))
+    # replicas must still be identical after the run: compare a checksum of every parameter bucket across ranks
+    replica_spread = None
+    if world > 1:
+        sums = [float(ops.float_sum(b["p"]).numpy()[0]) for b in arena.buckets]
+        t = torch.tensor(sums, device="cuda", dtype=torch.float64)
+        hi, lo = t.clone(), t.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        replica_spread = float((hi - lo).abs().max().item())
     ms_per_step = total_ms / steps
     tokens = B * S * world
     flops = model_flops(cfg) * world
@@ -205,6 +215,8 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
         "loss_first": round(losses[0], 5), "loss_last": round(losses[-1], 5),
     }
+    if replica_spread is not None:
+        out["replica_checksum_spread"] = replica_spread     # 0.0: every rank holds bit-identical parameters
     if graph is not None:
         check(lib.b200_device_sync())
         graph.destroy()             # before the communicator: NCCL waits for graphs that captured it
