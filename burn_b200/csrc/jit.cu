@@ -64,6 +64,13 @@ static bool load_nvrtc() {
   return true;
 }
 
+// B200_TAPE_JIT_STRICT=1 (set by the test-suite): a tape that qualifies for specialisation but fails to
+// compile or load is an error instead of a silent fall back to the interpreter.
+static bool strict() {
+  static const bool v = std::getenv("B200_TAPE_JIT_STRICT") != nullptr;
+  return v;
+}
+
 static bool dtype_in_ok(int32_t dt) { return dt == B200_F32 || dt == B200_I32 || dt == B200_BOOL || dt == B200_U8 || dt == B200_BF16; }
 static bool dtype_out_ok(int32_t dt) { return dt == B200_F32 || dt == B200_I32 || dt == B200_BOOL || dt == B200_U8; }
 
@@ -147,7 +154,8 @@ static std::string generate(const CompiledTape &ct, const TapeParams &p, bool ra
   return s;
 }
 
-static cudaKernel_t compile(const std::string &src, const char *kernel_name = "b200_jit_kernel") {
+static cudaKernel_t compile(const std::string &src, const char *kernel_name = "b200_jit_kernel", bool load = true,
+                            size_t *cubin_bytes = nullptr) {
   nvrtcProgram prog = nullptr;
   const char *hdr_src[] = {kJitSrc_burn_b200_h, kJitSrc_tape_eval_cuh, kJitSrc_tape_math_cuh, kJitSrc_erf_table_inc,
                            kJitSrc_stdint_h, kJitSrc_stdint_h};
@@ -166,8 +174,9 @@ static cudaKernel_t compile(const std::string &src, const char *kernel_name = "b
   } else {
     size_t n = 0;
     if (g_rtc.GetCUBINSize(prog, &n) == 0 && n) {
+      if (cubin_bytes) *cubin_bytes = n;
       std::string cubin(n, '\0');
-      if (g_rtc.GetCUBIN(prog, &cubin[0]) == 0) {
+      if (load && g_rtc.GetCUBIN(prog, &cubin[0]) == 0) {
         cudaLibrary_t lib = nullptr;
         if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess) {
           if (cudaLibraryGetKernel(&kern, lib, kernel_name) != cudaSuccess) kern = nullptr;
@@ -198,7 +207,8 @@ static std::string gen_reduce(const CompiledTape &ct, const TapeParams &p, int32
   s += "#include \"burn_b200.h\"\n#include \"tape_eval.cuh\"\nusing namespace b200;\n";
   s += "struct RedParams { float *out; uint32_t outer, R, inner4; uint32_t r4, splits, per_split; float div; };\n";
   const bool is_sum = kind == B200_RED_SUM || kind == B200_RED_MEAN, is_max = kind == B200_RED_MAX;
-  s += std::string("#define IDENT ") + (is_sum ? "0.0f" : (is_max ? "(-INFINITY)" : "INFINITY")) + "\n";
+  // NVRTC has no <math.h>: spell the infinities as bit patterns
+  s += std::string("#define IDENT ") + (is_sum ? "0.0f" : (is_max ? "__int_as_float(0xff800000)" : "__int_as_float(0x7f800000)")) + "\n";
   if (is_sum) s += "__device__ __forceinline__ float comb(float a, float b) { return __fadd_rn(a, b); }\n";
   else s += std::string("__device__ __forceinline__ float comb(float a, float b) { return (a != a) ? a : ((b != b) ? b : ") +
             (is_max ? "fmaxf" : "fminf") + "(a, b)); }\n";
@@ -371,7 +381,7 @@ int32_t jit_try_reduce(const CompiledTape &ct, const TapeParams &p, int rank_mod
     if (it == jit::g_cache.end()) it = jit::g_cache.emplace(key, jit::compile(src, kname)).first;
     kern = it->second;
   }
-  if (!kern) return 0;
+  if (!kern) return jit::strict() ? fail(B200_ERR_CUDA, "NVRTC specialisation failed (see stderr) and B200_TAPE_JIT_STRICT is set") : 0;
   float *partials = nullptr;
   if (splits > 1) B200_CUDA(cudaMallocAsync((void **)&partials, (size_t)outer * splits * (col ? inner : 1) * sizeof(float), stream));
   Q.out = splits > 1 ? partials : out;
@@ -425,7 +435,7 @@ int32_t jit_try_elemwise(const CompiledTape &ct, const TapeParams &p, int vec, i
     if (it == jit::g_cache.end()) it = jit::g_cache.emplace(src, jit::compile(src)).first;
     kern = it->second;
   }
-  if (!kern) return 0;
+  if (!kern) return jit::strict() ? fail(B200_ERR_CUDA, "NVRTC specialisation failed (see stderr) and B200_TAPE_JIT_STRICT is set") : 0;
   JitParams P;
   memset(&P, 0, sizeof(P));
   for (int i = 0; i < ct.n_in; ++i) P.in[i] = p.in[i].ptr;
@@ -442,3 +452,63 @@ int32_t jit_try_elemwise(const CompiledTape &ct, const TapeParams &p, int vec, i
 }
 
 }  // namespace b200
+
+// Generates and NVRTC-compiles (for sm_100a, without loading — no device needed) the specialised kernels of
+// a reference tape: the bench chain as an elementwise kernel (linear and rank-3 forms) and as a fuse-on-read
+// row / column reduction.  The "does the JIT path build" check of the CPU test-suite.
+extern "C" int32_t b200_jit_selftest(uint64_t *cubin_bytes_total) {
+  using namespace b200;
+  b200_tape_op ops[8];
+  memset(ops, 0, sizeof(ops));
+  auto set = [&](int i, int op, uint8_t a, uint8_t b, uint8_t c, uint8_t dt, uint8_t dout) {
+    ops[i].op = (uint8_t)op; ops[i].a = a; ops[i].b = b; ops[i].c = c; ops[i].dst_temp = dt; ops[i].dst_out = dout;
+  };
+  const uint8_t NONE = B200_DST_NONE;
+  set(0, B200_OP_MUL_F, B200_ARG_INPUT(0), B200_ARG_INPUT(1), 0, NONE, NONE);
+  set(1, B200_OP_ADD_F, B200_ARG_ACC, B200_ARG_INPUT(2), 0, 0, NONE);
+  set(2, B200_OP_DIV_F, B200_ARG_TEMP(0), B200_ARG_SCALAR(0), 0, NONE, NONE);
+  set(3, B200_OP_ERF_F, B200_ARG_ACC, 0, 0, NONE, NONE);
+  set(4, B200_OP_ADD_F, B200_ARG_ACC, B200_ARG_SCALAR(1), 0, NONE, NONE);
+  set(5, B200_OP_MUL_F, B200_ARG_TEMP(0), B200_ARG_ACC, 0, NONE, NONE);
+  set(6, B200_OP_DIV_F, B200_ARG_ACC, B200_ARG_SCALAR(2), 0, NONE, NONE);
+  set(7, B200_OP_SELECT, B200_ARG_ACC, B200_ARG_SCALAR(3), B200_ARG_INPUT(3), NONE, 0);
+  const float sc[4] = {1.41421356237f, 1.0f, 2.0f, 0.0f};
+  uint32_t scalars[4];
+  memcpy(scalars, sc, sizeof(sc));
+  b200_tape tape = {ops, 8, scalars, 4};
+  CompiledTape ct;
+  int32_t st = compile_tape(&tape, 4, 1, ct);
+  if (st != B200_OK) return st;
+  TapeParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < 4; ++i) {
+    p.in[i].mode = kModeVec;
+    p.in[i].dtype = i == 3 ? B200_BOOL : B200_F32;
+    p.in[i].s3[0] = 0; p.in[i].s3[1] = 4096; p.in[i].s3[2] = 1;
+  }
+  p.in[2].mode = kModeBcast;            // a per-row operand in the rank-3 form
+  p.in[2].s3[1] = 1; p.in[2].s3[2] = 0;
+  p.out[0].mode = kModeVec; p.out[0].dtype = B200_F32; p.out[0].s3[1] = 4096; p.out[0].s3[2] = 1;
+  p.shape[0] = 1; p.shape[1] = 1024; p.shape[2] = 4096;
+  std::lock_guard<std::mutex> lock(jit::g_mu);
+  B200_REQUIRE(jit::load_nvrtc(), B200_ERR_UNSUPPORTED, "libnvrtc is not available");
+  uint64_t total = 0;
+  auto check = [&](const std::string &src, const char *name) -> int32_t {
+    size_t n = 0;
+    jit::compile(src, name, false, &n);
+    B200_REQUIRE(n > 0, B200_ERR_CUDA, "NVRTC produced no cubin for %s", name);
+    total += n;
+    return B200_OK;
+  };
+  if ((st = check(jit::generate(ct, p, true), "b200_jit_kernel")) != B200_OK) return st;
+  p.in[2].mode = kModeVec; p.in[2].s3[1] = 4096; p.in[2].s3[2] = 1;
+  if ((st = check(jit::generate(ct, p, false), "b200_jit_kernel")) != B200_OK) return st;
+  // the same chain without its output as a fuse-on-read tape
+  ct.ops.back().dst_out = -1;
+  ct.n_out = 0;
+  if ((st = check(jit::gen_reduce(ct, p, B200_RED_SUM, false), "b200_jit_rows_cta")) != B200_OK) return st;
+  if ((st = check(jit::gen_reduce(ct, p, B200_RED_MIN, false), "b200_jit_rows_warp")) != B200_OK) return st;
+  if ((st = check(jit::gen_reduce(ct, p, B200_RED_MAX, true), "b200_jit_cols")) != B200_OK) return st;
+  if (cubin_bytes_total) *cubin_bytes_total = total;
+  return B200_OK;
+}

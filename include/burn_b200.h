@@ -431,6 +431,10 @@ int32_t b200_collective_sync(b200_comm comm, b200_stream consumer);
 int32_t b200_collective_mark(b200_comm comm, b200_event e);
 int32_t b200_stream_wait_event(b200_stream s, b200_event e);
 
+/* NVRTC specialisation self-test: generates and compiles (sm_100a, no device needed, nothing loaded)
+ * the specialised elementwise and fuse-on-read reduce kernels of the bench chain; reports the cubin bytes. */
+int32_t b200_jit_selftest(uint64_t *cubin_bytes_total);
+
 /* ------------------------------------------------ introspection */
 /* Number of kernels this library has launched since load (bench.py's
  * gpu_launches claim) and a reset. */

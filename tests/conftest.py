@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# a tape that qualifies for NVRTC specialisation must compile: no silent fall back to the interpreter in tests
+os.environ.setdefault("B200_TAPE_JIT_STRICT", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -68,3 +68,13 @@ def test_no_gpu_means_loud_failure_not_fallback():
     with pytest.raises(abi.B200Error):
         from burn_b200 import device
         device.DeviceTensor.empty((4,))
+
+
+def test_nvrtc_specialised_kernels_compile_without_a_device():
+    """jit.cu's generator + NVRTC on the bench chain (elementwise linear / rank-3 forms, row and column
+    fuse-on-read reductions), compiled for sm_100a — no GPU is touched, nothing is loaded."""
+    import ctypes as C
+    from burn_b200 import _abi as abi
+    n = C.c_uint64()
+    abi.check(abi.load().b200_jit_selftest(C.byref(n)))
+    assert n.value > 10_000
