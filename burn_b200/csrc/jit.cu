@@ -509,6 +509,12 @@ extern "C" int32_t b200_jit_selftest(uint64_t *cubin_bytes_total) {
   if ((st = check(jit::gen_reduce(ct, p, B200_RED_SUM, false), "b200_jit_rows_cta")) != B200_OK) return st;
   if ((st = check(jit::gen_reduce(ct, p, B200_RED_MIN, false), "b200_jit_rows_warp")) != B200_OK) return st;
   if ((st = check(jit::gen_reduce(ct, p, B200_RED_MAX, true), "b200_jit_cols")) != B200_OK) return st;
+  // every opcode of the ISA instantiated once, so an intrinsic NVRTC does not know surfaces here
+  std::string all = "#include \"burn_b200.h\"\n#include \"tape_eval.cuh\"\nusing namespace b200;\n"
+                    "extern \"C\" __global__ void b200_jit_allops(uint32_t *p) {\n  uint32_t a = p[0], b = p[1], c = p[2];\n";
+  for (int k = 0; k < kIOpCount; ++k) all += "  a = eval_op<" + std::to_string(k) + ">(a, b, c);\n";
+  all += "  p[3] = a;\n}\n";
+  if ((st = check(all, "b200_jit_allops")) != B200_OK) return st;
   if (cubin_bytes_total) *cubin_bytes_total = total;
   return B200_OK;
 }
