@@ -213,3 +213,29 @@ def log_softmax(x: LazyTensor, dim: int) -> LazyTensor:
     d.drop()
     ls.drop()
     return y
+
+
+def layer_norm(x: LazyTensor, gamma: LazyTensor, beta: LazyTensor | None, eps: float) -> LazyTensor:
+    """ModuleOps::layer_norm's default chain (ops/modules/base.rs:846-877) along the last axis; gamma / beta are
+    [1, …, d_model] tensors (the reference reshapes them, a metadata op)."""
+    dim = len(x.shape) - 1
+    mean = x.mean_dim(dim)
+    c = x.sub(mean)
+    mean.drop()
+    sq = c.mul(c)
+    var = sq.mean_dim(dim)
+    sq.drop()
+    ve = var.add_scalar(eps)
+    var.drop()
+    den = ve.sqrt()
+    ve.drop()
+    n = c.div(den)
+    c.drop()
+    den.drop()
+    y = n.mul(gamma)
+    n.drop()
+    if beta is not None:
+        z = y.add(beta)
+        y.drop()
+        return z
+    return y

@@ -202,7 +202,9 @@ struct Candidate {
   std::vector<const Op *> read_ops, write_ops;
   const Op *core = nullptr;  // the reduce / matmul op
   int64_t row_in = -1, row_out = -1;   // ROWNORM: the chain's input and output tensors
-  bool row_log = false;                // ROWNORM: log_softmax
+  int row_kind = 0;                    // ROWNORM: 0 softmax, 1 log_softmax, 2 layer_norm
+  int64_t row_gamma = -1, row_beta = -1;
+  double row_eps = 0;
   std::unordered_set<int64_t> dropped;
   TapeBuild read_tape, write_tape;
 };
@@ -270,40 +272,68 @@ struct Stream {
     c.kind = B200H_BLOCK_ROWNORM;
     std::vector<const Op *> ops;
     std::vector<size_t> pos;
-    std::unordered_set<int64_t> drops;
-    size_t q = 0;
-    for (; q < queue.size() && ops.size() < 6; ++q) {
-      if (queue[q].kind == Kind::Drop) { if (ops.empty()) return none; drops.insert(queue[q].in[0]); continue; }
+    for (size_t q = 0; q < queue.size() && ops.size() < 9; ++q) {
+      if (queue[q].kind == Kind::Drop) { if (ops.empty()) return none; continue; }
       ops.push_back(&queue[q]);
       pos.push_back(q);
     }
     if (ops.size() < 5) return none;
-    const Op &mx = *ops[0], &sb = *ops[1], &ex = *ops[2], &sm = *ops[3], &o4 = *ops[4];
-    const Tensor *x = get(mx.in[0]);
-    if (!x || x->dtype != B200_F32 || x->shape.empty()) return none;
+    const Op &o0 = *ops[0];
+    const Tensor *x = get(o0.in[0]);
+    if (!x || x->dtype != B200_F32 || x->shape.empty() || x->strides != contiguous(x->shape)) return none;
     const int last = (int)x->shape.size() - 1;
-    if (x->strides != contiguous(x->shape)) return none;
-    if (!(mx.kind == Kind::ReduceDim && mx.opcode == B200_RED_MAX && mx.dim == last)) return none;
-    if (!(sb.kind == Kind::Binary && sb.opcode == B200_OP_SUB_F && sb.in[0] == mx.in[0] && sb.in[1] == mx.out)) return none;
-    if (!(ex.kind == Kind::Unary && ex.opcode == B200_OP_EXP_F && ex.in[0] == sb.out)) return none;
-    if (!(sm.kind == Kind::ReduceDim && sm.opcode == B200_RED_SUM && sm.dim == last && sm.in[0] == ex.out)) return none;
-    std::vector<int64_t> inter = {mx.out, sb.out, ex.out, sm.out};
-    size_t n_ops;
-    if (o4.kind == Kind::Binary && o4.opcode == B200_OP_DIV_F && o4.in[0] == ex.out && o4.in[1] == sm.out) {
-      n_ops = 5;
-      c.row_out = o4.out;
-    } else if (ops.size() >= 6 && o4.kind == Kind::Unary && o4.opcode == B200_OP_LOG_F && o4.in[0] == sm.out &&
-               ops[5]->kind == Kind::Binary && ops[5]->opcode == B200_OP_SUB_F && ops[5]->in[0] == sb.out &&
-               ops[5]->in[1] == o4.out) {
-      n_ops = 6;
-      c.row_log = true;
-      c.row_out = ops[5]->out;
-      inter.push_back(o4.out);
+    auto is_bin = [](const Op &o, int opc, int64_t a, int64_t b) { return o.kind == Kind::Binary && o.opcode == opc && o.in[0] == a && o.in[1] == b; };
+    auto is_un = [](const Op &o, int opc, int64_t a) { return o.kind == Kind::Unary && o.opcode == opc && o.in[0] == a; };
+    auto is_red = [&](const Op &o, int kind, int64_t a) { return o.kind == Kind::ReduceDim && o.opcode == kind && o.dim == last && o.in[0] == a; };
+    std::vector<int64_t> inter;
+    size_t n_ops = 0;
+    const int64_t xid = o0.in[0];
+    if (is_red(o0, B200_RED_MAX, xid) && is_bin(*ops[1], B200_OP_SUB_F, xid, o0.out) && is_un(*ops[2], B200_OP_EXP_F, ops[1]->out) &&
+        is_red(*ops[3], B200_RED_SUM, ops[2]->out)) {
+      inter = {o0.out, ops[1]->out, ops[2]->out, ops[3]->out};
+      if (is_bin(*ops[4], B200_OP_DIV_F, ops[2]->out, ops[3]->out)) {
+        n_ops = 5;
+        c.row_kind = 0;
+        c.row_out = ops[4]->out;
+      } else if (ops.size() >= 6 && is_un(*ops[4], B200_OP_LOG_F, ops[3]->out) &&
+                 is_bin(*ops[5], B200_OP_SUB_F, ops[1]->out, ops[4]->out)) {
+        n_ops = 6;
+        c.row_kind = 1;
+        c.row_out = ops[5]->out;
+        inter.push_back(ops[4]->out);
+      } else {
+        return none;
+      }
+    } else if (ops.size() >= 8 && is_red(o0, B200_RED_MEAN, xid) && is_bin(*ops[1], B200_OP_SUB_F, xid, o0.out) &&
+               is_bin(*ops[2], B200_OP_MUL_F, ops[1]->out, ops[1]->out) && is_red(*ops[3], B200_RED_MEAN, ops[2]->out) &&
+               ops[4]->kind == Kind::Scalar && ops[4]->opcode == B200_OP_ADD_F && ops[4]->in[0] == ops[3]->out &&
+               is_un(*ops[5], B200_OP_SQRT_F, ops[4]->out) && is_bin(*ops[6], B200_OP_DIV_F, ops[1]->out, ops[5]->out) &&
+               ops[7]->kind == Kind::Binary && ops[7]->opcode == B200_OP_MUL_F && ops[7]->in[0] == ops[6]->out) {
+      // layer_norm = mean_dim, sub, mul, mean_dim, add_scalar, sqrt, div, mul(gamma) [, add(beta)]  (modules/base.rs:846-877)
+      auto is_vec = [&](int64_t id) {
+        const Tensor *t = get(id);
+        return t && t->dtype == B200_F32 && numel(t->shape) == x->shape[last] && !t->shape.empty() && t->shape.back() == x->shape[last] &&
+               t->strides == contiguous(t->shape);
+      };
+      if (!is_vec(ops[7]->in[1])) return none;
+      inter = {o0.out, ops[1]->out, ops[2]->out, ops[3]->out, ops[4]->out, ops[5]->out, ops[6]->out};
+      c.row_kind = 2;
+      c.row_gamma = ops[7]->in[1];
+      c.row_eps = ops[4]->scalar;
+      n_ops = 8;
+      c.row_out = ops[7]->out;
+      if (ops.size() >= 9 && ops[8]->kind == Kind::Binary && ops[8]->opcode == B200_OP_ADD_F && ops[8]->in[0] == ops[7]->out &&
+          is_vec(ops[8]->in[1])) {
+        inter.push_back(ops[7]->out);
+        c.row_beta = ops[8]->in[1];
+        c.row_out = ops[8]->out;
+        n_ops = 9;
+      }
     } else {
       return none;
     }
-    // drops seen up to the last op of the chain, plus the drops that directly follow it
-    drops.clear();
+    // drops seen up to the last op of the chain, plus the drops of intermediates that directly follow it
+    std::unordered_set<int64_t> drops;
     size_t end = pos[n_ops - 1] + 1;
     for (size_t i = 0; i < end; ++i)
       if (queue[i].kind == Kind::Drop) drops.insert(queue[i].in[0]);
@@ -315,8 +345,8 @@ struct Stream {
     for (int64_t id : inter)
       if (!drops.count(id)) return none;          // an intermediate is still wanted: leave it to the other fusers
     for (int64_t id : drops)
-      if (std::find(inter.begin(), inter.end(), id) == inter.end() && id != mx.in[0]) return none;
-    c.row_in = mx.in[0];
+      if (std::find(inter.begin(), inter.end(), id) == inter.end() && id != xid) return none;
+    c.row_in = xid;
     c.dropped = drops;
     c.n_ops = (int)n_ops;
     c.consumed = (int)end;
@@ -518,9 +548,16 @@ struct Stream {
       if ((st = materialise(c.row_out)) != B200_OK) return st;
       b200_tensor xin, yout;
       if ((st = desc_of(c.row_in, xin)) != B200_OK || (st = desc_of(c.row_out, yout)) != B200_OK) return st;
-      info.n_inputs = 1;
+      info.n_inputs = 1 + (c.row_gamma >= 0) + (c.row_beta >= 0);
       info.n_outputs = 1;
-      if (!plan_only) st = b200_launch_softmax(&xin, &yout, c.row_log ? 1 : 0, nullptr);
+      if (c.row_kind == 2) {
+        b200_tensor g, bt;
+        if ((st = desc_of(c.row_gamma, g)) != B200_OK) return st;
+        if (c.row_beta >= 0 && (st = desc_of(c.row_beta, bt)) != B200_OK) return st;
+        if (!plan_only) st = b200_launch_layer_norm(&xin, &g, c.row_beta >= 0 ? &bt : nullptr, c.row_eps, &yout, nullptr);
+      } else if (!plan_only) {
+        st = b200_launch_softmax(&xin, &yout, c.row_kind == 1 ? 1 : 0, nullptr);
+      }
     } else if (c.kind == B200H_BLOCK_MATMUL) {
       const Op &mm = *c.core;
       const int64_t out_id = c.write_ops.empty() ? mm.out : c.write_tape.outputs[0];

@@ -40,7 +40,7 @@ typedef enum {
   B200H_BLOCK_REDUCE = 1,
   B200H_BLOCK_MATMUL = 2,
   B200H_BLOCK_EAGER = 3, /* op no fuser accepts, executed on its own */
-  B200H_BLOCK_ROWNORM = 4 /* softmax / log_softmax chain → one row-resident kernel (ReduceBroadcasted) */
+  B200H_BLOCK_ROWNORM = 4 /* softmax / log_softmax / layer_norm chain → one row-resident kernel (ReduceBroadcasted) */
 } b200h_block_kind;
 
 /* One executed (or planned) optimization — the FusionInspector view

@@ -113,6 +113,23 @@ def test_softmax_chain_along_the_last_axis_is_one_row_resident_block(st):
     assert z.shape == (64, 256)
 
 
+def test_layer_norm_chain_is_one_row_resident_block(st):
+    # mean_dim, sub, mul, mean_dim, add_scalar, sqrt, div, mul(gamma), add(beta)  (modules/base.rs:846-877)
+    x = st.placeholder((32, 8, 512))
+    gamma, beta = st.placeholder((1, 1, 512)), st.placeholder((1, 1, 512))
+    y = F.layer_norm(x, gamma, beta, 1e-5)
+    st.sync()
+    (blk,) = st.blocks()
+    assert blk.kind == F.BLOCK_ROWNORM and blk.n_ops == 9 and blk.n_inputs == 3 and blk.n_outputs == 1
+    assert y.shape == (32, 8, 512)
+    st.clear_blocks()
+    z = F.layer_norm(x, gamma, None, 1e-5)
+    st.sync()
+    (blk,) = st.blocks()
+    assert blk.kind == F.BLOCK_ROWNORM and blk.n_ops == 8 and blk.n_inputs == 2
+    assert z.shape == (32, 8, 512)
+
+
 def test_softmax_with_a_live_intermediate_or_another_axis_decomposes(st):
     x = st.placeholder((64, 256))
     mx = x.max_dim(1)

@@ -84,6 +84,14 @@ def test_softmax_through_the_stream(st):
     assert sum(b.launches for b in st.blocks()) == len(st.blocks())   # one launch per block
 
 
+def test_layer_norm_through_the_stream(st):
+    x = rnd((16, 8, 256), 9, -2, 2)
+    g, b = rnd((1, 1, 256), 10, 0.5, 1.5), rnd((1, 1, 256), 11, -0.5, 0.5)
+    y = F.layer_norm(st.tensor(x), st.tensor(g), st.tensor(b), 1e-5)
+    H.assert_close(y.numpy(), oracle.layer_norm(x, g.reshape(256), b.reshape(256), 1e-5), 1e-5, 1e-6)
+    assert [(k.kind, k.n_ops, k.launches) for k in st.blocks()] == [(F.BLOCK_ROWNORM, 9, 1)]
+
+
 def test_argmax_and_sum_dim_exact(st):
     x = rnd((300, 1000), 6)
     tx = st.tensor(x)
