@@ -289,9 +289,30 @@ struct XentParams {
   float grad_scale;
 };
 
-__global__ void __launch_bounds__(kBlock) softmax_xent_kernel(const XentParams P) {
+// 1024 threads: a 200 KB vocabulary row leaves room for one CTA per SM, so the CTA itself has to keep
+// enough 128-bit loads in flight
+constexpr int kXBlock = 1024;
+__device__ __forceinline__ float xblock_sum(float v, float *scratch) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return warp_sum(scratch[threadIdx.x & 31]);          // kXBlock / 32 == 32 partials
+}
+__device__ __forceinline__ float xblock_max(float v, float *scratch) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) v = nan_max(v, __shfl_xor_sync(0xffffffffu, v, s));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = scratch[threadIdx.x & 31];
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) r = nan_max(r, __shfl_xor_sync(0xffffffffu, r, s));
+  return r;
+}
+__global__ void __launch_bounds__(kXBlock) softmax_xent_kernel(const XentParams P) {
   extern __shared__ __align__(16) float rowbuf[];
-  __shared__ float scratch[kWarps];
+  __shared__ float scratch[kXBlock / 32];
   for (uint32_t row = blockIdx.x; row < P.rows; row += gridDim.x) {
     const float *xr = P.x + (int64_t)row * P.x_stride;
     float *dr = P.dx + (int64_t)row * P.dx_stride;
@@ -301,28 +322,28 @@ __global__ void __launch_bounds__(kBlock) softmax_xent_kernel(const XentParams P
     if (P.vec) {
       const float4 *x4 = reinterpret_cast<const float4 *>(xr);
       float4 *b4 = reinterpret_cast<float4 *>(rowbuf);
-      for (uint32_t i = threadIdx.x; i < (P.R >> 2); i += kBlock) b4[i] = __ldcs(x4 + i);
+      for (uint32_t i = threadIdx.x; i < (P.R >> 2); i += kXBlock) b4[i] = __ldcs(x4 + i);
     } else {
-      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) rowbuf[i] = __ldcs(xr + i);
+      for (uint32_t i = threadIdx.x; i < P.R; i += kXBlock) rowbuf[i] = __ldcs(xr + i);
     }
     __syncthreads();
     float m = -INFINITY;
-    for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) m = nan_max(m, rowbuf[i]);
-    m = block_reduce_max(m, scratch);
+    for (uint32_t i = threadIdx.x; i < P.R; i += kXBlock) m = nan_max(m, rowbuf[i]);
+    m = xblock_max(m, scratch);
     float s = 0.f;
-    for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) {
+    for (uint32_t i = threadIdx.x; i < P.R; i += kXBlock) {
       const float sh = __fsub_rn(rowbuf[i], m);
       rowbuf[i] = sh;                      // shifted logit, as in log_softmax
       s = __fadd_rn(s, expf(sh));
     }
-    s = block_reduce_sum(s, scratch);
+    s = xblock_sum(s, scratch);
     const float ls = logf(s);
     if (threadIdx.x == 0 && t >= 0 && t < (int64_t)P.R) P.picked[row] = __fsub_rn(rowbuf[t], ls);
     // gradient: exp(log_softmax) - onehot, scaled — the same values the unfused tape produces
     if (P.vec) {
       const float4 *b4 = reinterpret_cast<const float4 *>(rowbuf);
       float4 *d4 = reinterpret_cast<float4 *>(dr);
-      for (uint32_t i = threadIdx.x; i < (P.R >> 2); i += kBlock) {
+      for (uint32_t i = threadIdx.x; i < (P.R >> 2); i += kXBlock) {
         const float4 sh = b4[i];
         float4 o;
         o.x = expf(__fsub_rn(sh.x, ls)); o.y = expf(__fsub_rn(sh.y, ls)); o.z = expf(__fsub_rn(sh.z, ls)); o.w = expf(__fsub_rn(sh.w, ls));
@@ -338,7 +359,7 @@ __global__ void __launch_bounds__(kBlock) softmax_xent_kernel(const XentParams P
         __stcs(d4 + i, o);
       }
     } else {
-      for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) {
+      for (uint32_t i = threadIdx.x; i < P.R; i += kXBlock) {
         float o = expf(__fsub_rn(rowbuf[i], ls));
         if ((int64_t)i == t) o = __fsub_rn(o, 1.0f);
         __stcs(dr + i, __fmul_rn(o, P.grad_scale));
@@ -441,9 +462,9 @@ extern "C" int32_t b200_launch_softmax_cross_entropy(const b200_tensor *logits, 
   auto kern = rn::softmax_xent_kernel;
   if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rn::kBlock, smem));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rn::kXBlock, smem));
   const unsigned grid = (unsigned)std::min<int64_t>(N, (int64_t)sm_count() * std::max(per_sm, 1));
-  kern<<<grid, rn::kBlock, smem, resolve_stream(s)>>>(P);
+  kern<<<grid, rn::kXBlock, smem, resolve_stream(s)>>>(P);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
