@@ -10,6 +10,7 @@ from pathlib import Path
 import numpy as np
 
 GOLDEN = Path(__file__).resolve().parent / "golden" / "burn_backend_tests.json"
+UNARY = ("erf", "exp", "log", "sqrt", "abs", "ceil", "floor", "neg", "recip", "round", "sign", "log1p", "tanh")
 
 
 def load_cases():
@@ -66,12 +67,16 @@ def run_oracle(case):
         return getattr(o, f"float_{op}")(f(0), f(1))
     if op.endswith("_scalar"):
         return getattr(o, f"float_{op}")(f(0), args["scalar"])
-    if op in ("erf", "exp", "log", "sqrt"):
+    if op in UNARY:
         return getattr(o, f"float_{op}")(f(0))
     if op in ("gelu", "relu", "sigmoid"):
         return getattr(o, op)(f(0))
     if op == "softmax":
         return o.softmax(f(0), args["dim"])
+    if op == "log_softmax":
+        return o.log_softmax(f(0), args["dim"])
+    if op == "clamp":
+        return o.float_clamp(f(0), args["min"], args["max"])
     if op == "mask_where":
         return o.float_mask_where(f(0), to_array(ins[1], bool), f(2))
     if op == "mask_fill_le":
@@ -120,12 +125,16 @@ def run_device(case):
         return getattr(ops, f"float_{op}")(t(0), t(1)).numpy()
     if op.endswith("_scalar"):
         return getattr(ops, f"float_{op}")(t(0), args["scalar"]).numpy()
-    if op in ("erf", "exp", "log", "sqrt"):
+    if op in UNARY:
         return getattr(ops, f"float_{op}")(t(0)).numpy()
     if op in ("gelu", "relu", "sigmoid"):
         return getattr(ops, op)(t(0)).numpy()
     if op == "softmax":
         return ops.softmax(t(0), args["dim"]).numpy()
+    if op == "log_softmax":
+        return ops.log_softmax(t(0), args["dim"]).numpy()
+    if op == "clamp":
+        return ops.float_clamp(t(0), args["min"], args["max"]).numpy()
     if op == "mask_where":
         return ops.float_mask_where(t(0), t(1, bool), t(2)).numpy()
     if op == "mask_fill_le":
