@@ -97,6 +97,8 @@ SIGNATURES = {
     "b200_device_sync": (_i32, []),
     "b200_last_error": (C.c_char_p, []),
     "b200_alloc": (_i32, [C.POINTER(_vp), _u64, _vp]),
+    "b200_retain": (_i32, [_vp]),
+    "b200_refcount": (_i32, [_vp, C.POINTER(C.c_uint32)]),
     "b200_free": (_i32, [_vp, _vp]),
     "b200_memory_cleanup": (_i32, []),
     "b200_memset": (_i32, [_vp, _i32, _u64, _vp]),

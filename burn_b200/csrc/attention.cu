@@ -656,9 +656,8 @@ extern "C" int32_t b200_launch_attention(const b200_tensor *q, const b200_tensor
   B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
   const size_t smem = 1024 + attn::kQBytes + attn::kKBytes + attn::kVBytes + attn::kPBytes + (P.mask_tma ? attn::kMBytes : 0) + 128;
   auto launch = [&](auto kern) -> int32_t {
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // two CTAs per SM need the largest shared-memory carveout
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    { const int32_t est = ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem, true); if (est != B200_OK) return est; }
     kern<<<(unsigned)ctas, attn::kThreads, smem, resolve_stream(s)>>>(P);
     B200_LAUNCH_CHECK();
     return B200_OK;
@@ -746,8 +745,7 @@ extern "C" int32_t b200_launch_attention_backward(const b200_tensor *d_out, cons
   const int64_t ctas = B * H * P.q_blocks;
   B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
   const size_t smem = 1024 + attn::kQBytes + attn::kKBytes + attn::kVBytes + attn::kPBytes + 128;
-  B200_CUDA(cudaFuncSetAttribute(attn::attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  B200_CUDA(cudaFuncSetAttribute(attn::attention_bwd_dq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  { const int32_t est = ensure_dyn_smem(reinterpret_cast<const void *>(attn::attention_bwd_dq_kernel), smem, true); if (est != B200_OK) return est; }
   attn::attention_bwd_dq_kernel<<<(unsigned)ctas, attn::kThreads, smem, resolve_stream(s)>>>(P);
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -127,12 +127,21 @@ extern "C" int32_t b200_comm_init(b200_comm *out, const uint8_t id[B200_NCCL_UNI
   c->world = world_size;
   ncclUniqueId uid;
   memcpy(uid.internal, id, B200_NCCL_UNIQUE_ID_BYTES);
-  B200_NCCL(g_nccl.CommInitRank(&c->comm, world_size, uid, rank));
-  int lo = 0, hi = 0;
-  B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  B200_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
-  B200_CUDA(cudaEventCreateWithFlags(&c->fence, cudaEventDisableTiming));
-  B200_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+  // a failure below must not leak the half-built communicator, its stream or its events
+  auto build = [&]() -> int32_t {
+    B200_NCCL(g_nccl.CommInitRank(&c->comm, world_size, uid, rank));
+    int lo = 0, hi = 0;
+    B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    B200_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+    B200_CUDA(cudaEventCreateWithFlags(&c->fence, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+    return B200_OK;
+  };
+  st = build();
+  if (st != B200_OK) {
+    b200_comm_destroy((b200_comm)c);
+    return st;
+  }
   *out = (b200_comm)c;
   return B200_OK;
 }

@@ -11,6 +11,9 @@
 
 namespace b200 {
 
+// Out-of-range indices: the reference panics (crates/burn-ndarray/src/ops/base.rs:106-183 index with
+// `as usize`); here the offending access is skipped, a sticky code lands in a host-mapped flag and the
+// next synchronising call (b200_stream_sync / b200_device_sync / blocking d2h copy) returns B200_ERR_SHAPE.
 struct IdxTensor {
   void *ptr;
   int64_t shape[kMaxDims];
@@ -46,7 +49,7 @@ __device__ __forceinline__ void copy_elem(void *dst, int64_t doff, const void *s
 }
 
 // out[c] = in[c with c[dim] = idx[c]]   (one thread per output element)
-__global__ void gather_kernel(IdxTensor in, IdxTensor idx, IdxTensor out, int dim, int es, int64_t n) {
+__global__ void gather_kernel(IdxTensor in, IdxTensor idx, IdxTensor out, int dim, int es, int64_t n, int32_t *err) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t rest = i, ioff = 0, xoff = 0, ooff = 0;
@@ -63,12 +66,13 @@ __global__ void gather_kernel(IdxTensor in, IdxTensor idx, IdxTensor out, int di
     }
     (void)cdim;
     const int64_t k = load_index(idx.ptr, idx.dtype, xoff);
+    if (k < 0 || k >= in.shape[dim]) { *err = kIdxErrGather; continue; }   // the reference panics; reported at the next sync
     copy_elem(out.ptr, ooff, in.ptr, ioff + k * in.strides[dim], es);
   }
 }
 
 // out[o, i, c] = in[o, idx[i], c]  (select / index_select; idx is 1-D)
-__global__ void select_kernel(IdxTensor in, IdxTensor idx, IdxTensor out, int dim, int es, int64_t n) {
+__global__ void select_kernel(IdxTensor in, IdxTensor idx, IdxTensor out, int dim, int es, int64_t n, int32_t *err) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t rest = i, ioff = 0, ooff = 0, k = 0;
@@ -82,6 +86,7 @@ __global__ void select_kernel(IdxTensor in, IdxTensor idx, IdxTensor out, int di
         else ioff += c * in.strides[d];
       }
     }
+    if (k < 0 || k >= in.shape[dim]) { *err = kIdxErrSelect; continue; }
     copy_elem(out.ptr, ooff, in.ptr, ioff + k * in.strides[dim], es);
   }
 }
@@ -111,13 +116,14 @@ __device__ __forceinline__ void add_elem(void *t, int64_t off, int32_t tdt, cons
 // The destination rows are partitioned into `chunks` ranges so that several
 // threads can share a lane without ever touching the same address.
 __global__ void scatter_add_kernel(IdxTensor t, IdxTensor idx, IdxTensor v, int dim, int64_t lanes,
-                                   int chunks, int64_t rows_per_chunk) {
+                                   int chunks, int64_t rows_per_chunk, int32_t *err) {
   const int64_t total = lanes * chunks;
   for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < total;
        w += (int64_t)gridDim.x * blockDim.x) {
     const int64_t lane = w % lanes;
     const int chunk = (int)(w / lanes);
-    const int64_t lo = chunk * rows_per_chunk, hi = lo + rows_per_chunk;
+    const int64_t rows = t.shape[dim];
+    const int64_t lo = chunk * rows_per_chunk, hi = min(rows, lo + rows_per_chunk);
     int64_t rest = lane, toff = 0, xoff = 0, voff = 0;
 #pragma unroll
     for (int d = kMaxDims - 1; d >= 0; --d) {
@@ -132,6 +138,7 @@ __global__ void scatter_add_kernel(IdxTensor t, IdxTensor idx, IdxTensor v, int 
     const int64_t n = idx.shape[dim];
     for (int64_t i = 0; i < n; ++i) {
       const int64_t k = load_index(idx.ptr, idx.dtype, xoff + i * idx.strides[dim]);
+      if (chunk == 0 && (k < 0 || k >= rows)) *err = kIdxErrScatter;
       if (k >= lo && k < hi)
         add_elem(t.ptr, toff + k * t.strides[dim], t.dtype, v.ptr, voff + i * v.strides[dim], v.dtype);
     }
@@ -140,13 +147,14 @@ __global__ void scatter_add_kernel(IdxTensor t, IdxTensor idx, IdxTensor v, int 
 
 // select_add: t[o, idx[i], c] += v[o, i, c], sequential in i per (o, c) lane.
 __global__ void select_add_kernel(IdxTensor t, IdxTensor idx, IdxTensor v, int dim, int64_t lanes,
-                                  int chunks, int64_t rows_per_chunk) {
+                                  int chunks, int64_t rows_per_chunk, int32_t *err) {
   const int64_t total = lanes * chunks;
   for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < total;
        w += (int64_t)gridDim.x * blockDim.x) {
     const int64_t lane = w % lanes;
     const int chunk = (int)(w / lanes);
-    const int64_t lo = chunk * rows_per_chunk, hi = lo + rows_per_chunk;
+    const int64_t rows = t.shape[dim];
+    const int64_t lo = chunk * rows_per_chunk, hi = min(rows, lo + rows_per_chunk);
     int64_t rest = lane, toff = 0, voff = 0;
 #pragma unroll
     for (int d = kMaxDims - 1; d >= 0; --d) {
@@ -160,6 +168,7 @@ __global__ void select_add_kernel(IdxTensor t, IdxTensor idx, IdxTensor v, int d
     const int64_t n = v.shape[dim];
     for (int64_t i = 0; i < n; ++i) {
       const int64_t k = load_index(idx.ptr, idx.dtype, i * idx.strides[0]);
+      if (chunk == 0 && (k < 0 || k >= rows)) *err = kIdxErrSelectAdd;
       if (k >= lo && k < hi)
         add_elem(t.ptr, toff + k * t.strides[dim], t.dtype, v.ptr, voff + i * v.strides[dim], v.dtype);
     }
@@ -175,7 +184,7 @@ __global__ void select_add_kernel(IdxTensor t, IdxTensor idx, IdxTensor v, int d
 __global__ void __launch_bounds__(256) select_add_rows_kernel(float *t, int64_t t_stride, const void *idx, int32_t idx_dtype,
                                                               int64_t idx_stride, const float *v, int64_t v_stride,
                                                               int64_t n, int64_t rows_t, int cols4, int col_groups,
-                                                              int chunks, int64_t rows_per_chunk) {
+                                                              int chunks, int64_t rows_per_chunk, int32_t *err) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -187,6 +196,7 @@ __global__ void __launch_bounds__(256) select_add_rows_kernel(float *t, int64_t 
     for (int64_t base = 0; base < n; base += 32) {
       const int64_t i = base + lane;
       const int64_t k = i < n ? load_index(idx, idx_dtype, i * idx_stride) : -1;
+      if (w == 0 && i < n && (k < 0 || k >= rows_t)) *err = kIdxErrSelectAdd;
       unsigned hits = __ballot_sync(0xffffffffu, k >= lo && k < hi);
       while (hits) {
         const int b = __ffs(hits) - 1;
@@ -324,7 +334,7 @@ extern "C" int32_t b200_launch_gather(int32_t dim, const b200_tensor *input, con
   const int64_t n = numel_of(out->shape, out->rank);
   if (n == 0) return B200_OK;
   gather_kernel<<<grid_for(n, 256), 256, 0, resolve_stream(s)>>>(to_idx(*input), to_idx(*indices), to_idx(*out),
-                                                                 dim, dtype_size(input->dtype), n);
+                                                                 dim, dtype_size(input->dtype), n, index_error_flag());
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -344,7 +354,7 @@ extern "C" int32_t b200_launch_select(int32_t dim, const b200_tensor *input, con
   const int64_t n = numel_of(out->shape, out->rank);
   if (n == 0) return B200_OK;
   select_kernel<<<grid_for(n, 256), 256, 0, resolve_stream(s)>>>(to_idx(*input), to_idx(*indices), to_idx(*out),
-                                                                 dim, dtype_size(input->dtype), n);
+                                                                 dim, dtype_size(input->dtype), n, index_error_flag());
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -378,7 +388,7 @@ extern "C" int32_t b200_launch_scatter_add(int32_t dim, const b200_tensor *tenso
   int64_t rpc;
   pick_chunks(lanes, tensor->shape[dim], chunks, rpc);
   scatter_add_kernel<<<grid_for(lanes * chunks, 128), 128, 0, resolve_stream(s)>>>(
-      to_idx(*tensor), to_idx(*indices), to_idx(*value), dim, lanes, chunks, rpc);
+      to_idx(*tensor), to_idx(*indices), to_idx(*value), dim, lanes, chunks, rpc, index_error_flag());
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -417,7 +427,7 @@ extern "C" int32_t b200_launch_select_add(int32_t dim, const b200_tensor *tensor
     select_add_rows_kernel<<<grid, 256, 0, resolve_stream(s)>>>(
         reinterpret_cast<float *>(tensor->ptr), tensor->strides[0], indices->ptr, indices->dtype, indices->strides[0],
         reinterpret_cast<const float *>(value->ptr), value->strides[0], indices->shape[0], rows_t, cols4, col_groups,
-        chunks_eff, rpc_r);
+        chunks_eff, rpc_r, index_error_flag());
     B200_LAUNCH_CHECK();
     return B200_OK;
   }
@@ -425,7 +435,7 @@ extern "C" int32_t b200_launch_select_add(int32_t dim, const b200_tensor *tensor
   int64_t rpc;
   pick_chunks(lanes, tensor->shape[dim], chunks, rpc);
   select_add_kernel<<<grid_for(lanes * chunks, 128), 128, 0, resolve_stream(s)>>>(
-      to_idx(*tensor), to_idx(*indices), to_idx(*value), dim, lanes, chunks, rpc);
+      to_idx(*tensor), to_idx(*indices), to_idx(*value), dim, lanes, chunks, rpc, index_error_flag());
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

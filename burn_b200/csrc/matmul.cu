@@ -33,6 +33,7 @@ constexpr int kThreads = 320;            // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kAccStages = 2;
 constexpr int kEpiBlock = 128, kEpiU = 4;  // epilogue tape geometry: 16 columns per dispatch
 constexpr int kMaxFastSteps = 6;
+constexpr int kRasterGroup = 8;         // m-blocks per rasterisation group (see tile_coords)
 constexpr int kOutStageBytes = 8 * 4096;  // 8 epilogue warps x one [32 rows x 128 B] staging buffer
 
 struct Params {
@@ -220,11 +221,20 @@ gemm_tcgen05_kernel(const __grid_constant__ Params P, const __grid_constant__ Ta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Grouped rasterisation: consecutive tile ids (= the tiles one wave of workers runs concurrently) walk
+  // kRasterGroup m-blocks down, then one n-block across, so a wave covers a near-square patch of the
+  // output and every A / B k-slice it streams is shared by ~8 CTAs through L2 (an m-fastest walk made
+  // each wave re-read all of A: 4.4 TB/s of HBM traffic at 16384^3).
+  const int per_batch = P.tiles_m * P.tiles_n;
   auto tile_coords = [&](int tile, int &m_blk, int &n_blk, int (&b)[kMaxBatchDims]) {
-    m_blk = tile % P.tiles_m;
-    int r = tile / P.tiles_m;
-    n_blk = r % P.tiles_n;
-    r /= P.tiles_n;
+    int r = tile / per_batch;
+    const int t = tile - r * per_batch;
+    const int span = kRasterGroup * P.tiles_n;
+    const int group = t / span, in_group = t - group * span;
+    const int first_m = group * kRasterGroup;
+    const int gsz = min(kRasterGroup, P.tiles_m - first_m);
+    n_blk = in_group / gsz;
+    m_blk = first_m + (in_group - n_blk * gsz);
     b[2] = r % P.batch[2];
     r /= P.batch[2];
     b[1] = r % P.batch[1];
@@ -667,7 +677,9 @@ static GemmConfig choose_config(const MatmulPlan &pl, int es, bool allow_split) 
   const bool can_split = allow_split && !no_split && pl.nb <= 2 && pl.batch[0] == 1;
   auto splits_for = [&](int64_t units, int64_t capacity) -> int64_t {
     if (!can_split) return 1;
-    return std::max<int64_t>(1, std::min<int64_t>({(int64_t)8, capacity / std::max<int64_t>(units, 1), pl.K / (16 * BK)}));
+    // each split must keep >= 32 k-blocks: below that the extra partials pass + combine launch cost more
+    // than the idle SMs they fill (1024^3 tf32 ran 2.6x slower split in two)
+    return std::max<int64_t>(1, std::min<int64_t>({(int64_t)8, capacity / std::max<int64_t>(units, 1), pl.K / (32 * BK)}));
   };
   const bool can_pair = !no_pair && pl.M > 128 && pl.N > 128;
   const int64_t s1 = splits_for(t128, sms), s2 = can_pair ? splits_for(t256, sms / 2) : 1;
@@ -719,7 +731,7 @@ static int32_t launch_gemm_n(const mm::Params &P, const TapeParams &T, size_t ep
   auto kern = mm::gemm_tcgen05_kernel<ES, A_MN, B_MN, CTAS>;
   const size_t stage_bytes = 32 * 1024;
   const size_t smem = 1024 + (size_t)P.stages * stage_bytes + (P.epi_fast ? mm::kOutStageBytes : 0) + 256 + epi_bytes + 64;
-  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int32_t est = ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem); if (est != B200_OK) return est; }
   const int n_tiles = P.tiles_m * P.tiles_n * P.batch[0] * P.batch[1] * P.batch[2];
   if (CTAS == 1) {
     const unsigned grid = (unsigned)std::max(1, std::min(n_tiles, sm_count()));

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -96,6 +97,50 @@ int max_smem_optin() {
   return g_dev[d].smem_optin;
 }
 
+static int32_t *g_idx_err = nullptr;
+int32_t *index_error_flag() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, 64, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
+      g_idx_err = reinterpret_cast<int32_t *>(p);
+      *g_idx_err = 0;
+    }
+  });
+  return g_idx_err;   // UVA: the same pointer is valid on every device
+}
+int32_t check_index_error() {
+  if (!g_idx_err) return B200_OK;
+  const int32_t code = *reinterpret_cast<volatile int32_t *>(g_idx_err);
+  if (code == 0) return B200_OK;
+  *reinterpret_cast<volatile int32_t *>(g_idx_err) = 0;
+  static const char *const what[] = {"?", "gather", "select", "scatter_add", "select_add", "softmax_cross_entropy targets"};
+  return fail(B200_ERR_SHAPE, "an index was out of range in an earlier %s launch (the reference panics; the access was skipped)",
+              what[code >= 1 && code <= 5 ? code : 0]);
+}
+
+// cudaFuncSetAttribute is a driver round trip (~1-2 us); a kernel's opt-in shared-memory limit only ever
+// needs raising, so remember the largest value set per (function, device) and skip the call afterwards.
+int32_t ensure_dyn_smem(const void *func, size_t bytes, bool max_carveout) {
+  struct Entry { const void *f; int dev; size_t bytes; };
+  static std::vector<Entry> table;
+  static std::mutex mu;
+  const int d = current_device();
+  std::lock_guard<std::mutex> lk(mu);
+  for (Entry &e : table)
+    if (e.f == func && e.dev == d) {
+      if (e.bytes >= bytes) return B200_OK;
+      B200_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      e.bytes = bytes;
+      return B200_OK;
+    }
+  B200_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (max_carveout)
+    B200_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  table.push_back({func, d, bytes});
+  return B200_OK;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -155,12 +200,12 @@ int32_t b200_stream_destroy(b200_stream s) {
 
 int32_t b200_stream_sync(b200_stream s) {
   B200_CUDA(cudaStreamSynchronize(resolve_stream(s)));
-  return B200_OK;
+  return check_index_error();
 }
 
 int32_t b200_device_sync(void) {
   B200_CUDA(cudaDeviceSynchronize());
-  return B200_OK;
+  return check_index_error();
 }
 
 int32_t b200_event_create(b200_event *out) {
@@ -255,15 +300,48 @@ int32_t b200_graph_node_count(b200_graph gh, uint64_t *kernel_nodes, uint64_t *t
   return B200_OK;
 }
 
+// Handle refcounts (Handle::can_mut, crates/burn-ir/src/handle.rs:92-111): b200_alloc hands out a buffer with
+// one owner, b200_retain adds one, b200_free drops one and releases the memory (stream-ordered) at zero.
+static std::unordered_map<void *, uint32_t> g_refs;
+static std::mutex g_refs_mu;
+
 int32_t b200_alloc(void **out, uint64_t bytes, b200_stream s) {
   B200_REQUIRE(out, B200_ERR_INVALID, "out is null");
   if (bytes == 0) bytes = 16;  // zero-sized tensors still get a distinct handle
   B200_CUDA(cudaMallocAsync(out, (size_t)bytes, resolve_stream(s)));
+  std::lock_guard<std::mutex> lk(g_refs_mu);
+  g_refs[*out] = 1;
+  return B200_OK;
+}
+
+int32_t b200_retain(void *ptr) {
+  B200_REQUIRE(ptr, B200_ERR_INVALID, "ptr is null");
+  std::lock_guard<std::mutex> lk(g_refs_mu);
+  auto it = g_refs.find(ptr);
+  B200_REQUIRE(it != g_refs.end(), B200_ERR_INVALID, "b200_retain: %p is not a live b200_alloc allocation", ptr);
+  ++it->second;
+  return B200_OK;
+}
+
+int32_t b200_refcount(const void *ptr, uint32_t *count) {
+  B200_REQUIRE(ptr && count, B200_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(g_refs_mu);
+  auto it = g_refs.find(const_cast<void *>(ptr));
+  B200_REQUIRE(it != g_refs.end(), B200_ERR_INVALID, "b200_refcount: %p is not a live b200_alloc allocation", ptr);
+  *count = it->second;
   return B200_OK;
 }
 
 int32_t b200_free(void *ptr, b200_stream s) {
   if (!ptr) return B200_OK;
+  {
+    std::lock_guard<std::mutex> lk(g_refs_mu);
+    auto it = g_refs.find(ptr);
+    if (it != g_refs.end()) {
+      if (--it->second > 0) return B200_OK;   // other owners remain
+      g_refs.erase(it);
+    }
+  }
   B200_CUDA(cudaFreeAsync(ptr, resolve_stream(s)));
   return B200_OK;
 }

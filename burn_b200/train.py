@@ -162,15 +162,18 @@ def add(tape: Tape, a: Var, b: Var) -> Var:
     return y
 
 
-def gelu(tape: Tape, x: Var) -> Var:
-    y = Var(ops.gelu(x.v), True)
+GELU_BWD_EXACT = os.environ.get("B200_GELU_BWD", "reference") == "exact"
 
-    def bw():
-        if y.g is None or not x.requires_grad:
-            return
-        # d/dx [x(1+erf(x/√2))/2] = (1+erf(x/√2))/2 + x·exp(-x²/2)/√(2π)  — the chain rule through the
-        # five primitive ops, as one fused tape over (x, dy)
-        tb = TapeBuilder()
+
+def gelu_backward_tape() -> TapeBuilder:
+    """B::gelu_backward as burn-autodiff calls it (crates/burn-autodiff/src/ops/activation.rs:35): the trait
+    default is the derivative of the TANH approximation, not of the erf form the forward uses
+    (crates/burn-backend/src/backend/ops/activation.rs:98-128) — same 20 primitive ops, same operation order,
+    one fused tape over (x, dy).  B200_GELU_BWD=exact selects the analytic erf derivative instead (a deliberate
+    deviation from the reference trajectory, kept for comparison)."""
+    tb = TapeBuilder()
+    if GELU_BWD_EXACT:
+        # d/dx [x(1+erf(x/sqrt2))/2] = (1+erf(x/sqrt2))/2 + x*exp(-x^2/2)/sqrt(2*pi)
         tb.op("MUL_F", ("in", 0), ("in", 0))
         tb.op("MUL_F", "acc", ("f", -0.5))
         tb.op("EXP_F", "acc")
@@ -182,7 +185,33 @@ def gelu(tape: Tape, x: Var) -> Var:
         tb.op("MUL_F", "acc", ("f", 0.5))
         tb.op("ADD_F", "acc", ("tmp", 0))
         tb.op("MUL_F", "acc", ("in", 1), out=0)
-        accumulate(x, _run(tb, [x.v, y.g], x.v.shape))
+        return tb
+    tb.op("POW_F", ("in", 0), ("f", 3.0), tmp=0)                 # x3 = powi_scalar(x, 3) -> powf_scalar_impl
+    tb.op("MUL_F", ("in", 0), ("f", 0.797885), tmp=1)            # c2
+    tb.op("MUL_F", ("tmp", 0), ("f", 0.0356774))                 # c1
+    tb.op("ADD_F", "acc", ("tmp", 1))                            # inner1 = c1 + c2
+    tb.op("TANH_F", "acc", tmp=1)                                # tanh
+    tb.op("MUL_F", ("in", 0), ("f", 0.398942), tmp=2)            # c4
+    tb.op("MUL_F", ("tmp", 0), ("f", 0.0535161))                 # c3
+    tb.op("ADD_F", "acc", ("tmp", 2), tmp=0)                     # inner2 = c3 + c4
+    tb.op("MUL_F", ("tmp", 1), ("tmp", 1))                       # powi_scalar(tanh, 2) = tanh * tanh
+    tb.op("NEG_F", "acc")
+    tb.op("ADD_F", "acc", ("f", 1.0))                            # sech = 1 - tanh^2
+    tb.op("MUL_F", ("tmp", 0), "acc")                            # inner2 * sech
+    tb.op("ADD_F", "acc", ("f", 0.5), tmp=0)                     # y2
+    tb.op("MUL_F", ("tmp", 1), ("f", 0.5))                       # y1
+    tb.op("ADD_F", "acc", ("tmp", 0))                            # y = y1 + y2
+    tb.op("MUL_F", "acc", ("in", 1), out=0)                      # y * grad
+    return tb
+
+
+def gelu(tape: Tape, x: Var) -> Var:
+    y = Var(ops.gelu(x.v), True)
+
+    def bw():
+        if y.g is None or not x.requires_grad:
+            return
+        accumulate(x, _run(gelu_backward_tape(), [x.v, y.g], x.v.shape))
     tape.add(bw)
     return y
 
@@ -334,13 +363,15 @@ def mean_square(tape: Tape, x: Var) -> Var:
 
 # ------------------------------------------------------------------ modules (burn-nn)
 class Param(Var):
-    __slots__ = ("m", "s", "on_grad", "grad_slot")
+    __slots__ = ("m", "s", "on_grad", "grad_slot", "uses", "_arrived")
 
     def __init__(self, a: np.ndarray, name: str):
         super().__init__(DeviceTensor.from_numpy(np.ascontiguousarray(a, dtype=np.float32)), True, name)
         self.m = self.s = None  # Adam moments
-        self.on_grad = None     # called once the gradient is final (each parameter is used once per step)
+        self.on_grad = None     # called on every gradient contribution (see ParamArena.ready)
         self.grad_slot = None   # where the gradient should be written (a view of a flat bucket), if any
+        self.uses = 1           # how many times the forward pass consumes this parameter (tied weights: 2)
+        self._arrived = 0       # contributions seen in the current step
 
 
 def _uniform(rng, shape, fan_in):
@@ -560,7 +591,18 @@ class ParamArena:
         dv.sync()
 
     def ready(self, p: Param) -> None:
+        """Called by `accumulate` on EVERY gradient contribution to p.  A parameter consumed `p.uses` times
+        in the forward pass (tied embedding / output weights, shared layers) is final only after that many
+        contributions — counting calls instead would fire the bucket's all-reduce before every member had
+        written its slot.  An unexpected extra contribution is an error, never a silently wrong gradient."""
         b = self.slot[id(p)]
+        p._arrived += 1
+        if p._arrived > p.uses:
+            raise RuntimeError(f"parameter {p.name!r} received {p._arrived} gradient contributions this step but "
+                               f"declares uses={p.uses}; set Param.uses for shared parameters")
+        if p._arrived < p.uses:
+            return                      # more contributions to come (accumulate() keeps summing into p.g)
+        p._arrived = 0
         if p.g.data_ptr() != p.grad_slot.data_ptr():
             src = p.g if p.g.is_contiguous() else p.g.contiguous()
             abi.check(abi.load().b200_memcpy_d2d(p.grad_slot.data_ptr(), src.data_ptr(), src.numel * 4, None))

@@ -85,6 +85,10 @@ int32_t b200_device_info(int32_t device, int32_t *sm_count, int32_t *cc_major,
                          int32_t *cc_minor, uint64_t *total_mem);
 int32_t b200_stream_create(b200_stream *out, int32_t high_priority);
 int32_t b200_stream_destroy(b200_stream s);
+/* Both also report (B200_ERR_SHAPE) an out-of-range index seen by an earlier gather / select /
+ * scatter_add / select_add / cross-entropy launch: the reference panics on those
+ * (crates/burn-ndarray/src/ops/base.rs:106-183), a kernel cannot, so the access is skipped and the error
+ * surfaces at the next synchronising call. */
 int32_t b200_stream_sync(b200_stream s);        /* Backend::sync */
 int32_t b200_device_sync(void);
 const char *b200_last_error(void);
@@ -117,8 +121,10 @@ int32_t b200_graph_node_count(b200_graph g, uint64_t *kernel_nodes, uint64_t *to
  * b200_memory_cleanup).  Replaces cubecl's memory pools behind
  * CubeTensor::handle; b200_retain/b200_free give the refcount semantics of
  * Handle::can_mut (crates/burn-ir/src/handle.rs:92-111). */
-int32_t b200_alloc(void **out, uint64_t bytes, b200_stream s);
-int32_t b200_free(void *ptr, b200_stream s);
+int32_t b200_alloc(void **out, uint64_t bytes, b200_stream s);   /* refcount 1 */
+int32_t b200_retain(void *ptr);                                   /* +1 owner (tensor clone = refcount bump) */
+int32_t b200_refcount(const void *ptr, uint32_t *count);          /* count == 1  <=>  Handle::can_mut */
+int32_t b200_free(void *ptr, b200_stream s);                      /* -1 owner; memory released at 0 */
 int32_t b200_memory_cleanup(void);
 int32_t b200_memset(void *ptr, int32_t byte, uint64_t bytes, b200_stream s);
 

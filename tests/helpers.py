@@ -8,9 +8,11 @@ from burn_b200 import _abi as abi
 from burn_b200 import device as dv
 from burn_b200.device import DeviceTensor, TapeBuilder
 
-# parity tolerances stated by BASELINE.json north_star
-REL_ELEMWISE = 1e-6
-REL_REDUCE = 1e-5
+# parity tolerances stated by BASELINE.json north_star.  The comparison is burn's Tolerance helper
+# |x-y| < max(R*|x+y|, A) (crates/burn-std/src/data/compare.rs:10-27): relative to |x+y| ~ 2|x|, so the
+# north_star's "<= 1e-6 relative error" is R = 5e-7 in that helper's terms.
+REL_ELEMWISE = 5e-7
+REL_REDUCE = 5e-6
 # gelu = x*(1+erf(x/sqrt2))/2: for negative x the 1+erf cancels, so one f32 ulp of erf
 # (2^-24 = 6e-8, times |x|/2 <= 2) is the absolute floor of any f32 implementation
 ABS_GELU = 1.2e-7

@@ -186,3 +186,65 @@ def test_gather_shape_mismatch_is_an_error(dev):
     out = DeviceTensor.empty((3, 3))
     a, b, c = t.desc(), idx.desc(), out.desc()
     assert lib().b200_launch_gather(1, C.byref(a), C.byref(b), C.byref(c), None) == abi.ERR_SHAPE
+
+
+@pytest.mark.parametrize("what", ["gather", "select", "scatter_add", "select_add", "select_add_rows"])
+def test_out_of_range_indices_fail_loudly(dev, what):
+    """The reference panics on an index >= the axis length (crates/burn-ndarray/src/ops/base.rs:106-183 index
+    with `as usize`).  A kernel cannot panic: the access is skipped (no out-of-bounds read or write — rows = 10
+    makes the chunked scatter kernels' rounded-up range [0, 12) cover the bad index) and the next synchronising
+    call reports B200_ERR_SHAPE."""
+    rows = 10
+    t = H.up(np.arange(rows * 8, dtype=np.float32).reshape(rows, 8))
+    before = t.numpy().copy()
+    if what == "gather":
+        idx = H.up(np.full((3, 8), 11, dtype=np.int64))
+        out = DeviceTensor.empty((3, 8))
+        a, b, c = t.desc(), idx.desc(), out.desc()
+        abi.check(lib().b200_launch_gather(0, C.byref(a), C.byref(b), C.byref(c), None))
+    elif what == "select":
+        idx = H.up(np.array([0, 10, -1], dtype=np.int32))
+        out = DeviceTensor.empty((3, 8))
+        a, b, c = t.desc(), idx.desc(), out.desc()
+        abi.check(lib().b200_launch_select(0, C.byref(a), C.byref(b), C.byref(c), None))
+    elif what == "scatter_add":
+        idx = H.up(np.full((2, 8), 11, dtype=np.int64))
+        v = H.up(np.ones((2, 8), dtype=np.float32))
+        a, b, c = t.desc(), idx.desc(), v.desc()
+        abi.check(lib().b200_launch_scatter_add(0, C.byref(a), C.byref(b), C.byref(c), None))
+    else:
+        tt = t if what == "select_add_rows" else H.up(before.T.copy()).swap_dims(0, 1)   # strided: generic kernel
+        idx = H.up(np.array([11, 3], dtype=np.int64))
+        v = H.up(np.ones((2, 8), dtype=np.float32))
+        a, b, c = tt.desc(), idx.desc(), v.desc()
+        abi.check(lib().b200_launch_select_add(0, C.byref(a), C.byref(b), C.byref(c), None))
+    with pytest.raises(abi.B200Error) as e:
+        dv.sync()
+    assert e.value.status == abi.ERR_SHAPE and "out of range" in e.value.message
+    dv.sync()                                   # the flag is sticky until reported, then cleared
+    if what == "scatter_add":
+        H.assert_exact(t.numpy(), before)       # nothing was written past (or into) the table
+    if what == "select_add_rows":
+        want = before.copy()
+        want[3] += 1.0
+        H.assert_exact(t.numpy(), want)         # the valid index still landed
+
+
+def test_retain_free_refcount(dev):
+    """b200_alloc / b200_retain / b200_free give Handle::can_mut's refcount semantics
+    (crates/burn-ir/src/handle.rs:92-111): a clone is a refcount bump, memory goes back at zero."""
+    p = C.c_void_p()
+    abi.check(lib().b200_alloc(C.byref(p), 4096, None))
+    n = C.c_uint32()
+    abi.check(lib().b200_refcount(p, C.byref(n)))
+    assert n.value == 1                         # sole owner: may be mutated in place
+    abi.check(lib().b200_retain(p))
+    abi.check(lib().b200_refcount(p, C.byref(n)))
+    assert n.value == 2
+    abi.check(lib().b200_free(p, None))         # drops one owner, memory stays
+    abi.check(lib().b200_refcount(p, C.byref(n)))
+    assert n.value == 1
+    abi.check(lib().b200_memset(p, 0, 4096, None))
+    abi.check(lib().b200_free(p, None))
+    assert lib().b200_refcount(p, C.byref(n)) == abi.ERR_INVALID
+    dv.sync()

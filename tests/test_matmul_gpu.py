@@ -199,3 +199,59 @@ def test_large_square_matmul_properties(dev):
         check(c[rows], a[rows], b, precision, f"n=4096 rows, precision {precision}")
         c2 = ops.float_matmul(da, H.up(b * np.float32(2.0)), precision).numpy()
         assert np.array_equal(c2, c * np.float32(2.0))
+
+
+def _pattern(shape, phase):
+    """The reference benches' deterministic generator ((i % 1000) / 1000) - 0.5
+    (crates/burn-backend-tests/benches/matmul.rs:30-35), offset by `phase` so lhs != rhs."""
+    n = int(np.prod(shape))
+    i = (np.arange(n, dtype=np.int64) + phase) % 1000
+    return (i.astype(np.float32) / np.float32(1000.0) - np.float32(0.5)).reshape(shape)
+
+
+@pytest.mark.parametrize("n", [8192, 16384])
+def test_configs2_large_squares_all_precisions(dev, n):
+    """BASELINE configs[2] members 8192^3 and 16384^3: sampled rows AND sampled columns (so every
+    rasterisation group and both CTAs of a pair are hit) against float64, in all three precisions."""
+    a = rnd((n, n), 50 + n)
+    b = _pattern((n, n), 7)
+    da, db = H.up(a), H.up(b)
+    rows = [0, 127, 128, 255, 256, 2049, n // 2 + 3, n - 129, n - 1]
+    cols = [0, 255, 256, 1023, n // 2 - 1, n - 257, n - 1]
+    for precision in (abi.MM_TF32, abi.MM_BF16, abi.MM_F32X3):
+        c = ops.float_matmul(da, db, precision).numpy()
+        check(c[rows], a[rows], b, precision, f"n={n} rows, precision {precision}")
+        check(c[:, cols], a, b[:, cols], precision, f"n={n} cols, precision {precision}")
+        del c
+
+
+def test_configs2_batched_2048(dev):
+    """BASELINE configs[2]: batched [64, 2048, 2048] x [64, 2048, 2048], tf32 and bf16; three whole batch
+    members (first, middle, last) against float64."""
+    a = rnd((64, 2048, 2048), 60)
+    b = rnd((64, 2048, 2048), 61)
+    da, db = H.up(a), H.up(b)
+    for precision in (abi.MM_TF32, abi.MM_BF16):
+        c = ops.float_matmul(da, db, precision).numpy()
+        for i in (0, 31, 63):
+            check(c[i], a[i], b[i], precision, f"batched member {i}, precision {precision}")
+        del c
+
+
+@pytest.mark.parametrize("precision", [abi.MM_TF32, abi.MM_BF16])
+def test_configs2_bias_gelu_epilogue_8192(dev, precision):
+    """BASELINE configs[2]: gelu(C + bias[N]) fused into the 8192^3 GEMM == the unfused chain on the plain
+    GEMM result (same accumulator in, same op chain: only the erf 1-ulp allowance)."""
+    n = 8192
+    a, b = rnd((n, n), 70), rnd((n, n), 71)
+    bias = rnd((1, n), 72)
+    da, db = H.up(a), H.up(b)
+    tb = TapeBuilder().op("ADD_F", ("in", 0), ("in", 1), tmp=0)
+    H.gelu_tape(tb, ("tmp", 0), out=0)
+    got = ops.float_matmul(da, db, precision, epilogue=tb.build(), epi_inputs=[H.up(bias)]).numpy()
+    plain = ops.float_matmul(da, db, precision).numpy()
+    rows = [0, 255, 256, 4097, n - 1]
+    check(plain[rows], a[rows], b, precision, "8192 plain rows")
+    # erf's 1-ulp allowance scales with |x|/2 where 1+erf cancels (x in about [-6, 0]): 3 * 2^-24 * ... < 4e-7
+    want = oracle.gelu(oracle.float_add(plain[::61], bias))
+    H.assert_close(got[::61], want, H.REL_ELEMWISE, 4e-7, "8192 fused bias+gelu epilogue == unfused chain")

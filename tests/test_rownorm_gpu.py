@@ -142,3 +142,34 @@ def test_softmax_cross_entropy_value_and_gradient(dev, n, v):
     dxi = H.up(x)
     _, same = ops.softmax_cross_entropy(dxi, H.up(t.astype(np.int64)), scale, inplace=True)
     assert same is dxi and np.array_equal(dxi.numpy(), got)
+
+
+def test_softmax_cross_entropy_many_rows_pipelined(dev):
+    """More rows than CTAs: every CTA walks several rows, prefetching row r + grid into the smem slots the
+    gradient pass of row r has just freed — values identical to the one-row-per-CTA case above."""
+    n, v = 1000, 50260
+    x = rnd((n, v), 11, -4.0, 4.0)
+    t = np.random.default_rng(12).integers(0, v, n).astype(np.int32)
+    picked, dx = ops.softmax_cross_entropy(H.up(x), H.up(t), 1.0 / n)
+    for r in (0, 1, 147, 148, 149, 500, 999):
+        logp = oracle.log_softmax(x[r:r + 1], 1)
+        H.assert_close(picked.numpy()[r:r + 1], logp[0, t[r]:t[r] + 1], 1e-5, 1e-6, f"picked row {r}")
+        want = np.exp(logp.astype(np.float64))
+        want[0, t[r]] -= 1.0
+        want /= n
+        assert np.abs(dx.numpy()[r:r + 1] - want).max() <= 1e-6 / n + 1e-5 * np.abs(want).max(), f"row {r}"
+
+
+def test_softmax_cross_entropy_invalid_target_is_reported(dev):
+    """A target outside [0, V) makes the reference's gather panic; here the row contributes a defined 0 to
+    `picked` (never uninitialised memory) and the next sync reports B200_ERR_SHAPE."""
+    from burn_b200 import _abi as abi
+    from burn_b200 import device as dv
+    x = rnd((4, 64), 13, -1.0, 1.0)
+    t = np.array([1, 64, -1, 3], dtype=np.int32)
+    picked, _ = ops.softmax_cross_entropy(H.up(x), H.up(t), 0.25)
+    with pytest.raises(abi.B200Error) as e:
+        dv.sync()
+    assert e.value.status == abi.ERR_SHAPE
+    got = picked.numpy()
+    assert got[1] == 0.0 and got[2] == 0.0 and got[0] != 0.0
