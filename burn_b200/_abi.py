@@ -123,6 +123,9 @@ SIGNATURES = {
     "b200_launch_layer_norm": (_i32, [_TP, _TP, _TP, C.c_double, _TP, _vp]),
     "b200_launch_attention": (_i32, [_TP, _TP, _TP, _TP, C.c_double, C.c_double, _i32, _TP, _TP, _vp]),
     "b200_launch_attention_backward": (_i32, [_TP, _TP, _TP, _TP, _TP, C.c_double, _i32, _TP, _TP, _vp]),
+    "b200_launch_attention_flash": (_i32, [_TP, _TP, _TP, _TP, C.c_double, C.c_double, _i32, _TP, _TP, _vp]),
+    "b200_launch_attention_flash_backward": (_i32, [_TP, _TP, _TP, _TP, _TP, _TP, _TP, C.c_double, C.c_double, _i32,
+                                                    _TP, _TP, _TP, _vp]),
     "b200_launch_softmax_cross_entropy": (_i32, [_TP, _TP, C.c_double, _TP, _TP, _vp]),
     "b200_collective_mark": (_i32, [_vp, _vp]),
     "b200_stream_wait_event": (_i32, [_vp, _vp]),

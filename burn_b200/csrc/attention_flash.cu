@@ -1,0 +1,936 @@
+// Flash-style attention for training: forward that keeps only per-row softmax statistics, backward that
+// recomputes the weights tile by tile — the [B,H,Sq,Sk] score / weight / dS tensors never exist in HBM
+// (SURVEY.md §8(f) row 2).  Semantics are ModuleOps::attention
+// (crates/burn-backend/src/backend/ops/modules/base.rs:822-830) as pinned by attention_fallback
+// (crates/burn-backend/src/backend/ops/modules/attention.rs:15-90): scores = q·kᵀ·scale, bool / causal
+// mask_fill(mask_value), NaN-safe softmax (row max clamped to the most negative finite value, row sum to the
+// smallest normal), context = weights·v; the backward is what burn-autodiff's reverse walk over that chain
+// yields (matmul / mask_fill / softmax backward), with the mask_fill backward zeroing dS where masked.
+//
+// Head dim 64, f32 storage, tf32 tcgen05 products, f32 softmax in the base-2 domain (one FMUL + one
+// MUFU.EX2 per element).  Three kernels, each a TMA → tcgen05 → TMEM → row-thread pipeline in which one
+// elected thread issues every TMA load and MMA and the row threads (thread = TMEM lane) do the softmax math:
+//
+//   flash_fwd_kernel   CTA = 128 query rows, loop over 64-key blocks.  S_j = Q·K_jᵀ lands in one of two TMEM
+//                      buffers (S_{j+1} is issued before the row threads have finished S_j), online softmax:
+//                      P_j = 2^(s−m_j) goes to smem as the tf32 A operand, PV_j = P_j·V_j into one of two TMEM
+//                      buffers with no accumulation, and the row threads fold it into a register accumulator
+//                      O = O·2^(m_{j−1}−m_j) + PV_j while the tensor core already works on block j+1.
+//                      Saves stats[row] = (m, 1/l): weights are recomputed as 2^(s−m)·(1/l), exactly the
+//                      forward's values (no log-sum-exp cancellation when a row is masked with −1e9).
+//                      96 KB smem + 256 TMEM columns: two CTAs per SM.
+//   flash_bwd_dq_kernel  CTA = 128 query rows, loop over 64-key blocks: S = Q·K_jᵀ and dP = dO·V_jᵀ (double
+//                      buffered in TMEM) → dS = P∘(dP − delta)·scale → smem → dQ += dS·K_j accumulated in TMEM.
+//                      delta = rowsum(dO∘O) is computed here and stored into stats[row].z for the second kernel.
+//   flash_bwd_dkv_kernel CTA = 128 key rows, loop over 64-query blocks, everything transposed so the row thread
+//                      is a key: Sᵀ = K·Q_iᵀ, dPᵀ = V·dO_iᵀ → Pᵀ, dSᵀ → smem → dV += Pᵀ·dO_i, dK += dSᵀ·Q_i in
+//                      TMEM.  Deterministic (no atomics): replicas stay bit-identical.
+// Algorithmic HBM bytes: forward q,k,v,out (+16 B/row); backward q,k,v,out,dO,dq,dk,dv — 4·B·H·S·D·4 and
+// 8·B·H·S·D·4 bytes; FLOPs 4·Sq·Sk·D forward, 14·Sq·Sk·D backward per head (7 products, S and dP twice).
+#include "tcgen05.cuh"
+
+namespace b200 {
+namespace fa {
+
+using namespace mm;
+
+constexpr int HD = 64;
+constexpr int kRows = 128;                      // rows a CTA owns (= TMEM lanes)
+constexpr int kCols = 64;                       // columns per loop iteration
+constexpr uint32_t kBig = kRows * HD * 4;       // [128 x 64] f32 tile: 32 KB
+constexpr uint32_t kSmall = kCols * HD * 4;     // [64 x 64] f32 tile: 16 KB
+constexpr uint32_t kPBytes = kRows * kCols * 4; // [128 x 64] f32 weights tile: 32 KB
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kFltMax = 3.402823466e+38f, kMinPos = 1.175494351e-38f;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// K-major [rows x 64] f32 tile = two [rows x 32] 128B-swizzled halves, `half_bytes` apart
+__device__ __forceinline__ void load_kmajor(uint8_t *dst, const CUtensorMap *map, uint64_t *bar, int row0, int h, int b,
+                                            uint32_t half_bytes) {
+  tma_load_5d(dst, map, bar, 0, row0, h, b, 0);
+  tma_load_5d(dst + half_bytes, map, bar, 32, row0, h, b, 0);
+}
+// MN-major [64 k-rows x 64 n] f32 tile: four [32 x 32] boxes (32-byte swizzle atoms)
+__device__ __forceinline__ void load_mnmajor(uint8_t *dst, const CUtensorMap *map, uint64_t *bar, int row0, int h, int b) {
+#pragma unroll
+  for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+    for (int g = 0; g < 2; ++g) tma_load_5d(dst + kb * 8192 + g * 4096, map, bar, g * 32, row0 + kb * 32, h, b, 0);
+}
+// D[128 x 64] (+)= A[128 x 64] · B[64 x 64]ᵀ, A and B K-major tiles (halves a_half / b_half bytes apart)
+__device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a, uint32_t a_half, uint32_t b, uint32_t b_half,
+                                       uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < HD / 8; ++k) {
+    const uint64_t da = make_desc(a + (k >> 2) * a_half + (k & 3) * 32, 16, 1024);
+    const uint64_t db = make_desc(b + (k >> 2) * b_half + (k & 3) * 32, 16, 1024);
+    umma<false>(tmem_d, da, db, idesc, (accumulate || k) ? 1u : 0u);
+  }
+}
+// D[128 x 64] (+)= A[128 x 64] (K-major, halves kPBytes/2 apart) · B[64 k x 64 n] (MN-major tile)
+__device__ __forceinline__ void mma_kmn(uint32_t tmem_d, uint32_t a, uint32_t b, uint32_t idesc_mn, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < kCols / 8; ++k) {
+    const uint64_t da = make_desc(a + (k >> 2) * (kPBytes / 2) + (k & 3) * 32, 16, 1024);
+    const uint64_t db = make_desc(b + (k >> 2) * 8192 + (k & 3) * 1024, 4096, 512, 1);
+    umma<false>(tmem_d, da, db, idesc_mn, (accumulate || k) ? 1u : 0u);
+  }
+}
+__device__ __forceinline__ uint32_t make_idesc() {
+  uint32_t idesc = 0;
+  idesc |= 1u << 4;                       // D = f32
+  idesc |= 2u << 7;                       // A = tf32
+  idesc |= 2u << 10;                      // B = tf32
+  idesc |= (uint32_t)(kCols >> 3) << 17;  // N = 64
+  idesc |= (uint32_t)(kRows >> 4) << 24;  // M = 128
+  return idesc;
+}
+// K-major A operand, 128-byte swizzle: 16-byte chunk q of row r lives at chunk q ^ (r & 7)
+__device__ __forceinline__ void store_a_chunk(uint8_t *tile_half, int r_in, int q, float4 v) {
+  *reinterpret_cast<float4 *>(tile_half + r_in * 128 + ((q ^ (r_in & 7)) << 4)) = v;
+}
+
+// Key blocks entirely above the causal diagonal are skipped: a filled score contributes 2^(fill - max) = 0
+// exactly.  Not when Sq > Sk with a FINITE fill value: the first Sq - Sk query rows then see no key at all, every
+// score of theirs equals the fill value and the reference's softmax is uniform over ALL keys (with -inf it is the
+// NaN-safe all-zero row, which skipping reproduces).
+__device__ __forceinline__ bool causal_skip(int causal, int Sq, int Sk, float mask_value) {
+  return causal && !(Sq > Sk && mask_value > -INFINITY);
+}
+
+// ------------------------------------------------------------------------------------------ forward
+struct FwdParams {
+  CUtensorMap tma_q, tma_k, tma_v;
+  float *out;
+  int64_t o_sb, o_sh, o_ss;
+  float4 *stats;                 // [B, H, Sq] (m2, 1/l, delta, -)
+  const uint8_t *mask;           // optional bool mask, nonzero = masked
+  int64_t m_sb, m_sh, m_ss;
+  int32_t B, H, Sq, Sk;
+  int32_t causal, q_blocks;
+  float scale, mask_value;
+};
+
+__global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant__ FwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sQ = smem, *sK = sQ + kBig, *sV = sK + kSmall, *sP = sV + kSmall;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + kPBytes);
+  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s0 = bars + 3, *bar_s1 = bars + 4, *bar_p = bars + 5,
+           *bar_o = bars + 6;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int work = blockIdx.x;
+  const int qb = P.q_blocks - 1 - (work % P.q_blocks);      // heavy (late, under a causal mask) query blocks first
+  const int bh = work / P.q_blocks, h = bh % P.H, b = bh / P.H;
+  const int q0 = qb * kRows;
+  const int nkv_all = (P.Sk + kCols - 1) / kCols;
+  int nkv = nkv_all;
+  if (causal_skip(P.causal, P.Sq, P.Sk, P.mask_value)) {
+    const int last_col = min(P.Sk - 1, q0 + kRows - 1 + (P.Sk - P.Sq));
+    nkv = last_col < 0 ? 0 : min(nkv_all, last_col / kCols + 1);
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tma_q);
+    tma_prefetch_desc(&P.tma_k);
+    tma_prefetch_desc(&P.tma_v);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s0, 1);
+    mbar_init(bar_s1, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;        // S0 @0, S1 @64, PV0 @128, PV1 @192
+
+  if (warp == 0) {
+    // ===================== TMA producers: lane 0 streams K tiles, lane 1 streams V tiles =====================
+    // Two independent streams so that neither load waits behind the other's buffer: K_{j+1} is requested the
+    // moment S_j retires (about one block ahead of the row threads), V_{j+1} the moment PV_j retires.
+    if (lane == 0 && nkv > 0) {
+      mbar_expect_tx(bar_q, kBig);
+      load_kmajor(sQ, &P.tma_q, bar_q, q0, h, b, kBig / 2);
+      uint32_t ph_s0 = 0, ph_s1 = 0;
+      for (int j = 0; j < nkv; ++j) {
+        if (j > 0) {                                              // S_{j-1} retired → sK is free
+          if ((j - 1) & 1) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+        }
+        mbar_expect_tx(bar_k, kSmall);
+        load_kmajor(sK, &P.tma_k, bar_k, j * kCols, h, b, kSmall / 2);
+      }
+    } else if (lane == 1 && nkv > 0) {
+      uint32_t ph_o = 0;
+      for (int j = 0; j < nkv; ++j) {
+        if (j > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }         // PV_{j-1} retired → sV is free
+        mbar_expect_tx(bar_v, kSmall);
+        load_mnmajor(sV, &P.tma_v, bar_v, j * kCols, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkv > 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      uint32_t ph_k = 0, ph_v = 0, ph_p = 0;
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, ph_k); ph_k ^= 1;
+      tc_fence_after();
+      mma_kk(tmem, aQ, kBig / 2, aK, kSmall / 2, idesc, false);
+      umma_commit(bar_s0);
+      for (int j = 0; j < nkv; ++j) {
+        const int cur = j & 1;
+        if (j + 1 < nkv) {
+          // S_{j+1} into the other TMEM buffer while the row threads are still busy with S_j (they released
+          // that buffer when they delivered P_{j-1})
+          mbar_wait(bar_k, ph_k); ph_k ^= 1;
+          tc_fence_after();
+          mma_kk(tmem + (cur ? 0u : 64u), aQ, kBig / 2, aK, kSmall / 2, idesc, false);
+          umma_commit(cur ? bar_s0 : bar_s1);
+        }
+        mbar_wait(bar_v, ph_v); ph_v ^= 1;
+        mbar_wait(bar_p, ph_p); ph_p ^= 1;                       // P_j is in smem; PV_{j-1} has been folded in
+        tc_fence_after();
+        mma_kmn(tmem + 128u + (cur ? 64u : 0u), aP, aV, idesc_mn, false);
+        umma_commit(bar_o);
+      }
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax warps: thread = query row = TMEM lane =====================
+    const int quarter = warp & 3;
+    const int r_in = quarter * 32 + lane, row = q0 + r_in;
+    const bool row_ok = row < P.Sq;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int causal_limit = row + (P.Sk - P.Sq);
+    const uint8_t *mrow = P.mask ? P.mask + (int64_t)b * P.m_sb + (int64_t)h * P.m_sh + (int64_t)row * P.m_ss : nullptr;
+    const float scale2 = P.scale * kLog2e, mask2 = P.mask_value * kLog2e;
+    uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
+    float m = -kFltMax, l = 0.0f, alpha_prev = 1.0f;
+    float o[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) o[c] = 0.0f;
+
+    for (int j = 0; j < nkv; ++j) {
+      const int cur = j & 1;
+      uint32_t mw[16];                                            // this block's mask bytes, fetched before the wait
+      if (mrow && row_ok) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          mw[q] = (j * kCols + q * 4 < P.Sk) ? __ldg(reinterpret_cast<const uint32_t *>(mrow + j * kCols) + q) : 0u;
+      }
+      if (cur) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+      tc_fence_after();
+      // Two passes over the S tile in TMEM (reads are ~free next to the exp math) keep 32 instead of 64 score
+      // registers live beside the 64-wide output accumulator: pass 1 row max, pass 2 weights.
+      const int col0 = j * kCols;
+      const uint32_t ts = tmem + (cur ? 64u : 0u) + lane_addr;
+      auto load_scores = [&](int kb, float (&s)[32]) {   // scaled, masked scores of columns col0 + kb*32 + [0, 32)
+        uint32_t r[32];
+        tmem_ld32(ts + kb * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) s[c] = __fmul_rn(__uint_as_float(r[c]), scale2);
+        const int c0 = col0 + kb * 32;
+        if (mrow && row_ok) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t w = mw[kb * 8 + q];
+            if (w & 0xFFu) s[q * 4] = mask2;
+            if (w & 0xFF00u) s[q * 4 + 1] = mask2;
+            if (w & 0xFF0000u) s[q * 4 + 2] = mask2;
+            if (w & 0xFF000000u) s[q * 4 + 3] = mask2;
+          }
+        }
+        if (P.causal && c0 + 31 > q0 + (P.Sk - P.Sq)) {   // only chunks crossing the diagonal
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c0 + c > causal_limit) s[c] = mask2;
+        }
+        if (c0 + 32 > P.Sk) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c0 + c >= P.Sk) s[c] = -INFINITY;
+        }
+      };
+      float bm = -INFINITY;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        float s[32];
+        load_scores(kb, s);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) bm = fmaxf(bm, s[c]);
+      }
+      const float m_new = fmaxf(m, bm);               // m starts at -FLT_MAX: the finfo.min clamp (attention.rs:70-72)
+      const float alpha = ex2(m - m_new);
+      if (j > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }          // PV_{j-1} retired: sP is free, PV buffer readable
+      float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        float s[32];
+        load_scores(kb, s);
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          s[c] = ex2(s[c] - m_new);
+          s[c + 1] = ex2(s[c + 1] - m_new);
+          acc0 += s[c];
+          acc1 += s[c + 1];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          store_a_chunk(sP + kb * (kPBytes / 2), r_in, q, make_float4(s[q * 4], s[q * 4 + 1], s[q * 4 + 2], s[q * 4 + 3]));
+      }
+      l = l * alpha + (acc0 + acc1);
+      m = m_new;
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+      if (j > 0) {
+        // fold PV_{j-1} (other TMEM buffer) into the register accumulator while the tensor core runs block j
+        tc_fence_after();
+        const uint32_t to = tmem + 128u + (cur ? 0u : 64u) + lane_addr;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[16];
+          tmem_ld16(to + ch * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[ch * 16 + c] = fmaf(o[ch * 16 + c], alpha_prev, __uint_as_float(r[c]));
+        }
+        tc_fence_before();
+      }
+      alpha_prev = alpha;
+    }
+    const float l_fin = fmaxf(l, kMinPos);                       // min_positive clamp (attention.rs:75-76)
+    const float rinv = __frcp_rn(l_fin);
+    float *orow = P.out + (int64_t)b * P.o_sb + (int64_t)h * P.o_sh + (int64_t)row * P.o_ss;
+    if (nkv > 0) {
+      mbar_wait(bar_o, ph_o); ph_o ^= 1;
+      tc_fence_after();
+      const uint32_t to = tmem + 128u + (((nkv - 1) & 1) ? 64u : 0u) + lane_addr;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[16];
+        tmem_ld16(to + ch * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[ch * 16 + c] = __fmul_rn(fmaf(o[ch * 16 + c], alpha_prev, __uint_as_float(r[c])), rinv);
+      }
+    }
+    if (row_ok) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        reinterpret_cast<float4 *>(orow)[q] = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+      P.stats[((int64_t)b * P.H + h) * P.Sq + row] = make_float4(m, rinv, 0.0f, 0.0f);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+struct BwdParams {
+  // dq kernel: q, d_out boxes of 128 rows; k, v boxes of 64 rows (K-major); k_mn MN-major
+  // dkv kernel: k, v boxes of 128 rows; q, d_out boxes of 64 rows (K-major); q_mn, do_mn MN-major
+  CUtensorMap tma_q, tma_do, tma_k, tma_v, tma_mn0, tma_mn1;
+  const float *o_fwd, *d_out;    // rows read directly for delta
+  int64_t of_sb, of_sh, of_ss, do_sb, do_sh, do_ss;
+  float *g0, *g1;                // dq | dk, dv
+  int64_t g0_sb, g0_sh, g0_ss, g1_sb, g1_sh, g1_ss;
+  float4 *stats;
+  const uint8_t *mask;
+  int64_t m_sb, m_sh, m_ss;
+  int32_t B, H, Sq, Sk;
+  int32_t causal, blocks;        // row tiles per (b, h)
+  float scale, mask_value;
+};
+
+constexpr int kBwdThreads = 320;   // issuer warp, TMEM-allocator warp, 8 row warps (two per TMEM lane quarter)
+
+__global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __grid_constant__ BwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sQ = smem, *sdO = sQ + kBig, *sKk = sdO + kBig, *sVk = sKk + kSmall, *sKmn = sVk + kSmall, *sdS = sKmn + kSmall;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sdS + kPBytes);
+  uint64_t *bar_q = bars, *bar_kv = bars + 1, *bar_mn = bars + 2, *bar_s0 = bars + 3, *bar_s1 = bars + 4, *bar_p = bars + 5,
+           *bar_o = bars + 6;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int work = blockIdx.x;
+  const int qb = P.blocks - 1 - (work % P.blocks);
+  const int bh = work / P.blocks, h = bh % P.H, b = bh / P.H;
+  const int q0 = qb * kRows;
+  const int nkv_all = (P.Sk + kCols - 1) / kCols;
+  int nkv = nkv_all;
+  if (causal_skip(P.causal, P.Sq, P.Sk, P.mask_value)) {
+    const int last_col = min(P.Sk - 1, q0 + kRows - 1 + (P.Sk - P.Sq));
+    nkv = last_col < 0 ? 0 : min(nkv_all, last_col / kCols + 1);
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tma_q);
+    tma_prefetch_desc(&P.tma_do);
+    tma_prefetch_desc(&P.tma_k);
+    tma_prefetch_desc(&P.tma_v);
+    tma_prefetch_desc(&P.tma_mn0);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_mn, 1);
+    mbar_init(bar_s0, 1);
+    mbar_init(bar_s1, 1);
+    mbar_init(bar_p, 8);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;        // S0 @0, S1 @64, dP0 @128, dP1 @192, dQ @256
+
+  if (warp == 0) {
+    // TMA producers: lane 0 streams the K-major K_j / V_j tiles (free when S_j / dP_j retire), lane 1 the
+    // MN-major K_j tile (free when the dQ MMA of block j retires)
+    if (lane == 0 && nkv > 0) {
+      mbar_expect_tx(bar_q, 2 * kBig);
+      load_kmajor(sQ, &P.tma_q, bar_q, q0, h, b, kBig / 2);
+      load_kmajor(sdO, &P.tma_do, bar_q, q0, h, b, kBig / 2);
+      uint32_t ph_s0 = 0, ph_s1 = 0;
+      for (int j = 0; j < nkv; ++j) {
+        if (j > 0) {
+          if ((j - 1) & 1) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+        }
+        mbar_expect_tx(bar_kv, 2 * kSmall);
+        load_kmajor(sKk, &P.tma_k, bar_kv, j * kCols, h, b, kSmall / 2);
+        load_kmajor(sVk, &P.tma_v, bar_kv, j * kCols, h, b, kSmall / 2);
+      }
+    } else if (lane == 1 && nkv > 0) {
+      uint32_t ph_o = 0;
+      for (int j = 0; j < nkv; ++j) {
+        if (j > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }
+        mbar_expect_tx(bar_mn, kSmall);
+        load_mnmajor(sKmn, &P.tma_mn0, bar_mn, j * kCols, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkv > 0) {
+      const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKk = smem_u32(sKk), aVk = smem_u32(sVk), aKmn = smem_u32(sKmn),
+                     adS = smem_u32(sdS);
+      auto mma_s_dp = [&](int buf) {
+        tc_fence_after();
+        mma_kk(tmem + (buf ? 64u : 0u), aQ, kBig / 2, aKk, kSmall / 2, idesc, false);          // S = Q·Kᵀ
+        mma_kk(tmem + 128u + (buf ? 64u : 0u), adO, kBig / 2, aVk, kSmall / 2, idesc, false);  // dP = dO·Vᵀ
+        umma_commit(buf ? bar_s1 : bar_s0);
+      };
+      uint32_t ph_kv = 0, ph_mn = 0, ph_p = 0;
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
+      mma_s_dp(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int cur = j & 1;
+        if (j + 1 < nkv) {
+          mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
+          mma_s_dp(cur ^ 1);
+        }
+        mbar_wait(bar_mn, ph_mn); ph_mn ^= 1;
+        mbar_wait(bar_p, ph_p); ph_p ^= 1;                         // dS_j is in smem
+        tc_fence_after();
+        mma_kmn(tmem + 256u, adS, aKmn, idesc_mn, j > 0);          // dQ += dS_j·K_j
+        umma_commit(bar_o);
+      }
+    }
+  } else if (warp >= 2) {
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int r_in = quarter * 32 + lane, row = q0 + r_in;
+    const bool row_ok = row < P.Sq;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int causal_limit = row + (P.Sk - P.Sq);
+    const uint8_t *mrow = P.mask ? P.mask + (int64_t)b * P.m_sb + (int64_t)h * P.m_sh + (int64_t)row * P.m_ss : nullptr;
+    const float scale2 = P.scale * kLog2e, mask2 = P.mask_value * kLog2e;
+    float4 *stat = P.stats + ((int64_t)b * P.H + h) * P.Sq + row;
+    float m2 = 0.0f, rinv = 0.0f, delta = 0.0f;
+    if (row_ok) {
+      const float4 st = *stat;
+      m2 = st.x;
+      rinv = st.y;
+      // delta = sum_d dO[row, d] * O[row, d]  (= rowsum(dP ∘ P))
+      const float4 *orow = reinterpret_cast<const float4 *>(P.o_fwd + (int64_t)b * P.of_sb + (int64_t)h * P.of_sh + (int64_t)row * P.of_ss);
+      const float4 *grow = reinterpret_cast<const float4 *>(P.d_out + (int64_t)b * P.do_sb + (int64_t)h * P.do_sh + (int64_t)row * P.do_ss);
+#pragma unroll
+      for (int q = 0; q < HD / 4; ++q) {
+        const float4 ov = __ldg(orow + q), g = __ldg(grow + q);
+        delta = __fadd_rn(delta, __fadd_rn(__fadd_rn(__fmul_rn(ov.x, g.x), __fmul_rn(ov.y, g.y)),
+                                           __fadd_rn(__fmul_rn(ov.z, g.z), __fmul_rn(ov.w, g.w))));
+      }
+      if (half == 0) stat->z = delta;      // the dK/dV kernel (launched after this one) reads it per query column
+    }
+    uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
+    for (int j = 0; j < nkv; ++j) {
+      const int cur = j & 1;
+      const int col0 = j * kCols + half * 32;
+      uint32_t masked = 0;                                         // bit c: column col0 + c is masked
+      if (mrow && row_ok) {                                        // fetched before the wait: latency overlaps it
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (col0 + q * 4 < P.Sk) {
+            const uint32_t mw = __ldg(reinterpret_cast<const uint32_t *>(mrow + col0) + q);
+            if (mw & 0xFFu) masked |= 1u << (q * 4);
+            if (mw & 0xFF00u) masked |= 2u << (q * 4);
+            if (mw & 0xFF0000u) masked |= 4u << (q * 4);
+            if (mw & 0xFF000000u) masked |= 8u << (q * 4);
+          }
+        }
+      }
+      if (P.causal && col0 + 31 > causal_limit) {
+        const int first = causal_limit + 1 - col0;                 // first masked column of this chunk
+        masked |= first <= 0 ? 0xFFFFFFFFu : (first >= 32 ? 0u : (0xFFFFFFFFu << first));
+      }
+      if (cur) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+      tc_fence_after();
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tmem + (cur ? 64u : 0u) + lane_addr + half * 32, rs);
+      tmem_ld32(tmem + 128u + (cur ? 64u : 0u) + lane_addr + half * 32, rp);
+      tmem_ld_wait();
+      float ds[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const bool mk = (masked >> c) & 1u;
+        const float t = mk ? mask2 : __fmul_rn(__uint_as_float(rs[c]), scale2);
+        float p = __fmul_rn(ex2(t - m2), rinv);
+        if (col0 + c >= P.Sk) p = 0.0f;
+        const float d = __fmul_rn(__fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), delta)), P.scale);
+        ds[c] = mk ? 0.0f : d;                                     // mask_fill backward: no gradient through a filled score
+      }
+      if (j > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }            // dQ MMA of block j-1 no longer reads sdS
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        store_a_chunk(sdS + half * (kPBytes / 2), r_in, q, make_float4(ds[q * 4], ds[q * 4 + 1], ds[q * 4 + 2], ds[q * 4 + 3]));
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+    }
+    float *grow_out = P.g0 + (int64_t)b * P.g0_sb + (int64_t)h * P.g0_sh + (int64_t)row * P.g0_ss + half * 32;
+    if (nkv > 0) {
+      mbar_wait(bar_o, ph_o); ph_o ^= 1;
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tmem + 256u + lane_addr + half * 32, r);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          reinterpret_cast<uint4 *>(grow_out)[q] = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+      }
+    } else if (row_ok) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) reinterpret_cast<uint4 *>(grow_out)[q] = make_uint4(0, 0, 0, 0);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __grid_constant__ BwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sK = smem, *sV = sK + kBig, *sQk = sV + kBig, *sdOk = sQk + kSmall, *sQmn = sdOk + kSmall, *sdOmn = sQmn + kSmall,
+          *sP = sdOmn + kSmall, *sdS = sP + kPBytes;
+  // [3][64] (m2, 1/l, delta, -) of the block's queries.  Three buffers: the producer refills buffer it % 3 once
+  // Sᵀ_{it-1} has retired, and that MMA is only issued after the row threads delivered block it-3 — the last
+  // reader of the buffer (with two buffers the refill could overtake the readers of block it-2).
+  float4 *sStats = reinterpret_cast<float4 *>(sdS + kPBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sStats + 3 * kCols);
+  uint64_t *bar_res = bars, *bar_qk = bars + 1, *bar_mn = bars + 2, *bar_s0 = bars + 3, *bar_s1 = bars + 4, *bar_p = bars + 5,
+           *bar_o = bars + 6, *bar_st = bars + 7;     // bar_st[3]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int work = blockIdx.x;
+  const int kb_ = work % P.blocks;                                  // early key tiles see the most queries under a causal mask
+  const int bh = work / P.blocks, h = bh % P.H, b = bh / P.H;
+  const int kv0 = kb_ * kRows;
+  const int nq = (P.Sq + kCols - 1) / kCols;
+  int i_start = 0;
+  if (causal_skip(P.causal, P.Sq, P.Sk, P.mask_value)) {
+    const int first_q = kv0 - (P.Sk - P.Sq);                        // first query row that sees key kv0
+    i_start = first_q <= 0 ? 0 : min(nq, first_q / kCols);
+  }
+  const int n_it = nq - i_start;
+  const int64_t stat_base = ((int64_t)b * P.H + h) * P.Sq;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tma_q);
+    tma_prefetch_desc(&P.tma_do);
+    tma_prefetch_desc(&P.tma_k);
+    tma_prefetch_desc(&P.tma_v);
+    tma_prefetch_desc(&P.tma_mn0);
+    tma_prefetch_desc(&P.tma_mn1);
+    mbar_init(bar_res, 1);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_mn, 1);
+    mbar_init(bar_s0, 1);
+    mbar_init(bar_s1, 1);
+    mbar_init(bar_p, 8);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_st, 1);
+    mbar_init(bar_st + 1, 1);
+    mbar_init(bar_st + 2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;        // ST0 @0, ST1 @64, dPT0 @128, dPT1 @192, dV @256, dK @320
+
+  if (warp == 0) {
+    // TMA producers: lane 0 streams the K-major Q_i / dO_i tiles + the block's row statistics (free when Sᵀ_i / dPᵀ_i
+    // retire), lane 1 the MN-major Q_i / dO_i tiles (free when the dV / dK MMAs of block i retire)
+    if (lane == 0 && n_it > 0) {
+      mbar_expect_tx(bar_res, 2 * kBig);
+      load_kmajor(sK, &P.tma_k, bar_res, kv0, h, b, kBig / 2);
+      load_kmajor(sV, &P.tma_v, bar_res, kv0, h, b, kBig / 2);
+      uint32_t ph_s0 = 0, ph_s1 = 0;
+      for (int it = 0; it < n_it; ++it) {
+        if (it > 0) {
+          if ((it - 1) & 1) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+        }
+        const int r0 = (i_start + it) * kCols, buf = it % 3;
+        mbar_expect_tx(bar_qk, 2 * kSmall);
+        load_kmajor(sQk, &P.tma_q, bar_qk, r0, h, b, kSmall / 2);
+        load_kmajor(sdOk, &P.tma_do, bar_qk, r0, h, b, kSmall / 2);
+        // the block's per-query statistics: one bulk copy, clipped at the end of the sequence
+        const uint32_t bytes = (uint32_t)min(kCols, P.Sq - r0) * 16u;
+        uint64_t *bst = bar_st + buf;
+        mbar_expect_tx(bst, bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sStats + buf * kCols)),
+                     "l"(P.stats + stat_base + r0), "r"(bytes), "r"(smem_u32(bst))
+                     : "memory");
+      }
+    } else if (lane == 1 && n_it > 0) {
+      uint32_t ph_o = 0;
+      for (int it = 0; it < n_it; ++it) {
+        if (it > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }
+        const int r0 = (i_start + it) * kCols;
+        mbar_expect_tx(bar_mn, 2 * kSmall);
+        load_mnmajor(sQmn, &P.tma_mn0, bar_mn, r0, h, b);
+        load_mnmajor(sdOmn, &P.tma_mn1, bar_mn, r0, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_it > 0) {
+      const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQk = smem_u32(sQk), adOk = smem_u32(sdOk), aQmn = smem_u32(sQmn),
+                     adOmn = smem_u32(sdOmn), aP = smem_u32(sP), adS = smem_u32(sdS);
+      auto mma_s_dp = [&](int buf) {
+        tc_fence_after();
+        mma_kk(tmem + (buf ? 64u : 0u), aK, kBig / 2, aQk, kSmall / 2, idesc, false);          // Sᵀ = K·Qᵀ
+        mma_kk(tmem + 128u + (buf ? 64u : 0u), aV, kBig / 2, adOk, kSmall / 2, idesc, false);  // dPᵀ = V·dOᵀ
+        umma_commit(buf ? bar_s1 : bar_s0);
+      };
+      uint32_t ph_qk = 0, ph_mn = 0, ph_p = 0;
+      mbar_wait(bar_res, 0);
+      mbar_wait(bar_qk, ph_qk); ph_qk ^= 1;
+      mma_s_dp(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int cur = it & 1;
+        if (it + 1 < n_it) {
+          mbar_wait(bar_qk, ph_qk); ph_qk ^= 1;
+          mma_s_dp(cur ^ 1);
+        }
+        mbar_wait(bar_mn, ph_mn); ph_mn ^= 1;
+        mbar_wait(bar_p, ph_p); ph_p ^= 1;                         // Pᵀ and dSᵀ are in smem
+        tc_fence_after();
+        mma_kmn(tmem + 256u, aP, adOmn, idesc_mn, it > 0);         // dV += Pᵀ·dO_i
+        mma_kmn(tmem + 320u, adS, aQmn, idesc_mn, it > 0);         // dK += dSᵀ·Q_i
+        umma_commit(bar_o);
+      }
+    }
+  } else if (warp >= 2) {
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int r_in = quarter * 32 + lane, kv = kv0 + r_in;
+    const bool kv_ok = kv < P.Sk;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int shift = P.Sk - P.Sq;
+    const uint8_t *mcol = P.mask ? P.mask + (int64_t)b * P.m_sb + (int64_t)h * P.m_sh + kv : nullptr;
+    const float scale2 = P.scale * kLog2e, mask2 = P.mask_value * kLog2e;
+    uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int cur = it & 1, sb = it % 3;
+      const int qc0 = (i_start + it) * kCols + half * 32;
+      uint32_t mbits = 0;                                           // bit c: explicit mask at (query qc0 + c, key kv)
+      if (mcol && kv_ok) {                                          // fetched before the waits
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (qc0 + c < P.Sq && __ldg(mcol + (int64_t)(qc0 + c) * P.m_ss)) mbits |= 1u << c;
+      }
+      mbar_wait(bar_st + sb, (uint32_t)((it / 3) & 1));
+      if (cur) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+      tc_fence_after();
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tmem + (cur ? 64u : 0u) + lane_addr + half * 32, rs);
+      tmem_ld32(tmem + 128u + (cur ? 64u : 0u) + lane_addr + half * 32, rp);
+      tmem_ld_wait();
+      const float4 *st = sStats + sb * kCols + half * 32;
+      float pv[32], ds[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int q = qc0 + c;
+        const bool q_ok = q < P.Sq;
+        const float4 sq = st[c];                                    // smem broadcast; garbage past Sq is never used
+        const bool mk = (P.causal && kv > q + shift) || ((mbits >> c) & 1u);
+        const float t = mk ? mask2 : __fmul_rn(__uint_as_float(rs[c]), scale2);
+        float p = (q_ok && kv_ok) ? __fmul_rn(ex2(t - sq.x), sq.y) : 0.0f;
+        const float d = __fmul_rn(__fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), sq.z)), P.scale);
+        pv[c] = p;
+        ds[c] = (mk || !(q_ok && kv_ok)) ? 0.0f : d;
+      }
+      if (it > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }            // dV / dK MMAs of block it-1 no longer read sP / sdS
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        store_a_chunk(sP + half * (kPBytes / 2), r_in, q, make_float4(pv[q * 4], pv[q * 4 + 1], pv[q * 4 + 2], pv[q * 4 + 3]));
+        store_a_chunk(sdS + half * (kPBytes / 2), r_in, q, make_float4(ds[q * 4], ds[q * 4 + 1], ds[q * 4 + 2], ds[q * 4 + 3]));
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
+    }
+    float *dk_row = P.g0 + (int64_t)b * P.g0_sb + (int64_t)h * P.g0_sh + (int64_t)kv * P.g0_ss + half * 32;
+    float *dv_row = P.g1 + (int64_t)b * P.g1_sb + (int64_t)h * P.g1_sh + (int64_t)kv * P.g1_ss + half * 32;
+    if (n_it > 0) {
+      mbar_wait(bar_o, ph_o); ph_o ^= 1;
+      tc_fence_after();
+      uint32_t rv[32], rk[32];
+      tmem_ld32(tmem + 256u + lane_addr + half * 32, rv);
+      tmem_ld32(tmem + 320u + lane_addr + half * 32, rk);
+      tmem_ld_wait();
+      if (kv_ok) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          reinterpret_cast<uint4 *>(dv_row)[q] = make_uint4(rv[q * 4], rv[q * 4 + 1], rv[q * 4 + 2], rv[q * 4 + 3]);
+          reinterpret_cast<uint4 *>(dk_row)[q] = make_uint4(rk[q * 4], rk[q * 4 + 1], rk[q * 4 + 2], rk[q * 4 + 3]);
+        }
+      }
+    } else if (kv_ok) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        reinterpret_cast<uint4 *>(dv_row)[q] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4 *>(dk_row)[q] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace fa
+
+// ------------------------------------------------------------------------------------------ host
+static int32_t fa_operand(const b200_tensor *t, bool mn_major, int64_t B, int64_t H, Operand &o) {
+  o.ptr = t->ptr;
+  o.es = 4;
+  o.mn_major = mn_major;
+  o.s_mn = mn_major ? t->strides[3] : t->strides[2];
+  o.s_k = mn_major ? t->strides[2] : t->strides[3];
+  o.s_b[0] = 0; o.s_b[1] = t->strides[0]; o.s_b[2] = t->strides[1];
+  o.bsz[0] = 1; o.bsz[1] = (int32_t)B; o.bsz[2] = (int32_t)H;
+  B200_REQUIRE(t->strides[3] == 1 && ((uintptr_t)t->ptr % 16) == 0, B200_ERR_UNSUPPORTED,
+               "attention operands need a contiguous, 16-byte aligned head dim");
+  const int64_t mn = mn_major ? t->shape[3] : t->shape[2], kk = mn_major ? t->shape[2] : t->shape[3];
+  B200_REQUIRE(tma_ok(o, mn, kk), B200_ERR_UNSUPPORTED, "attention operand strides must be multiples of 4 elements");
+  return B200_OK;
+}
+static int32_t fa_map(CUtensorMap *map, const b200_tensor *t, bool mn_major, int box_rows, int64_t B, int64_t H) {
+  Operand o;
+  int32_t st = fa_operand(t, mn_major, B, H, o);
+  if (st != B200_OK) return st;
+  return mn_major ? make_tmap(map, o, t->shape[3], t->shape[2]) : make_tmap(map, o, t->shape[2], t->shape[3], box_rows);
+}
+static bool fa_rows_ok(const b200_tensor *t) {
+  return t->strides[3] == 1 && ((uintptr_t)t->ptr % 16) == 0 && t->strides[0] % 4 == 0 && t->strides[1] % 4 == 0 && t->strides[2] % 4 == 0;
+}
+struct FaMask {
+  const uint8_t *ptr;
+  int64_t sb, sh, ss;
+};
+static int32_t fa_mask(const b200_tensor *mask, int64_t B, int64_t H, int64_t Sq, int64_t Sk, FaMask &m) {
+  m.ptr = nullptr;
+  m.sb = m.sh = m.ss = 0;
+  if (!mask) return B200_OK;
+  B200_REQUIRE(mask->rank == 4 && (mask->dtype == B200_BOOL || mask->dtype == B200_U8) && mask->ptr, B200_ERR_UNSUPPORTED,
+               "attention mask must be bool [B|1, H|1, Sq, Sk]");
+  B200_REQUIRE((mask->shape[0] == B || mask->shape[0] == 1) && (mask->shape[1] == H || mask->shape[1] == 1) &&
+                   mask->shape[2] == Sq && mask->shape[3] == Sk,
+               B200_ERR_SHAPE, "attention mask is not broadcastable to [B, H, Sq, Sk]");
+  B200_REQUIRE(mask->strides[3] == 1 && Sk % 4 == 0 && ((uintptr_t)mask->ptr % 4) == 0 && mask->strides[2] % 4 == 0 &&
+                   mask->strides[0] % 4 == 0 && mask->strides[1] % 4 == 0,
+               B200_ERR_UNSUPPORTED, "attention mask needs Sk %% 4 == 0 and 4-byte-multiple strides");
+  m.ptr = reinterpret_cast<const uint8_t *>(mask->ptr);
+  m.sb = mask->shape[0] == 1 ? 0 : mask->strides[0];
+  m.sh = mask->shape[1] == 1 ? 0 : mask->strides[1];
+  m.ss = mask->strides[2];
+  return B200_OK;
+}
+static int32_t fa_stats_ok(const b200_tensor *stats, int64_t B, int64_t H, int64_t Sq) {
+  B200_REQUIRE(stats && stats->ptr && stats->rank == 4 && stats->dtype == B200_F32 && stats->shape[0] == B && stats->shape[1] == H &&
+                   stats->shape[2] == Sq && stats->shape[3] == 4 && is_contiguous(*stats) && ((uintptr_t)stats->ptr % 16) == 0,
+               B200_ERR_SHAPE, "attention stats must be a contiguous, 16-byte aligned f32 [B, H, Sq, 4] tensor");
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int32_t b200_launch_attention_flash(const b200_tensor *q, const b200_tensor *k, const b200_tensor *v,
+                                               const b200_tensor *mask, double scale, double mask_value, int32_t is_causal,
+                                               const b200_tensor *out, const b200_tensor *stats, b200_stream s) {
+  B200_REQUIRE(q && k && v && out && stats, B200_ERR_INVALID, "null argument");
+  for (const b200_tensor *t : {q, k, v, out})
+    B200_REQUIRE(t->rank == 4 && t->dtype == B200_F32 && t->ptr, B200_ERR_UNSUPPORTED, "attention operands must be f32 [B, H, S, D]");
+  const int64_t B = q->shape[0], H = q->shape[1], Sq = q->shape[2], D = q->shape[3], Sk = k->shape[2], Dv = v->shape[3];
+  B200_REQUIRE(k->shape[0] == B && k->shape[1] == H && k->shape[3] == D && v->shape[0] == B && v->shape[1] == H &&
+                   v->shape[2] == Sk && out->shape[0] == B && out->shape[1] == H && out->shape[2] == Sq && out->shape[3] == Dv,
+               B200_ERR_SHAPE, "attention shape mismatch");
+  B200_REQUIRE(D == fa::HD && Dv == fa::HD, B200_ERR_UNSUPPORTED,
+               "the fused attention kernels are built for head dim 64 (got %lld / %lld); use the op chain", (long long)D, (long long)Dv);
+  int32_t st = fa_stats_ok(stats, B, H, Sq);
+  if (st != B200_OK) return st;
+  if (B == 0 || H == 0 || Sq == 0) return B200_OK;
+  B200_REQUIRE(Sk > 0 && Sq < (1ll << 30) && Sk < (1ll << 30), B200_ERR_UNSUPPORTED, "attention sequence lengths out of range");
+  fa::FwdParams P;
+  memset(&P, 0, sizeof(P));
+  if ((st = fa_map(&P.tma_q, q, false, fa::kRows, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_k, k, false, fa::kCols, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_v, v, true, 0, B, H)) != B200_OK) return st;
+  B200_REQUIRE(fa_rows_ok(out), B200_ERR_UNSUPPORTED, "attention output needs a contiguous head dim and 16-byte-multiple strides");
+  P.out = reinterpret_cast<float *>(out->ptr);
+  P.o_sb = out->strides[0]; P.o_sh = out->strides[1]; P.o_ss = out->strides[2];
+  P.stats = reinterpret_cast<float4 *>(stats->ptr);
+  FaMask fm;
+  if ((st = fa_mask(mask, B, H, Sq, Sk, fm)) != B200_OK) return st;
+  P.mask = fm.ptr; P.m_sb = fm.sb; P.m_sh = fm.sh; P.m_ss = fm.ss;
+  P.B = (int32_t)B; P.H = (int32_t)H; P.Sq = (int32_t)Sq; P.Sk = (int32_t)Sk;
+  P.causal = is_causal ? 1 : 0;
+  P.q_blocks = (int32_t)((Sq + fa::kRows - 1) / fa::kRows);
+  P.scale = (float)scale;
+  P.mask_value = (float)mask_value;
+  const int64_t ctas = B * H * P.q_blocks;
+  B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
+  const size_t smem = 1024 + fa::kBig + 2 * fa::kSmall + fa::kPBytes + 128;
+  if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_fwd_kernel), smem, true)) != B200_OK) return st;
+  fa::flash_fwd_kernel<<<(unsigned)ctas, 192, smem, resolve_stream(s)>>>(P);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out, const b200_tensor *q, const b200_tensor *k,
+                                                        const b200_tensor *v, const b200_tensor *out, const b200_tensor *stats,
+                                                        const b200_tensor *mask, double scale, double mask_value,
+                                                        int32_t is_causal, const b200_tensor *dq, const b200_tensor *dk,
+                                                        const b200_tensor *dv, b200_stream s) {
+  B200_REQUIRE(d_out && q && k && v && out && stats && dq && dk && dv, B200_ERR_INVALID, "null argument");
+  for (const b200_tensor *t : {d_out, q, k, v, out, dq, dk, dv})
+    B200_REQUIRE(t->rank == 4 && t->dtype == B200_F32 && t->ptr, B200_ERR_UNSUPPORTED, "attention operands must be f32 rank-4");
+  const int64_t B = q->shape[0], H = q->shape[1], Sq = q->shape[2], D = q->shape[3], Sk = k->shape[2];
+  B200_REQUIRE(D == fa::HD, B200_ERR_UNSUPPORTED, "the fused attention kernels are built for head dim 64; use the op chain");
+  auto same = [&](const b200_tensor *t, int64_t s2) {
+    return t->shape[0] == B && t->shape[1] == H && t->shape[2] == s2 && t->shape[3] == D;
+  };
+  B200_REQUIRE(same(d_out, Sq) && same(out, Sq) && same(dq, Sq) && same(k, Sk) && same(v, Sk) && same(dk, Sk) && same(dv, Sk),
+               B200_ERR_SHAPE, "attention backward shape mismatch");
+  int32_t st = fa_stats_ok(stats, B, H, Sq);
+  if (st != B200_OK) return st;
+  if (B == 0 || H == 0 || Sq == 0 || Sk == 0) return B200_OK;
+  B200_REQUIRE(Sq < (1ll << 30) && Sk < (1ll << 30), B200_ERR_UNSUPPORTED, "attention sequence lengths out of range");
+  B200_REQUIRE(fa_rows_ok(out) && fa_rows_ok(d_out) && fa_rows_ok(dq) && fa_rows_ok(dk) && fa_rows_ok(dv), B200_ERR_UNSUPPORTED,
+               "attention rows need a contiguous head dim and 16-byte-multiple strides");
+  FaMask fm;
+  if ((st = fa_mask(mask, B, H, Sq, Sk, fm)) != B200_OK) return st;
+  fa::BwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.o_fwd = reinterpret_cast<const float *>(out->ptr);
+  P.of_sb = out->strides[0]; P.of_sh = out->strides[1]; P.of_ss = out->strides[2];
+  P.d_out = reinterpret_cast<const float *>(d_out->ptr);
+  P.do_sb = d_out->strides[0]; P.do_sh = d_out->strides[1]; P.do_ss = d_out->strides[2];
+  P.stats = reinterpret_cast<float4 *>(stats->ptr);
+  P.mask = fm.ptr; P.m_sb = fm.sb; P.m_sh = fm.sh; P.m_ss = fm.ss;
+  P.B = (int32_t)B; P.H = (int32_t)H; P.Sq = (int32_t)Sq; P.Sk = (int32_t)Sk;
+  P.causal = is_causal ? 1 : 0;
+  P.scale = (float)scale;
+  P.mask_value = (float)mask_value;
+  cudaStream_t stream = resolve_stream(s);
+
+  // ---- kernel 1: dQ (and delta into stats.z)
+  if ((st = fa_map(&P.tma_q, q, false, fa::kRows, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_do, d_out, false, fa::kRows, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_k, k, false, fa::kCols, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_v, v, false, fa::kCols, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_mn0, k, true, 0, B, H)) != B200_OK) return st;
+  P.g0 = reinterpret_cast<float *>(dq->ptr);
+  P.g0_sb = dq->strides[0]; P.g0_sh = dq->strides[1]; P.g0_ss = dq->strides[2];
+  P.blocks = (int32_t)((Sq + fa::kRows - 1) / fa::kRows);
+  {
+    const int64_t ctas = B * H * P.blocks;
+    B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
+    const size_t smem = 1024 + 2 * fa::kBig + 3 * fa::kSmall + fa::kPBytes + 128;
+    if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dq_kernel), smem)) != B200_OK) return st;
+    fa::flash_bwd_dq_kernel<<<(unsigned)ctas, fa::kBwdThreads, smem, stream>>>(P);
+    B200_LAUNCH_CHECK();
+  }
+  // ---- kernel 2: dK, dV
+  if ((st = fa_map(&P.tma_k, k, false, fa::kRows, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_v, v, false, fa::kRows, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_q, q, false, fa::kCols, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_do, d_out, false, fa::kCols, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_mn0, q, true, 0, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_mn1, d_out, true, 0, B, H)) != B200_OK) return st;
+  P.g0 = reinterpret_cast<float *>(dk->ptr);
+  P.g0_sb = dk->strides[0]; P.g0_sh = dk->strides[1]; P.g0_ss = dk->strides[2];
+  P.g1 = reinterpret_cast<float *>(dv->ptr);
+  P.g1_sb = dv->strides[0]; P.g1_sh = dv->strides[1]; P.g1_ss = dv->strides[2];
+  P.blocks = (int32_t)((Sk + fa::kRows - 1) / fa::kRows);
+  {
+    const int64_t ctas = B * H * P.blocks;
+    B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
+    const size_t smem = 1024 + 2 * fa::kBig + 4 * fa::kSmall + 2 * fa::kPBytes + 3 * fa::kCols * 16 + 128;
+    if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dkv_kernel), smem)) != B200_OK) return st;
+    fa::flash_bwd_dkv_kernel<<<(unsigned)ctas, fa::kBwdThreads, smem, stream>>>(P);
+    B200_LAUNCH_CHECK();
+  }
+  return B200_OK;
+}

@@ -356,6 +356,42 @@ def attention_backward(d_out: DeviceTensor, k: DeviceTensor, v: DeviceTensor, ou
     return dq, ds
 
 
+def attention_flash(q: DeviceTensor, k: DeviceTensor, v: DeviceTensor, mask: DeviceTensor | None = None,
+                    scale: float | None = None, mask_value: float = float("-inf"), is_causal: bool = False,
+                    out: DeviceTensor | None = None):
+    """ModuleOps::attention for training (b200_launch_attention_flash): returns (out, stats) where stats
+    [B,H,Sq,4] holds the per-row softmax statistics the backward recomputes the weights from — no
+    [B,H,Sq,Sk] tensor is written."""
+    B, H, Sq, D = q.shape
+    if scale is None:
+        scale = 1.0 / float(np.sqrt(D))
+    out = DeviceTensor.empty((B, H, Sq, v.shape[3])) if out is None else out
+    stats = DeviceTensor.empty((B, H, Sq, 4))
+    qd, kd, vd, od, sd = q.desc(), k.desc(), v.desc(), out.desc(), stats.desc()
+    md = mask.desc() if mask is not None else None
+    check(abi.load().b200_launch_attention_flash(C.byref(qd), C.byref(kd), C.byref(vd), C.byref(md) if md is not None else None,
+                                                 float(scale), float(mask_value), 1 if is_causal else 0, C.byref(od),
+                                                 C.byref(sd), None))
+    return out, stats
+
+
+def attention_flash_backward(d_out: DeviceTensor, q: DeviceTensor, k: DeviceTensor, v: DeviceTensor, out: DeviceTensor,
+                             stats: DeviceTensor, mask: DeviceTensor | None, scale: float, mask_value: float,
+                             is_causal: bool = False, dq=None, dk=None, dv=None):
+    """(dq, dk, dv) of the attention core, weights recomputed from q, k and the saved statistics
+    (b200_launch_attention_flash_backward)."""
+    dq = DeviceTensor.empty(q.shape) if dq is None else dq
+    dk = DeviceTensor.empty(k.shape) if dk is None else dk
+    dv = DeviceTensor.empty(v.shape) if dv is None else dv
+    ds = [t.desc() for t in (d_out, q, k, v, out, stats, dq, dk, dv)]
+    md = mask.desc() if mask is not None else None
+    check(abi.load().b200_launch_attention_flash_backward(
+        C.byref(ds[0]), C.byref(ds[1]), C.byref(ds[2]), C.byref(ds[3]), C.byref(ds[4]), C.byref(ds[5]),
+        C.byref(md) if md is not None else None, float(scale), float(mask_value), 1 if is_causal else 0,
+        C.byref(ds[6]), C.byref(ds[7]), C.byref(ds[8]), None))
+    return dq, dk, dv
+
+
 def softmax_cross_entropy(logits: DeviceTensor, targets: DeviceTensor, grad_scale: float, inplace: bool = False):
     """(picked, dlogits): log_softmax(logits)[target] per row and (softmax - onehot) * grad_scale, one pass
     (b200_launch_softmax_cross_entropy).  `inplace` writes the gradient over the logits."""

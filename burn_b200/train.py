@@ -235,26 +235,37 @@ def layer_norm(tape: Tape, x: Var, gamma: Var, beta: Var, eps: float = 1e-5) -> 
     return y
 
 
-FUSED_ATTENTION = os.environ.get("B200_FUSED_ATTENTION", "1") != "0"
+# B200_FUSED_ATTENTION: "flash" (default) = forward keeps per-row statistics, backward recomputes the weights — no
+# [B,H,S,S] tensor in HBM; "weights" = the round-1 fused kernels that save the weights (what burn-nn's MHA does when
+# its `weights` output is asked for); "0" = the scores-GEMM -> softmax -> context-GEMM chain.
+_ATTN_MODE = {"1": "flash", "flash": "flash", "weights": "weights", "0": "chain"}[os.environ.get("B200_FUSED_ATTENTION", "flash")]
+FUSED_ATTENTION = _ATTN_MODE != "chain"
 
 
 def attention(tape: Tape, q: Var, k: Var, v: Var, n_heads: int, mask: DeviceTensor | None, causal: bool = False) -> Var:
     """softmax(q·kᵀ/√dk [mask_fill -1e9]) · v on [B,S,d] projections viewed as [B,H,S,dk] (mha.rs:212-311).
     Heads are strided views and the context lands straight in the [B,S,H,dk] layout (no swap_dims copy).
-    `causal` says that `mask` is the autoregressive mask (generate_autoregressive_mask): the fused kernel
-    then builds it from indices and skips the fully masked key blocks — identical results, since a
+    `causal` says that `mask` is the autoregressive mask (generate_autoregressive_mask): the fused kernels
+    then build it from indices and skip the fully masked key blocks — identical results, since a
     -1e9 score contributes exp(-1e9 - max) = 0 exactly.
-    Forward: the fused attention kernel (head dim 64, tf32) returning the weights the backward needs;
-    otherwise scores GEMM (scaling + mask fill as its epilogue) → row softmax → context GEMM."""
+    Default: flash-style kernels (head dim 64, tf32) — forward saves only per-row softmax statistics, the
+    backward recomputes the weights tile by tile and produces dq, dk, dv in two kernels."""
     B, S, d = q.v.shape
     dk = d // n_heads
     def heads(t):
         return t.reshape((B, S, n_heads, dk)).swap_dims(1, 2)
     qh, kh, vh = heads(q.v), heads(k.v), heads(v.v)
     ctx_buf = DeviceTensor.empty((B, S, n_heads, dk))
-    if FUSED_ATTENTION and dk == 64 and tape.precision == abi.MM_TF32 and S % 4 == 0:
-        _, w = ops.attention(qh, kh, vh, None if causal else mask, 1.0 / math.sqrt(dk), -1.0e9, causal and mask is not None,
-                             out=ctx_buf.swap_dims(1, 2), want_weights=True)
+    ok = dk == 64 and tape.precision == abi.MM_TF32 and S % 4 == 0
+    mode = _ATTN_MODE if ok else "chain"
+    is_causal = causal and mask is not None
+    kmask = None if causal else mask
+    scale = 1.0 / math.sqrt(dk)
+    w = stats = None
+    if mode == "flash":
+        _, stats = ops.attention_flash(qh, kh, vh, kmask, scale, -1.0e9, is_causal, out=ctx_buf.swap_dims(1, 2))
+    elif mode == "weights":
+        _, w = ops.attention(qh, kh, vh, kmask, scale, -1.0e9, is_causal, out=ctx_buf.swap_dims(1, 2), want_weights=True)
     else:
         # scores = mask_fill(q·kᵀ/√dk, mask, -1e9): scaling and mask fill are the GEMM's fused epilogue
         epi = TapeBuilder().op("DIV_F", ("in", 0), ("f", math.sqrt(dk)), out=0 if mask is None else None)
@@ -264,29 +275,28 @@ def attention(tape: Tape, q: Var, k: Var, v: Var, n_heads: int, mask: DeviceTens
         w = ops.softmax_rows(scores)
         _mm(w, vh, tape.precision, out=ctx_buf.swap_dims(1, 2))
     y = Var(ctx_buf.reshape((B, S, d)), True)
-
-    fused = FUSED_ATTENTION and dk == 64 and tape.precision == abi.MM_TF32 and S % 4 == 0
     ctx_h = ctx_buf.swap_dims(1, 2)
 
     def bw():
         if y.g is None:
             return
         gh = y.g.reshape((B, S, n_heads, dk)).swap_dims(1, 2)          # [B,H,S,dk] view
-        # dV = Pᵀ·g
-        dv_buf = DeviceTensor.empty((B, S, n_heads, dk))
-        _mm(w.swap_dims(2, 3), gh, tape.precision, out=dv_buf.swap_dims(1, 2))
-        dq_buf, dk_buf = DeviceTensor.empty((B, S, n_heads, dk)), DeviceTensor.empty((B, S, n_heads, dk))
-        if fused:
-            # one kernel: dP = g·Vᵀ in TMEM → dS = P∘(dP − rowsum(g∘ctx))/√dk (masked positions have P = 0) → dQ = dS·K
-            _, ds = ops.attention_backward(gh, kh, vh, ctx_h, w, 1.0 / math.sqrt(dk), causal and mask is not None,
-                                           dq=dq_buf.swap_dims(1, 2))
+        dq_buf, dk_buf, dv_buf = (DeviceTensor.empty((B, S, n_heads, dk)) for _ in range(3))
+        if mode == "flash":
+            ops.attention_flash_backward(gh, qh, kh, vh, ctx_h, stats, kmask, scale, -1.0e9, is_causal,
+                                         dq_buf.swap_dims(1, 2), dk_buf.swap_dims(1, 2), dv_buf.swap_dims(1, 2))
         else:
-            dp = ops.float_matmul(gh, vh.swap_dims(2, 3), tape.precision)
-            # softmax backward dS = (dP - sum(dP∘P, -1)) ∘ P, the 1/√dk of the scores and the mask_fill
-            # backward (0 where masked) in one row-resident kernel
-            ds = ops.softmax_backward(w, dp, mask, math.sqrt(dk))
-            _mm(ds, kh, tape.precision, out=dq_buf.swap_dims(1, 2))
-        _mm(ds.swap_dims(2, 3), qh, tape.precision, out=dk_buf.swap_dims(1, 2))
+            _mm(w.swap_dims(2, 3), gh, tape.precision, out=dv_buf.swap_dims(1, 2))     # dV = Pᵀ·g
+            if mode == "weights":
+                # one kernel: dP = g·Vᵀ in TMEM → dS = P∘(dP − rowsum(g∘ctx))/√dk (masked positions have P = 0) → dQ = dS·K
+                _, ds = ops.attention_backward(gh, kh, vh, ctx_h, w, scale, is_causal, dq=dq_buf.swap_dims(1, 2))
+            else:
+                dp = ops.float_matmul(gh, vh.swap_dims(2, 3), tape.precision)
+                # softmax backward dS = (dP - sum(dP∘P, -1)) ∘ P, the 1/√dk of the scores and the mask_fill
+                # backward (0 where masked) in one row-resident kernel
+                ds = ops.softmax_backward(w, dp, mask, math.sqrt(dk))
+                _mm(ds, kh, tape.precision, out=dq_buf.swap_dims(1, 2))
+            _mm(ds.swap_dims(2, 3), qh, tape.precision, out=dk_buf.swap_dims(1, 2))
         accumulate(q, dq_buf.reshape((B, S, d)))
         accumulate(k, dk_buf.reshape((B, S, d)))
         accumulate(v, dv_buf.reshape((B, S, d)))

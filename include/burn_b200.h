@@ -395,6 +395,28 @@ int32_t b200_launch_attention_backward(const b200_tensor *d_out, const b200_tens
                                        int32_t is_causal, const b200_tensor *dq,
                                        const b200_tensor *ds, b200_stream s);
 
+/* Flash-style attention for training (burn_b200/csrc/attention_flash.cu): the same ModuleOps::attention
+ * forward, but instead of the weights it saves per-row softmax statistics — `stats` f32 [B,H,Sq,4] =
+ * (row max in the base-2 domain, 1 / row sum, delta (filled by the backward), unused) — so no
+ * [B,H,Sq,Sk] tensor is ever written.  mask: optional bool [B|1,H|1,Sq,Sk]; is_causal as above. */
+int32_t b200_launch_attention_flash(const b200_tensor *q, const b200_tensor *k,
+                                    const b200_tensor *v, const b200_tensor *mask,
+                                    double scale, double mask_value, int32_t is_causal,
+                                    const b200_tensor *out, const b200_tensor *stats,
+                                    b200_stream s);
+/* Its backward (what burn-autodiff's reverse walk over attention.rs:15-90 / mha.rs:253-311 computes:
+ * matmul backward ×2, softmax backward, mask_fill backward, scaling): recomputes the weights tile by
+ * tile from q, k and `stats`; dq in one kernel (query-row CTAs), dk and dv in a second (key-row CTAs),
+ * all three accumulated in TMEM, no atomics (bit-reproducible).  Pass the forward's mask / scale /
+ * mask_value / is_causal.  `stats` is updated in place (delta). */
+int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out, const b200_tensor *q,
+                                             const b200_tensor *k, const b200_tensor *v,
+                                             const b200_tensor *out, const b200_tensor *stats,
+                                             const b200_tensor *mask, double scale,
+                                             double mask_value, int32_t is_causal,
+                                             const b200_tensor *dq, const b200_tensor *dk,
+                                             const b200_tensor *dv, b200_stream s);
+
 /* ------------------------------------------------ optimizer */
 /* Multi-tensor Adam over one flat buffer, in place: the op sequence of
  * AdaptiveMomentum::transform + Adam::step

@@ -33,3 +33,14 @@ for name, kw in (("fused, causal flag, weights", dict(is_causal=True, want_weigh
     t = timed(lambda: ops.attention(q, k, v, kw.get("mask"), 0.125, -1.0e9, kw.get("is_causal", False), out=ctx.swap_dims(1, 2),
                                     want_weights=kw.get("want_weights", False)))
     print(f"{name:34s}: {t:8.1f} us")
+# ---- flash variants (no [B,H,S,S] tensor): forward + backward
+g = heads()
+dqb, dkb, dvb = (DeviceTensor.empty((B, S, Hh, dk)) for _ in range(3))
+for name, causal, m in (("flash fwd, causal", True, None), ("flash fwd, no mask", False, None), ("flash fwd, mask tensor", False, mask)):
+    t = timed(lambda: ops.attention_flash(q, k, v, m, 0.125, -1.0e9, causal, out=ctx.swap_dims(1, 2)))
+    print(f"{name:34s}: {t:8.1f} us")
+for name, causal, m in (("flash bwd (dq + dkv), causal", True, None), ("flash bwd (dq + dkv), no mask", False, None)):
+    _, stats = ops.attention_flash(q, k, v, m, 0.125, -1.0e9, causal, out=ctx.swap_dims(1, 2))
+    t = timed(lambda: ops.attention_flash_backward(g, q, k, v, ctx.swap_dims(1, 2), stats, m, 0.125, -1.0e9, causal,
+                                                   dqb.swap_dims(1, 2), dkb.swap_dims(1, 2), dvb.swap_dims(1, 2)))
+    print(f"{name:34s}: {t:8.1f} us")

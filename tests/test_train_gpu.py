@@ -163,9 +163,9 @@ def test_param_arena_matches_per_parameter_adam_bit_for_bit(dev):
 
 
 def test_fused_attention_training_step_matches_the_unfused_chain(dev):
-    """dk = 64, tf32: the fused attention forward (weights kept for the unchanged backward) against the
-    scores-GEMM → softmax → context-GEMM chain — same loss and gradients to tf32 accuracy, with an explicit
-    mask tensor and with the causal flag (block skipping)."""
+    """dk = 64, tf32: the flash kernels (statistics saved, weights recomputed in the backward) and the
+    weights-saving fused kernels against the scores-GEMM → softmax → context-GEMM chain — same loss and gradients
+    to tf32 accuracy, with the causal flag (block skipping)."""
     vocab, S, d, ff, h, L, B = 64, 256, 128, 256, 2, 1, 2
     rng = np.random.default_rng(21)
     tok = rng.integers(0, vocab, (B, S)).astype(np.int32)
@@ -173,16 +173,17 @@ def test_fused_attention_training_step_matches_the_unfused_chain(dev):
     pos = np.tile(np.arange(S, dtype=np.int32), (B, 1))
     causal = np.triu(np.ones((S, S), dtype=bool), k=1)[None, None]
     results = {}
-    for fused in (False, True):
-        T.FUSED_ATTENTION = fused
+    for fused in ("chain", "flash", "weights"):
+        T._ATTN_MODE = fused
         lm = T.LanguageModel(3, vocab, S, d, ff, h, L)
         tape = T.Tape(abi.MM_TF32)
         loss = lm.loss(tape, H.up(tok), H.up(tgt), H.up(pos), H.up(causal))
         tape.backward()
         results[fused] = (float(loss.v.numpy()[0]), [p.g.numpy() for p in lm.params()])
-    T.FUSED_ATTENTION = True
-    assert abs(results[True][0] - results[False][0]) <= 2e-3 * abs(results[False][0])
-    for a, b in zip(results[True][1], results[False][1]):
-        scale = np.abs(b).max()
-        # 1e-6 floor: the key-bias gradient is mathematically zero (softmax ignores a shift of all keys)
-        assert np.abs(a - b).max() <= 2e-2 * scale + 1e-6
+    T._ATTN_MODE = "flash"
+    for mode in ("flash", "weights"):
+        assert abs(results[mode][0] - results["chain"][0]) <= 2e-3 * abs(results["chain"][0])
+        for a, b in zip(results[mode][1], results["chain"][1]):
+            scale = np.abs(b).max()
+            # 1e-6 floor: the key-bias gradient is mathematically zero (softmax ignores a shift of all keys)
+            assert np.abs(a - b).max() <= 2e-2 * scale + 1e-6, mode
