@@ -117,6 +117,10 @@ SIGNATURES = {
     "b200_launch_scatter_add": (_i32, [_i32, _TP, _TP, _TP, _vp]),
     "b200_launch_select": (_i32, [_i32, _TP, _TP, _TP, _vp]),
     "b200_launch_select_add": (_i32, [_i32, _TP, _TP, _TP, _vp]),
+    "b200_launch_slice_assign": (_i32, [_TP, C.POINTER(_i64), C.POINTER(_i64), _TP, _vp]),
+    "b200_launch_cat": (_i32, [_TP, _i32, _i32, _TP, _vp]),
+    "b200_launch_repeat_dim": (_i32, [_TP, _i32, _i64, _TP, _vp]),
+    "b200_launch_flip": (_i32, [_TP, C.POINTER(_i32), _i32, _TP, _vp]),
     "b200_launch_random": (_i32, [_TP, _i32, C.c_double, C.c_double, _u64, _u64, _vp]),
     "b200_launch_arange": (_i32, [_TP, _i64, _i64, _vp]),
     "b200_launch_softmax": (_i32, [_TP, _TP, _i32, _vp]),
@@ -143,6 +147,7 @@ SIGNATURES = {
     "b200_event_create": (_i32, [C.POINTER(_vp)]),
     "b200_event_destroy": (_i32, [_vp]),
     "b200_event_record": (_i32, [_vp, _vp]),
+    "b200_event_query": (_i32, [_vp, C.POINTER(_i32)]),
     "b200_event_elapsed_ms": (_i32, [_vp, _vp, C.POINTER(C.c_float)]),
     "b200_graph_begin": (_i32, [_vp]),
     "b200_graph_end": (_i32, [_vp, C.POINTER(C.c_void_p)]),

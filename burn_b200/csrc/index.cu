@@ -212,6 +212,24 @@ __global__ void __launch_bounds__(256) select_add_rows_kernel(float *t, int64_t 
   }
 }
 
+// out[c] = in[c with c[d] -> shape[d] - 1 - c[d] on the flipped axes]  (bit mask `axes`)
+__global__ void flip_kernel(IdxTensor in, IdxTensor out, uint32_t axes, int es, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rest = i, ioff = 0, ooff = 0;
+#pragma unroll
+    for (int d = kMaxDims - 1; d >= 0; --d) {
+      if (d < out.rank) {
+        const int64_t c = rest % out.shape[d];
+        rest /= out.shape[d];
+        ooff += c * out.strides[d];
+        ioff += (((axes >> d) & 1u) ? out.shape[d] - 1 - c : c) * in.strides[d];
+      }
+    }
+    copy_elem(out.ptr, ooff, in.ptr, ioff, es);
+  }
+}
+
 __global__ void arange_kernel(void *out, int32_t dtype, int64_t n, int64_t start, int64_t step) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -461,6 +479,101 @@ extern "C" int32_t b200_launch_random(const b200_tensor *out, int32_t kind, doub
   if (n == 0) return B200_OK;
   random_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, resolve_stream(s)>>>(out->ptr, out->dtype, n, kind, (float)lo,
                                                                           (float)hi, seed, offset);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// ---- data movement composed from strided copies (no kernel of their own but flip):
+// float_slice_assign / float_cat / float_repeat_dim / float_flip
+// (crates/burn-cubecl/src/kernel/index/{slice_assign,flip,repeat_dim}.rs, crates/burn-backend/src/backend/ops/tensor.rs:161,410,592,1460)
+static b200_tensor slice_view(const b200_tensor &t, const int64_t *starts, const int64_t *ends) {
+  b200_tensor v = t;
+  int64_t off = 0;
+  for (int d = 0; d < t.rank; ++d) {
+    off += starts[d] * t.strides[d];
+    v.shape[d] = ends[d] - starts[d];
+  }
+  v.ptr = reinterpret_cast<char *>(t.ptr) + off * dtype_size(t.dtype);
+  return v;
+}
+
+extern "C" int32_t b200_launch_slice_assign(const b200_tensor *tensor, const int64_t *starts, const int64_t *ends,
+                                            const b200_tensor *value, b200_stream s) {
+  B200_REQUIRE(tensor && starts && ends && value, B200_ERR_INVALID, "null argument");
+  B200_REQUIRE(tensor->rank == value->rank, B200_ERR_SHAPE, "slice_assign rank mismatch %d vs %d", tensor->rank, value->rank);
+  for (int d = 0; d < tensor->rank; ++d) {
+    B200_REQUIRE(starts[d] >= 0 && starts[d] <= ends[d] && ends[d] <= tensor->shape[d], B200_ERR_SHAPE,
+                 "slice_assign: range [%lld, %lld) out of bounds for dim %d of size %lld", (long long)starts[d], (long long)ends[d], d,
+                 (long long)tensor->shape[d]);
+    B200_REQUIRE(value->shape[d] == ends[d] - starts[d], B200_ERR_SHAPE, "slice_assign: value dim %d is %lld, the range holds %lld", d,
+                 (long long)value->shape[d], (long long)(ends[d] - starts[d]));
+  }
+  const b200_tensor view = slice_view(*tensor, starts, ends);
+  if (numel_of(view.shape, view.rank) == 0) return B200_OK;
+  return b200_launch_copy(value, &view, s);
+}
+
+extern "C" int32_t b200_launch_cat(const b200_tensor *inputs, int32_t n, int32_t dim, const b200_tensor *out, b200_stream s) {
+  B200_REQUIRE(inputs && out && n >= 1, B200_ERR_INVALID, "null argument / no inputs");
+  B200_REQUIRE(dim >= 0 && dim < out->rank, B200_ERR_SHAPE, "cat dim %d out of range", dim);
+  int64_t starts[B200_MAX_RANK] = {0}, ends[B200_MAX_RANK];
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    B200_REQUIRE(inputs[i].rank == out->rank, B200_ERR_SHAPE, "cat: input %d has rank %d, expected %d", i, inputs[i].rank, out->rank);
+    for (int d = 0; d < out->rank; ++d)
+      if (d != dim)
+        B200_REQUIRE(inputs[i].shape[d] == out->shape[d], B200_ERR_SHAPE, "cat: input %d dim %d is %lld, expected %lld", i, d,
+                     (long long)inputs[i].shape[d], (long long)out->shape[d]);
+    total += inputs[i].shape[dim];
+  }
+  B200_REQUIRE(total == out->shape[dim], B200_ERR_SHAPE, "cat: inputs hold %lld along dim %d, the output %lld", (long long)total, dim,
+               (long long)out->shape[dim]);
+  for (int d = 0; d < out->rank; ++d) ends[d] = out->shape[d];
+  int64_t at = 0;
+  for (int i = 0; i < n; ++i) {
+    if (inputs[i].shape[dim] == 0) continue;         // empty tensors are skipped (cat.rs:92-150)
+    starts[dim] = at;
+    ends[dim] = at + inputs[i].shape[dim];
+    const b200_tensor view = slice_view(*out, starts, ends);
+    if (numel_of(view.shape, view.rank) > 0) {
+      int32_t st = b200_launch_copy(&inputs[i], &view, s);
+      if (st != B200_OK) return st;
+    }
+    at = ends[dim];
+  }
+  return B200_OK;
+}
+
+extern "C" int32_t b200_launch_repeat_dim(const b200_tensor *input, int32_t dim, int64_t times, const b200_tensor *out, b200_stream s) {
+  B200_REQUIRE(input && out, B200_ERR_INVALID, "null argument");
+  B200_REQUIRE(input->rank == out->rank && dim >= 0 && dim < input->rank && times >= 0, B200_ERR_SHAPE, "repeat_dim: bad rank / dim / times");
+  for (int d = 0; d < input->rank; ++d)
+    B200_REQUIRE(out->shape[d] == (d == dim ? input->shape[d] * times : input->shape[d]), B200_ERR_SHAPE, "repeat_dim: bad output dim %d", d);
+  int64_t starts[B200_MAX_RANK] = {0}, ends[B200_MAX_RANK];
+  for (int d = 0; d < out->rank; ++d) ends[d] = out->shape[d];
+  if (numel_of(out->shape, out->rank) == 0) return B200_OK;
+  for (int64_t t = 0; t < times; ++t) {
+    starts[dim] = t * input->shape[dim];
+    ends[dim] = starts[dim] + input->shape[dim];
+    const b200_tensor view = slice_view(*out, starts, ends);
+    int32_t st = b200_launch_copy(input, &view, s);
+    if (st != B200_OK) return st;
+  }
+  return B200_OK;
+}
+
+extern "C" int32_t b200_launch_flip(const b200_tensor *input, const int32_t *axes, int32_t n_axes, const b200_tensor *out, b200_stream s) {
+  B200_REQUIRE(input && out && (axes || n_axes == 0), B200_ERR_INVALID, "null argument");
+  B200_REQUIRE(input->rank == out->rank && input->dtype == out->dtype, B200_ERR_SHAPE, "flip: rank / dtype mismatch");
+  uint32_t mask = 0;
+  for (int i = 0; i < n_axes; ++i) {
+    B200_REQUIRE(axes[i] >= 0 && axes[i] < input->rank, B200_ERR_SHAPE, "flip axis %d out of range", axes[i]);
+    mask |= 1u << axes[i];
+  }
+  for (int d = 0; d < input->rank; ++d) B200_REQUIRE(input->shape[d] == out->shape[d], B200_ERR_SHAPE, "flip: shape mismatch at dim %d", d);
+  const int64_t n = numel_of(out->shape, out->rank);
+  if (n == 0) return B200_OK;
+  flip_kernel<<<grid_for(n, 256), 256, 0, resolve_stream(s)>>>(to_idx(*input), to_idx(*out), mask, dtype_size(input->dtype), n);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -226,6 +226,16 @@ int32_t b200_event_record(b200_event e, b200_stream s) {
   return B200_OK;
 }
 
+/* 1 = every launch recorded before `e` has finished, 0 = still running: the poll behind an async
+ * float_into_data Future (crates/burn-backend/src/backend/ops/tensor.rs:109-111). */
+int32_t b200_event_query(b200_event e, int32_t *done) {
+  B200_REQUIRE(e && done, B200_ERR_INVALID, "null argument");
+  cudaError_t r = cudaEventQuery((cudaEvent_t)e);
+  if (r == cudaSuccess) { *done = 1; return check_index_error(); }
+  if (r == cudaErrorNotReady) { *done = 0; return B200_OK; }
+  return fail_cuda(r, "cudaEventQuery", __FILE__, __LINE__);
+}
+
 int32_t b200_event_elapsed_ms(b200_event start, b200_event stop, float *ms) {
   B200_REQUIRE(ms, B200_ERR_INVALID, "ms is null");
   B200_CUDA(cudaEventSynchronize((cudaEvent_t)stop));

@@ -92,6 +92,34 @@ def float_ceil(a): return _unary("CEIL_F", a)
 def float_round(a): return _unary("ROUND_F", a)
 def float_trunc(a): return _unary("TRUNC_F", a)
 def float_sign(a): return _unary("SIGN_F", a)
+def float_tan(a): return _unary("TAN_F", a)
+
+
+def float_powi_scalar(a, s):
+    """float_powi_scalar (crates/burn-backend/src/backend/ops/tensor.rs:1095-1104): small exponents are products /
+    reciprocals, everything else defers to powf_scalar."""
+    s = int(s)
+    if s == 0:
+        return _launch(TapeBuilder().op("MOV", ("f", 1.0), out=0), [a], a.shape)      # float_ones
+    if s == 1:
+        return a
+    if s == 2:
+        return float_mul(a, a)
+    if s == -1:
+        return float_recip(a)
+    if s == -2:
+        return float_recip(float_mul(a, a))
+    return float_powf_scalar(a, float(s))
+
+
+def float_clamp_min(a, lo):
+    """float_clamp_min default (tensor.rs:207-214): mask_fill(x, x < min, min)."""
+    return float_mask_fill(a, float_lower_elem(a, lo), lo)
+
+
+def float_clamp_max(a, hi):
+    """float_clamp_max default (tensor.rs:223-230): mask_fill(x, x > max, max)."""
+    return float_mask_fill(a, float_greater_elem(a, hi), hi)
 
 
 def float_clamp(a, lo, hi):
@@ -100,6 +128,10 @@ def float_clamp(a, lo, hi):
 
 # ---- comparisons → bool (tensor.rs:675-850)
 def float_equal(a, b): return _binary("EQ_F", a, b, abi.BOOL)
+def float_not_equal(a, b): return _binary("NE_F", a, b, abi.BOOL)
+def float_not_equal_elem(a, s): return _scalar("NE_F", a, s, abi.BOOL)
+def float_is_nan(a): return _unary("ISNAN_F", a, abi.BOOL)
+def float_is_inf(a): return _unary("ISINF_F", a, abi.BOOL)
 def float_greater(a, b): return _binary("GT_F", a, b, abi.BOOL)
 def float_greater_equal(a, b): return _binary("GE_F", a, b, abi.BOOL)
 def float_lower(a, b): return _binary("LT_F", a, b, abi.BOOL)
@@ -131,6 +163,11 @@ def float_into_int(x: DeviceTensor, dtype=abi.I32) -> DeviceTensor:
 
 def float_cast(x: DeviceTensor, dtype: int) -> DeviceTensor:
     return _unary("MOV", x, dtype)
+
+
+def int_into_float(x: DeviceTensor, dtype=abi.F32) -> DeviceTensor:
+    """int_into_float / bool_into_float (int_tensor.rs:119, bool_tensor.rs:102)."""
+    return _unary("B2F" if x.dtype in (abi.BOOL, abi.U8) else "I2F", x, dtype)
 
 
 # ---- reductions (tensor.rs:883-949,1484-1636)
@@ -171,6 +208,9 @@ def float_sum(x): return _reduce_full(abi.RED_SUM, x)
 def float_mean(x): return _reduce_full(abi.RED_MEAN, x)
 def float_max(x): return _reduce_full(abi.RED_MAX, x)
 def float_min(x): return _reduce_full(abi.RED_MIN, x)
+def float_prod(x): return _reduce_full(abi.RED_PROD, x)
+def float_max_abs(x): return _reduce_full(abi.RED_MAXABS, x)
+def float_max_abs_dim(x, dim): return _reduce(abi.RED_MAXABS, x, dim)
 
 
 # ---- matmul (tensor.rs:341)
@@ -223,6 +263,76 @@ def float_select_add(x: DeviceTensor, dim: int, indices: DeviceTensor, value: De
     out = x.contiguous()
     a, b, c = out.desc(), indices.desc(), value.desc()
     check(abi.load().b200_launch_select_add(dim, C.byref(a), C.byref(b), C.byref(c), None))
+    return out
+
+
+# ---- data movement (tensor.rs:161,410,592,1460)
+def _clone(x: DeviceTensor) -> DeviceTensor:
+    out = DeviceTensor.empty(x.shape, x.dtype)
+    if out.numel:
+        a, b = x.desc(), out.desc()
+        check(abi.load().b200_launch_copy(C.byref(a), C.byref(b), None))
+    return out
+
+
+def _canon_ranges(shape, ranges):
+    """Tensor::slice canonicalisation (crates/burn-tensor/src/tensor/api/base.rs `slice`): negative bounds count from
+    the end, ends clamp to the dimension, unspecified trailing dims are full, a descending range is empty."""
+    full = []
+    for i, n in enumerate(shape):
+        if i < len(ranges):
+            lo, hi = ranges[i]
+            lo = lo + n if lo < 0 else lo
+            hi = n if hi is None else (hi + n if hi < 0 else hi)
+            lo, hi = min(max(lo, 0), n), min(max(hi, 0), n)
+            full.append((lo, max(hi, lo)))
+        else:
+            full.append((0, n))
+    return full
+
+
+def float_slice(x: DeviceTensor, ranges) -> DeviceTensor:
+    """float_slice (tensor.rs:580): a strided view — no launch; consumers read it in place."""
+    return x.slice(_canon_ranges(x.shape, ranges))
+
+
+def float_slice_assign(x: DeviceTensor, ranges, value: DeviceTensor) -> DeviceTensor:
+    """x[ranges] = value on a copy (the reference mutates in place only when it owns `x`)."""
+    out = _clone(x)
+    full = _canon_ranges(x.shape, ranges)
+    starts = (C.c_int64 * x.ndim)(*[r[0] for r in full])
+    ends = (C.c_int64 * x.ndim)(*[r[1] for r in full])
+    a, b = out.desc(), value.desc()
+    check(abi.load().b200_launch_slice_assign(C.byref(a), starts, ends, C.byref(b), None))
+    return out
+
+
+def float_cat(tensors: Sequence[DeviceTensor], dim: int) -> DeviceTensor:
+    dim = _check_dim(tensors[0], dim)
+    shape = list(next((t for t in tensors if t.numel), tensors[0]).shape)
+    shape[dim] = sum(t.shape[dim] for t in tensors if t.ndim == len(shape))
+    out = DeviceTensor.empty(shape, tensors[0].dtype)
+    descs = (abi.Tensor * len(tensors))(*[t.desc() for t in tensors])
+    od = out.desc()
+    check(abi.load().b200_launch_cat(descs, len(tensors), dim, C.byref(od), None))
+    return out
+
+
+def float_repeat_dim(x: DeviceTensor, dim: int, times: int) -> DeviceTensor:
+    dim = _check_dim(x, dim)
+    shape = list(x.shape)
+    shape[dim] *= times
+    out = DeviceTensor.empty(shape, x.dtype)
+    a, b = x.desc(), out.desc()
+    check(abi.load().b200_launch_repeat_dim(C.byref(a), dim, times, C.byref(b), None))
+    return out
+
+
+def float_flip(x: DeviceTensor, axes: Sequence[int]) -> DeviceTensor:
+    out = DeviceTensor.empty(x.shape, x.dtype)
+    ax = (C.c_int32 * max(len(axes), 1))(*[_check_dim(x, a) for a in axes])
+    a, b = x.desc(), out.desc()
+    check(abi.load().b200_launch_flip(C.byref(a), ax, len(axes), C.byref(b), None))
     return out
 
 

@@ -97,6 +97,7 @@ typedef void *b200_event;
 int32_t b200_event_create(b200_event *out);
 int32_t b200_event_destroy(b200_event e);
 int32_t b200_event_record(b200_event e, b200_stream s);
+int32_t b200_event_query(b200_event e, int32_t *done);   /* async into_data: poll instead of blocking */
 int32_t b200_event_elapsed_ms(b200_event start, b200_event stop, float *ms); /* syncs on stop */
 
 /* CUDA-graph capture of a launch sequence (the replacement
@@ -317,6 +318,19 @@ int32_t b200_launch_select(int32_t dim, const b200_tensor *input,
 int32_t b200_launch_select_add(int32_t dim, const b200_tensor *tensor,
                                const b200_tensor *indices,
                                const b200_tensor *value, b200_stream s);
+/* float_slice_assign (tensor.rs:592; crates/burn-cubecl/src/kernel/index/slice_assign.rs): tensor[starts..ends] = value,
+ * in place on `tensor` (the caller owns it, as the by-value trait signature implies); unit steps. */
+int32_t b200_launch_slice_assign(const b200_tensor *tensor, const int64_t *starts,
+                                 const int64_t *ends, const b200_tensor *value, b200_stream s);
+/* float_cat (tensor.rs:1460): inputs[0..n) concatenated along dim into `out`; empty inputs are skipped. */
+int32_t b200_launch_cat(const b200_tensor *inputs, int32_t n, int32_t dim,
+                        const b200_tensor *out, b200_stream s);
+/* float_repeat_dim (tensor.rs:161; kernel/index/repeat_dim.rs): out = input tiled `times` along dim. */
+int32_t b200_launch_repeat_dim(const b200_tensor *input, int32_t dim, int64_t times,
+                               const b200_tensor *out, b200_stream s);
+/* float_flip (tensor.rs:410; kernel/index/flip.rs): out = input reversed along each of axes[0..n_axes). */
+int32_t b200_launch_flip(const b200_tensor *input, const int32_t *axes, int32_t n_axes,
+                         const b200_tensor *out, b200_stream s);
 /* float_random (crates/burn-backend/src/backend/ops/tensor.rs:39): Philox4x32-10.
  * kind 0 = uniform[lo,hi), 1 = normal(mean=lo,std=hi), 2 = bernoulli(p=lo). */
 int32_t b200_launch_random(const b200_tensor *out, int32_t kind, double lo,

@@ -296,6 +296,53 @@ def float_select_add(t, dim, indices, value) -> np.ndarray:
     return t
 
 
+# ---------------------------------------------------------------- data movement (unit steps; pure copies, so numpy
+# slicing IS the restatement — there is no arithmetic whose order could differ)
+def _ranges(shape, ranges):
+    """Tensor::slice canonicalisation (crates/burn-tensor/src/tensor/api/base.rs `slice`; burn-std Slice::to_range):
+    negative bounds count from the end, ends clamp to the dimension, unspecified trailing dims are full."""
+    out = []
+    for i, n in enumerate(shape):
+        if i < len(ranges):
+            lo, hi = ranges[i]
+            lo = lo + n if lo < 0 else lo
+            hi = n if hi is None else (hi + n if hi < 0 else hi)
+            lo, hi = min(max(lo, 0), n), min(max(hi, 0), n)
+            out.append((lo, max(hi, lo)))
+        else:
+            out.append((0, n))
+    return out
+
+
+def float_slice(t, ranges) -> np.ndarray:
+    """NdArrayOps::slice (crates/burn-ndarray/src/ops/base.rs:62-65)."""
+    t = _f32(t)
+    return np.ascontiguousarray(t[tuple(slice(a, b) for a, b in _ranges(t.shape, ranges))])
+
+
+def float_slice_assign(t, ranges, value) -> np.ndarray:
+    """NdArrayOps::slice_assign (crates/burn-ndarray/src/ops/base.rs:67-76): owned copy, slice_mut().assign(value)."""
+    out = _f32(t).copy()
+    out[tuple(slice(a, b) for a, b in _ranges(out.shape, ranges))] = _f32(value)
+    return out
+
+
+def float_cat(tensors, dim: int) -> np.ndarray:
+    """NdArrayOps::cat (crates/burn-ndarray/src/ops/base.rs:437-440)."""
+    return np.concatenate([_f32(t) for t in tensors], axis=dim)
+
+
+def float_flip(t, axes) -> np.ndarray:
+    """NdArrayOps::flip (crates/burn-ndarray/src/ops/base.rs:507-529): step -1 on the named axes, then owned."""
+    return np.ascontiguousarray(np.flip(_f32(t), tuple(axes)))
+
+
+def float_repeat_dim(t, dim: int, times: int) -> np.ndarray:
+    """float_repeat_dim default (crates/burn-backend/src/backend/ops/tensor.rs:161-163 → repeat_with_slice_assign):
+    `times` copies laid one after the other along `dim`."""
+    return np.concatenate([_f32(t)] * int(times), axis=dim)
+
+
 # ---------------------------------------------------------------- composites
 SQRT_2 = np.float32(1.4142135623730951)
 

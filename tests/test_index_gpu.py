@@ -248,3 +248,55 @@ def test_retain_free_refcount(dev):
     abi.check(lib().b200_free(p, None))
     assert lib().b200_refcount(p, C.byref(n)) == abi.ERR_INVALID
     dv.sync()
+
+
+# ---- data movement: cat / slice / slice_assign / flip / repeat_dim
+# (crates/burn-backend-tests/tests/tensor/float/ops/{cat,slice,slice_assign,flip,repeat_dim}.rs; copies → bit-exact)
+def test_cat_matches_oracle_on_strided_and_empty_inputs(dev):
+    from burn_b200 import ops
+    rng = np.random.default_rng(11)
+    a = rng.uniform(-1, 1, (37, 5, 130)).astype(np.float32)
+    b = rng.uniform(-1, 1, (37, 9, 130)).astype(np.float32)
+    c = rng.uniform(-1, 1, (130, 3, 37)).astype(np.float32)          # joins as a permuted (strided) view
+    e = np.zeros((37, 0, 130), dtype=np.float32)
+    got = ops.float_cat([H.up(a), H.up(e), H.up(b), H.up(c).permute([2, 1, 0])], 1).numpy()
+    H.assert_exact(got, oracle.float_cat([a, e, b, np.transpose(c, (2, 1, 0))], 1))
+    for dim in (0, 2, -1):
+        H.assert_exact(ops.float_cat([H.up(a), H.up(a)], dim).numpy(), oracle.float_cat([a, a], dim % 3))
+    with pytest.raises(abi.B200Error):
+        ops.float_cat([H.up(a), H.up(c)], 1)                          # cat.rs:47-56: mismatched dims must fail
+
+
+def test_slice_and_slice_assign_match_oracle(dev):
+    from burn_b200 import ops
+    rng = np.random.default_rng(12)
+    x = rng.uniform(-1, 1, (64, 33, 70)).astype(np.float32)
+    v = rng.uniform(-1, 1, (10, 33, 21)).astype(np.float32)
+    ranges = [(5, 15), (0, 33), (-30, -9)]
+    H.assert_exact(ops.float_slice(H.up(x), ranges).contiguous().numpy(), oracle.float_slice(x, ranges))
+    dx = H.up(x)
+    got = ops.float_slice_assign(dx, ranges, H.up(v)).numpy()
+    H.assert_exact(got, oracle.float_slice_assign(x, ranges, v))
+    H.assert_exact(dx.numpy(), x)                                     # the still-referenced input is untouched
+    # clamp_when_slice_exceeds_dimension (slice.rs:362) and a reduction reading the view in place
+    H.assert_exact(ops.float_slice(H.up(x), [(60, 999)]).contiguous().numpy(), x[60:])
+    s = ops.float_sum_dim(ops.float_slice(H.up(x), [(0, 64), (3, 20)]), 2).numpy()
+    assert oracle.approx_eq_mask(s, oracle.float_sum_dim(np.ascontiguousarray(x[:, 3:20]), 2), H.REL_REDUCE, 1e-6).all()
+    with pytest.raises(abi.B200Error):
+        ops.float_slice_assign(H.up(x), ranges, H.up(v[:, :, :20]))
+
+
+@pytest.mark.parametrize("axes", [[0], [2], [0, 1, 2], [1, -1]])
+def test_flip_matches_oracle(dev, axes):
+    from burn_b200 import ops
+    x = np.random.default_rng(13).uniform(-1, 1, (19, 8, 257)).astype(np.float32)
+    H.assert_exact(ops.float_flip(H.up(x), axes).numpy(), oracle.float_flip(x, [a % 3 for a in axes]))
+    xt = H.up(x).swap_dims(0, 2)
+    H.assert_exact(ops.float_flip(xt, [0]).numpy(), oracle.float_flip(np.swapaxes(x, 0, 2), [0]))
+
+
+@pytest.mark.parametrize("dim,times", [(0, 3), (1, 1), (2, 4)])
+def test_repeat_dim_matches_oracle(dev, dim, times):
+    from burn_b200 import ops
+    x = np.random.default_rng(14).uniform(-1, 1, (6, 1 if dim == 1 else 7, 65)).astype(np.float32)
+    H.assert_exact(ops.float_repeat_dim(H.up(x), dim, times).numpy(), oracle.float_repeat_dim(x, dim, times))

@@ -8,14 +8,37 @@ the GPU parity tests trust it.
 import numpy as np
 import pytest
 
+from tests import golden_expr as X
 from tests import golden_runner as G
 
 CASES = G.load_cases()
+EXPR_CASES = X.load_cases()
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_oracle_reproduces_reference_golden(case):
     G.check(case, G.run_oracle(case))
+
+
+@pytest.fixture(scope="module")
+def oracle_backend():
+    return X.OracleBackend()
+
+
+@pytest.mark.parametrize("case", EXPR_CASES, ids=[c["name"] for c in EXPR_CASES])
+def test_oracle_reproduces_reference_test_expression(case, oracle_backend):
+    """tests/golden/burn_backend_tests_expr.json: assertions transliterated from the reference's own tests by
+    scripts/extract_goldens.py (op tree over literal tensors → the literal the reference asserts)."""
+    X.check(case, X.evaluate(case["expr"], oracle_backend))
+
+
+def test_expression_fixture_file_is_well_formed():
+    assert len(EXPR_CASES) + len(CASES) >= 250
+    files = {c["cite"].split(":")[0] for c in EXPR_CASES}
+    for must in ("maxmin.rs", "comparison.rs", "mask.rs", "aggregation.rs", "matmul.rs", "reduce_broadcasted.rs"):
+        assert any(f.endswith(must) for f in files), must
+    for c in EXPR_CASES:
+        assert {"name", "cite", "expr", "expected", "tol"} <= set(c)
 
 
 def test_fixture_file_is_well_formed():
