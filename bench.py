@@ -116,6 +116,67 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- our arm
+def bind_to_gpu_numa(local_rank: int, world: int):
+    """Pin this rank's host threads (and therefore its first-touched pinned staging buffers) to the CPUs next to its
+    GPU: the PCI device's local_cpulist when sysfs reports a NUMA node, else an even slice of the allowed CPUs so the
+    ranks at least do not migrate over each other.  Returns a short description for the bench line."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus, how = None, "even slice of the allowed CPUs"
+        q = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                           capture_output=True, text=True, timeout=20)
+        bus = q.stdout.strip().lower()
+        if bus:
+            bus = bus[-12:] if len(bus) > 12 else bus               # 00000000:1B:00.0 -> 0000:1b:00.0
+            base = f"/sys/bus/pci/devices/{bus}"
+            node = open(f"{base}/numa_node").read().strip() if os.path.exists(f"{base}/numa_node") else "-1"
+            if node not in ("-1", "") and os.path.exists(f"{base}/local_cpulist"):
+                local = set()
+                for part in open(f"{base}/local_cpulist").read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    local.update(range(int(lo), int(hi or lo) + 1))
+                local &= set(allowed)
+                n_nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]) \
+                    if os.path.isdir("/sys/devices/system/node") else 1
+                if local and n_nodes > 1:
+                    cpus, how = sorted(local), f"NUMA node {node} (sysfs local_cpulist)"
+        if cpus is None:
+            per = max(1, len(allowed) // max(world, 1))
+            cpus = allowed[local_rank * per:(local_rank + 1) * per] or allowed
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs [{cpus[0]}..{cpus[-1]}], {how}"
+    except Exception as e:                                           # binding is an optimisation, never a failure
+        return f"unbound ({type(e).__name__})"
+
+
+def allreduce_value_check(rank: int, world: int, local_rank: int):
+    """The protocol of crates/burn-backend-tests/tests/tensor/distributed.rs:26-62 on our b200_all_reduce: every rank
+    contributes different [20, 20] data for many iterations, Sum must equal the element-wise sum over ranks (and Mean
+    that sum / world) — plus one bucket-sized tensor.  Raises on any mismatch: the bench run fails (rc != 0)."""
+    import torch
+    from burn_b200.device import DeviceTensor
+    from burn_b200.distributed import Communicator
+    from burn_b200 import device as dv
+    comm = Communicator(rank, world, device=torch.device("cuda", local_rank))
+    for it in range(25):
+        n = 400 if it < 24 else (4 << 20) + 3
+        data = [np.random.default_rng([4242, it, r]).uniform(0.0, 10.0, n).astype(np.float32) for r in range(world)]
+        want = np.sum(np.stack(data).astype(np.float64), axis=0)
+        for mean in (False, True):
+            t = DeviceTensor.from_numpy(data[rank].reshape(20, 20) if n == 400 else data[rank])
+            comm.all_reduce(t, mean=mean)
+            comm.sync()
+            dv.sync()
+            got = t.numpy().reshape(-1).astype(np.float64)
+            ref = want / world if mean else want
+            # burn's Tolerance::default(): |x-y| < max(5e-3*|x+y|, 1e-5) — here far tighter: f32 sums of <= 8 terms
+            if not np.all(np.abs(got - ref) <= 1e-6 * np.abs(ref) * world + 1e-6):
+                raise AssertionError(f"all_reduce({'Mean' if mean else 'Sum'}) mismatch on rank {rank}, iteration {it}: "
+                                     f"max err {np.abs(got - ref).max():.3e}")
+    comm.close()
+    return "ok"
+
+
 def chain_tape():
     from burn_b200.device import TapeBuilder
     tb = TapeBuilder()
@@ -137,6 +198,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     from burn_b200 import device as dv
     from burn_b200.device import DeviceTensor
 
+    binding = bind_to_gpu_numa(local_rank, world)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -144,6 +206,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     lib = abi.load()
     check = abi.check
     shape = (N_ROWS, N_COLS)
+    allreduce = allreduce_value_check(rank, world, local_rank) if world > 1 else None
 
     # synthetic inputs, seeded per rank, staged in PINNED host memory
     rng = np.random.default_rng(1000 + rank)
@@ -266,13 +329,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             enc = train_bench.run("encoder", steps=args.train_steps, warmup=3, rank=rank, world=world,
                                   local_rank=local_rank, mm="tf32", use_graph=True, init_device=False)
             train["encoder_configs3"] = {k: enc[k] for k in ("value", "unit", "ms_per_step", "model_tflops_per_s", "config")}
+            if world == 1:
+                train["mnist_fc_head_configs0"] = train_bench.run_fc_head()
         except Exception as e:  # the headline metric above stands on its own
             train = train if isinstance(train, dict) and "value" in train else {"error": repr(e)[:300]}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the box's host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_run(steps=1, warmup=0, rows=N_ROWS, arrays=(host["a"][1], host["b"][1], host["c"][1], marr))
+        cpu = cpu_reference_run(rows=N_ROWS, reps=5, arrays=(host["a"][1], host["b"][1], host["c"][1], marr))
+        try:
+            cpu["configs0_mnist_fc_head"] = mnist_fc_head_cpu()
+        except Exception as e:
+            cpu["configs0_mnist_fc_head"] = {"error": repr(e)[:200]}
 
     if rank == 0:
         sb = step_bytes(N_ROWS, N_COLS)
@@ -299,13 +368,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "ms_per_step": round(e2e_ms / args.steps, 3),
                     "note": "pinned host buffers -> C ABI memcpy_h2d -> 6 launches -> memcpy_d2h of all reduction results"},
             "gpu_launches": launches,
+            "host_binding": binding,
             "roofline": {"bound": "hbm", "kernel": "b200_jit_kernel (NVRTC-specialised fused chain: 4 inputs, 8 ops, 1 output)",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "peak_source": peak_src,
-                         "traffic": ncu_traffic(), "avg_launch_ms": round(chain_avg_ms, 4),
+                         "traffic": ncu_traffic(),
+                         "traffic_source": "profiles/roofline_traffic.json: dram bytes of this kernel from the committed "
+                                           "ncu --set full capture (not re-measured in this run)",
+                         "avg_launch_ms": round(chain_avg_ms, 4), "median_launch_ms": round(float(np.median(chain_ms)), 4),
+                         "min_launch_ms": round(float(np.min(chain_ms)), 4),
                          "share_of_step": round(chain_avg_ms / ms_per_step, 3)},
             "clocks": clocks,
         }
+        if allreduce is not None:
+            line["allreduce_check"] = allreduce
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if train is not None:
@@ -317,63 +393,111 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
 
 # --------------------------------------------------------------------------- reference arm
-def cpu_reference_run(steps: int, warmup: int, rows: int, arrays=None):
-    """Times the burn-ndarray restatement (oracle/) on the host: op-by-op, unfused, single
-    thread — ndarray's elementwise and reduce ops are single-threaded
-    (crates/burn-ndarray/src/ops/base.rs)."""
-    from oracle import oracle
-    oracle.build()
-    if arrays is None:
-        rng = np.random.default_rng(1000)
-        a = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
-        b = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
-        c = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
-        m = (a < 0).astype(np.uint8)
-    else:
-        a, b, c, m = (np.ascontiguousarray(x[:rows]) for x in arrays)
-
-    def one():
-        y = oracle.bench_chain_unfused(a, b, c, m)
-        oracle.float_sum_dim(y, 1)
-        oracle.float_sum_dim(y, 0)
-        oracle.float_mean_dim(y, 1)
-        oracle.float_argmax(y, 1)
-        oracle.float_sum(y)
-
-    for _ in range(warmup):
-        one()
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        one()
-        times.append(time.perf_counter() - t0)
-    sec = float(np.mean(times))
-    return {"value": round(step_bytes(rows, N_COLS) / sec / 1e9, 3), "unit": "GB/s", "cores": 1, "kind": "port",
-            "sample": f"{steps} step(s) of the same workload on [{rows}, {N_COLS}] f32 "
-                      f"({sec:.2f} s/step), oracle/ndarray_oracle.c (gcc -O2), unfused op-by-op",
-            "host_cores_available": os.cpu_count()}
-
-
-def run_reference(args, rank: int, world: int):
-    if rank != 0:
-        return
-    total = args.steps + args.warmup
-    rows = N_ROWS if total <= 12 else max(256, (N_ROWS * 12 // total) // 256 * 256)
-    from oracle import oracle
-    oracle.build()
+def _cpu_inputs(rows: int, arrays=None):
+    if arrays is not None:
+        return tuple(np.ascontiguousarray(x[:rows]) for x in arrays)
     rng = np.random.default_rng(1000)
     a = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
     b = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
     c = rng.uniform(-1, 1, (rows, N_COLS)).astype(np.float32)
-    m = (a < 0).astype(np.uint8)
+    return a, b, c, (a < 0).astype(np.uint8)
+
+
+def _cpu_step_unfused(oracle, a, b, c, m):
+    """The step as burn-ndarray executes it: one pass per primitive op, no fusion, on the calling thread."""
+    y = oracle.bench_chain_unfused(a, b, c, m)
+    oracle.float_sum_dim(y, 1)
+    col = oracle.float_sum_dim(y, 0)
+    oracle.float_mean_dim(y, 1)
+    oracle.float_argmax(y, 1)
+    oracle.float_sum(y)
+    return col
+
+
+def cpu_variants(rows: int, reps: int, arrays=None, threads: int | None = None):
+    """the configs[1] step on the host cores, op-by-op (what burn-ndarray does) AND single-pass fused
+    (what it does not), on 1 thread (ndarray's elementwise / reduce ops are single-threaded:
+    crates/burn-ndarray/src/ops/base.rs has no run_par! on them) AND on all cores (independent row shards, one
+    worker per core — the CPU counterpart of the GPU arm's independent replicas).  Median and min of `reps`."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    oracle.build()
+    a, b, c, m = _cpu_inputs(rows, arrays)
+    cores = threads or len(os.sched_getaffinity(0))
+    edges = np.linspace(0, rows, cores + 1).astype(int)
+    shards = [(a[lo:hi], b[lo:hi], c[lo:hi], m[lo:hi]) for lo, hi in zip(edges[:-1], edges[1:]) if hi > lo]
+    pool = ThreadPoolExecutor(len(shards))
+
+    def unfused_all():
+        cols = list(pool.map(lambda sh: _cpu_step_unfused(oracle, *sh), shards))
+        np.sum(cols, axis=0, dtype=np.float32)                      # combine the per-shard column sums
+
+    runs = {
+        "unfused_1thread": lambda: _cpu_step_unfused(oracle, a, b, c, m),
+        "unfused_allcores": unfused_all,
+        "fused_1thread": lambda: oracle.bench_step_fused(a, b, c, m, 1),
+        "fused_allcores": lambda: oracle.bench_step_fused(a, b, c, m, cores),
+    }
+    sb = step_bytes(rows, N_COLS)
+    out = {}
+    for name, fn in runs.items():
+        fn()                                                        # warm-up (page faults, thread start)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            times.append(time.perf_counter() - t0)
+        out[name] = {"gbs_median": round(sb / float(np.median(times)) / 1e9, 3), "gbs_best": round(sb / min(times) / 1e9, 3),
+                     "s_per_step_median": round(float(np.median(times)), 4), "threads": 1 if name.endswith("1thread") else cores}
+    pool.shutdown()
+    return out, cores, sb
+
+
+def mnist_fc_head_cpu(steps: int = 200):
+    """BASELINE.json configs[0] (the one CPU tokens/s figure): training steps/s of the MNIST example's
+    FC head [1600->128->128->10], batch 64, f32, on the CPU restatement (oracle/train_ref.py)."""
+    from oracle import train_ref as R
+    R.train(0, 5)
+    t0 = time.perf_counter()
+    losses, _ = R.train(0, steps)
+    sec = time.perf_counter() - t0
+    return {"workload": "configs[0]: examples/mnist FC head 1600-128-128-10, batch 64, f32, fwd+bwd+Adam, synthetic features",
+            "value": round(64 * steps / sec, 1), "unit": "samples/s", "steps": steps, "kind": "port (numpy f32 + OpenBLAS sgemm)",
+            "loss_first": round(losses[0], 4), "loss_last": round(losses[-1], 4)}
+
+
+def cpu_reference_run(rows: int, reps: int, arrays=None):
+    variants, cores, _ = cpu_variants(rows, reps, arrays)
+    head = variants["unfused_allcores"]
+    return {"value": head["gbs_median"], "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": f"median of {reps} steps of the same workload on [{rows}, {N_COLS}] f32; headline = op-by-op "
+                      f"(unfused, as burn-ndarray executes it) on {cores} threads over independent row shards; "
+                      "oracle/ndarray_oracle.c, gcc -O3 -march=native -ffp-contract=off",
+            "variants": variants, "host_cores_available": os.cpu_count()}
+
+
+def run_reference(args, rank: int, world: int):
+    """The reference's CPU implementation of the path (restatement: no cargo here), all host threads it can use: the
+    op-by-op step on independent row shards, one worker per core.  Each timed step is the full [8192, 8192] workload
+    unless the requested step count would run past a few minutes, in which case the rows are cut."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    oracle.build()
+    cores = len(os.sched_getaffinity(0))
+    total = args.steps + args.warmup
+    est_full = 1.3 / max(1, min(cores, 16)) + 0.05                    # s per full step, op-by-op over `cores` shards
+    rows = N_ROWS if total * est_full <= 120 else max(256 * cores, int(N_ROWS * 120 / (total * est_full)) // 256 * 256)
+    rows = min(rows, N_ROWS)
+    a, b, c, m = _cpu_inputs(rows)
+    edges = np.linspace(0, rows, cores + 1).astype(int)
+    shards = [(a[lo:hi], b[lo:hi], c[lo:hi], m[lo:hi]) for lo, hi in zip(edges[:-1], edges[1:]) if hi > lo]
+    pool = ThreadPoolExecutor(len(shards))
 
     def one():
-        y = oracle.bench_chain_unfused(a, b, c, m)
-        oracle.float_sum_dim(y, 1)
-        oracle.float_sum_dim(y, 0)
-        oracle.float_mean_dim(y, 1)
-        oracle.float_argmax(y, 1)
-        oracle.float_sum(y)
+        cols = list(pool.map(lambda sh: _cpu_step_unfused(oracle, *sh), shards))
+        np.sum(cols, axis=0, dtype=np.float32)
 
     for _ in range(args.warmup):
         one()
@@ -381,17 +505,18 @@ def run_reference(args, rank: int, world: int):
     for _ in range(args.steps):
         one()
     sec = (time.perf_counter() - t0) / args.steps
+    pool.shutdown()
     sb = step_bytes(rows, N_COLS)
     value = round(sb / sec / 1e9, 3)
-    sample = (f"each step = the configs[1] workload on a [{rows}, {N_COLS}] f32 sample "
-              f"({sb} algorithmic bytes), burn-ndarray restatement oracle/ndarray_oracle.c, unfused, 1 thread")
+    sample = (f"each step = the configs[1] workload on a [{rows}, {N_COLS}] f32 sample ({sb} algorithmic bytes), "
+              f"burn-ndarray restatement oracle/ndarray_oracle.c (gcc -O3 -march=native), op-by-op, {cores} threads over row shards")
     line = {
         "impl": "reference", "metric": "fused elemwise/reduce GB/s vs HBM", "value": value, "unit": "GB/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1] on the CPU restatement of burn-ndarray (the Rust reference cannot be "
                                "built here: no cargo, un-vendored crates)", "sample_rows": rows},
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -456,6 +456,32 @@ class LanguageModel:
         return cross_entropy(tape, _reshape(tape, logits, (B * S, logits.v.shape[-1])), targets.reshape((B * S,)))
 
 
+class FcHead:
+    """The fully connected head of examples/mnist (model.rs:26-73 after the conv blocks; BASELINE.json configs[0]):
+    fc1(1600,128) → gelu → fc2(128,128) → gelu → fc3(128,10) → cross-entropy.  Dropout is the identity (evaluation
+    semantics: a seeded dropout mask is backend-specific).  Weights are [d_in, d_out], KaimingUniform(1/√3)."""
+    DIMS = (1600, 128, 128, 10)
+
+    def __init__(self, seed: int):
+        rng = np.random.default_rng(seed)
+        self.layers = []
+        for i, (d_in, d_out) in enumerate(zip(self.DIMS[:-1], self.DIMS[1:])):
+            w = Param(_uniform(rng, (d_in, d_out), d_in), f"fc{i + 1}.weight")
+            b = Param(_uniform(rng, (d_out,), d_in), f"fc{i + 1}.bias")
+            self.layers.append((w, b))
+
+    def params(self):
+        return [p for wb in self.layers for p in wb]
+
+    def loss(self, tape: Tape, x: DeviceTensor, targets: DeviceTensor) -> Var:
+        h = Var(x, False)
+        for i, (w, b) in enumerate(self.layers):
+            h = linear(tape, h, w, b)
+            if i < len(self.layers) - 1:
+                h = gelu(tape, h)
+        return cross_entropy(tape, h, targets)
+
+
 def scale(tape: Tape, x: Var, c: float) -> Var:
     y = Var(ops.float_mul_scalar(x.v, c), True)
 

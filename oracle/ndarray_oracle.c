@@ -294,3 +294,38 @@ API void o_bench_chain_unfused(const float *a, const float *b, const float *c, c
   o_binary_scalar_f32(O_DIV, t, 2.0f, t, n);
   o_mask_fill_f32(t, m, 0.0f, out, n);
 }
+
+/*
+ * The same configs[1] step as ONE pass over the data — what a hand-fused CPU implementation would do, NOT what
+ * burn-ndarray does (it has no fusion); reported beside the op-by-op figure as BASELINE.md §3 promises.  Per element:
+ * y = mask_fill(gelu(a*b+c), m, 0) with the same roundings as the op-by-op chain (erf in f64, then f32), y stored,
+ * and on the fly: row sum, row argmax (first max wins), column sums (accumulated into col_sum — the caller zeroes it
+ * and, when sharding rows over threads, adds the per-thread partials), block total in f64.
+ */
+API void o_bench_step_fused(const float *a, const float *b, const float *c, const uint8_t *m, float *y,
+                            float *row_sum, float *row_mean, int64_t *row_argmax, float *col_sum, double *total,
+                            size_t rows, size_t cols) {
+  const float sqrt2 = (float)1.4142135623730951;
+  double tot = 0.0;
+  for (size_t r = 0; r < rows; ++r) {
+    const size_t base = r * cols;
+    float acc = 0.0f, best = 0.0f;
+    int64_t best_i = 0;
+    for (size_t j = 0; j < cols; ++j) {
+      const float t = a[base + j] * b[base + j] + c[base + j];
+      float u = (float)erf((double)(t / sqrt2));
+      u = u + 1.0f;
+      float v = (t * u) / 2.0f;
+      if (m[base + j]) v = 0.0f;
+      y[base + j] = v;
+      acc += v;
+      col_sum[j] += v;
+      if (j == 0 || v > best) { best = v; best_i = (int64_t)j; }
+    }
+    row_sum[r] = acc;
+    row_mean[r] = acc / (float)cols;
+    row_argmax[r] = best_i;
+    tot += (double)acc;
+  }
+  *total = tot;
+}

@@ -43,23 +43,28 @@ def test_flash_forward_matches_reference(dev, B, Hh, Sq, Sk, mode):
     # the saved statistics reproduce the weights: 2^(s2 - m2) / l
     st = stats.numpy().astype(np.float64)
     s2 = np.einsum("bhqd,bhkd->bhqk", q.astype(np.float64), k.astype(np.float64)) * 0.125 * np.log2(np.e)
+    # a filled score is the f32 product mask_value * log2(e) in the kernel; at -1e9 the f32 spacing is 128, so the
+    # float64 value would be off by a whole power of two on a fully masked row
+    with np.errstate(invalid="ignore"):
+        mask2 = float(np.float32(mask_value) * np.float32(np.log2(np.e)))
     if mask is not None:
-        s2 = np.where(np.broadcast_to(mask, s2.shape), mask_value * np.log2(np.e), s2)
+        s2 = np.where(np.broadcast_to(mask, s2.shape), mask2, s2)
     if causal:
         cm = np.arange(Sk)[None, :] > (np.arange(Sq)[:, None] + (Sk - Sq))
-        s2 = np.where(cm, mask_value * np.log2(np.e), s2)
+        s2 = np.where(cm, mask2, s2)
     with np.errstate(over="ignore", invalid="ignore"):
         p = np.exp2(s2 - st[..., 0:1]) * st[..., 1:2]
     assert np.abs(p - ref_p).max() <= 2e-3
 
 
 def test_flash_forward_equals_the_weights_kernel(dev):
-    """Same tf32 products, same base-2 softmax: the flash forward agrees with the weights-returning kernel far
-    inside the tf32 tolerance (only the online rescaling order differs)."""
+    """Same tf32 QK^T products and base-2 softmax; the flash kernel rounds the UNNORMALISED weights to tf32 for the
+    PV product and divides afterwards, the weights kernel normalises first — so they agree to tf32 accuracy of P
+    (2^-11 relative per term), not bit for bit: 5e-4 of max|v|."""
     q, k, v = rnd((2, 4, 512, 64), 21, 0.5), rnd((2, 4, 512, 64), 22, 0.5), rnd((2, 4, 512, 64), 23)
     a = ops.attention(H.up(q), H.up(k), H.up(v), None, 0.125, -1.0e9, True).numpy()
     b, _ = ops.attention_flash(H.up(q), H.up(k), H.up(v), None, 0.125, -1.0e9, True)
-    assert np.abs(a - b.numpy()).max() <= 2e-4 * np.abs(v).max()
+    assert np.abs(a - b.numpy()).max() <= 5e-4 * np.abs(v).max()
 
 
 def grads_reference(q, k, v, g, mask, scale, mask_value, causal):

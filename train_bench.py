@@ -225,6 +225,76 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
     return out
 
 
+def run_fc_head(steps: int = 200, warmup: int = 10, mm: str = "f32x3"):
+    """BASELINE.json configs[0] on the GPU path: the MNIST example's FC head (burn_b200.train.FcHead), batch 64,
+    one captured graph per step; every step uploads a fresh [64, 1600] batch from pinned memory and reads the loss."""
+    from burn_b200 import _abi as abi
+    from burn_b200 import device as dv
+    from burn_b200 import train as T
+    from burn_b200.device import DeviceTensor
+    lib, check = abi.load(), abi.check
+    prec = {"tf32": abi.MM_TF32, "bf16": abi.MM_BF16, "f32x3": abi.MM_F32X3}[mm]
+    model = T.FcHead(0)
+    params, opt = model.params(), T.Adam(lr=1e-3)
+    arena = T.ParamArena(params, None)
+    B, D = 64, T.FcHead.DIMS[0]
+    rng = np.random.default_rng(9)
+    xp, tp, lp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    check(lib.b200_host_alloc(C.byref(xp), B * D * 4))
+    check(lib.b200_host_alloc(C.byref(tp), B * 4))
+    check(lib.b200_host_alloc(C.byref(lp), 4))
+    xh = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_float)), shape=(B, D))
+    th = np.ctypeslib.as_array(C.cast(tp, C.POINTER(C.c_int32)), shape=(B,))
+    lh = np.ctypeslib.as_array(C.cast(lp, C.POINTER(C.c_float)), shape=(1,))
+    xh[...] = np.maximum(rng.standard_normal((B, D)), 0).astype(np.float32)
+    th[...] = rng.integers(0, 10, B)
+    xd, td, ld = DeviceTensor.empty((B, D)), DeviceTensor.empty((B,), abi.I32), DeviceTensor.empty((1,))
+
+    def device_step():
+        tape = T.Tape(prec)
+        loss = model.loss(tape, xd, td)
+        check(lib.b200_memcpy_d2d(ld.data_ptr(), loss.v.data_ptr(), 4, None))
+        del loss
+        tape.backward()
+        arena.wait()
+        opt.apply_arena(arena)
+        T.Adam.zero_grad(params)
+
+    def io_in():
+        check(lib.b200_memcpy_h2d(xd.data_ptr(), xp, B * D * 4, None))
+        check(lib.b200_memcpy_h2d(td.data_ptr(), tp, B * 4, None))
+
+    io_in(); opt.advance(); device_step()
+    check(lib.b200_device_sync())
+    with dv.Graph.capture() as graph:
+        device_step()
+
+    def step():
+        io_in()
+        opt.advance()
+        graph.launch()
+        check(lib.b200_memcpy_d2h(lp, ld.data_ptr(), 4, None))
+
+    for _ in range(warmup):
+        step()
+    check(lib.b200_device_sync())
+    first = float(lh[0])
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    check(lib.b200_event_create(C.byref(e0))); check(lib.b200_event_create(C.byref(e1)))
+    check(lib.b200_event_record(e0, None))
+    for _ in range(steps):
+        step()
+    check(lib.b200_event_record(e1, None))
+    check(lib.b200_device_sync())
+    ms = C.c_float()
+    check(lib.b200_event_elapsed_ms(e0, e1, C.byref(ms)))
+    graph.destroy()
+    return {"workload": "configs[0]: examples/mnist FC head 1600-128-128-10, batch 64, fwd+bwd+Adam, one CUDA graph per step, "
+                        "H2D of the batch and D2H of the loss inside the timed region",
+            "value": round(B * steps / (ms.value * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms.value / steps, 4),
+            "gemm": mm, "loss_first": round(first, 4), "loss_last": round(float(lh[0]), 4)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="lm", choices=sorted(CONFIGS))
