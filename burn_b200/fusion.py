@@ -17,12 +17,18 @@ import numpy as np
 from . import _abi as abi
 from ._abi import check
 
-BLOCK_ELEMWISE, BLOCK_REDUCE, BLOCK_MATMUL, BLOCK_EAGER, BLOCK_ROWNORM = range(5)
+BLOCK_ELEMWISE, BLOCK_REDUCE, BLOCK_MATMUL, BLOCK_EAGER, BLOCK_ROWNORM, BLOCK_VIEW = range(6)
+FUSER_OPEN, FUSER_CLOSED = 0, 1
 
 
 class BlockInfo(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_ops", C.c_int32), ("n_inputs", C.c_int32), ("n_outputs", C.c_int32),
-                ("n_tape_ops", C.c_int32), ("launches", C.c_int32)]
+                ("n_tape_ops", C.c_int32), ("launches", C.c_int32), ("aliased", C.c_int32), ("from_cache", C.c_int32),
+                ("score", C.c_uint64)]
+
+
+class CacheStats(C.Structure):
+    _fields_ = [("hits", C.c_uint64), ("misses", C.c_uint64), ("plans", C.c_uint64), ("inplace_aliases", C.c_uint64)]
 
 
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
@@ -33,6 +39,31 @@ HOST_SIGNATURES = {
     "b200h_read": (_i32, [_vp, _i64, _vp, C.c_uint64]),
     "b200h_shape": (_i32, [_vp, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64)]),
     "b200h_sync": (_i32, [_vp]),
+    "b200h_flush": (_i32, [_vp]),
+    "b200h_reshape": (_i64, [_vp, _i64, _i32, C.POINTER(_i64)]),
+    "b200h_expand": (_i64, [_vp, _i64, _i32, C.POINTER(_i64)]),
+    "b200h_slice": (_i64, [_vp, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    "b200h_gather": (_i64, [_vp, _i32, _i64, _i64]),
+    "b200h_select": (_i64, [_vp, _i32, _i64, _i64]),
+    "b200h_from_device": (_i64, [_vp, _vp, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
+    "b200h_device_tensor": (_i32, [_vp, _i64, C.POINTER(abi.Tensor)]),
+    "b200h_cache_stats_get": (_i32, [_vp, C.POINTER(CacheStats)]),
+    "b200h_cache_clear": (_i32, [_vp]),
+    "b200h_fuser_create": (_i32, [_vp, _i32, C.POINTER(_vp)]),
+    "b200h_fuser_destroy": (_i32, [_vp]),
+    "b200h_fuser_fuse_next": (_i32, [_vp]),
+    "b200h_fuser_status_get": (_i32, [_vp]),
+    "b200h_fuser_properties": (_i32, [_vp, C.POINTER(C.c_uint64), C.POINTER(_i32)]),
+    "b200h_fuser_len": (_i32, [_vp]),
+    "b200h_fuser_reset": (_i32, [_vp]),
+    "b200h_fuser_clone": (_i32, [_vp, C.POINTER(_vp)]),
+    "b200h_fuser_finish": (_i32, [_vp, C.POINTER(_vp)]),
+    "b200h_optimization_destroy": (_i32, [_vp]),
+    "b200h_optimization_len": (_i32, [_vp]),
+    "b200h_optimization_name": (C.c_char_p, [_vp]),
+    "b200h_optimization_execute": (_i32, [_vp, _vp]),
+    "b200h_optimization_to_state": (_i32, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "b200h_optimization_from_state": (_i32, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "b200h_binary": (_i64, [_vp, _i32, _i64, _i64]),
     "b200h_scalar": (_i64, [_vp, _i32, _i64, C.c_double]),
     "b200h_unary": (_i64, [_vp, _i32, _i64]),
@@ -132,6 +163,29 @@ class LazyTensor:
     def matmul(self, o, precision=abi.MM_F32X3): return LazyTensor(self.stream, _id(_lib().b200h_matmul(self.stream.h, self.id, o.id, precision)))
     def swap_dims(self, d0, d1): return LazyTensor(self.stream, _id(_lib().b200h_swap_dims(self.stream.h, self.id, d0, d1)))
 
+    def reshape(self, shape):
+        sh = (C.c_int64 * len(shape))(*shape)
+        return LazyTensor(self.stream, _id(_lib().b200h_reshape(self.stream.h, self.id, len(shape), sh)))
+
+    def expand(self, shape):
+        sh = (C.c_int64 * len(shape))(*shape)
+        return LazyTensor(self.stream, _id(_lib().b200h_expand(self.stream.h, self.id, len(shape), sh)))
+
+    def slice(self, ranges):
+        """ranges: one (start, end) per dim, already canonical."""
+        st = (C.c_int64 * len(ranges))(*[r[0] for r in ranges])
+        en = (C.c_int64 * len(ranges))(*[r[1] for r in ranges])
+        return LazyTensor(self.stream, _id(_lib().b200h_slice(self.stream.h, self.id, st, en)))
+
+    def gather(self, dim, indices): return LazyTensor(self.stream, _id(_lib().b200h_gather(self.stream.h, dim, self.id, indices.id)))
+    def select(self, dim, indices): return LazyTensor(self.stream, _id(_lib().b200h_select(self.stream.h, dim, self.id, indices.id)))
+
+    def device_tensor(self) -> "abi.Tensor":
+        """Drain the stream and return the kernel-ABI descriptor of this tensor's storage."""
+        d = abi.Tensor()
+        check(_lib().b200h_device_tensor(self.stream.h, self.id, C.byref(d)))
+        return d
+
 
 class FusionStream:
     def __init__(self, plan_only: bool = False):
@@ -158,8 +212,31 @@ class FusionStream:
         sh = (C.c_int64 * len(shape))(*shape)
         return LazyTensor(self, _id(_lib().b200h_from_host(self.h, None, dtype, len(shape), sh)))
 
+    def wrap(self, desc: "abi.Tensor") -> LazyTensor:
+        """Non-owning handle on device memory the caller owns (a DeviceTensor's descriptor)."""
+        sh = (C.c_int64 * desc.rank)(*desc.shape[:desc.rank])
+        st = (C.c_int64 * desc.rank)(*desc.strides[:desc.rank])
+        return LazyTensor(self, _id(_lib().b200h_from_device(self.h, desc.ptr, desc.dtype, desc.rank, sh, st)))
+
     def sync(self):
         check(_lib().b200h_sync(self.h))
+
+    def flush(self):
+        """Plan and launch everything pending without waiting for the device."""
+        check(_lib().b200h_flush(self.h))
+
+    def cache_stats(self) -> CacheStats:
+        cs = CacheStats()
+        check(_lib().b200h_cache_stats_get(self.h, C.byref(cs)))
+        return cs
+
+    def clear_cache(self):
+        check(_lib().b200h_cache_clear(self.h))
+
+    def fuser(self, kind: int) -> "Fuser":
+        h = C.c_void_p()
+        check(_lib().b200h_fuser_create(self.h, kind, C.byref(h)))
+        return Fuser(self, h)
 
     def blocks(self):
         out = []
@@ -171,6 +248,77 @@ class FusionStream:
 
     def clear_blocks(self):
         check(_lib().b200h_block_clear(self.h))
+
+
+class Fuser:
+    """`OperationFuser` (crates/burn-fusion/src/backend.rs:187-206) over the stream's pending queue."""
+
+    def __init__(self, stream: FusionStream, h):
+        self.stream, self.h = stream, h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _lib().b200h_fuser_destroy(self.h)
+            self.h = None
+
+    def fuse_next(self): check(_lib().b200h_fuser_fuse_next(self.h))
+    @property
+    def status(self): return _lib().b200h_fuser_status_get(self.h)
+    def __len__(self): return _lib().b200h_fuser_len(self.h)
+    def reset(self): check(_lib().b200h_fuser_reset(self.h))
+
+    def properties(self):
+        score, ready = C.c_uint64(), C.c_int32()
+        check(_lib().b200h_fuser_properties(self.h, C.byref(score), C.byref(ready)))
+        return score.value, bool(ready.value)
+
+    def clone_dyn(self) -> "Fuser":
+        h = C.c_void_p()
+        check(_lib().b200h_fuser_clone(self.h, C.byref(h)))
+        return Fuser(self.stream, h)
+
+    def fuse_until_closed(self):
+        while self.status == FUSER_OPEN:
+            try:
+                self.fuse_next()
+            except abi.B200Error:
+                break                       # queue exhausted while still open
+        return self
+
+    def finish(self) -> "Optimization":
+        h = C.c_void_p()
+        check(_lib().b200h_fuser_finish(self.h, C.byref(h)))
+        return Optimization(h)
+
+
+class Optimization:
+    """`Optimization` (backend.rs:226-234): execute on a stream's queue head, to_state / from_state."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _lib().b200h_optimization_destroy(self.h)
+            self.h = None
+
+    def __len__(self): return _lib().b200h_optimization_len(self.h)
+    @property
+    def name(self): return _lib().b200h_optimization_name(self.h).decode()
+    def execute(self, stream: FusionStream): check(_lib().b200h_optimization_execute(self.h, stream.h))
+
+    def to_state(self) -> bytes:
+        n = C.c_uint64()
+        check(_lib().b200h_optimization_to_state(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        check(_lib().b200h_optimization_to_state(self.h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    @staticmethod
+    def from_state(state: bytes) -> "Optimization":
+        h = C.c_void_p()
+        check(_lib().b200h_optimization_from_state(state, len(state), C.byref(h)))
+        return Optimization(h)
 
 
 def gelu(x: LazyTensor) -> LazyTensor:

@@ -117,3 +117,143 @@ def test_matmul_on_swap_dims_view(st):
     ta, tb = st.tensor(a), st.tensor(b)
     got = ta.matmul(tb.swap_dims(0, 1)).numpy()      # grad·rhsᵀ shape of work
     H.assert_close(got, oracle.float_matmul(a[None], b.T[None])[0], 1e-5, 1e-5)
+
+
+# ---------------------------------------------------------------- round 2: relative plans, state, in place, views
+def _bias_gelu_softmax(st, x, w, bias, scale):
+    tx, tw, tb = st.tensor(x), st.tensor(w), st.tensor(bias)
+    h = tx.matmul(tw)
+    hb = h.add(tb); h.drop()
+    g = F.gelu(hb); hb.drop()
+    a = g.mul_scalar(scale); g.drop()
+    y = F.softmax(a, 1); a.drop()
+    return y
+
+
+def _bias_gelu_softmax_ref(x, w, bias, scale):
+    h = oracle.float_add(oracle.float_matmul(x[None], w[None])[0], bias)
+    return oracle.softmax(oracle.float_mul_scalar(oracle.gelu(h), scale), 1)
+
+
+def test_cached_plan_reexecutes_with_new_shapes_and_scalars(st):
+    """A plan built once is re-executed through a new Context (context.rs:11-26): other extents, other scalar."""
+    x, w, b = rnd((64, 32), 20, -0.5, 0.5), rnd((32, 128), 21, -0.5, 0.5), rnd((1, 128), 22)
+    H.assert_close(_bias_gelu_softmax(st, x, w, b, 0.5).numpy(), _bias_gelu_softmax_ref(x, w, b, 0.5), 2e-5, 1e-7)
+    first = [(k.kind, k.n_ops) for k in st.blocks()]
+    assert all(k.from_cache == 0 for k in st.blocks())
+    st.clear_blocks()
+    x, w, b = rnd((200, 96), 23, -0.5, 0.5), rnd((96, 320), 24, -0.5, 0.5), rnd((1, 320), 25)
+    H.assert_close(_bias_gelu_softmax(st, x, w, b, 1.75).numpy(), _bias_gelu_softmax_ref(x, w, b, 1.75), 2e-5, 1e-7)
+    assert [(k.kind, k.n_ops) for k in st.blocks()] == first
+    assert all(k.from_cache == 1 for k in st.blocks())
+    cs = st.cache_stats()
+    assert cs.hits >= 1 and cs.plans >= 1
+
+
+def test_optimization_state_round_trip_on_the_device(st):
+    def record(x, m, c):
+        tx, tm = st.tensor(x), st.tensor(m)
+        t = tx.mul_scalar(c)
+        u = t.exp(); t.drop()
+        return u.mask_fill(tm, -1.0), u
+    x1 = rnd((32, 48), 30)
+    y1, u1 = record(x1, x1 > 0, 0.5)
+    u1.drop()
+    opt = st.fuser(F.BLOCK_ELEMWISE).fuse_until_closed().finish()
+    state = opt.to_state()
+    opt.execute(st)
+    H.assert_close(y1.numpy(), oracle.float_mask_fill(oracle.float_exp(oracle.float_mul_scalar(x1, 0.5)), x1 > 0, -1.0), H.REL_ELEMWISE)
+    x2 = rnd((100, 20), 31)
+    y2, u2 = record(x2, x2 < 0.3, -2.0)
+    u2.drop()
+    F.Optimization.from_state(state).execute(st)         # rebuilt from bytes, bound to new tensors and scalars
+    H.assert_close(y2.numpy(), oracle.float_mask_fill(oracle.float_exp(oracle.float_mul_scalar(x2, -2.0)), x2 < 0.3, -1.0), H.REL_ELEMWISE)
+
+
+def test_in_place_output_matches_the_out_of_place_result(st):
+    """tests/fusion/inplace.rs: an output written over a consumed input must equal the fresh-buffer result."""
+    x, o = rnd((257, 129), 40), rnd((257, 129), 41)
+    tx, to = st.tensor(x), st.tensor(o)
+    y = tx.add(to); tx.drop()
+    z = F.gelu(y); y.drop()
+    got = z.numpy()
+    blk = st.blocks()[0]
+    assert blk.aliased == 1 and blk.launches == 1
+    H.assert_close(got, oracle.gelu(oracle.float_add(x, o)), H.REL_ELEMWISE)
+    H.assert_exact(to.numpy(), o)                        # the other input is untouched
+
+
+def test_views_in_the_stream(st):
+    x = rnd((6, 8, 10), 50)
+    tx = st.tensor(x)
+    H.assert_exact(tx.reshape((48, 10)).exp().numpy(), oracle.float_exp(x.reshape(48, 10)))
+    sl = tx.slice([(1, 5), (2, 8), (0, 10)])
+    H.assert_exact(sl.mul_scalar(2.0).numpy(), oracle.float_mul_scalar(x[1:5, 2:8, :], 2.0))
+    row = rnd((1, 1, 10), 51)
+    ex = st.tensor(row).expand((6, 8, 10))
+    H.assert_exact(tx.add(ex).numpy(), oracle.float_add(x, np.broadcast_to(row, x.shape)))
+    # a view of a pending tensor: lone view block, then the consumer reads through the new strides
+    t = tx.mul_scalar(3.0)
+    v = t.swap_dims(0, 2)
+    w = v.reshape((10, 48))                              # strided → copies, then reshapes
+    H.assert_exact(w.numpy(), np.ascontiguousarray(oracle.float_mul_scalar(x, 3.0).transpose(2, 1, 0)).reshape(10, 48))
+    kinds = [b.kind for b in st.blocks()]
+    assert F.BLOCK_VIEW in kinds
+
+
+def test_gather_and_select_through_the_stream(st):
+    x = rnd((50, 24), 60)
+    rng = np.random.default_rng(61)
+    idx = rng.integers(0, 50, size=17).astype(np.int64)
+    gi = rng.integers(0, 24, size=(50, 7)).astype(np.int64)
+    tx = st.tensor(x)
+    s = tx.select(0, st.tensor(idx))
+    H.assert_exact(s.exp().numpy(), oracle.float_exp(oracle.float_select(x, 0, idx)))
+    g = tx.gather(1, st.tensor(gi))
+    H.assert_exact(g.numpy(), oracle.float_gather(1, x, gi))
+    assert [b.kind for b in st.blocks()].count(F.BLOCK_EAGER) == 2
+
+
+def test_wrap_device_memory_and_read_it_back(st, dev):
+    from burn_b200.device import DeviceTensor
+    a = rnd((33, 65), 70)
+    da = DeviceTensor.from_numpy(a)
+    la = st.wrap(da.desc())
+    y = la.mul_scalar(2.0); la.drop()                    # dropped, but caller-owned memory is never reused in place
+    d = y.device_tensor()
+    assert d.ptr and d.rank == 2 and st.blocks()[0].aliased == 0
+    H.assert_exact(y.numpy(), oracle.float_mul_scalar(a, 2.0))
+    H.assert_exact(da.numpy(), a)
+
+
+def test_encoder_forward_through_the_stream_matches_the_hand_sequenced_forward(st, dev):
+    """burn-nn's primitive op stream for the TransformerEncoder (burn_b200/stream_model.py) → fusers → kernels,
+    against burn_b200.train's hand-sequenced forward (same GEMM precision, unfused attention chain)."""
+    from burn_b200 import train as T
+    from burn_b200.device import DeviceTensor
+    from burn_b200.stream_model import StreamEncoder
+    B, S, d = 4, 48, 128
+    model = T.Encoder(5, d, 256, 2, 2)
+    x = rnd((B, S, d), 80)
+    xd = DeviceTensor.from_numpy(x)
+    old = T._ATTN_MODE
+    T._ATTN_MODE = "chain"
+    try:
+        want = model.forward(T.Tape(abi.MM_F32X3), T.Var(xd, False)).v.numpy()
+    finally:
+        T._ATTN_MODE = old
+    enc = StreamEncoder(st, model, abi.MM_F32X3)
+    got = enc.forward(st.wrap(xd.desc())).numpy()
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    n_first = len(st.blocks())
+    assert all(b.launches <= 1 for b in st.blocks())                     # one kernel per block (views: none, or the one copy)
+    st.clear_blocks()
+    x2 = rnd((3, 40, d), 81)
+    got2 = enc.forward(st.tensor(x2)).numpy()                            # other extents → the cached plan, new Context
+    assert len(st.blocks()) == n_first and all(b.from_cache for b in st.blocks())
+    T._ATTN_MODE = "chain"
+    try:
+        want2 = model.forward(T.Tape(abi.MM_F32X3), T.Var(DeviceTensor.from_numpy(x2), False)).v.numpy()
+    finally:
+        T._ATTN_MODE = old
+    assert np.abs(got2 - want2).max() <= 2e-5 * np.abs(want2).max()

@@ -295,6 +295,116 @@ def run_fc_head(steps: int = 200, warmup: int = 10, mm: str = "f32x3"):
             "gemm": mm, "loss_first": round(first, 4), "loss_last": round(float(lh[0]), 4)}
 
 
+def run_via_stream(steps: int = 20, warmup: int = 3, mm: str = "tf32"):
+    """configs[3] encoder FORWARD issued as the primitive operation stream burn-nn emits (burn_b200/stream_model.py),
+    planned and launched by the host fusion layer — beside the same forward sequenced by hand (burn_b200/train.py,
+    the path `run` measures).  The stream materialises the attention weights (burn-nn's MultiHeadAttention does;
+    the hand-sequenced forward is timed both ways: the same chain, and the flash kernel)."""
+    import time
+    from collections import Counter
+    from burn_b200 import _abi as abi
+    from burn_b200 import device as dv
+    from burn_b200 import fusion as F
+    from burn_b200 import train as T
+    from burn_b200.device import DeviceTensor
+    from burn_b200.stream_model import StreamEncoder
+    lib, check = abi.load(), abi.check
+    cfg = CONFIGS["encoder"]
+    prec = {"tf32": abi.MM_TF32, "bf16": abi.MM_BF16, "f32x3": abi.MM_F32X3}[mm]
+    dv.init(int(os.environ.get("LOCAL_RANK", "0")))
+    B, S, d = cfg["B"], cfg["S"], cfg["d"]
+    model = T.Encoder(11, d, cfg["ff"], cfg["h"], cfg["L"])
+    x_dev = DeviceTensor.from_numpy(np.random.default_rng(3).standard_normal((B, S, d)).astype(np.float32))
+    out_stream, out_hand = DeviceTensor.empty((B, S, d)), DeviceTensor.empty((B, S, d))
+    nbytes = B * S * d * 4
+
+    def timed(fn, n):
+        e0, e1 = C.c_void_p(), C.c_void_p()
+        check(lib.b200_event_create(C.byref(e0))); check(lib.b200_event_create(C.byref(e1)))
+        check(lib.b200_device_sync())
+        t0 = time.perf_counter()
+        check(lib.b200_event_record(e0, None))
+        for _ in range(n):
+            fn()
+        check(lib.b200_event_record(e1, None))
+        host_ms = (time.perf_counter() - t0) * 1e3 / n
+        check(lib.b200_device_sync())
+        ms = C.c_float()
+        check(lib.b200_event_elapsed_ms(e0, e1, C.byref(ms)))
+        return ms.value / n, host_ms
+
+    # ---- hand-sequenced forward (attention as the configured mode, and as the unfused chain)
+    def hand_forward():
+        tape = T.Tape(prec)
+        y = model.forward(tape, T.Var(x_dev, False))
+        check(lib.b200_memcpy_d2d(out_hand.data_ptr(), y.v.data_ptr(), nbytes, None))
+    res = {}
+    for mode in ("chain", "flash"):
+        T._ATTN_MODE = mode
+        for _ in range(warmup):
+            hand_forward()
+        lib.b200_launch_count_reset()
+        ms, host = timed(hand_forward, steps)
+        res[f"hand_{mode}"] = {"ms": round(ms, 3), "host_ms": round(host, 3), "launches": int(lib.b200_launch_count()) // steps}
+    T._ATTN_MODE = "chain"
+    hand_forward()                       # reference values for the stream: same attention decomposition
+    check(lib.b200_device_sync())
+    want = out_hand.numpy()
+
+    # ---- the same forward as an operation stream
+    st = F.FusionStream()
+    enc = StreamEncoder(st, model, prec)
+    xs = st.wrap(x_dev.desc())
+
+    def stream_forward():
+        y = enc.forward(xs)
+        d_ = y.device_tensor()            # flush: plan (or fetch the cached plan) and launch
+        check(lib.b200_memcpy_d2d(out_stream.data_ptr(), d_.ptr, nbytes, None))
+        y.drop()
+    t0 = time.perf_counter()
+    stream_forward()
+    check(lib.b200_device_sync())
+    first_ms = (time.perf_counter() - t0) * 1e3
+    blocks = st.blocks()
+    kinds = Counter({0: "ElementWise", 1: "Reduce", 2: "Matmul", 3: "Unfused", 4: "ReduceBroadcasted", 5: "View"}[b.kind] for b in blocks)
+    got = out_stream.numpy()
+    err = float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+    for _ in range(warmup):
+        stream_forward()
+    st.clear_blocks()
+    lib.b200_launch_count_reset()
+    ms, host = timed(stream_forward, steps)
+    launches = int(lib.b200_launch_count()) // steps
+    cached = st.blocks()
+    cs = st.cache_stats()
+    res["via_stream"] = {
+        "ms": round(ms, 3), "host_ms": round(host, 3), "launches": launches,
+        "first_call_ms": round(first_ms, 2), "blocks_per_forward": len(blocks), "block_kinds": dict(kinds),
+        "ops_per_forward": int(sum(b.n_ops for b in blocks)),
+        "fused_ops_in_matmul_epilogues": int(sum(b.n_ops - 1 for b in blocks if b.kind == 2)),
+        "in_place_outputs": int(sum(b.aliased for b in blocks)),
+        "served_from_plan_cache": bool(cached) and all(b.from_cache for b in cached),
+        "plan_cache": {"hits": int(cs.hits), "misses": int(cs.misses), "plans": int(cs.plans)},
+        "max_rel_diff_vs_hand_chain": err,
+    }
+    # ---- the cached plan captured in a CUDA graph (what a burn-fusion + graph_capture integration replays)
+    try:
+        with dv.Graph.capture() as graph:
+            stream_forward()
+        for _ in range(warmup):
+            graph.launch()
+        gms, ghost = timed(graph.launch, steps)
+        res["via_stream_graph"] = {"ms": round(gms, 3), "host_ms": round(ghost, 3), "kernel_nodes": int(graph.kernel_nodes)}
+        check(lib.b200_device_sync())
+        graph.destroy()
+    except abi.B200Error as e:           # reported, not hidden
+        res["via_stream_graph"] = {"error": str(e)[:200]}
+    xs.drop()
+    st.close()
+    return {"workload": f"configs[3] TransformerEncoder forward d_model {d}, {cfg['L']} layers, {cfg['h']} heads, seq {S}, batch {B}, {mm}",
+            "tokens": B * S, **res}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="lm", choices=sorted(CONFIGS))
@@ -303,7 +413,12 @@ def main():
     ap.add_argument("--mm", default="tf32", choices=["tf32", "bf16", "f32x3"])
     ap.add_argument("--eager", action="store_true")
     ap.add_argument("--bucket-mb", type=int, default=32)
+    ap.add_argument("--via-stream", action="store_true",
+                    help="configs[3] forward through the host fusion layer's operation stream vs the hand-sequenced forward")
     args = ap.parse_args()
+    if args.via_stream:
+        print(json.dumps(run_via_stream(args.steps, args.warmup, args.mm)), flush=True)
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
