@@ -177,6 +177,75 @@ def allreduce_value_check(rank: int, world: int, local_rank: int):
     return "ok"
 
 
+def peer_value_check(rank: int, world: int, local_rank: int):
+    """The same protocol on the peer-memory kernels (burn_b200/csrc/peer.cu): Sum / Mean on rank-dependent data must be the
+    element-wise sum over ranks IN RANK ORDER (bit-exact: the kernel adds rank 0, 1, … N-1 whoever owns the shard), and
+    the fused reduce-scatter + Adam + all-gather must equal b200_launch_adam applied to that mean, bit for bit, with
+    every rank ending on identical parameters.  Raises on mismatch."""
+    import torch
+    import torch.distributed as dist
+    from burn_b200 import _abi as abi
+    from burn_b200 import device as dv
+    from burn_b200.device import DeviceTensor
+    from burn_b200.distributed import PeerGroup
+    lib = abi.load()
+    n_small, n_big = 400, (4 << 20) + 4
+    grp = PeerGroup(rank, world, 4 * 4 * (n_small + n_big) + 4096, device=torch.device("cuda", local_rank))
+    try:
+        for n in (n_small, n_big):
+            g, g_off = grp.carve(n)
+            p, p_off = grp.carve(n)
+            slot_ar, slot_adam = grp.slot(), grp.slot()
+            for it in range(6 if n == n_small else 2):
+                data = [np.random.default_rng([777, it, r, n]).uniform(-10.0, 10.0, n).astype(np.float32) for r in range(world)]
+                acc = data[0].copy()
+                for r in range(1, world):
+                    acc = acc + data[r]                                   # f32, rank order: what the kernel computes
+                for mean in (False, True):
+                    abi.check(lib.b200_memcpy_h2d(g.data_ptr(), data[rank].ctypes.data, n * 4, None))
+                    dv.sync()
+                    grp.all_reduce(g_off, n, slot_ar, mean=mean)
+                    grp.sync()
+                    dv.sync()
+                    want = (acc / np.float32(world)) if mean else acc
+                    if not np.array_equal(g.numpy(), want):
+                        raise AssertionError(f"peer all_reduce({'Mean' if mean else 'Sum'}) mismatch on rank {rank}, n {n}, iteration {it}")
+                    dist.barrier()
+            # fused: gradients differ per rank, parameters start identical; 3 steps against the unfused reference
+            rng = np.random.default_rng([99, n])
+            p0 = rng.standard_normal(n).astype(np.float32)
+            abi.check(lib.b200_memcpy_h2d(p.data_ptr(), p0.ctypes.data, n * 4, None))
+            m, v = DeviceTensor.from_numpy(np.zeros(n, np.float32)), DeviceTensor.from_numpy(np.zeros(n, np.float32))
+            rp, rm, rv = DeviceTensor.from_numpy(p0), DeviceTensor.from_numpy(np.zeros(n, np.float32)), DeviceTensor.from_numpy(np.zeros(n, np.float32))
+            coef = DeviceTensor.from_numpy(np.array([0.31622776, 3.1622776e-7], dtype=np.float32))
+            dv.sync()
+            dist.barrier()
+            for it in range(3):
+                data = [np.random.default_rng([555, it, r, n]).standard_normal(n).astype(np.float32) for r in range(world)]
+                acc = data[0].copy()
+                for r in range(1, world):
+                    acc = acc + data[r]
+                mean_g = DeviceTensor.from_numpy(acc / np.float32(world))
+                abi.check(lib.b200_memcpy_h2d(g.data_ptr(), data[rank].ctypes.data, n * 4, None))
+                dv.sync()
+                grp.adam(g_off, p_off, m, v, coef, n, 1e-3, 0.9, 0.999, slot_adam)
+                grp.sync()
+                a, b_, c_, d_, e_ = rp.desc(), rm.desc(), rv.desc(), mean_g.desc(), coef.desc()
+                abi.check(lib.b200_launch_adam(C.byref(a), C.byref(b_), C.byref(c_), C.byref(d_), C.byref(e_), 1e-3, 0.9, 0.999, None))
+                dv.sync()
+                if not np.array_equal(p.numpy(), rp.numpy()):
+                    raise AssertionError(f"fused reduce-scatter+Adam+all-gather: parameters differ from the unfused reference on rank {rank}, n {n}, step {it}")
+                per = ((n // 4 + world - 1) // world) * 4
+                lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+                if not (np.array_equal(m.numpy()[lo:hi], rm.numpy()[lo:hi]) and np.array_equal(v.numpy()[lo:hi], rv.numpy()[lo:hi])):
+                    raise AssertionError(f"fused Adam: owned moment shard differs on rank {rank}, n {n}, step {it}")
+                dist.barrier()
+    finally:
+        dv.sync()
+        dist.barrier()
+        grp.close()
+
+
 def chain_tape():
     from burn_b200.device import TapeBuilder
     tb = TapeBuilder()
@@ -207,6 +276,21 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     check = abi.check
     shape = (N_ROWS, N_COLS)
     allreduce = allreduce_value_check(rank, world, local_rank) if world > 1 else None
+    # the peer-memory kernels (fused gradient sync) are checked the same way; where peer mapping is not available
+    # (no IPC between the ranks' processes, no P2P) the training leg says so and synchronises through NCCL instead
+    peer_check, grad_sync = None, os.environ.get("B200_GRAD_SYNC")
+    if world > 1:
+        try:
+            peer_value_check(rank, world, local_rank)
+            peer_check = "ok"
+        except Exception as e:
+            peer_check = f"failed: {e!r}"[:300]
+        flag = torch.tensor([1 if peer_check == "ok" else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                # every rank must agree on the mode
+        if int(flag.item()) == 0:
+            grad_sync = "nccl"
+            if peer_check == "ok":
+                peer_check = "failed on another rank"
 
     # synthetic inputs, seeded per rank, staged in PINNED host memory
     rng = np.random.default_rng(1000 + rank)
@@ -325,9 +409,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         try:
             import train_bench
             train = train_bench.run("lm", steps=args.train_steps, warmup=3, rank=rank, world=world,
-                                    local_rank=local_rank, mm="tf32", use_graph=True, init_device=False)
+                                    local_rank=local_rank, mm="tf32", use_graph=True, init_device=False, sync=grad_sync)
             enc = train_bench.run("encoder", steps=args.train_steps, warmup=3, rank=rank, world=world,
-                                  local_rank=local_rank, mm="tf32", use_graph=True, init_device=False)
+                                  local_rank=local_rank, mm="tf32", use_graph=True, init_device=False, sync=grad_sync)
             train["encoder_configs3"] = {k: enc[k] for k in ("value", "unit", "ms_per_step", "model_tflops_per_s", "config")}
             if world == 1:
                 train["mnist_fc_head_configs0"] = train_bench.run_fc_head()
@@ -382,6 +466,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         }
         if allreduce is not None:
             line["allreduce_check"] = allreduce
+            line["peer_collective_check"] = peer_check
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if train is not None:

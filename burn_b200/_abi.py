@@ -144,6 +144,22 @@ SIGNATURES = {
     "b200_all_reduce": (_i32, [_vp, _vp, _u64, _i32, _i32, _vp]),
     "b200_all_reduce_multi": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_u64), _i32, _i32, _i32, _vp]),
     "b200_collective_sync": (_i32, [_vp, _vp]),
+    "b200_comm_init_all": (_i32, [C.POINTER(_vp), C.POINTER(_i32), _i32]),
+    "b200_all_reduce_group": (_i32, [C.POINTER(_vp), C.POINTER(_vp), _u64, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "b200_comm_host_sync": (_i32, [_vp]),
+    "b200_peer_alloc": (_i32, [C.POINTER(_vp), _u64]),
+    "b200_peer_free": (_i32, [_vp]),
+    "b200_peer_export": (_i32, [_vp, C.POINTER(C.c_uint8)]),
+    "b200_peer_flag_bytes": (_u64, []),
+    "b200_peer_group_create": (_i32, [C.POINTER(_vp), _i32, _i32, _vp, _u64, C.POINTER(C.c_uint8)]),
+    "b200_peer_group_create_local": (_i32, [C.POINTER(_vp), C.POINTER(_i32), _i32, _u64]),
+    "b200_peer_data": (_vp, [_vp]),
+    "b200_peer_group_destroy": (_i32, [_vp]),
+    "b200_launch_peer_all_reduce": (_i32, [_vp, _u64, _u64, _i32, _i32, _vp]),
+    "b200_launch_peer_adam": (_i32, [_vp, _u64, _u64, _vp, _vp, _vp, _u64, C.c_double, C.c_double, C.c_double, _i32, _vp]),
+    "b200_peer_sync": (_i32, [_vp, _vp]),
+    "b200_peer_mark": (_i32, [_vp, _vp]),
+    "b200_peer_host_sync": (_i32, [_vp]),
     "b200_event_create": (_i32, [C.POINTER(_vp)]),
     "b200_event_destroy": (_i32, [_vp]),
     "b200_event_record": (_i32, [_vp, _vp]),

@@ -20,6 +20,7 @@
 #include <cstring>
 
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -38,6 +39,7 @@ struct NcclApi {
   void *handle = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
@@ -64,6 +66,7 @@ static int32_t load_nccl() {
   if (!g_nccl.field) return fail(B200_ERR_NCCL, "libnccl lacks symbol %s", name);
   B200_SYM(GetUniqueId, "ncclGetUniqueId")
   B200_SYM(CommInitRank, "ncclCommInitRank")
+  B200_SYM(CommInitAll, "ncclCommInitAll")
   B200_SYM(CommDestroy, "ncclCommDestroy")
   B200_SYM(AllReduce, "ncclAllReduce")
   B200_SYM(GroupStart, "ncclGroupStart")
@@ -88,6 +91,7 @@ struct Comm {
   cudaEvent_t fence = nullptr;    // producer → collective stream
   cudaEvent_t done = nullptr;     // collective stream → consumer
   int rank = 0, world = 1;
+  int device = -1;                // >= 0: made by b200_comm_init_all for that device (single-process multi-device)
 };
 
 static int32_t nccl_dtype(int32_t dt, ncclDataType_t *out) {
@@ -149,12 +153,111 @@ extern "C" int32_t b200_comm_init(b200_comm *out, const uint8_t id[B200_NCCL_UNI
 extern "C" int32_t b200_comm_destroy(b200_comm comm) {
   if (!comm) return B200_OK;
   Comm *c = (Comm *)comm;
+  int prev = -1;
+  if (c->device >= 0) {
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+  }
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   if (c->fence) cudaEventDestroy(c->fence);
   if (c->done) cudaEventDestroy(c->done);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (prev >= 0) cudaSetDevice(prev);
   delete c;
+  return B200_OK;
+}
+
+extern "C" int32_t b200_comm_init_all(b200_comm *out, const int32_t *devices, int32_t n) {
+  B200_REQUIRE(out && devices && n >= 1 && n <= 64, B200_ERR_INVALID, "bad arguments to b200_comm_init_all");
+  int32_t st = load_nccl();
+  if (st != B200_OK) return st;
+  std::vector<ncclComm_t> raw(n, nullptr);
+  std::vector<int> devs(devices, devices + n);
+  B200_NCCL(g_nccl.CommInitAll(raw.data(), n, devs.data()));
+  int prev = 0;
+  cudaGetDevice(&prev);
+  std::vector<Comm *> cs(n, nullptr);
+  auto build = [&]() -> int32_t {
+    for (int i = 0; i < n; ++i) {
+      Comm *c = new Comm();
+      cs[i] = c;
+      c->comm = raw[i];
+      raw[i] = nullptr;
+      c->rank = i;
+      c->world = n;
+      c->device = devs[i];
+      B200_CUDA(cudaSetDevice(devs[i]));
+      int lo = 0, hi = 0;
+      B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      B200_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+      B200_CUDA(cudaEventCreateWithFlags(&c->fence, cudaEventDisableTiming));
+      B200_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+    }
+    return B200_OK;
+  };
+  st = build();
+  cudaSetDevice(prev);
+  if (st != B200_OK) {
+    for (int i = 0; i < n; ++i) {
+      if (cs[i]) b200_comm_destroy((b200_comm)cs[i]);
+      else if (raw[i]) g_nccl.CommDestroy(raw[i]);
+    }
+    return st;
+  }
+  for (int i = 0; i < n; ++i) out[i] = (b200_comm)cs[i];
+  return B200_OK;
+}
+
+extern "C" int32_t b200_all_reduce_group(const b200_comm *comms, void *const *ptrs, uint64_t count, int32_t n,
+                                         int32_t dtype, int32_t op, void *const *producers) {
+  B200_REQUIRE(comms && ptrs && n >= 1, B200_ERR_INVALID, "null argument");
+  B200_REQUIRE(op == B200_REDUCE_SUM || op == B200_REDUCE_MEAN, B200_ERR_INVALID, "bad reduce op %d", op);
+  ncclDataType_t dt;
+  int32_t st = nccl_dtype(dtype, &dt);
+  if (st != B200_OK) return st;
+  if (count == 0) return B200_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  const ncclRedOp_t rop = op == B200_REDUCE_MEAN ? ncclAvg : ncclSum;
+  auto issue = [&]() -> int32_t {
+    for (int i = 0; i < n; ++i) {
+      Comm *c = (Comm *)comms[i];
+      B200_REQUIRE(c && c->device >= 0, B200_ERR_INVALID, "communicator %d was not made by b200_comm_init_all", i);
+      B200_CUDA(cudaSetDevice(c->device));
+      B200_CUDA(cudaEventRecord(c->fence, producers ? (cudaStream_t)producers[i] : (cudaStream_t) nullptr));
+      B200_CUDA(cudaStreamWaitEvent(c->stream, c->fence, 0));
+    }
+    // ONE group for all devices: a single thread issuing N blocking-order collectives outside a group deadlocks
+    B200_NCCL(g_nccl.GroupStart());
+    for (int i = 0; i < n; ++i) {
+      Comm *c = (Comm *)comms[i];
+      ncclResult_t r = g_nccl.AllReduce(ptrs[i], ptrs[i], (size_t)count, dt, rop, c->comm, c->stream);
+      if (r != ncclSuccess) {
+        g_nccl.GroupEnd();
+        return fail(B200_ERR_NCCL, "NCCL error %d (%s) in ncclAllReduce for device %d", (int)r, g_nccl.GetErrorString(r), c->device);
+      }
+    }
+    B200_NCCL(g_nccl.GroupEnd());
+    return B200_OK;
+  };
+  st = issue();
+  cudaSetDevice(prev);
+  if (st == B200_OK) count_launch(n);
+  return st;
+}
+
+extern "C" int32_t b200_comm_host_sync(b200_comm comm) {
+  B200_REQUIRE(comm, B200_ERR_INVALID, "comm is null");
+  Comm *c = (Comm *)comm;
+  int prev = -1;
+  if (c->device >= 0) {
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->device);
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (prev >= 0) cudaSetDevice(prev);
+  B200_CUDA(e);
   return B200_OK;
 }
 

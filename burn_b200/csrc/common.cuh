@@ -18,7 +18,7 @@ int sm_count();
 int max_smem_optin();
 // sticky device-side error flag (host-mapped pinned int32): kernels store one of these codes, the next
 // synchronising ABI call reports it as B200_ERR_SHAPE and clears it
-enum : int32_t { kIdxErrGather = 1, kIdxErrSelect = 2, kIdxErrScatter = 3, kIdxErrSelectAdd = 4, kIdxErrTarget = 5 };
+enum : int32_t { kIdxErrGather = 1, kIdxErrSelect = 2, kIdxErrScatter = 3, kIdxErrSelectAdd = 4, kIdxErrTarget = 5, kPeerTimeout = 6 };
 int32_t *index_error_flag();
 int32_t check_index_error();
 int32_t ensure_dyn_smem(const void *func, size_t bytes, bool max_carveout = false);

@@ -114,6 +114,9 @@ int32_t check_index_error() {
   const int32_t code = *reinterpret_cast<volatile int32_t *>(g_idx_err);
   if (code == 0) return B200_OK;
   *reinterpret_cast<volatile int32_t *>(g_idx_err) = 0;
+  if (code == kPeerTimeout)
+    return fail(B200_ERR_NCCL, "a peer-memory collective gave up waiting for another rank (10 s): ranks issued different "
+                               "collectives, or a rank died; the buffers it touched are not valid");
   static const char *const what[] = {"?", "gather", "select", "scatter_add", "select_add", "softmax_cross_entropy targets"};
   return fail(B200_ERR_SHAPE, "an index was out of range in an earlier %s launch (the reference panics; the access was skipped)",
               what[code >= 1 && code <= 5 ? code : 0]);

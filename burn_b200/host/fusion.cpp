@@ -1591,6 +1591,10 @@ b200h_id b200h_select(b200h_stream s, int32_t dim, b200h_id x, b200h_id indices)
 
 int32_t b200h_drop(b200h_stream s, b200h_id id) {
   B200_REQUIRE(S(s)->get(id), B200_ERR_INVALID, "unknown tensor id %lld", (long long)id);
+  if (S(s)->queue.empty()) {  // nothing pending can still read it: release the handle now
+    S(s)->tensors.erase(id);
+    return B200_OK;
+  }
   Op o;
   o.kind = Kind::Drop;
   o.in[0] = id;

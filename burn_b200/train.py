@@ -545,6 +545,9 @@ class Adam:
     def apply_arena(self, arena: "ParamArena") -> None:
         """Multi-tensor Adam: one b200_launch_adam per flat bucket instead of one launch per parameter."""
         lib = abi.load()
+        if arena.fused:              # the update already ran inside the gradient-sync kernels
+            arena.join()
+            return
         c = self.coef.desc()
         for b in arena.buckets:      # backward order: early buckets update while late all-reduces still run
             arena.fence(b)
@@ -595,8 +598,18 @@ class ParamArena:
         (multi-tensor Adam) instead of one launch per parameter.
     Persistent storage keeps every address fixed across CUDA-graph replays."""
 
-    def __init__(self, params: Sequence[Param], comm=None, bucket_bytes: int = 32 << 20):
+    @staticmethod
+    def peer_bytes(params: Sequence[Param]) -> int:
+        """Data-area bytes a PeerGroup needs for these parameters (p and g buckets)."""
+        return 2 * 4 * sum((p.v.numel + 3) // 4 * 4 for p in params) + 4096
+
+    def __init__(self, params: Sequence[Param], comm=None, bucket_bytes: int = 32 << 20, peer=None, fused: bool = False):
+        """comm: NCCL communicator (one ncclAllReduce per bucket).  peer: a distributed.PeerGroup — the p and g buckets
+        then live in the peer region and gradient sync is the peer-memory kernel: `fused=False` all-reduces the bucket
+        (Adam runs later, as with NCCL), `fused=True` runs reduce-scatter → Adam on the owned 1/N → all-gather of the
+        parameters in ONE kernel per bucket as soon as the bucket is complete (attach the optimizer first)."""
         self.comm = comm
+        self.peer, self.fused, self.opt = peer, bool(fused and peer is not None), None
         self.buckets: list[dict] = []
         self.slot: dict[int, dict] = {}
         lib = abi.load()
@@ -606,11 +619,18 @@ class ParamArena:
             members.append(p)
             size += (p.v.numel + 3) // 4 * 4              # 16-byte aligned slots
             if size * 4 >= bucket_bytes or i == len(order) - 1:
-                flats = {k: DeviceTensor.empty((size,)) for k in ("p", "m", "s", "g")}
+                flats = {k: DeviceTensor.empty((size,)) for k in ("m", "s")}
+                offs = {}
+                for k in ("p", "g"):
+                    if peer is not None:
+                        flats[k], offs[k] = peer.carve(size)
+                    else:
+                        flats[k] = DeviceTensor.empty((size,))
                 for t in flats.values():
                     abi.check(lib.b200_memset(t.data_ptr(), 0, size * 4, None))
-                b = dict(flats, n=len(members), arrived=0, done=None)
-                if comm is not None:          # per-bucket fence: Adam on this bucket waits for its all-reduce only
+                b = dict(flats, n=len(members), arrived=0, done=None, size=size, offs=offs,
+                         flag_slot=peer.slot() if peer is not None else -1)
+                if comm is not None or peer is not None:   # per-bucket fence: Adam on this bucket waits for its all-reduce only
                     ev = C.c_void_p()
                     abi.check(lib.b200_event_create(C.byref(ev)))
                     b["done"] = ev
@@ -645,10 +665,26 @@ class ParamArena:
             p.g = p.grad_slot
         b["arrived"] += 1
         if b["arrived"] == b["n"]:
-            if self.comm is not None:
+            if self.fused:
+                # reduce-scatter → Adam on this rank's 1/N → all-gather of the new parameters, one kernel, beside backward.
+                # Safe to update p now: every backward consumer of these parameters has already been launched (a
+                # gradient is final only after all of them), and the kernel is fenced behind them.
+                o = self.opt
+                if o is None or o.coef is None:
+                    raise RuntimeError("fused gradient sync needs attach_optimizer(opt) and opt.advance() before backward")
+                self.peer.adam(b["offs"]["g"], b["offs"]["p"], b["m"], b["s"], o.coef, b["size"],
+                               float(o.lr), float(o.b1), float(o.b2), b["flag_slot"])
+                self.peer.mark(b["done"])
+            elif self.peer is not None:
+                self.peer.all_reduce(b["offs"]["g"], b["size"], b["flag_slot"], mean=True)
+                self.peer.mark(b["done"])
+            elif self.comm is not None:
                 self.comm.all_reduce(b["g"], mean=True)
                 abi.check(abi.load().b200_collective_mark(self.comm.handle, b["done"]))
             b["arrived"] = 0
+
+    def attach_optimizer(self, opt: "Adam") -> None:
+        self.opt = opt
 
     def wait(self) -> None:
         """Every gradient has arrived (their all-reduces may still be in flight: the optimizer fences per
@@ -659,10 +695,12 @@ class ParamArena:
 
     def fence(self, b: dict) -> None:
         """The compute stream waits for bucket b's all-reduce only."""
-        if self.comm is not None:
+        if self.comm is not None or self.peer is not None:
             abi.check(abi.load().b200_stream_wait_event(None, b["done"]))
 
     def join(self) -> None:
         """sync_collective: the compute stream rejoins the collective stream completely."""
-        if self.comm is not None:
+        if self.peer is not None:
+            self.peer.sync()
+        elif self.comm is not None:
             self.comm.sync()

@@ -473,6 +473,54 @@ int32_t b200_collective_sync(b200_comm comm, b200_stream consumer);
 int32_t b200_collective_mark(b200_comm comm, b200_event e);
 int32_t b200_stream_wait_event(b200_stream s, b200_event e);
 
+/* Single-process multi-device form — the reference's DDP contract: one process, a thread per GPU, ONE sync thread
+ * issuing all_reduce for every device (crates/burn-backend/src/backend/distributed/server.rs:100-139).
+ * b200_comm_init_all = ncclCommInitAll over `devices`; b200_all_reduce_group issues the n per-device all-reduces of
+ * one tensor inside a single ncclGroupStart/End, so one thread can drive all communicators without deadlock.
+ * ptrs[i] lives on devices[i]; producers[i] is a cudaStream_t of that device (NULL = its default stream). */
+int32_t b200_comm_init_all(b200_comm *out, const int32_t *devices, int32_t n);
+int32_t b200_all_reduce_group(const b200_comm *comms, void *const *ptrs, uint64_t count, int32_t n,
+                              int32_t dtype, int32_t op, void *const *producers);
+int32_t b200_comm_host_sync(b200_comm comm); /* block the host until the communicator's stream is idle */
+
+/* ------------------------------------------------ peer-memory collectives (NVLink loads / stores, no NCCL) */
+/* Every rank owns one REGION (b200_peer_alloc: cudaMalloc'd, zeroed, IPC-exportable) whose first
+ * b200_peer_flag_bytes() bytes are synchronisation flags and whose remainder — the data area, b200_peer_data —
+ * holds the flat gradient and parameter buckets at the SAME offsets on every rank.  A group maps all regions into
+ * the caller: between processes through the 64-byte handles of b200_peer_export (gathered by the host bootstrap),
+ * inside one process through b200_peer_group_create_local (peer access between the listed devices; out[i] is
+ * device i's group and owns its region).
+ *
+ * b200_launch_peer_all_reduce: DistributedOps::all_reduce on `count` f32 at element `offset` of the data area —
+ *   reduce-scatter + all-gather in one kernel, each rank reducing 1/N and storing it into every rank's bucket.
+ * b200_launch_peer_adam: the gradient all-reduce (Mean) FUSED with the Adam step that consumes it
+ *   (crates/burn-optim/src/optim/adam.rs:149-210): each rank reduces 1/N of the bucket, updates that shard of the
+ *   parameters with its shard of the moments (optimizer state sharded N ways; `moment1/2` are full-size local
+ *   buffers of which only the owned shard is used) and stores the new parameters into every rank's bucket.
+ * Both run on the group's own high-priority stream, ordered after `producer` (event fence), identically on every
+ * rank and in the same order; `slot` (one per bucket) names the flag words.  Results are bit-identical on all ranks.
+ * b200_peer_sync = sync_collective: `consumer` waits for everything issued so far. */
+#define B200_PEER_MAX_RANKS 8
+#define B200_PEER_HANDLE_BYTES 64
+typedef void *b200_peer_group;
+int32_t b200_peer_alloc(void **out, uint64_t bytes);
+int32_t b200_peer_free(void *ptr);
+int32_t b200_peer_export(void *ptr, uint8_t handle[B200_PEER_HANDLE_BYTES]);
+uint64_t b200_peer_flag_bytes(void);
+int32_t b200_peer_group_create(b200_peer_group *out, int32_t rank, int32_t world, void *local_region,
+                               uint64_t bytes, const uint8_t *handles /* world x 64, own entry ignored */);
+int32_t b200_peer_group_create_local(b200_peer_group *out /* [n] */, const int32_t *devices, int32_t n, uint64_t bytes);
+void *b200_peer_data(b200_peer_group group);
+int32_t b200_peer_group_destroy(b200_peer_group group);
+int32_t b200_launch_peer_all_reduce(b200_peer_group group, uint64_t offset, uint64_t count, int32_t op,
+                                    int32_t slot, b200_stream producer);
+int32_t b200_launch_peer_adam(b200_peer_group group, uint64_t grad_offset, uint64_t param_offset,
+                              void *moment1, void *moment2, const void *coef, uint64_t count,
+                              double lr, double beta1, double beta2, int32_t slot, b200_stream producer);
+int32_t b200_peer_sync(b200_peer_group group, b200_stream consumer);
+int32_t b200_peer_mark(b200_peer_group group, b200_event e);
+int32_t b200_peer_host_sync(b200_peer_group group);
+
 /* NVRTC specialisation self-test: generates and compiles (sm_100a, no device needed, nothing loaded)
  * the specialised elementwise and fuse-on-read reduce kernels of the bench chain; reports the cubin bytes. */
 int32_t b200_jit_selftest(uint64_t *cubin_bytes_total);

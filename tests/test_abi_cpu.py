@@ -13,7 +13,7 @@ HEADER = (ROOT / "include" / "burn_b200.h").read_text()
 
 
 def declared_symbols():
-    names = set(re.findall(r"^(?:int32_t|uint64_t|void|const char \*)\s*(b200_[a-z0-9_]+)\s*\(", HEADER, re.M))
+    names = set(re.findall(r"^(?:int32_t|uint64_t|void \*|void|const char \*)\s*(b200_[a-z0-9_]+)\s*\(", HEADER, re.M))
     return sorted(names)
 
 

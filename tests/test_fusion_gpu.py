@@ -186,7 +186,7 @@ def test_in_place_output_matches_the_out_of_place_result(st):
 def test_views_in_the_stream(st):
     x = rnd((6, 8, 10), 50)
     tx = st.tensor(x)
-    H.assert_exact(tx.reshape((48, 10)).exp().numpy(), oracle.float_exp(x.reshape(48, 10)))
+    H.assert_close(tx.reshape((48, 10)).exp().numpy(), oracle.float_exp(x.reshape(48, 10)), H.REL_ELEMWISE)
     sl = tx.slice([(1, 5), (2, 8), (0, 10)])
     H.assert_exact(sl.mul_scalar(2.0).numpy(), oracle.float_mul_scalar(x[1:5, 2:8, :], 2.0))
     row = rnd((1, 1, 10), 51)
@@ -208,7 +208,7 @@ def test_gather_and_select_through_the_stream(st):
     gi = rng.integers(0, 24, size=(50, 7)).astype(np.int64)
     tx = st.tensor(x)
     s = tx.select(0, st.tensor(idx))
-    H.assert_exact(s.exp().numpy(), oracle.float_exp(oracle.float_select(x, 0, idx)))
+    H.assert_close(s.exp().numpy(), oracle.float_exp(oracle.float_select(x, 0, idx)), H.REL_ELEMWISE)
     g = tx.gather(1, st.tensor(gi))
     H.assert_exact(g.numpy(), oracle.float_gather(1, x, gi))
     assert [b.kind for b in st.blocks()].count(F.BLOCK_EAGER) == 2
@@ -246,7 +246,7 @@ def test_encoder_forward_through_the_stream_matches_the_hand_sequenced_forward(s
     got = enc.forward(st.wrap(xd.desc())).numpy()
     assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
     n_first = len(st.blocks())
-    assert all(b.launches <= 1 for b in st.blocks())                     # one kernel per block (views: none, or the one copy)
+    assert all(b.launches <= 1 for b in st.blocks() if b.kind != F.BLOCK_MATMUL)   # one kernel per block (a 3xTF32 GEMM splits its operands first)
     st.clear_blocks()
     x2 = rnd((3, 40, d), 81)
     got2 = enc.forward(st.tensor(x2)).numpy()                            # other extents → the cached plan, new Context

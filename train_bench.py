@@ -51,7 +51,13 @@ def model_flops(cfg) -> float:
 
 
 def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_rank: int,
-        mm: str = "tf32", use_graph: bool = True, bucket_mb: int = 32, init_device: bool = True):
+        mm: str = "tf32", use_graph: bool = True, bucket_mb: int = 32, init_device: bool = True,
+        sync: str | None = None):
+    """sync: how gradients are synchronised at world > 1 —
+         "nccl"   one ncclAllReduce(avg) per bucket on the collective stream, multi-tensor Adam afterwards
+         "peer"   the peer-memory all-reduce kernel (burn_b200/csrc/peer.cu) per bucket, Adam afterwards
+         "fused"  reduce-scatter → Adam on the owned 1/N shard → parameter all-gather in ONE peer-memory kernel per bucket
+       default: $B200_GRAD_SYNC, else "fused"."""
     import torch
     import torch.distributed as dist
     from burn_b200 import _abi as abi
@@ -78,11 +84,18 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
     params = model.params()
     n_params = sum(p.v.numel for p in params)
     opt = T.Adam(lr=1e-4)
-    comm = None
-    if world > 1:
+    comm = peer = None
+    sync = (sync or os.environ.get("B200_GRAD_SYNC", "fused")) if world > 1 else "none"
+    if sync not in ("none", "nccl", "peer", "fused"):
+        raise ValueError(f"unknown gradient sync mode {sync!r}")
+    if sync == "nccl":
         comm = Communicator(rank, world, device=torch.device("cuda", local_rank))
+    elif sync in ("peer", "fused"):
+        from burn_b200.distributed import PeerGroup
+        peer = PeerGroup(rank, world, T.ParamArena.peer_bytes(params), device=torch.device("cuda", local_rank))
     # flat p/m/v/g buckets: direct-to-bucket gradients, one all-reduce and one Adam launch per bucket
-    arena = T.ParamArena(params, comm, bucket_bytes=bucket_mb << 20)
+    arena = T.ParamArena(params, comm, bucket_bytes=bucket_mb << 20, peer=peer, fused=sync == "fused")
+    arena.attach_optimizer(opt)
 
     # ---- this rank's synthetic batch, pinned on the host, persistent device buffers
     rng = np.random.default_rng(5000 + rank)
@@ -206,9 +219,16 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
             f"decoder LM d_model {d}, {cfg['L']} layers, {cfg['h']} heads, d_ff {cfg['ff']}, vocab {cfg['vocab']}, seq {S}, "
             f"batch {B}/GPU, fwd+bwd+NCCL grad all-reduce+Adam"),
             "params": n_params, "tokens_per_step": tokens,
-            "parallelism": f"dp{world}" + (f", {len(arena.buckets)} ncclAllReduce(avg) per step on ~{bucket_mb} MiB flat buckets, "
-                                            f"overlapped with backward on the collective stream" if comm else "")
-                           + f"; multi-tensor Adam: {len(arena.buckets)} launches",
+            "parallelism": f"dp{world}" + {
+                "none": f"; multi-tensor Adam: {len(arena.buckets)} launches",
+                "nccl": f", {len(arena.buckets)} ncclAllReduce(avg) per step on ~{bucket_mb} MiB flat buckets, overlapped with "
+                        f"backward on the collective stream; multi-tensor Adam: {len(arena.buckets)} launches",
+                "peer": f", {len(arena.buckets)} peer-memory all-reduce kernels (NVLink loads/stores, no NCCL) per step on "
+                        f"~{bucket_mb} MiB flat buckets beside backward; multi-tensor Adam: {len(arena.buckets)} launches",
+                "fused": f", {len(arena.buckets)} fused reduce-scatter + Adam(1/{world} shard) + parameter all-gather kernels over "
+                         f"NVLink peer memory per step (~{bucket_mb} MiB flat buckets), running beside backward; optimizer state "
+                         f"sharded {world} ways; no NCCL on the data path"}[sync],
+            "grad_sync": sync,
             "launch": "cuda graph replay" if graph is not None else "eager (python launch loop)"},
         "model_tflops_per_s": round(flops / (ms_per_step * 1e-3) / 1e12, 1),
         "gpu_launches": launches, "kernels_per_step": launches // max(steps, 1),
@@ -222,6 +242,9 @@ def run(cfg_name: str, steps: int, warmup: int, rank: int, world: int, local_ran
         graph.destroy()             # before the communicator: NCCL waits for graphs that captured it
     if comm is not None:
         comm.close()
+    if peer is not None:
+        barrier()                   # nobody may still be writing into a region that is about to be unmapped
+        peer.close()
     return out
 
 
@@ -360,7 +383,7 @@ def run_via_stream(steps: int = 20, warmup: int = 3, mm: str = "tf32"):
         y = enc.forward(xs)
         d_ = y.device_tensor()            # flush: plan (or fetch the cached plan) and launch
         check(lib.b200_memcpy_d2d(out_stream.data_ptr(), d_.ptr, nbytes, None))
-        y.drop()
+        y.drop()                          # queue is empty here: the handle (and its buffer) is released at once
     t0 = time.perf_counter()
     stream_forward()
     check(lib.b200_device_sync())
@@ -413,6 +436,8 @@ def main():
     ap.add_argument("--mm", default="tf32", choices=["tf32", "bf16", "f32x3"])
     ap.add_argument("--eager", action="store_true")
     ap.add_argument("--bucket-mb", type=int, default=32)
+    ap.add_argument("--sync", default=None, choices=["nccl", "peer", "fused"],
+                    help="gradient synchronisation at world > 1 (default: $B200_GRAD_SYNC, else fused)")
     ap.add_argument("--via-stream", action="store_true",
                     help="configs[3] forward through the host fusion layer's operation stream vs the hand-sequenced forward")
     args = ap.parse_args()
@@ -427,7 +452,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    out = run(args.config, args.steps, args.warmup, rank, world, local_rank, args.mm, not args.eager, args.bucket_mb)
+    out = run(args.config, args.steps, args.warmup, rank, world, local_rank, args.mm, not args.eager, args.bucket_mb, sync=args.sync)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
