@@ -134,6 +134,7 @@ SIGNATURES = {
     "b200_collective_mark": (_i32, [_vp, _vp]),
     "b200_stream_wait_event": (_i32, [_vp, _vp]),
     "b200_jit_selftest": (_i32, [C.POINTER(C.c_uint64)]),
+    "b200_jit_cache_stats": (_i32, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "b200_launch_adam": (_i32, [_TP, _TP, _TP, _TP, _TP, C.c_double, C.c_double, C.c_double, _vp]),
     "b200_launch_softmax_backward": (_i32, [_TP, _TP, _TP, C.c_double, _TP, _vp]),
     "b200_layer_norm_backward_partials": (_i32, [_TP, C.POINTER(C.c_int32)]),

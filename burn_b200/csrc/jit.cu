@@ -36,7 +36,24 @@ struct Nvrtc {
 };
 static Nvrtc g_rtc;
 static std::mutex g_mu;
-static std::unordered_map<std::string, cudaKernel_t> g_cache;   // nullptr = compile failed, do not retry
+// Specialised kernels are shape-specialised, so a dynamic-shape workload keeps producing new ones: the cache is a
+// bounded LRU (B200_JIT_CACHE_MAX entries, default 512).  Evicting unloads the cubin; kernels of it may still be in
+// flight, so the device is drained first — never inside a stream capture, where eviction is simply postponed.
+struct CacheEntry {
+  cudaKernel_t kern = nullptr;   // nullptr = compile failed, do not retry
+  cudaLibrary_t lib = nullptr;
+  uint64_t tick = 0;
+};
+static std::unordered_map<std::string, CacheEntry> g_cache;
+static uint64_t g_tick = 0, g_evictions = 0;
+static size_t cache_max() {
+  static const size_t v = [] {
+    const char *e = std::getenv("B200_JIT_CACHE_MAX");
+    const long n = e ? atol(e) : 512;
+    return (size_t)(n >= 1 ? n : 512);
+  }();
+  return v;
+}
 
 static bool load_nvrtc() {
   if (g_rtc.tried) return g_rtc.ok;
@@ -71,8 +88,10 @@ static bool strict() {
   return v;
 }
 
-static bool dtype_in_ok(int32_t dt) { return dt == B200_F32 || dt == B200_I32 || dt == B200_BOOL || dt == B200_U8 || dt == B200_BF16; }
-static bool dtype_out_ok(int32_t dt) { return dt == B200_F32 || dt == B200_I32 || dt == B200_BOOL || dt == B200_U8; }
+static bool dtype_in_ok(int32_t dt) {
+  return dt == B200_F32 || dt == B200_I32 || dt == B200_BOOL || dt == B200_U8 || dt == B200_BF16 || dt == B200_F16;
+}
+static bool dtype_out_ok(int32_t dt) { return dtype_in_ok(dt); }
 
 // Generates the kernel source for a compiled tape over linear operands.
 struct Tuning {
@@ -155,7 +174,7 @@ static std::string generate(const CompiledTape &ct, const TapeParams &p, bool ra
 }
 
 static cudaKernel_t compile(const std::string &src, const char *kernel_name = "b200_jit_kernel", bool load = true,
-                            size_t *cubin_bytes = nullptr) {
+                            size_t *cubin_bytes = nullptr, cudaLibrary_t *lib_out = nullptr) {
   nvrtcProgram prog = nullptr;
   const char *hdr_src[] = {kJitSrc_burn_b200_h, kJitSrc_tape_eval_cuh, kJitSrc_tape_math_cuh, kJitSrc_erf_table_inc,
                            kJitSrc_stdint_h, kJitSrc_stdint_h};
@@ -180,6 +199,8 @@ static cudaKernel_t compile(const std::string &src, const char *kernel_name = "b
         cudaLibrary_t lib = nullptr;
         if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess) {
           if (cudaLibraryGetKernel(&kern, lib, kernel_name) != cudaSuccess) kern = nullptr;
+          if (kern && lib_out) *lib_out = lib;
+          else if (!kern) cudaLibraryUnload(lib);
         }
         if (!kern) {
           fprintf(stderr, "[burn_b200] loading a specialised kernel failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -189,6 +210,33 @@ static cudaKernel_t compile(const std::string &src, const char *kernel_name = "b
   }
   g_rtc.DestroyProgram(&prog);
   return kern;
+}
+
+// g_mu held.  Looks the source up, compiling on a miss; keeps the cache within its bound.
+static cudaKernel_t cached(const std::string &key, const std::string &src, const char *kernel_name, cudaStream_t stream) {
+  auto it = g_cache.find(key);
+  if (it == g_cache.end()) {
+    if (g_cache.size() >= cache_max()) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) cudaGetLastError();
+      if (cs == cudaStreamCaptureStatusNone) {
+        auto victim = g_cache.begin();
+        for (auto e = g_cache.begin(); e != g_cache.end(); ++e)
+          if (e->second.tick < victim->second.tick) victim = e;
+        if (victim->second.lib) {
+          cudaDeviceSynchronize();
+          cudaLibraryUnload(victim->second.lib);
+        }
+        g_cache.erase(victim);
+        ++g_evictions;
+      }
+    }
+    CacheEntry e;
+    e.kern = compile(src, kernel_name, true, nullptr, &e.lib);
+    it = g_cache.emplace(key, e).first;
+  }
+  it->second.tick = ++g_tick;
+  return it->second.kern;
 }
 
 // ---- fuse-on-read reductions --------------------------------------------------------------
@@ -377,9 +425,7 @@ int32_t jit_try_reduce(const CompiledTape &ct, const TapeParams &p, int rank_mod
     if (!jit::load_nvrtc()) return 0;
     const std::string src = jit::gen_reduce(ct, p, kind, col);
     const std::string key = src + "//" + kname;
-    auto it = jit::g_cache.find(key);
-    if (it == jit::g_cache.end()) it = jit::g_cache.emplace(key, jit::compile(src, kname)).first;
-    kern = it->second;
+    kern = jit::cached(key, src, kname, stream);
   }
   if (!kern) return jit::strict() ? fail(B200_ERR_CUDA, "NVRTC specialisation failed (see stderr) and B200_TAPE_JIT_STRICT is set") : 0;
   float *partials = nullptr;
@@ -431,9 +477,7 @@ int32_t jit_try_elemwise(const CompiledTape &ct, const TapeParams &p, int vec, i
     std::lock_guard<std::mutex> lock(jit::g_mu);
     if (!jit::load_nvrtc()) return 0;
     const std::string src = jit::generate(ct, p, rank3);
-    auto it = jit::g_cache.find(src);
-    if (it == jit::g_cache.end()) it = jit::g_cache.emplace(src, jit::compile(src)).first;
-    kern = it->second;
+    kern = jit::cached(src, src, "b200_jit_kernel", stream);
   }
   if (!kern) return jit::strict() ? fail(B200_ERR_CUDA, "NVRTC specialisation failed (see stderr) and B200_TAPE_JIT_STRICT is set") : 0;
   JitParams P;
@@ -516,5 +560,12 @@ extern "C" int32_t b200_jit_selftest(uint64_t *cubin_bytes_total) {
   all += "  p[3] = a;\n}\n";
   if ((st = check(all, "b200_jit_allops")) != B200_OK) return st;
   if (cubin_bytes_total) *cubin_bytes_total = total;
+  return B200_OK;
+}
+
+extern "C" int32_t b200_jit_cache_stats(uint64_t *entries, uint64_t *evictions) {
+  std::lock_guard<std::mutex> lock(b200::jit::g_mu);
+  if (entries) *entries = b200::jit::g_cache.size();
+  if (evictions) *evictions = b200::jit::g_evictions;
   return B200_OK;
 }

@@ -23,6 +23,7 @@
 // register, 225 KiB GEMM CTA leaves free on an SM.  NCCL's ring kernels cannot co-reside and time-slice with the GEMMs
 // (round-1 finding: +2.3 ms per step at N=2 with ~2 ms of wire time).  Epochs live in device memory and advance in the
 // kernel itself, so a captured CUDA graph replays without host patching.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -89,7 +90,7 @@ __device__ __forceinline__ void adam1(float &p, float &m, float &v, float g, con
 }
 
 template <int W, int MODE>
-__global__ void __launch_bounds__(kThreads) peer_bucket_kernel(const Args A) {
+__global__ void __launch_bounds__(kThreads, 6) peer_bucket_kernel(const Args A) {
   uint32_t *mine = A.flags[A.rank] + (size_t)A.slot * kSlotWords;
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t *>(mine + 16) + 1u;
   const int tid = threadIdx.x;
@@ -112,41 +113,56 @@ __global__ void __launch_bounds__(kThreads) peer_bucket_kernel(const Args A) {
     cf = __ldg(A.coef);
     eps_t = __ldg(A.coef + 1);
   }
-  for (uint64_t i = lo + (uint64_t)blockIdx.x * kThreads + tid; i < hi; i += (uint64_t)gridDim.x * kThreads) {
-    float4 part[W];
+  // U vectors per thread per trip so that U x W = 8 sixteen-byte loads are in flight per thread whatever the world size:
+  // an NVLink round trip is ~2-3 us, and 148 CTAs x 128 threads x 128 B = 2.4 MB in flight is what keeps ~0.8 TB/s busy
+  constexpr int U = W <= 2 ? 4 : (W <= 4 ? 2 : 1);
+  const uint64_t tpg = (uint64_t)gridDim.x * kThreads;
+  for (uint64_t i0 = lo + (uint64_t)blockIdx.x * kThreads + tid; i0 < hi; i0 += tpg * U) {
+    float4 part[U][W];
 #pragma unroll
-    for (int k = 0; k < W; ++k) part[k] = __ldcg(reinterpret_cast<const float4 *>(A.data[k] + A.g_off) + i);
-    float4 g = part[0];
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + u * tpg;
+      if (i < hi) {
 #pragma unroll
-    for (int k = 1; k < W; ++k) {
-      g.x = __fadd_rn(g.x, part[k].x);
-      g.y = __fadd_rn(g.y, part[k].y);
-      g.z = __fadd_rn(g.z, part[k].z);
-      g.w = __fadd_rn(g.w, part[k].w);
-    }
-    if (A.mean) {
-      if (A.pow2) {
-        g.x = __fmul_rn(g.x, A.inv_world); g.y = __fmul_rn(g.y, A.inv_world);
-        g.z = __fmul_rn(g.z, A.inv_world); g.w = __fmul_rn(g.w, A.inv_world);
-      } else {
-        g.x = __fdiv_rn(g.x, A.world_f); g.y = __fdiv_rn(g.y, A.world_f);
-        g.z = __fdiv_rn(g.z, A.world_f); g.w = __fdiv_rn(g.w, A.world_f);
+        for (int k = 0; k < W; ++k) part[u][k] = __ldcg(reinterpret_cast<const float4 *>(A.data[k] + A.g_off) + i);
       }
     }
-    if (MODE == MODE_ADAM) {
-      float4 p = __ldcg(reinterpret_cast<const float4 *>(A.data[A.rank] + A.p_off) + i);
-      float4 m = reinterpret_cast<float4 *>(A.m)[i], v = reinterpret_cast<float4 *>(A.v)[i];
-      adam1(p.x, m.x, v.x, g.x, A, cf, eps_t);
-      adam1(p.y, m.y, v.y, g.y, A, cf, eps_t);
-      adam1(p.z, m.z, v.z, g.z, A, cf, eps_t);
-      adam1(p.w, m.w, v.w, g.w, A, cf, eps_t);
-      reinterpret_cast<float4 *>(A.m)[i] = m;
-      reinterpret_cast<float4 *>(A.v)[i] = v;
 #pragma unroll
-      for (int k = 0; k < W; ++k) __stcg(reinterpret_cast<float4 *>(A.data[k] + A.p_off) + i, p);
-    } else {
+    for (int u = 0; u < U; ++u) {
+      const uint64_t i = i0 + u * tpg;
+      if (i >= hi) break;
+      float4 g = part[u][0];
 #pragma unroll
-      for (int k = 0; k < W; ++k) __stcg(reinterpret_cast<float4 *>(A.data[k] + A.g_off) + i, g);
+      for (int k = 1; k < W; ++k) {
+        g.x = __fadd_rn(g.x, part[u][k].x);
+        g.y = __fadd_rn(g.y, part[u][k].y);
+        g.z = __fadd_rn(g.z, part[u][k].z);
+        g.w = __fadd_rn(g.w, part[u][k].w);
+      }
+      if (A.mean) {
+        if (A.pow2) {
+          g.x = __fmul_rn(g.x, A.inv_world); g.y = __fmul_rn(g.y, A.inv_world);
+          g.z = __fmul_rn(g.z, A.inv_world); g.w = __fmul_rn(g.w, A.inv_world);
+        } else {
+          g.x = __fdiv_rn(g.x, A.world_f); g.y = __fdiv_rn(g.y, A.world_f);
+          g.z = __fdiv_rn(g.z, A.world_f); g.w = __fdiv_rn(g.w, A.world_f);
+        }
+      }
+      if (MODE == MODE_ADAM) {
+        float4 p = __ldcg(reinterpret_cast<const float4 *>(A.data[A.rank] + A.p_off) + i);
+        float4 m = __ldcs(reinterpret_cast<const float4 *>(A.m) + i), v = __ldcs(reinterpret_cast<const float4 *>(A.v) + i);
+        adam1(p.x, m.x, v.x, g.x, A, cf, eps_t);
+        adam1(p.y, m.y, v.y, g.y, A, cf, eps_t);
+        adam1(p.z, m.z, v.z, g.z, A, cf, eps_t);
+        adam1(p.w, m.w, v.w, g.w, A, cf, eps_t);
+        __stcs(reinterpret_cast<float4 *>(A.m) + i, m);
+        __stcs(reinterpret_cast<float4 *>(A.v) + i, v);
+#pragma unroll
+        for (int k = 0; k < W; ++k) __stcg(reinterpret_cast<float4 *>(A.data[k] + A.p_off) + i, p);
+      } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) __stcg(reinterpret_cast<float4 *>(A.data[k] + A.g_off) + i, g);
+      }
     }
   }
 
@@ -182,9 +198,12 @@ struct Group {
 
 template <int MODE>
 static int32_t launch(Group *g, const Args &A, cudaStream_t stream) {
-  // one CTA per SM is plenty: 148 x 128 threads x N 16-byte loads in flight
+  // two CTAs per SM: beside a persistent GEMM only one of them fits at a time (the other follows when the first is
+  // done); beside lighter kernels, or alone at the end of backward, both run
   const uint64_t per = ((A.n >> 2) + A.world - 1) / A.world;
-  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((per + kThreads - 1) / kThreads, (uint64_t)sm_count()));
+  const int u = A.world <= 2 ? 4 : (A.world <= 4 ? 2 : 1);
+  static const int ctas_per_sm = [] { const char *e = std::getenv("B200_PEER_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v >= 1 && v <= 16 ? v : 2; }();
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((per + kThreads * u - 1) / (kThreads * u), (uint64_t)ctas_per_sm * sm_count()));
   switch (A.world) {
 #define B200_PEER_CASE(W) \
   case W: peer_bucket_kernel<W, MODE><<<grid, kThreads, 0, stream>>>(A); break;

@@ -111,6 +111,26 @@ __device__ __forceinline__ uint32_t eval_op(uint32_t a, uint32_t b, uint32_t c) 
 }
 
 // ---- typed 4-element vector IO of the specialised kernels (subset of tape.cuh load_vec4/store_vec4)
+// Half-precision conversions as PTX (NVRTC sees no cuda_fp16.h): the instructions __half22float2,
+// __floats2half2_rn and __floats2bfloat162_rn compile to, so both execution modes round identically.
+__device__ __forceinline__ void jit_h2_to_f2(uint32_t h2, uint32_t &lo, uint32_t &hi) {
+  asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=r"(lo), "=r"(hi) : "r"(h2));
+}
+__device__ __forceinline__ uint32_t jit_h1_to_f(unsigned short h) {
+  uint32_t f;
+  asm("{ .reg .b16 l; mov.b16 l, %1; cvt.f32.f16 %0, l; }" : "=r"(f) : "h"(h));
+  return f;
+}
+__device__ __forceinline__ uint32_t jit_f2_to_h2(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(f_of(hi)), "f"(f_of(lo)));
+  return d;
+}
+__device__ __forceinline__ uint32_t jit_f2_to_bf2(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(f_of(hi)), "f"(f_of(lo)));
+  return d;
+}
 template <int DT>
 __device__ __forceinline__ void jit_ld4(const void *base, uint32_t v, uint32_t (&r)[4]) {
   if (DT == B200_F32 || DT == B200_I32) {
@@ -119,6 +139,10 @@ __device__ __forceinline__ void jit_ld4(const void *base, uint32_t v, uint32_t (
   } else if (DT == B200_BF16) {
     const uint2 q = __ldcs(reinterpret_cast<const uint2 *>(base) + v);
     r[0] = q.x << 16; r[1] = q.x & 0xFFFF0000u; r[2] = q.y << 16; r[3] = q.y & 0xFFFF0000u;
+  } else if (DT == B200_F16) {
+    const uint2 q = __ldcs(reinterpret_cast<const uint2 *>(base) + v);
+    jit_h2_to_f2(q.x, r[0], r[1]);
+    jit_h2_to_f2(q.y, r[2], r[3]);
   } else {  // BOOL / U8
     const uint32_t q = __ldcs(reinterpret_cast<const uint32_t *>(base) + v);
     r[0] = q & 0xFFu; r[1] = (q >> 8) & 0xFFu; r[2] = (q >> 16) & 0xFFu; r[3] = q >> 24;
@@ -128,18 +152,24 @@ template <int DT>
 __device__ __forceinline__ uint32_t jit_ld1(const void *base) {
   if (DT == B200_F32 || DT == B200_I32) return __ldg(reinterpret_cast<const uint32_t *>(base));
   if (DT == B200_BF16) return (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(base)) << 16;
+  if (DT == B200_F16) return jit_h1_to_f(__ldg(reinterpret_cast<const unsigned short *>(base)));
   return (uint32_t)__ldg(reinterpret_cast<const unsigned char *>(base));
 }
 template <int DT>
 __device__ __forceinline__ uint32_t jit_ld1_at(const void *base, uint32_t off) {
   if (DT == B200_F32 || DT == B200_I32) return __ldg(reinterpret_cast<const uint32_t *>(base) + off);
   if (DT == B200_BF16) return (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(base) + off) << 16;
+  if (DT == B200_F16) return jit_h1_to_f(__ldg(reinterpret_cast<const unsigned short *>(base) + off));
   return (uint32_t)__ldg(reinterpret_cast<const unsigned char *>(base) + off);
 }
 template <int DT>
 __device__ __forceinline__ void jit_st4(void *base, uint32_t v, const uint32_t (&r)[4]) {
   if (DT == B200_F32 || DT == B200_I32) {
     __stcs(reinterpret_cast<uint4 *>(base) + v, make_uint4(r[0], r[1], r[2], r[3]));
+  } else if (DT == B200_BF16) {
+    __stcs(reinterpret_cast<uint2 *>(base) + v, make_uint2(jit_f2_to_bf2(r[0], r[1]), jit_f2_to_bf2(r[2], r[3])));
+  } else if (DT == B200_F16) {
+    __stcs(reinterpret_cast<uint2 *>(base) + v, make_uint2(jit_f2_to_h2(r[0], r[1]), jit_f2_to_h2(r[2], r[3])));
   } else {  // BOOL / U8
     __stcs(reinterpret_cast<uint32_t *>(base) + v,
            (r[0] & 0xFFu) | ((r[1] & 0xFFu) << 8) | ((r[2] & 0xFFu) << 16) | (r[3] << 24));

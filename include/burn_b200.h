@@ -524,6 +524,9 @@ int32_t b200_peer_host_sync(b200_peer_group group);
 /* NVRTC specialisation self-test: generates and compiles (sm_100a, no device needed, nothing loaded)
  * the specialised elementwise and fuse-on-read reduce kernels of the bench chain; reports the cubin bytes. */
 int32_t b200_jit_selftest(uint64_t *cubin_bytes_total);
+/* The specialised-kernel cache is a bounded LRU (B200_JIT_CACHE_MAX, default 512 kernels; an evicted cubin is
+ * unloaded): how many kernels it holds and how many it has evicted. */
+int32_t b200_jit_cache_stats(uint64_t *entries, uint64_t *evictions);
 
 /* ------------------------------------------------ introspection */
 /* Number of kernels this library has launched since load (bench.py's

@@ -60,6 +60,15 @@ run(TapeBuilder().op("I2F", ("in", 0), out=0), [dia])
 run(TapeBuilder().op("B2F", ("in", 0), out=0), [dm])
 tb = TapeBuilder(); tb.op("MUL_F", ("in", 0), ("in", 1), tmp=0, out=1); tb.op("ADD_F", ("tmp", 0), ("in", 2)); tb.op("EXP_F", "acc", out=0)
 run(tb, [da, db, H.up(np.float32([0.25]).reshape(1)).expand((n,))], n_out=2, dts=(abi.F32, abi.F32))
+# half-precision storage on both sides of a specialised tape: bf16 / f16 inputs and OUTPUTS (rounded RN-even by the same
+# instructions in both modes)
+hb = H.up((rng.uniform(-3, 3, n).astype(np.float32).view(np.uint32) >> 16).astype(np.uint16), abi.BF16)
+hf = H.up(rng.uniform(-3, 3, n).astype(np.float16).view(np.uint16), abi.F16)
+for odt in (abi.BF16, abi.F16):
+    tb = TapeBuilder(); tb.op("MUL_F", ("in", 0), ("in", 1)); tb.op("ADD_F", "acc", ("in", 2)); tb.op("TANH_F", "acc", out=0)
+    run(tb, [hb, hf, da], dts=(odt,))
+    tb = TapeBuilder(); tb.op("MUL_F", ("in", 0), ("f", 1.0009765625), out=0); tb.op("EXP_F", "acc", out=1)
+    run(tb, [hf if odt == abi.F16 else hb], n_out=2, dts=(odt, abi.F32))
 # rank-3 specialisation: row / column broadcasts, a sliced (row-strided) operand and a strided output
 R, Cc = 2048, 1024
 x2 = rng.uniform(-2, 2, (R, Cc)).astype(np.float32); rowv = rng.uniform(-2, 2, (1, Cc)).astype(np.float32)
@@ -98,3 +107,38 @@ def test_specialised_kernels_match_the_interpreter_bit_for_bit(dev):
     assert len(jit) == len(interp) > 50
     differing = [k for k in interp if jit.get(k) != interp[k]]
     assert not differing, f"specialised kernel != interpreter for {differing}"
+
+
+EVICT = r'''
+import sys, ctypes as C
+import numpy as np
+sys.path.insert(0, %r)
+from burn_b200 import _abi as abi, device as dv
+from burn_b200.device import DeviceTensor, TapeBuilder
+from oracle import oracle
+dv.init(0)
+lib = abi.load()
+rng = np.random.default_rng(1)
+def once(rows):
+    x = rng.uniform(-2, 2, (rows, 1024)).astype(np.float32)
+    row = rng.uniform(-2, 2, (1, 1024)).astype(np.float32)
+    out = DeviceTensor.empty((rows, 1024))
+    tb = TapeBuilder().op("ADD_F", ("in", 0), ("in", 1)); tb.op("MUL_F", "acc", ("f", 0.5), out=0)
+    dv.launch_elemwise(tb.build(), [DeviceTensor.from_numpy(x), DeviceTensor.from_numpy(row).expand((rows, 1024))], [out], (rows, 1024))
+    assert np.array_equal(out.numpy(), oracle.float_mul_scalar(oracle.float_add(x, row), 0.5)), rows
+for rows in (1100, 1200, 1300, 1400, 1100, 1500, 1200):      # shape-specialised: every new row count is a new kernel
+    once(rows)
+n, ev = C.c_uint64(), C.c_uint64()
+abi.check(lib.b200_jit_cache_stats(C.byref(n), C.byref(ev)))
+print("STATS", n.value, ev.value)
+'''
+
+
+def test_specialised_kernel_cache_is_bounded(dev):
+    """Dynamic shapes must not grow the cache (and the loaded cubins) without bound: with room for two kernels, seven
+    launches over five shapes evict at least three times and every result is still right."""
+    env = dict(os.environ, B200_JIT_CACHE_MAX="2", B200_TAPE_JIT="1", B200_TAPE_JIT_STRICT="1")
+    r = subprocess.run([sys.executable, "-c", EVICT % ROOT], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    entries, evictions = map(int, [l for l in r.stdout.splitlines() if l.startswith("STATS")][0].split()[1:])
+    assert entries <= 2 and evictions >= 3
