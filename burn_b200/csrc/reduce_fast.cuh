@@ -76,6 +76,59 @@ __device__ __forceinline__ VI fold(VI a, float x, int32_t idx) {
   return a;
 }
 
+// NaN-propagating extremes in one instruction (max.NaN / min.NaN, sm_80+)
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float min_nan(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+// Folds a batch of four vectors (element index of v[k].x = first[k], increasing in k; ok[k] = vector in range; vectors out
+// of range hold the identity).  Sum: 16 adds.  Extremes: ONE instruction per element — the batch extreme by a
+// NaN-propagating tree — and one test per batch: only when the batch holds something that beats the running value
+// (a new extreme, or the first NaN) is it walked element by element with the sequential rule, which is what keeps
+// "first extreme / first NaN wins" exact.  For random data a thread takes the slow walk O(log n) times.
+template <int K>
+__device__ __forceinline__ VI fold_batch(VI a, const float4 (&v)[4], const int32_t (&first)[4], const bool (&ok)[4]) {
+  if constexpr (K == kSum) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ok[k]) {
+        a.v = __fadd_rn(a.v, v[k].x); a.v = __fadd_rn(a.v, v[k].y); a.v = __fadd_rn(a.v, v[k].z); a.v = __fadd_rn(a.v, v[k].w);
+      }
+    return a;
+  } else {
+    constexpr bool kIsMax = (K == kMax || K == kArgMax);
+    auto ext = [](float x, float y) { return kIsMax ? max_nan(x, y) : min_nan(x, y); };
+    float m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = ext(ext(v[k].x, v[k].y), ext(v[k].z, v[k].w));
+    const float mm = ext(ext(m[0], m[1]), ext(m[2], m[3]));
+    if constexpr (K == kMax || K == kMin) {
+      a.v = ext(a.v, mm);                       // NaN sticks: ext(NaN, x) = NaN
+      return a;
+    } else {
+      const bool beats = kIsMax ? !(mm <= a.v) : !(mm >= a.v);
+      if (beats && a.v == a.v) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (ok[k]) {
+            a = fold<K>(a, v[k].x, first[k]);
+            a = fold<K>(a, v[k].y, first[k] + 1);
+            a = fold<K>(a, v[k].z, first[k] + 2);
+            a = fold<K>(a, v[k].w, first[k] + 3);
+          }
+      }
+      return a;
+    }
+  }
+}
+
 template <int K>
 __device__ __forceinline__ VI warp_reduce(VI a) {
 #pragma unroll
@@ -139,21 +192,17 @@ __global__ void __launch_bounds__(kBlock) reduce_row_fast_kernel(const RowParams
     if (begin + threadIdx.x < end) a.i = (int32_t)((begin + threadIdx.x) * 4);
     for (uint32_t base = begin + threadIdx.x; base < end; base += kBlock * 4) {
       float4 v[4];
+      int32_t first[4];
+      bool ok[4];
+      const float idv = identity<K>().v;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t i = base + k * kBlock;
-        v[k] = i < end ? __ldcs(p + i) : make_float4(0, 0, 0, 0);
+        ok[k] = i < end;
+        first[k] = (int32_t)(i * 4);
+        v[k] = ok[k] ? __ldcs(p + i) : make_float4(idv, idv, idv, idv);
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t i = base + k * kBlock;
-        if (i < end) {
-          a = fold<K>(a, v[k].x, (int32_t)(i * 4));
-          a = fold<K>(a, v[k].y, (int32_t)(i * 4 + 1));
-          a = fold<K>(a, v[k].z, (int32_t)(i * 4 + 2));
-          a = fold<K>(a, v[k].w, (int32_t)(i * 4 + 3));
-        }
-      }
+      a = fold_batch<K>(a, v, first, ok);
     }
     a = block_reduce<K>(a, scratch);
     if (P.splits == 1) {
@@ -196,21 +245,17 @@ __global__ void __launch_bounds__(kBlock) reduce_row_warp_fast_kernel(const RowP
     if ((uint32_t)lane < P.r4) a.i = lane * 4;
     for (uint32_t base = lane; base < P.r4; base += 32 * 4) {
       float4 v[4];
+      int32_t first[4];
+      bool ok[4];
+      const float idv = identity<K>().v;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t i = base + k * 32;
-        v[k] = i < P.r4 ? __ldcs(p + i) : make_float4(0, 0, 0, 0);
+        ok[k] = i < P.r4;
+        first[k] = (int32_t)(i * 4);
+        v[k] = ok[k] ? __ldcs(p + i) : make_float4(idv, idv, idv, idv);
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t i = base + k * 32;
-        if (i < P.r4) {
-          a = fold<K>(a, v[k].x, (int32_t)(i * 4));
-          a = fold<K>(a, v[k].y, (int32_t)(i * 4 + 1));
-          a = fold<K>(a, v[k].z, (int32_t)(i * 4 + 2));
-          a = fold<K>(a, v[k].w, (int32_t)(i * 4 + 3));
-        }
-      }
+      a = fold_batch<K>(a, v, first, ok);
     }
     a = warp_reduce<K>(a);
     if (lane == 0) store_result<K>(P.out, P.out_dtype, row, a, P.mean, P.div);
