@@ -139,6 +139,7 @@ SIGNATURES = {
     "b200_launch_softmax_backward": (_i32, [_TP, _TP, _TP, C.c_double, _TP, _vp]),
     "b200_layer_norm_backward_partials": (_i32, [_TP, C.POINTER(C.c_int32)]),
     "b200_launch_layer_norm_backward": (_i32, [_TP, _TP, _TP, C.c_double, _TP, _TP, _TP, _vp]),
+    "b200_launch_layer_norm_backward_ex": (_i32, [_TP, _TP, _TP, C.c_double, _TP, _TP, _TP, _TP, _vp]),
     "b200_comm_unique_id": (_i32, [C.POINTER(C.c_uint8)]),
     "b200_comm_init": (_i32, [C.POINTER(_vp), C.POINTER(C.c_uint8), _i32, _i32]),
     "b200_comm_destroy": (_i32, [_vp]),

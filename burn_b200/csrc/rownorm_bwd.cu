@@ -38,6 +38,7 @@ struct SoftmaxBwd {
 struct LayerNormBwd {
   const float *x, *dy, *gamma;
   float *dx, *pgamma, *pbeta;  // partials [gridDim.x, R]
+  float *pdx;                  // optional third partial: column sums of dx (the bias gradient of the Linear that fed x)
   int64_t x_stride, dy_stride, dx_stride;
   uint32_t rows, R;
   float eps;
@@ -133,9 +134,10 @@ __global__ void __launch_bounds__(kBlock) layer_norm_bwd_warp_kernel(const Layer
   extern __shared__ float4 part[];   // [2][kWarps][r4] cross-warp combine of the dgamma / dbeta partials
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t r4 = P.R >> 2;
-  float4 ag[V], ab[V];
+  float4 ag[V], ab[V], ad[V];
 #pragma unroll
-  for (int k = 0; k < V; ++k) ag[k] = ab[k] = make_float4(0, 0, 0, 0);
+  for (int k = 0; k < V; ++k) ag[k] = ab[k] = ad[k] = make_float4(0, 0, 0, 0);
+  const bool want_dx = P.pdx != nullptr;
   const float invR = 1.0f / (float)P.R;
   for (uint32_t row = blockIdx.x * kWarps + warp; row < P.rows; row += gridDim.x * kWarps) {
     const float4 *xr = reinterpret_cast<const float4 *>(P.x + (int64_t)row * P.x_stride);
@@ -188,6 +190,10 @@ __global__ void __launch_bounds__(kBlock) layer_norm_bwd_warp_kernel(const Layer
       o.z = __fdiv_rn(__fsub_rn(__fsub_rn(g[k].z, m1), __fmul_rn(x[k].z, m2)), denom);
       o.w = __fdiv_rn(__fsub_rn(__fsub_rn(g[k].w, m1), __fmul_rn(x[k].w, m2)), denom);
       __stcs(dxr + i, o);
+      if (want_dx) {
+        ad[k].x = __fadd_rn(ad[k].x, o.x); ad[k].y = __fadd_rn(ad[k].y, o.y);
+        ad[k].z = __fadd_rn(ad[k].z, o.z); ad[k].w = __fadd_rn(ad[k].w, o.w);
+      }
     }
   }
   // combine the CTA's warps (fixed order), one partial row per CTA
@@ -208,6 +214,23 @@ __global__ void __launch_bounds__(kBlock) layer_norm_bwd_warp_kernel(const Layer
     reinterpret_cast<float4 *>(P.pgamma + (size_t)blockIdx.x * P.R)[i] = a;
     reinterpret_cast<float4 *>(P.pbeta + (size_t)blockIdx.x * P.R)[i] = b;
   }
+  if (want_dx) {   // third partial through the same (now free) staging area
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const uint32_t i = lane + k * 32;
+      if (i < r4) pg[(size_t)warp * r4 + i] = ad[k];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < r4; i += kBlock) {
+      float4 a = pg[i];
+      for (int w = 1; w < kWarps; ++w) {
+        const float4 a2 = pg[(size_t)w * r4 + i];
+        a.x = __fadd_rn(a.x, a2.x); a.y = __fadd_rn(a.y, a2.y); a.z = __fadd_rn(a.z, a2.z); a.w = __fadd_rn(a.w, a2.w);
+      }
+      reinterpret_cast<float4 *>(P.pdx + (size_t)blockIdx.x * P.R)[i] = a;
+    }
+  }
 }
 
 // generic R: one CTA per row, three streaming passes; column partials accumulated per thread
@@ -216,7 +239,11 @@ __global__ void __launch_bounds__(kBlock) layer_norm_bwd_cta_kernel(const LayerN
   __shared__ float scratch[kWarps];
   const float invR = 1.0f / (float)P.R;
   float *pg = P.pgamma + (size_t)blockIdx.x * P.R, *pb = P.pbeta + (size_t)blockIdx.x * P.R;
-  for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) pg[i] = pb[i] = 0.f;
+  float *pd = P.pdx ? P.pdx + (size_t)blockIdx.x * P.R : nullptr;
+  for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) {
+    pg[i] = pb[i] = 0.f;
+    if (pd) pd[i] = 0.f;
+  }
   for (uint32_t row = blockIdx.x; row < P.rows; row += gridDim.x) {
     const float *xr = P.x + (int64_t)row * P.x_stride;
     const float *gr = P.dy + (int64_t)row * P.dy_stride;
@@ -246,7 +273,9 @@ __global__ void __launch_bounds__(kBlock) layer_norm_bwd_cta_kernel(const LayerN
     for (uint32_t i = threadIdx.x; i < P.R; i += kBlock) {
       const float xh = __fdiv_rn(__fsub_rn(xr[i], mean), denom);
       const float g = P.gamma ? __fmul_rn(gr[i], __ldg(P.gamma + i)) : gr[i];
-      dxr[i] = __fdiv_rn(__fsub_rn(__fsub_rn(g, m1), __fmul_rn(xh, m2)), denom);
+      const float o = __fdiv_rn(__fsub_rn(__fsub_rn(g, m1), __fmul_rn(xh, m2)), denom);
+      dxr[i] = o;
+      if (pd) pd[i] = __fadd_rn(pd[i], o);
     }
   }
 }
@@ -360,6 +389,13 @@ extern "C" int32_t b200_launch_layer_norm_backward(const b200_tensor *input, con
                                                    const b200_tensor *gamma, double eps, const b200_tensor *dx,
                                                    const b200_tensor *partial_gamma, const b200_tensor *partial_beta,
                                                    b200_stream s) {
+  return b200_launch_layer_norm_backward_ex(input, dy, gamma, eps, dx, partial_gamma, partial_beta, nullptr, s);
+}
+
+extern "C" int32_t b200_launch_layer_norm_backward_ex(const b200_tensor *input, const b200_tensor *dy,
+                                                      const b200_tensor *gamma, double eps, const b200_tensor *dx,
+                                                      const b200_tensor *partial_gamma, const b200_tensor *partial_beta,
+                                                      const b200_tensor *partial_dx, b200_stream s) {
   B200_REQUIRE(input && dy && dx && partial_gamma && partial_beta, B200_ERR_INVALID, "null argument");
   B200_REQUIRE(input->rank == dy->rank && input->rank == dx->rank, B200_ERR_SHAPE, "layer_norm_backward rank mismatch");
   for (int d = 0; d < input->rank; ++d)
@@ -374,7 +410,8 @@ extern "C" int32_t b200_launch_layer_norm_backward(const b200_tensor *input, con
   if ((st = rnb::rows_view(*dx, rows2, R2, P.dx_stride, "layer_norm_backward dx")) != B200_OK) return st;
   int32_t G = 0;
   if ((st = b200_layer_norm_backward_partials(input, &G)) != B200_OK) return st;
-  for (const b200_tensor *t : {partial_gamma, partial_beta}) {
+  for (const b200_tensor *t : {partial_gamma, partial_beta, partial_dx}) {
+    if (!t) continue;
     B200_REQUIRE(t->dtype == B200_F32 && t->ptr && t->rank == 2 && t->shape[0] == G && t->shape[1] == (int64_t)P.R &&
                      t->strides[1] == 1 && t->strides[0] == (int64_t)P.R,
                  B200_ERR_SHAPE, "layer_norm_backward partials must be contiguous f32 [%d, %u]", G, P.R);
@@ -392,15 +429,17 @@ extern "C" int32_t b200_launch_layer_norm_backward(const b200_tensor *input, con
   P.dx = reinterpret_cast<float *>(dx->ptr);
   P.pgamma = reinterpret_cast<float *>(partial_gamma->ptr);
   P.pbeta = reinterpret_cast<float *>(partial_beta->ptr);
+  P.pdx = partial_dx ? reinterpret_cast<float *>(partial_dx->ptr) : nullptr;
   P.eps = (float)eps;
   cudaStream_t stream = resolve_stream(s);
   if (P.rows == 0 || P.R == 0) {
     B200_CUDA(cudaMemsetAsync(P.pgamma, 0, (size_t)G * P.R * 4, stream));
     B200_CUDA(cudaMemsetAsync(P.pbeta, 0, (size_t)G * P.R * 4, stream));
+    if (P.pdx) B200_CUDA(cudaMemsetAsync(P.pdx, 0, (size_t)G * P.R * 4, stream));
     return B200_OK;
   }
   const bool vec_ok = P.R % 4 == 0 && P.R <= 2048 && rnb::aligned16(P.x) && rnb::aligned16(P.dy) && rnb::aligned16(P.dx) &&
-                      rnb::aligned16(P.pgamma) && rnb::aligned16(P.pbeta) && (!P.gamma || rnb::aligned16(P.gamma)) &&
+                      rnb::aligned16(P.pgamma) && rnb::aligned16(P.pbeta) && (!P.pdx || rnb::aligned16(P.pdx)) && (!P.gamma || rnb::aligned16(P.gamma)) &&
                       P.x_stride % 4 == 0 && P.dy_stride % 4 == 0 && P.dx_stride % 4 == 0;
   if (vec_ok) {
     const uint32_t r4 = P.R / 4;

@@ -416,9 +416,11 @@ def softmax_backward(y: DeviceTensor, dy: DeviceTensor, mask: DeviceTensor | Non
     return out
 
 
-def layer_norm_backward(x: DeviceTensor, dy: DeviceTensor, gamma: DeviceTensor | None, eps: float):
+def layer_norm_backward(x: DeviceTensor, dy: DeviceTensor, gamma: DeviceTensor | None, eps: float, want_dx_sum: bool = False):
     """(dx, dgamma, dbeta) of layer_norm over the last axis: one row-resident kernel plus the
-    deterministic column reduce of its per-CTA partials (b200_launch_layer_norm_backward)."""
+    deterministic column reduce of its per-CTA partials (b200_launch_layer_norm_backward).
+    want_dx_sum: also return colsum(dx) — the bias gradient of the Linear that produced x — from a third partial the
+    same kernel emits (b200_launch_layer_norm_backward_ex), instead of a separate pass over dx."""
     lib = abi.load()
     d = x.shape[-1]
     dx = DeviceTensor.empty(x.shape)
@@ -428,9 +430,15 @@ def layer_norm_backward(x: DeviceTensor, dy: DeviceTensor, gamma: DeviceTensor |
     pg, pb = DeviceTensor.empty((n.value, d)), DeviceTensor.empty((n.value, d))
     pgd, pbd = pg.desc(), pb.desc()
     gm = gamma.desc() if gamma is not None else None
-    check(lib.b200_launch_layer_norm_backward(C.byref(a), C.byref(g), C.byref(gm) if gm is not None else None,
-                                              float(eps), C.byref(o), C.byref(pgd), C.byref(pbd), None))
-    return dx, float_sum_dim(pg, 0).reshape((d,)), float_sum_dim(pb, 0).reshape((d,))
+    if not want_dx_sum:
+        check(lib.b200_launch_layer_norm_backward(C.byref(a), C.byref(g), C.byref(gm) if gm is not None else None,
+                                                  float(eps), C.byref(o), C.byref(pgd), C.byref(pbd), None))
+        return dx, float_sum_dim(pg, 0).reshape((d,)), float_sum_dim(pb, 0).reshape((d,))
+    pd = DeviceTensor.empty((n.value, d))
+    pdd = pd.desc()
+    check(lib.b200_launch_layer_norm_backward_ex(C.byref(a), C.byref(g), C.byref(gm) if gm is not None else None,
+                                                 float(eps), C.byref(o), C.byref(pgd), C.byref(pbd), C.byref(pdd), None))
+    return dx, float_sum_dim(pg, 0).reshape((d,)), float_sum_dim(pb, 0).reshape((d,)), float_sum_dim(pd, 0).reshape((d,))
 
 
 def attention(q: DeviceTensor, k: DeviceTensor, v: DeviceTensor, mask: DeviceTensor | None = None, scale: float | None = None,

@@ -32,10 +32,11 @@ from .device import DeviceTensor, TapeBuilder
 # ------------------------------------------------------------------ reverse tape (burn-autodiff)
 class Var:
     """A tensor on the autodiff tape."""
-    __slots__ = ("v", "g", "requires_grad", "name")
+    __slots__ = ("v", "g", "requires_grad", "name", "aux")
 
     def __init__(self, v: DeviceTensor, requires_grad: bool = False, name: str = ""):
         self.v, self.g, self.requires_grad, self.name = v, None, requires_grad, name
+        self.aux = None     # notes between backward steps (e.g. a bias gradient the consumer's backward already produced)
 
 
 class Tape:
@@ -130,6 +131,8 @@ def linear(tape: Tape, x: Var, w: Var, b: Var | None, residual: Var | None = Non
         if residual is not None:
             y2 = ops.float_add(residual.v.reshape((m, n_out)), y2)
     y = Var(y2.reshape(tuple(lead) + (n_out,)), True)
+    if b is not None and b.requires_grad:
+        y.aux = {"wants_bias_grad": True}     # a consumer whose backward streams dy anyway may leave colsum(dy) here
 
     def bw():
         if y.g is None:
@@ -138,7 +141,15 @@ def linear(tape: Tape, x: Var, w: Var, b: Var | None, residual: Var | None = Non
             accumulate(residual, y.g)
         g2 = y.g.reshape((m, w.v.shape[1]))
         if x.requires_grad:
-            accumulate(x, ops.float_matmul(g2, w.v.swap_dims(0, 1), tape.precision).reshape(x.v.shape))
+            if x.g is not None and x.v.shape[-1] % 4 == 0 and x.g.is_contiguous() and getattr(x, "on_grad", None) is None:
+                # x already holds a gradient (the residual branch, the other projections of the same input): the
+                # accumulation `x.g + dx` (burn-autodiff sums contributions with float_add) rides this GEMM's epilogue
+                # instead of a separate pass over three [tokens, d] tensors — same single rounded add
+                epi = TapeBuilder().op("ADD_F", ("in", 1), ("in", 0), out=0).build()
+                x.g = ops.float_matmul(g2, w.v.swap_dims(0, 1), tape.precision, epi,
+                                       (x.g.reshape((m, x.v.shape[-1])),)).reshape(x.v.shape)
+            else:
+                accumulate(x, ops.float_matmul(g2, w.v.swap_dims(0, 1), tape.precision).reshape(x.v.shape))
         if w.requires_grad:
             slot = getattr(w, "grad_slot", None)
             if slot is not None and w.g is None:      # the GEMM writes the bucket slot directly
@@ -146,7 +157,11 @@ def linear(tape: Tape, x: Var, w: Var, b: Var | None, residual: Var | None = Non
             else:
                 accumulate(w, ops.float_matmul(x2.swap_dims(0, 1), g2, tape.precision))
         if b is not None and b.requires_grad:
-            accumulate(b, ops.float_sum_dim(g2, 0).reshape(b.v.shape))   # linear_bias_backward: column reduce
+            ready = (y.aux or {}).get("bias_grad")
+            if ready is not None and ready[1] is y.g:                    # colsum of exactly this gradient, made by its producer
+                accumulate(b, ready[0].reshape(b.v.shape))
+            else:
+                accumulate(b, ops.float_sum_dim(g2, 0).reshape(b.v.shape))   # linear_bias_backward: column reduce
     tape.add(bw)
     return y
 
@@ -224,7 +239,12 @@ def layer_norm(tape: Tape, x: Var, gamma: Var, beta: Var, eps: float = 1e-5) -> 
             return
         # one row-resident kernel: statistics recomputed on chip, dx written once, dgamma/dbeta as
         # per-CTA partials finished by a column reduce
-        dx, dgamma, dbeta = ops.layer_norm_backward(x.v, y.g, gamma.v, eps)
+        want = bool(x.aux and x.aux.get("wants_bias_grad")) and x.g is None
+        if want:       # x = Linear(...) and this is its only gradient: the kernel also emits colsum(dx) = that Linear's bias gradient
+            dx, dgamma, dbeta, dxsum = ops.layer_norm_backward(x.v, y.g, gamma.v, eps, want_dx_sum=True)
+            x.aux["bias_grad"] = (dxsum, dx)
+        else:
+            dx, dgamma, dbeta = ops.layer_norm_backward(x.v, y.g, gamma.v, eps)
         if gamma.requires_grad:
             accumulate(gamma, dgamma.reshape(gamma.v.shape))
         if beta.requires_grad:

@@ -372,6 +372,14 @@ int32_t b200_launch_layer_norm_backward(const b200_tensor *input, const b200_ten
                                         const b200_tensor *dx,
                                         const b200_tensor *partial_gamma,
                                         const b200_tensor *partial_beta, b200_stream s);
+/* Same, plus an optional third partial `partial_dx` [n_partials, R]: per-CTA column sums of dx.  When x came from a
+ * Linear (x = h·W + b [+ residual]), colsum(dx) IS that Linear's bias gradient (linear_bias_backward,
+ * crates/burn-backend/src/backend/ops/modules/linear.rs:117-128): the [tokens, d] column reduce that would re-read
+ * dx disappears.  NULL = not wanted. */
+int32_t b200_launch_layer_norm_backward_ex(const b200_tensor *input, const b200_tensor *dy,
+                                           const b200_tensor *gamma, double eps, const b200_tensor *dx,
+                                           const b200_tensor *partial_gamma, const b200_tensor *partial_beta,
+                                           const b200_tensor *partial_dx, b200_stream s);
 
 /* Cross-entropy on logits, value and gradient in one row-resident pass:
  * picked[r] = log_softmax(logits[r])[targets[r]] (the tensor CrossEntropyLoss::forward_default
