@@ -13,6 +13,9 @@
 // registers (128-bit loads, shuffle trees); longer rows (up to ~57 K f32, e.g. a 50 257-entry
 // vocabulary) are staged once in shared memory by a whole CTA.  HBM traffic = one read + one
 // write of the tensor.  Roofline: HBM; algorithmic bytes = 8 B / element.
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -401,6 +404,117 @@ __global__ void __launch_bounds__(kXBlock) softmax_xent_kernel(const XentParams 
   }
 }
 
+// The same computation for rows too long for two CTAs per SM (a 50 260-class row is 196 KB): a CLUSTER of two CTAs
+// owns a row, each staging one half (98 KB, 512 threads), so every SM hosts halves of two different rows whose phases
+// drift apart — one streams its gradient out / its next row in while the other runs the shared-memory-only max and
+// sum passes.  The halves meet twice per row through distributed shared memory (max, then sum-of-exponentials, added
+// rank 0 first so the result does not depend on which CTA asks).  Exchange slots are double-buffered by row parity:
+// a slot is rewritten two rows later, after a cluster barrier the peer can only have passed once it had read it.
+constexpr int kXPair = 512;
+__device__ __forceinline__ float pblock_sum(float v, float *scratch) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return warp_sum((threadIdx.x & 31) < kXPair / 32 ? scratch[threadIdx.x & 31] : 0.0f);
+}
+__device__ __forceinline__ float pblock_max(float v, float *scratch) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) v = nan_max(v, __shfl_xor_sync(0xffffffffu, v, s));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = (threadIdx.x & 31) < kXPair / 32 ? scratch[threadIdx.x & 31] : -INFINITY;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) r = nan_max(r, __shfl_xor_sync(0xffffffffu, r, s));
+  return r;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXPair, 2) softmax_xent_pair_kernel(const XentParams P) {
+  namespace cg = cooperative_groups;
+  extern __shared__ __align__(16) float rowbuf[];   // this CTA's half of the row
+  __shared__ float scratch[kXPair / 32];
+  __shared__ float xch[2][2];                        // [row parity][0 = max, 1 = sum]
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t crank = cluster.block_rank();
+  const float *peer = cluster.map_shared_rank(&xch[0][0], crank ^ 1u);
+  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint32_t R4 = P.R >> 2, h4 = (R4 + 1) >> 1;
+  const uint32_t lo4 = crank * h4, hi4 = min(R4, lo4 + h4), n4 = hi4 > lo4 ? hi4 - lo4 : 0u;
+  float4 *b4 = reinterpret_cast<float4 *>(rowbuf);
+  if (pair < P.rows) {
+    const float4 *x4 = reinterpret_cast<const float4 *>(P.x + (int64_t)pair * P.x_stride) + lo4;
+    for (uint32_t i = threadIdx.x; i < n4; i += kXPair) xent_cp16(b4 + i, x4 + i);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  const float kL2e = 1.4426950408889634f;
+  uint32_t parity = 0;
+  for (uint32_t row = pair; row < P.rows; row += n_pairs, parity ^= 1u) {
+    float *dr = P.dx + (int64_t)row * P.dx_stride;
+    int64_t t = P.target_i64 ? reinterpret_cast<const long long *>(P.targets)[row]
+                             : (int64_t) reinterpret_cast<const int32_t *>(P.targets)[row];
+    if (t < 0 || t >= (int64_t)P.R) {
+      if (threadIdx.x == 0 && crank == 0) *P.err = kIdxErrTarget;
+      t = -1;
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();
+    float m = -INFINITY;
+    for (uint32_t i = threadIdx.x; i < n4; i += kXPair) {
+      const float4 v = b4[i];
+      m = nan_max(m, nan_max(nan_max(v.x, v.y), nan_max(v.z, v.w)));
+    }
+    m = pblock_max(m, scratch);
+    if (threadIdx.x == 0) xch[parity][0] = m;
+    cluster.sync();
+    m = nan_max(m, peer[parity * 2 + 0]);
+    const float mb = __fmul_rn(m, kL2e);
+    float s = 0.f;
+    for (uint32_t i = threadIdx.x; i < n4; i += kXPair) {
+      const float4 v = b4[i];
+      s = __fadd_rn(s, __fadd_rn(__fadd_rn(xent_ex2(fmaf(v.x, kL2e, -mb)), xent_ex2(fmaf(v.y, kL2e, -mb))),
+                                 __fadd_rn(xent_ex2(fmaf(v.z, kL2e, -mb)), xent_ex2(fmaf(v.w, kL2e, -mb)))));
+    }
+    s = pblock_sum(s, scratch);
+    if (threadIdx.x == 0) xch[parity][1] = s;
+    cluster.sync();
+    const float other = peer[parity * 2 + 1];
+    s = crank == 0 ? __fadd_rn(s, other) : __fadd_rn(other, s);      // rank 0's half first, on both CTAs
+    const float ls = logf(s);
+    const int64_t tl = t - (int64_t)lo4 * 4;                          // the target's position inside this half
+    const bool mine = t >= 0 && tl >= 0 && tl < (int64_t)n4 * 4;
+    if (threadIdx.x == 0) {
+      if (mine) P.picked[row] = __fsub_rn(__fsub_rn(rowbuf[tl], m), ls);
+      else if (t < 0 && crank == 0) P.picked[row] = 0.0f;
+    }
+    const float shift = __fadd_rn(mb, __log2f(s));
+    __syncthreads();                       // rowbuf[tl] has been read before any slot is refilled
+    float4 *d4 = reinterpret_cast<float4 *>(dr) + lo4;
+    const uint32_t next = row + n_pairs;
+    const float4 *n4p = reinterpret_cast<const float4 *>(P.x + (int64_t)next * P.x_stride) + lo4;
+    const bool more = next < P.rows;
+    for (uint32_t i = threadIdx.x; i < n4; i += kXPair) {
+      const float4 xv = b4[i];
+      if (more) xent_cp16(b4 + i, n4p + i);
+      float4 o;
+      o.x = xent_ex2(fmaf(xv.x, kL2e, -shift)); o.y = xent_ex2(fmaf(xv.y, kL2e, -shift));
+      o.z = xent_ex2(fmaf(xv.z, kL2e, -shift)); o.w = xent_ex2(fmaf(xv.w, kL2e, -shift));
+      const int64_t c = (int64_t)i * 4;
+      if (mine && tl >= c && tl < c + 4) {
+        if (tl == c) o.x = __fsub_rn(o.x, 1.0f);
+        else if (tl == c + 1) o.y = __fsub_rn(o.y, 1.0f);
+        else if (tl == c + 2) o.z = __fsub_rn(o.z, 1.0f);
+        else o.w = __fsub_rn(o.w, 1.0f);
+      }
+      o.x = __fmul_rn(o.x, P.grad_scale); o.y = __fmul_rn(o.y, P.grad_scale);
+      o.z = __fmul_rn(o.z, P.grad_scale); o.w = __fmul_rn(o.w, P.grad_scale);
+      __stcs(d4 + i, o);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  cluster.sync();                          // no CTA may exit while its peer can still read its exchange slots
+}
+
 }  // namespace rn
 }  // namespace b200
 
@@ -497,6 +611,22 @@ extern "C" int32_t b200_launch_softmax_cross_entropy(const b200_tensor *logits, 
   if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rn::kXBlock, smem));
+  static const bool pair_ok = [] { const char *e = std::getenv("B200_XENT_NO_PAIR"); return !(e && e[0] == '1'); }();
+  if (per_sm <= 1 && P.vec && V >= 8 && N >= 2 && pair_ok) {
+    // one full-row CTA per SM leaves HBM idle during the smem-only passes: a 2-CTA cluster per row, two half rows per SM
+    const size_t half = (size_t)(((V / 4) + 1) / 2) * 16;
+    auto pk = rn::softmax_xent_pair_kernel;
+    int32_t st = ensure_dyn_smem((const void *)pk, half);
+    if (st != B200_OK) return st;
+    int pair_per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pair_per_sm, pk, rn::kXPair, half));
+    if (pair_per_sm >= 2) {
+      const int64_t pairs = std::min<int64_t>(N, (int64_t)sm_count() * pair_per_sm / 2);
+      pk<<<(unsigned)(2 * pairs), rn::kXPair, half, resolve_stream(s)>>>(P);
+      B200_LAUNCH_CHECK();
+      return B200_OK;
+    }
+  }
   const unsigned grid = (unsigned)std::min<int64_t>(N, (int64_t)sm_count() * std::max(per_sm, 1));
   kern<<<grid, rn::kXBlock, smem, resolve_stream(s)>>>(P);
   B200_LAUNCH_CHECK();

@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -q --timeout 600 --timeout-method thread > gpurun_out/r02_pytest8.log 2>&1; echo "pytest rc=$?"
 tail -12 gpurun_out/r02_pytest8.log
 timeout 600 python bench.py > gpurun_out/r02_bench8.json 2> gpurun_out/r02_bench8.err; echo "bench rc=$?"; cut -c1-1200 gpurun_out/r02_bench8.json; tail -3 gpurun_out/r02_bench8.err
+timeout 200 python scripts/measure_tf32_peak.py 2>&1 | tail -1 | tee gpurun_out/r02_tf32_peak.json
 timeout 120 python scripts/reduce_bench.py 2>&1 | tee gpurun_out/r02_reduce_bench.txt
 timeout 120 python scripts/fused_reduce_bench.py 2>&1 | tee gpurun_out/r02_fused_reduce.txt
 timeout 120 python scripts/xent_bench.py 2>&1 | tee gpurun_out/r02_xent3.txt

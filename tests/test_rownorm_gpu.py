@@ -123,7 +123,24 @@ def test_layer_norm_backward_rows(dev, shape, with_gamma):
         assert err <= 2e-5 * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
 
 
-@pytest.mark.parametrize("n,v", [(8, 16), (33, 1001), (64, 4096), (5, 50257), (4, 50260)])
+@pytest.mark.parametrize("shape", [(64, 256), (8, 130, 1024), (37, 3000), (5, 11)])
+def test_layer_norm_backward_also_emits_the_producing_linears_bias_gradient(dev, shape):
+    """b200_launch_layer_norm_backward_ex: the third partial is colsum(dx) — linear_bias_backward of the Linear that
+    produced the normalised tensor (crates/burn-backend/src/backend/ops/modules/linear.rs:117-128) — and asking for it
+    changes nothing else."""
+    d = shape[-1]
+    x, dy, gamma = rnd(shape, 16), rnd(shape, 17, -1.0, 1.0), rnd((d,), 18, 0.5, 1.5)
+    dx0, dg0, db0 = ops.layer_norm_backward(H.up(x), H.up(dy), H.up(gamma), 1e-5)
+    dx, dg, db, dxsum = ops.layer_norm_backward(H.up(x), H.up(dy), H.up(gamma), 1e-5, want_dx_sum=True)
+    H.assert_exact(dx.numpy(), dx0.numpy())
+    H.assert_exact(dg.numpy(), dg0.numpy())
+    H.assert_exact(db.numpy(), db0.numpy())
+    want = dx.numpy().astype(np.float64).reshape(-1, d).sum(0)
+    scale = np.abs(dx.numpy()).reshape(-1, d).sum(0).max() + 1e-30
+    assert np.abs(dxsum.numpy() - want).max() <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("n,v", [(8, 16), (33, 1001), (64, 4096), (5, 50257), (4, 50260), (450, 40004), (3, 30000)])
 def test_softmax_cross_entropy_value_and_gradient(dev, n, v):
     """picked = log_softmax(x)[t] and dx = (softmax(x) − onehot(t))·scale against the oracle's log_softmax
     (the chain CrossEntropyLoss::forward_default records) — and in place over the logits."""
