@@ -176,10 +176,10 @@ static std::string generate(const CompiledTape &ct, const TapeParams &p, bool ra
 static cudaKernel_t compile(const std::string &src, const char *kernel_name = "b200_jit_kernel", bool load = true,
                             size_t *cubin_bytes = nullptr, cudaLibrary_t *lib_out = nullptr) {
   nvrtcProgram prog = nullptr;
-  const char *hdr_src[] = {kJitSrc_burn_b200_h, kJitSrc_tape_eval_cuh, kJitSrc_tape_math_cuh, kJitSrc_erf_table_inc,
+  const char *hdr_src[] = {kJitSrc_burn_b200_h, kJitSrc_tape_eval_cuh, kJitSrc_tape_math_cuh, kJitSrc_erf_table_inc, kJitSrc_tanh_table_inc,
                            kJitSrc_stdint_h, kJitSrc_stdint_h};
-  const char *hdr_name[] = {"burn_b200.h", "tape_eval.cuh", "tape_math.cuh", "erf_table.inc", "stdint.h", "stddef.h"};
-  if (g_rtc.CreateProgram(&prog, src.c_str(), "b200_jit.cu", 6, hdr_src, hdr_name) != 0) return nullptr;
+  const char *hdr_name[] = {"burn_b200.h", "tape_eval.cuh", "tape_math.cuh", "erf_table.inc", "tanh_table.inc", "stdint.h", "stddef.h"};
+  if (g_rtc.CreateProgram(&prog, src.c_str(), "b200_jit.cu", 7, hdr_src, hdr_name) != 0) return nullptr;
   // -default-device: burn_b200.h's host prototypes are only declarations here
   const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "-diag-suppress=177"};
   const int rc = g_rtc.CompileProgram(prog, 5, opts);

@@ -129,16 +129,53 @@ __device__ __forceinline__ VI fold_batch(VI a, const float4 (&v)[4], const int32
   }
 }
 
+// (value, index) packed into one 64-bit key whose unsigned maximum IS the arg-reduction rule: the high word orders
+// the values (monotone image of the float, complemented for argmin, NaN above everything, -0 folded onto +0 because
+// they compare equal), the low word is ~index so that among equal values the smallest index wins.  The tree combine
+// of an arg reduction is then two shuffles and one 64-bit max per step instead of a dozen predicated instructions.
 template <int K>
-__device__ __forceinline__ VI warp_reduce(VI a) {
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    VI b;
-    b.v = __shfl_xor_sync(0xffffffffu, a.v, m);
-    b.i = (K >= kArgMax) ? __shfl_xor_sync(0xffffffffu, a.i, m) : 0;
-    a = combine<K>(a, b);
+__device__ __forceinline__ unsigned long long vi_key(VI a) {
+  uint32_t u = __float_as_uint(a.v);
+  u = (a.v == 0.0f) ? 0u : u;
+  uint32_t k = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  if (K == kArgMin) k = ~k;
+  k = (a.v != a.v) ? 0xFFFFFFFFu : k;
+  return ((unsigned long long)k << 32) | (unsigned long long)(~(uint32_t)a.i);
+}
+template <int K>
+__device__ __forceinline__ VI vi_unkey(unsigned long long key) {
+  uint32_t k = (uint32_t)(key >> 32);
+  VI a;
+  a.i = (int32_t)(~(uint32_t)key);
+  if (k == 0xFFFFFFFFu) {
+    a.v = __int_as_float(0x7fc00000);
+  } else {
+    if (K == kArgMin) k = ~k;
+    a.v = __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
   }
   return a;
+}
+
+template <int K>
+__device__ __forceinline__ VI warp_reduce(VI a) {
+  if constexpr (K >= kArgMax) {
+    unsigned long long key = vi_key<K>(a);
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, m);
+      key = other > key ? other : key;
+    }
+    return vi_unkey<K>(key);
+  } else {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      VI b;
+      b.v = __shfl_xor_sync(0xffffffffu, a.v, m);
+      b.i = 0;
+      a = combine<K>(a, b);
+    }
+    return a;
+  }
 }
 
 template <int K>

@@ -468,6 +468,8 @@ __device__ __forceinline__ void run_tape(const TapeParams &p, const SlotFile<VEC
         }
         break;
       }
+      case kOpSquare: B200_UN(__fmul_rn(x, x)) break;
+      case kOpCube: B200_UN(__fmul_rn(__fmul_rn(x, x), x)) break;
       case kOpMulAdd:
         fetch_operand<VEC, U, BLOCK>(slots, hi >> 16, flags & kFlagCInput, flags & kFlagCShared, stage_off, c);
 #pragma unroll
@@ -526,7 +528,7 @@ __device__ __forceinline__ void run_tape(const TapeParams &p, const SlotFile<VEC
       case B200_OP_LOG1P_F: B200_UN(log1pf(x)) break;
       case B200_OP_SQRT_F: B200_UN(__fsqrt_rn(x)) break;
       case B200_OP_RECIP_F: B200_UN(__fdiv_rn(1.0f, x)) break;
-      case B200_OP_TANH_F: B200_UN(tanh_oracle(x)) break;
+      case B200_OP_TANH_F: B200_UN(tanh_f32(x)) break;
       case B200_OP_ERF_F: B200_UN(erf_f32(x)) break;
       case B200_OP_FLOOR_F: B200_UN(floorf(x)) break;
       case B200_OP_CEIL_F: B200_UN(ceilf(x)) break;

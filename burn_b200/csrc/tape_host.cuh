@@ -206,6 +206,13 @@ static inline int32_t compile_tape(const b200_tape *tape, int n_in, int n_out, C
         op = kOpDivScalar;
       }
     }
+    // powf_scalar with exponent 2 or 3 (powi_scalar lowers to it: the reference gelu_backward's x^3): multiplications
+    // instead of the ~40-instruction powf
+    if (op == B200_OP_POW_F && b.kind == 3) {
+      const uint32_t bits = ct.scalars[b.idx];
+      if (bits == 0x40000000u) { op = kOpSquare; b = none; }
+      else if (bits == 0x40400000u) { op = kOpCube; b = none; }
+    }
     // mul-then-add with both extra operands in memory: acc = acc*B + C (two roundings)
     if (op == B200_OP_MUL_F && dt < 0 && dout < 0 && b.kind != 0 && i + 1 < tape->n_ops) {
       const b200_tape_op &o1 = tape->ops[i + 1];

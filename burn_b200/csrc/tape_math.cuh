@@ -3,6 +3,7 @@
 // burn_b200.h's opcode enum and CUDA built-ins).
 #pragma once
 #include "erf_table.inc"
+#include "tanh_table.inc"
 
 namespace b200 {
 // Internal opcodes = public opcodes + a few compiler-generated ones.
@@ -12,6 +13,8 @@ enum : int {
   kOpDivScalar,             // acc = acc / B, B a scalar: exact Markstein sequence
   kOpMulAdd,                // acc = RN(RN(acc * B) + C)   (two roundings, never an FMA)
   kOpGelu,                  // acc = gelu(B): the reference's 5-op chain executed in one dispatch
+  kOpSquare,                // acc = acc*acc          powf_scalar(x, 2): exactly the correctly rounded power
+  kOpCube,                  // acc = (acc*acc)*acc    powf_scalar(x, 3) = powi_scalar(x, 3): within 1 ulp of it (libm powf: 1-4 ulp)
   kIOpCount
 };
 
@@ -20,36 +23,27 @@ enum : int {
 __device__ __forceinline__ float f_of(uint32_t u) { return __uint_as_float(u); }
 __device__ __forceinline__ uint32_t u_of(float f) { return __float_as_uint(f); }
 
-// tanh evaluated the way the oracle does: f64 libm, rounded to f32
-// (crates/burn-ndarray/src/ops/tensor.rs:620-626).
-__device__ __forceinline__ float tanh_oracle(float x) { return (float)tanh((double)x); }
-
-// erf.  The oracle computes libm::erf in f64 and rounds to f32
-// (crates/burn-ndarray/src/ops/tensor.rs:714-720); FP64 runs at half rate on B200
-// and would cap a fused gelu chain below the HBM roofline, so this is an f32
-// routine designed (scripts/fit_erf.py) to land within 1 ulp of that correctly
-// rounded value — equal to it for ~99% of inputs:
-//   |x| < 0.5      : x*K_hi + x*(K_lo + t*Q(t)), t = x^2 (single final rounding)
-//   0.5 <= |x| < 4 : 28 table intervals of width 1/8: H_i + (d*Q_i(d) + L_i), d = |x| - c_i exact
-//   |x| >= 4       : +-1 (erfc(4) < half an ulp of 1)
-__device__ __forceinline__ float erf_f32(float x) {
-  // Branch-free: both regions are evaluated and selected, so the 16 independent
-  // evaluations a thread performs interleave freely.
+// tanh.  The oracle computes tanh in f64 and rounds to f32 (crates/burn-ndarray/src/ops/tensor.rs:620-626).  Round 1
+// did exactly that on the device; ~150 FP64 instructions per element made the reference's gelu_backward (one tanh per
+// element of a [tokens, d_ff] tensor) run at a third of the HBM roofline.  This is an f32 routine built like erf_f32
+// (scripts/fit_tanh.py): within 1 ulp of the correctly rounded value everywhere, equal to it for > 98 % of inputs.
+//   |x| < 0.5          : fma(x, t*Q(t), x), t = x^2
+//   0.5 <= |x| < 9.125 : 69 table intervals of width 1/8: H_i + (d*Q_i(d) + L_i), d = |x| - c_i exact
+//   |x| >= 9.125       : +-1
+__device__ __forceinline__ float tanh_f32(float x) {
   const float ax = fabsf(x);
-  // region A
   const float t = __fmul_rn(ax, ax);
-  float qa = B200_ERF_Q4;
-  qa = __fmaf_rn(qa, t, B200_ERF_Q3);
-  qa = __fmaf_rn(qa, t, B200_ERF_Q2);
-  qa = __fmaf_rn(qa, t, B200_ERF_Q1);
-  qa = __fmaf_rn(qa, t, B200_ERF_Q0);
-  const float e = __fmaf_rn(t, qa, B200_ERF_K_LO);
-  const float ra = __fmaf_rn(ax, B200_ERF_K_HI, __fmul_rn(ax, e));
-  // region B (index clamped so the table read is always in range; NaN -> row 0 -> NaN)
-  const int i = min(max(__float2int_rz(__fmul_rn(__fsub_rn(ax, 0.5f), 8.0f)), 0), 27);
+  float qa = B200_TANH_Q5;
+  qa = __fmaf_rn(qa, t, B200_TANH_Q4);
+  qa = __fmaf_rn(qa, t, B200_TANH_Q3);
+  qa = __fmaf_rn(qa, t, B200_TANH_Q2);
+  qa = __fmaf_rn(qa, t, B200_TANH_Q1);
+  qa = __fmaf_rn(qa, t, B200_TANH_Q0);
+  const float ra = __fmaf_rn(ax, __fmul_rn(t, qa), ax);
+  const int i = min(max(__float2int_rz(__fmul_rn(__fsub_rn(ax, 0.5f), 8.0f)), 0), 68);
   const float c = __fmaf_rn((float)i, 0.125f, 0.5625f);
   const float d = __fsub_rn(ax, c);
-  const float4 r0 = __ldg(&kErfB[2 * i]), r1 = __ldg(&kErfB[2 * i + 1]);
+  const float4 r0 = __ldg(&kTanhB[2 * i]), r1 = __ldg(&kTanhB[2 * i + 1]);
   float qb = r1.z;
   qb = __fmaf_rn(qb, d, r1.y);
   qb = __fmaf_rn(qb, d, r1.x);
@@ -57,7 +51,49 @@ __device__ __forceinline__ float erf_f32(float x) {
   qb = __fmaf_rn(qb, d, r0.z);
   const float rb = __fadd_rn(r0.x, __fmaf_rn(d, qb, r0.y));
   float r = ax < 0.5f ? ra : rb;
-  r = ax >= 4.0f ? 1.0f : r;
+  r = ax >= 9.125f ? 1.0f : r;
+  return copysignf(r, x);
+}
+
+// erf.  The oracle computes libm::erf in f64 and rounds to f32
+// (crates/burn-ndarray/src/ops/tensor.rs:714-720); FP64 runs at half rate on B200
+// and would cap a fused gelu chain below the HBM roofline, so this is an f32
+// routine designed (scripts/fit_erf.py) to land within 1 ulp of that correctly
+// rounded value — equal to it for ~99% of inputs:
+//   |x| < 0.75      : x*K_hi + x*(K_lo + t*Q(t)), t = x^2 (single final rounding), Q of degree 6
+//   0.75 <= |x| < 4 : table intervals of width 1/8: H_i + (d*Q_i(d) + L_i), d = |x| - c_i exact
+//   |x| >= 4        : +-1 (erfc(4) < half an ulp of 1)
+// The table region costs more than half of the instructions; the lanes that execute together skip it when none of
+// them needs it (a gelu of inputs within +-1 — the fuse-on-read reduce of the benchmark — never does).
+__device__ __forceinline__ float erf_f32(float x) {
+  const float ax = fabsf(x);
+  // region A
+  const float t = __fmul_rn(ax, ax);
+  float qa = B200_ERF_Q6;
+  qa = __fmaf_rn(qa, t, B200_ERF_Q5);
+  qa = __fmaf_rn(qa, t, B200_ERF_Q4);
+  qa = __fmaf_rn(qa, t, B200_ERF_Q3);
+  qa = __fmaf_rn(qa, t, B200_ERF_Q2);
+  qa = __fmaf_rn(qa, t, B200_ERF_Q1);
+  qa = __fmaf_rn(qa, t, B200_ERF_Q0);
+  const float e = __fmaf_rn(t, qa, B200_ERF_K_LO);
+  float r = __fmaf_rn(ax, B200_ERF_K_HI, __fmul_rn(ax, e));
+  const bool outer = !(ax < 0.75f);                      // NaN takes the table path (row 0 -> NaN)
+  if (__any_sync(__activemask(), outer)) {
+    // region B (index clamped so the table read is always in range)
+    const int i = min(max(__float2int_rz(__fmul_rn(__fsub_rn(ax, 0.5f), 8.0f)), 0), 27);
+    const float c = __fmaf_rn((float)i, 0.125f, 0.5625f);
+    const float d = __fsub_rn(ax, c);
+    const float4 r0 = __ldg(&kErfB[2 * i]), r1 = __ldg(&kErfB[2 * i + 1]);
+    float qb = r1.z;
+    qb = __fmaf_rn(qb, d, r1.y);
+    qb = __fmaf_rn(qb, d, r1.x);
+    qb = __fmaf_rn(qb, d, r0.w);
+    qb = __fmaf_rn(qb, d, r0.z);
+    const float rb = __fadd_rn(r0.x, __fmaf_rn(d, qb, r0.y));
+    r = outer ? rb : r;
+    r = ax >= 4.0f ? 1.0f : r;
+  }
   return copysignf(r, x);
 }
 

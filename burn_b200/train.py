@@ -141,15 +141,9 @@ def linear(tape: Tape, x: Var, w: Var, b: Var | None, residual: Var | None = Non
             accumulate(residual, y.g)
         g2 = y.g.reshape((m, w.v.shape[1]))
         if x.requires_grad:
-            if x.g is not None and x.v.shape[-1] % 4 == 0 and x.g.is_contiguous() and getattr(x, "on_grad", None) is None:
-                # x already holds a gradient (the residual branch, the other projections of the same input): the
-                # accumulation `x.g + dx` (burn-autodiff sums contributions with float_add) rides this GEMM's epilogue
-                # instead of a separate pass over three [tokens, d] tensors — same single rounded add
-                epi = TapeBuilder().op("ADD_F", ("in", 1), ("in", 0), out=0).build()
-                x.g = ops.float_matmul(g2, w.v.swap_dims(0, 1), tape.precision, epi,
-                                       (x.g.reshape((m, x.v.shape[-1])),)).reshape(x.v.shape)
-            else:
-                accumulate(x, ops.float_matmul(g2, w.v.swap_dims(0, 1), tape.precision).reshape(x.v.shape))
+            # (folding `x.g + dx` into this GEMM's epilogue was measured: the full-size epilogue operand costs the GEMM
+            # +50 us against a 20 us add — the separate fused add stays)
+            accumulate(x, ops.float_matmul(g2, w.v.swap_dims(0, 1), tape.precision).reshape(x.v.shape))
         if w.requires_grad:
             slot = getattr(w, "grad_slot", None)
             if slot is not None and w.g is None:      # the GEMM writes the bucket slot directly

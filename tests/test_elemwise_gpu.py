@@ -68,17 +68,23 @@ def test_unary(dev, op, fn, lo, hi):
     H.assert_close(got, fn(a), H.REL_ELEMWISE, 0.0, op)
 
 
-def test_erf_within_one_ulp_of_oracle_and_tanh_exact(dev):
-    # The oracle evaluates erf / tanh in f64 and rounds.  tanh does the same here (bit-exact);
-    # erf is an f32 routine designed to land within 1 ulp of the correctly rounded value
-    # (scripts/fit_erf.py): <= 1 ulp everywhere and identical for > 97 % of inputs.
-    a = np.concatenate([rnd((1 << 18,), -5, 5), rnd((1 << 18,), -0.5, 0.5),
-                        np.array([0.0, -0.0, 0.5, -0.5, 4.0, -4.0, 3.9999998, 1e-30, -1e-38, np.inf, -np.inf],
-                                 dtype=np.float32)])
+def test_erf_and_tanh_within_one_ulp_of_oracle(dev):
+    # The oracle evaluates erf / tanh in f64 and rounds.  Both are f32 routines here, designed to land within 1 ulp of
+    # that correctly rounded value (scripts/fit_erf.py, scripts/fit_tanh.py): <= 1 ulp everywhere and identical for
+    # > 97 % of inputs (f64 on the device cost the gelu chains a large part of the HBM roofline).
+    a = np.concatenate([rnd((1 << 18,), -5, 5), rnd((1 << 18,), -0.75, 0.75), rnd((1 << 16,), -12, 12),
+                        np.array([0.0, -0.0, 0.5, -0.5, 0.75, -0.75, 0.7499999, 4.0, -4.0, 3.9999998, 9.125, 9.1249, -9.2, 1e-30,
+                                  -1e-38, np.inf, -np.inf], dtype=np.float32)])
     got = H.unary("ERF_F", H.up(a))
     H.assert_ulp(got, oracle.float_erf(a), 1, 0.03, "erf")
     assert np.isnan(H.unary("ERF_F", H.up(np.array([np.nan], dtype=np.float32)))[0])
-    H.assert_exact(H.unary("TANH_F", H.up(a)), oracle.float_tanh(a), "tanh")
+    H.assert_ulp(H.unary("TANH_F", H.up(a)), oracle.float_tanh(a), 1, 0.03, "tanh")
+    assert np.isnan(H.unary("TANH_F", H.up(np.array([np.nan], dtype=np.float32)))[0])
+    # mixed groups: lanes inside and outside the polynomial region in the same warp, and a launch that is entirely inside
+    mix = np.tile(np.array([0.1, 2.0, -0.3, -3.5], dtype=np.float32), 4096)
+    H.assert_ulp(H.unary("ERF_F", H.up(mix)), oracle.float_erf(mix), 1, 0.03, "erf (mixed warps)")
+    inner = rnd((1 << 16,), -0.74, 0.74)
+    H.assert_ulp(H.unary("ERF_F", H.up(inner)), oracle.float_erf(inner), 1, 0.05, "erf (polynomial region only)")
 
 
 def test_special_values(dev):
