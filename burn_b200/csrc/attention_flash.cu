@@ -367,11 +367,14 @@ constexpr int kBwdThreads = 320;   // issuer warp, TMEM-allocator warp, 8 row wa
 __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *sQ = smem, *sdO = sQ + kBig, *sKk = sdO + kBig, *sVk = sKk + kSmall, *sKmn = sVk + kSmall, *sdS = sKmn + kSmall;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sdS + kPBytes);
-  uint64_t *bar_q = bars, *bar_kv = bars + 1, *bar_mn = bars + 2, *bar_s0 = bars + 3, *bar_s1 = bars + 4, *bar_p = bars + 5,
-           *bar_o = bars + 6;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
+  // K-major K_j / V_j tiles are DOUBLE-buffered (buffer j & 1): the load of block j+1 is in flight while block j is
+  // multiplied — with one buffer every iteration exposed a full TMA round trip between S_{j-1} retiring and S_j starting
+  uint8_t *sQ = smem, *sdO = sQ + kBig, *sKk = sdO + kBig, *sVk = sKk + 2 * kSmall, *sKmn = sVk + 2 * kSmall, *sdS = sKmn + kSmall;
+  float *sDelta = reinterpret_cast<float *>(sdS + kPBytes);          // [128] rowsum(dO ∘ O)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sDelta + kRows);
+  uint64_t *bar_q = bars, *bar_kv = bars + 1 /* [2] */, *bar_mn = bars + 3, *bar_s0 = bars + 4, *bar_s1 = bars + 5, *bar_p = bars + 6,
+           *bar_o = bars + 7;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int work = blockIdx.x;
@@ -393,6 +396,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
     tma_prefetch_desc(&P.tma_mn0);
     mbar_init(bar_q, 1);
     mbar_init(bar_kv, 1);
+    mbar_init(bar_kv + 1, 1);
     mbar_init(bar_mn, 1);
     mbar_init(bar_s0, 1);
     mbar_init(bar_s1, 1);
@@ -415,12 +419,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
       load_kmajor(sdO, &P.tma_do, bar_q, q0, h, b, kBig / 2);
       uint32_t ph_s0 = 0, ph_s1 = 0;
       for (int j = 0; j < nkv; ++j) {
-        if (j > 0) {
-          if ((j - 1) & 1) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+        const int buf = j & 1;
+        if (j >= 2) {   // buffer j & 1 is free once S_{j-2} / dP_{j-2} (same parity) have retired
+          if (buf) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
         }
-        mbar_expect_tx(bar_kv, 2 * kSmall);
-        load_kmajor(sKk, &P.tma_k, bar_kv, j * kCols, h, b, kSmall / 2);
-        load_kmajor(sVk, &P.tma_v, bar_kv, j * kCols, h, b, kSmall / 2);
+        mbar_expect_tx(bar_kv + buf, 2 * kSmall);
+        load_kmajor(sKk + buf * kSmall, &P.tma_k, bar_kv + buf, j * kCols, h, b, kSmall / 2);
+        load_kmajor(sVk + buf * kSmall, &P.tma_v, bar_kv + buf, j * kCols, h, b, kSmall / 2);
       }
     } else if (lane == 1 && nkv > 0) {
       uint32_t ph_o = 0;
@@ -437,18 +442,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
                      adS = smem_u32(sdS);
       auto mma_s_dp = [&](int buf) {
         tc_fence_after();
-        mma_kk(tmem + (buf ? 64u : 0u), aQ, kBig / 2, aKk, kSmall / 2, idesc, false);          // S = Q·Kᵀ
-        mma_kk(tmem + 128u + (buf ? 64u : 0u), adO, kBig / 2, aVk, kSmall / 2, idesc, false);  // dP = dO·Vᵀ
+        mma_kk(tmem + (buf ? 64u : 0u), aQ, kBig / 2, aKk + buf * kSmall, kSmall / 2, idesc, false);          // S = Q·Kᵀ
+        mma_kk(tmem + 128u + (buf ? 64u : 0u), adO, kBig / 2, aVk + buf * kSmall, kSmall / 2, idesc, false);  // dP = dO·Vᵀ
         umma_commit(buf ? bar_s1 : bar_s0);
       };
-      uint32_t ph_kv = 0, ph_mn = 0, ph_p = 0;
+      uint32_t ph_kv[2] = {0, 0}, ph_mn = 0, ph_p = 0;
       mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
+      mbar_wait(bar_kv, ph_kv[0]); ph_kv[0] ^= 1;
       mma_s_dp(0);
       for (int j = 0; j < nkv; ++j) {
         const int cur = j & 1;
         if (j + 1 < nkv) {
-          mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
+          mbar_wait(bar_kv + (cur ^ 1), ph_kv[cur ^ 1]); ph_kv[cur ^ 1] ^= 1;
           mma_s_dp(cur ^ 1);
         }
         mbar_wait(bar_mn, ph_mn); ph_mn ^= 1;
@@ -468,19 +473,31 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
     const float scale2 = P.scale * kLog2e, mask2 = P.mask_value * kLog2e;
     float4 *stat = P.stats + ((int64_t)b * P.H + h) * P.Sq + row;
     float m2 = 0.0f, rinv = 0.0f, delta = 0.0f;
+    {
+      // delta = sum_d dO[row, d] * O[row, d]  (= rowsum(dP ∘ P)): each of the 8 row warps takes 16 rows and reads them
+      // coalesced (a row is 256 contiguous bytes: lane l holds columns 2l, 2l+1), instead of every thread walking its
+      // own row — 32 uncoalesced 16-byte loads per thread that kept the load/store unit queue full (ncu: lg_throttle)
+      const int w8 = warp - 2;
+#pragma unroll 4
+      for (int rr = 0; rr < 16; ++rr) {
+        const int rl = w8 * 16 + rr, rg = q0 + rl;
+        float part = 0.0f;
+        if (rg < P.Sq) {
+          const float2 ov = __ldg(reinterpret_cast<const float2 *>(P.o_fwd + (int64_t)b * P.of_sb + (int64_t)h * P.of_sh + (int64_t)rg * P.of_ss) + lane);
+          const float2 gv = __ldg(reinterpret_cast<const float2 *>(P.d_out + (int64_t)b * P.do_sb + (int64_t)h * P.do_sh + (int64_t)rg * P.do_ss) + lane);
+          part = __fadd_rn(__fmul_rn(ov.x, gv.x), __fmul_rn(ov.y, gv.y));
+        }
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, sft));
+        if (lane == 0) sDelta[rl] = part;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 row warps only
+      delta = sDelta[r_in];
+    }
     if (row_ok) {
       const float4 st = *stat;
       m2 = st.x;
       rinv = st.y;
-      // delta = sum_d dO[row, d] * O[row, d]  (= rowsum(dP ∘ P))
-      const float4 *orow = reinterpret_cast<const float4 *>(P.o_fwd + (int64_t)b * P.of_sb + (int64_t)h * P.of_sh + (int64_t)row * P.of_ss);
-      const float4 *grow = reinterpret_cast<const float4 *>(P.d_out + (int64_t)b * P.do_sb + (int64_t)h * P.do_sh + (int64_t)row * P.do_ss);
-#pragma unroll
-      for (int q = 0; q < HD / 4; ++q) {
-        const float4 ov = __ldg(orow + q), g = __ldg(grow + q);
-        delta = __fadd_rn(delta, __fadd_rn(__fadd_rn(__fmul_rn(ov.x, g.x), __fmul_rn(ov.y, g.y)),
-                                           __fadd_rn(__fmul_rn(ov.z, g.z), __fmul_rn(ov.w, g.w))));
-      }
       if (half == 0) stat->z = delta;      // the dK/dV kernel (launched after this one) reads it per query column
     }
     uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
@@ -559,16 +576,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
 __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *sK = smem, *sV = sK + kBig, *sQk = sV + kBig, *sdOk = sQk + kSmall, *sQmn = sdOk + kSmall, *sdOmn = sQmn + kSmall,
+  // K-major Q_i / dO_i tiles are DOUBLE-buffered (buffer it & 1) so the load of query block it+1 overlaps the products of
+  // block it; the per-query statistics are read straight from global memory (one broadcast line per column) — staging
+  // them in shared memory is what the second tile buffer now occupies (224 KB of tiles + barriers)
+  uint8_t *sK = smem, *sV = sK + kBig, *sQk = sV + kBig, *sdOk = sQk + 2 * kSmall, *sQmn = sdOk + 2 * kSmall, *sdOmn = sQmn + kSmall,
           *sP = sdOmn + kSmall, *sdS = sP + kPBytes;
-  // [3][64] (m2, 1/l, delta, -) of the block's queries.  Three buffers: the producer refills buffer it % 3 once
-  // Sᵀ_{it-1} has retired, and that MMA is only issued after the row threads delivered block it-3 — the last
-  // reader of the buffer (with two buffers the refill could overtake the readers of block it-2).
-  float4 *sStats = reinterpret_cast<float4 *>(sdS + kPBytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sStats + 3 * kCols);
-  uint64_t *bar_res = bars, *bar_qk = bars + 1, *bar_mn = bars + 2, *bar_s0 = bars + 3, *bar_s1 = bars + 4, *bar_p = bars + 5,
-           *bar_o = bars + 6, *bar_st = bars + 7;     // bar_st[3]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sdS + kPBytes);
+  uint64_t *bar_res = bars, *bar_qk = bars + 1 /* [2] */, *bar_mn = bars + 3, *bar_s0 = bars + 4, *bar_s1 = bars + 5, *bar_p = bars + 6,
+           *bar_o = bars + 7;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int work = blockIdx.x;
@@ -593,14 +609,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
     tma_prefetch_desc(&P.tma_mn1);
     mbar_init(bar_res, 1);
     mbar_init(bar_qk, 1);
+    mbar_init(bar_qk + 1, 1);
     mbar_init(bar_mn, 1);
     mbar_init(bar_s0, 1);
     mbar_init(bar_s1, 1);
     mbar_init(bar_p, 8);
     mbar_init(bar_o, 1);
-    mbar_init(bar_st, 1);
-    mbar_init(bar_st + 1, 1);
-    mbar_init(bar_st + 2, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -618,21 +632,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
       load_kmajor(sV, &P.tma_v, bar_res, kv0, h, b, kBig / 2);
       uint32_t ph_s0 = 0, ph_s1 = 0;
       for (int it = 0; it < n_it; ++it) {
-        if (it > 0) {
-          if ((it - 1) & 1) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+        const int buf = it & 1;
+        if (it >= 2) {   // buffer it & 1 is free once Sᵀ_{it-2} / dPᵀ_{it-2} (same parity) have retired
+          if (buf) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
         }
-        const int r0 = (i_start + it) * kCols, buf = it % 3;
-        mbar_expect_tx(bar_qk, 2 * kSmall);
-        load_kmajor(sQk, &P.tma_q, bar_qk, r0, h, b, kSmall / 2);
-        load_kmajor(sdOk, &P.tma_do, bar_qk, r0, h, b, kSmall / 2);
-        // the block's per-query statistics: one bulk copy, clipped at the end of the sequence
-        const uint32_t bytes = (uint32_t)min(kCols, P.Sq - r0) * 16u;
-        uint64_t *bst = bar_st + buf;
-        mbar_expect_tx(bst, bytes);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(sStats + buf * kCols)),
-                     "l"(P.stats + stat_base + r0), "r"(bytes), "r"(smem_u32(bst))
-                     : "memory");
+        const int r0 = (i_start + it) * kCols;
+        mbar_expect_tx(bar_qk + buf, 2 * kSmall);
+        load_kmajor(sQk + buf * kSmall, &P.tma_q, bar_qk + buf, r0, h, b, kSmall / 2);
+        load_kmajor(sdOk + buf * kSmall, &P.tma_do, bar_qk + buf, r0, h, b, kSmall / 2);
       }
     } else if (lane == 1 && n_it > 0) {
       uint32_t ph_o = 0;
@@ -651,18 +658,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
                      adOmn = smem_u32(sdOmn), aP = smem_u32(sP), adS = smem_u32(sdS);
       auto mma_s_dp = [&](int buf) {
         tc_fence_after();
-        mma_kk(tmem + (buf ? 64u : 0u), aK, kBig / 2, aQk, kSmall / 2, idesc, false);          // Sᵀ = K·Qᵀ
-        mma_kk(tmem + 128u + (buf ? 64u : 0u), aV, kBig / 2, adOk, kSmall / 2, idesc, false);  // dPᵀ = V·dOᵀ
+        mma_kk(tmem + (buf ? 64u : 0u), aK, kBig / 2, aQk + buf * kSmall, kSmall / 2, idesc, false);          // Sᵀ = K·Qᵀ
+        mma_kk(tmem + 128u + (buf ? 64u : 0u), aV, kBig / 2, adOk + buf * kSmall, kSmall / 2, idesc, false);  // dPᵀ = V·dOᵀ
         umma_commit(buf ? bar_s1 : bar_s0);
       };
-      uint32_t ph_qk = 0, ph_mn = 0, ph_p = 0;
+      uint32_t ph_qk[2] = {0, 0}, ph_mn = 0, ph_p = 0;
       mbar_wait(bar_res, 0);
-      mbar_wait(bar_qk, ph_qk); ph_qk ^= 1;
+      mbar_wait(bar_qk, ph_qk[0]); ph_qk[0] ^= 1;
       mma_s_dp(0);
       for (int it = 0; it < n_it; ++it) {
         const int cur = it & 1;
         if (it + 1 < n_it) {
-          mbar_wait(bar_qk, ph_qk); ph_qk ^= 1;
+          mbar_wait(bar_qk + (cur ^ 1), ph_qk[cur ^ 1]); ph_qk[cur ^ 1] ^= 1;
           mma_s_dp(cur ^ 1);
         }
         mbar_wait(bar_mn, ph_mn); ph_mn ^= 1;
@@ -683,7 +690,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
     const float scale2 = P.scale * kLog2e, mask2 = P.mask_value * kLog2e;
     uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
     for (int it = 0; it < n_it; ++it) {
-      const int cur = it & 1, sb = it % 3;
+      const int cur = it & 1;
       const int qc0 = (i_start + it) * kCols + half * 32;
       uint32_t mbits = 0;                                           // bit c: explicit mask at (query qc0 + c, key kv)
       if (mcol && kv_ok) {                                          // fetched before the waits
@@ -691,20 +698,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
         for (int c = 0; c < 32; ++c)
           if (qc0 + c < P.Sq && __ldg(mcol + (int64_t)(qc0 + c) * P.m_ss)) mbits |= 1u << c;
       }
-      mbar_wait(bar_st + sb, (uint32_t)((it / 3) & 1));
       if (cur) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
       tc_fence_after();
       uint32_t rs[32], rp[32];
       tmem_ld32(tmem + (cur ? 64u : 0u) + lane_addr + half * 32, rs);
       tmem_ld32(tmem + 128u + (cur ? 64u : 0u) + lane_addr + half * 32, rp);
       tmem_ld_wait();
-      const float4 *st = sStats + sb * kCols + half * 32;
+      const float4 *st = P.stats + stat_base + qc0;                // same address for the whole warp: one broadcast line
       float pv[32], ds[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         const int q = qc0 + c;
         const bool q_ok = q < P.Sq;
-        const float4 sq = st[c];                                    // smem broadcast; garbage past Sq is never used
+        const float4 sq = q_ok ? __ldg(st + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         const bool mk = (P.causal && kv > q + shift) || ((mbits >> c) & 1u);
         const float t = mk ? mask2 : __fmul_rn(__uint_as_float(rs[c]), scale2);
         float p = (q_ok && kv_ok) ? __fmul_rn(ex2(t - sq.x), sq.y) : 0.0f;
@@ -907,7 +913,7 @@ extern "C" int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out
   {
     const int64_t ctas = B * H * P.blocks;
     B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
-    const size_t smem = 1024 + 2 * fa::kBig + 3 * fa::kSmall + fa::kPBytes + 128;
+    const size_t smem = 1024 + 2 * fa::kBig + 5 * fa::kSmall + fa::kPBytes + fa::kRows * 4 + 128;
     if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dq_kernel), smem)) != B200_OK) return st;
     fa::flash_bwd_dq_kernel<<<(unsigned)ctas, fa::kBwdThreads, smem, stream>>>(P);
     B200_LAUNCH_CHECK();
@@ -927,7 +933,7 @@ extern "C" int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out
   {
     const int64_t ctas = B * H * P.blocks;
     B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
-    const size_t smem = 1024 + 2 * fa::kBig + 4 * fa::kSmall + 2 * fa::kPBytes + 3 * fa::kCols * 16 + 128;
+    const size_t smem = 1024 + 2 * fa::kBig + 6 * fa::kSmall + 2 * fa::kPBytes + 128;
     if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dkv_kernel), smem)) != B200_OK) return st;
     fa::flash_bwd_dkv_kernel<<<(unsigned)ctas, fa::kBwdThreads, smem, stream>>>(P);
     B200_LAUNCH_CHECK();

@@ -518,6 +518,11 @@ static int32_t launch_fast(bool col, const fast::RowParams &rp, const fast::ColP
     B200_LAUNCH_CHECK();
     return B200_OK;
   }
+  if (cp.tx == 0) {   // short reduced axis, many columns: thread per column-vector
+    fast::reduce_col_short_kernel<K><<<grid, fast::kBlock, 0, stream>>>(cp);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, cp.splits, 1);
   cfg.blockDim = dim3(cp.tx, fast::kBlock / cp.tx, 1);
@@ -617,6 +622,11 @@ static int32_t try_fast_reduce(int32_t kind, int64_t outer, int64_t R, int64_t i
     cp.splits = splits;
     cp.rows_per_split = (cp.R + splits - 1) / splits;
     grid = tiles;
+    const uint64_t colvecs = (uint64_t)cp.outer * cp.inner4;
+    if (cp.R <= 64u && colvecs >= (uint64_t)sms * fast::kBlock * 2u) {
+      cp.tx = 0;
+      grid = (unsigned)std::min<uint64_t>((colvecs + fast::kBlock - 1) / fast::kBlock, (uint64_t)sms * 8u);
+    }
   }
   int32_t st;
   switch (K) {

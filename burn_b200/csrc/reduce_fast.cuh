@@ -386,5 +386,39 @@ __global__ void __launch_bounds__(kBlock) reduce_col_fast_kernel(const ColParams
   }
 }
 
+// Short reduced axis over many columns ([outer, R <= 64, inner] with inner in the hundreds of thousands: the split-K
+// combine of a weight-gradient GEMM, per-CTA partial rows of a fused kernel): one thread per column-vector walks all R
+// rows with four loads in flight — no shared memory, no cluster; the tiled kernel above would give every CTA 4 KB.
+template <int K>
+__global__ void __launch_bounds__(kBlock) reduce_col_short_kernel(const ColParams P) {
+  const uint64_t total = (uint64_t)P.outer * P.inner4;
+  for (uint64_t g = (uint64_t)blockIdx.x * kBlock + threadIdx.x; g < total; g += (uint64_t)gridDim.x * kBlock) {
+    const uint32_t o = (uint32_t)(g / P.inner4), c4 = (uint32_t)(g - (uint64_t)o * P.inner4);
+    const float4 *p = reinterpret_cast<const float4 *>(P.x) + (size_t)o * P.R * P.inner4 + c4;
+    VI a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a[j] = identity<K>();
+      a[j].i = 0;
+    }
+    for (uint32_t base = 0; base < P.R; base += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = base + k < P.R ? __ldcs(p + (size_t)(base + k) * P.inner4) : make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (base + k < P.R) {
+          a[0] = fold<K>(a[0], v[k].x, (int32_t)(base + k));
+          a[1] = fold<K>(a[1], v[k].y, (int32_t)(base + k));
+          a[2] = fold<K>(a[2], v[k].z, (int32_t)(base + k));
+          a[3] = fold<K>(a[3], v[k].w, (int32_t)(base + k));
+        }
+    }
+    const int64_t ob = ((int64_t)o * P.inner4 + c4) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) store_result<K>(P.out, P.out_dtype, ob + j, a[j], P.mean, P.div);
+  }
+}
+
 }  // namespace fast
 }  // namespace b200

@@ -427,18 +427,22 @@ def layer_norm_backward(x: DeviceTensor, dy: DeviceTensor, gamma: DeviceTensor |
     a, g, o = x.desc(), dy.desc(), dx.desc()
     n = C.c_int32()
     check(lib.b200_layer_norm_backward_partials(C.byref(a), C.byref(n)))
-    pg, pb = DeviceTensor.empty((n.value, d)), DeviceTensor.empty((n.value, d))
+    # the per-CTA partial rows of all outputs live in ONE [k, G, d] buffer, finished by ONE column reduce over axis 1
+    k = 3 if want_dx_sum else 2
+    parts = DeviceTensor.empty((k, n.value, d))
+    pg, pb = parts.slice([(0, 1), (0, n.value), (0, d)]).reshape((n.value, d)), parts.slice([(1, 2), (0, n.value), (0, d)]).reshape((n.value, d))
     pgd, pbd = pg.desc(), pb.desc()
     gm = gamma.desc() if gamma is not None else None
     if not want_dx_sum:
         check(lib.b200_launch_layer_norm_backward(C.byref(a), C.byref(g), C.byref(gm) if gm is not None else None,
                                                   float(eps), C.byref(o), C.byref(pgd), C.byref(pbd), None))
-        return dx, float_sum_dim(pg, 0).reshape((d,)), float_sum_dim(pb, 0).reshape((d,))
-    pd = DeviceTensor.empty((n.value, d))
-    pdd = pd.desc()
-    check(lib.b200_launch_layer_norm_backward_ex(C.byref(a), C.byref(g), C.byref(gm) if gm is not None else None,
-                                                 float(eps), C.byref(o), C.byref(pgd), C.byref(pbd), C.byref(pdd), None))
-    return dx, float_sum_dim(pg, 0).reshape((d,)), float_sum_dim(pb, 0).reshape((d,)), float_sum_dim(pd, 0).reshape((d,))
+    else:
+        pdd = parts.slice([(2, 3), (0, n.value), (0, d)]).reshape((n.value, d)).desc()
+        check(lib.b200_launch_layer_norm_backward_ex(C.byref(a), C.byref(g), C.byref(gm) if gm is not None else None,
+                                                     float(eps), C.byref(o), C.byref(pgd), C.byref(pbd), C.byref(pdd), None))
+    sums = float_sum_dim(parts, 1)                                  # [k, 1, d]
+    outs = tuple(sums.slice([(i, i + 1), (0, 1), (0, d)]).reshape((d,)) for i in range(k))
+    return (dx,) + outs
 
 
 def attention(q: DeviceTensor, k: DeviceTensor, v: DeviceTensor, mask: DeviceTensor | None = None, scale: float | None = None,

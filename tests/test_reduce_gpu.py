@@ -92,6 +92,21 @@ def test_arg_on_constant_infinite_rows(dev):
         H.assert_exact(reduce_axis(abi.RED_MAX, x, axis), oracle.float_max_dim(x, axis))
 
 
+@pytest.mark.parametrize("shape", [(2, 7, 160000), (1, 16, 1 << 20), (3, 64, 110000)])
+def test_short_axis_over_many_columns(dev, shape):
+    """[outer, R <= 64, inner] with hundreds of thousands of columns (a split-K combine, per-CTA partial rows): the
+    thread-per-column kernel — every kind, ties and NaNs included."""
+    x = rnd(shape, seed=21)
+    x[0, 3, 5] = np.nan
+    x[0, 1, 9] = x[0, 4, 9] = 7.0                                     # a tie: the first index wins
+    H.assert_close(reduce_axis(abi.RED_SUM, np.nan_to_num(x), 1), oracle.float_sum_dim(np.nan_to_num(x), 1), H.REL_REDUCE, 1e-6 * shape[1], "sum")
+    H.assert_close(reduce_axis(abi.RED_MEAN, np.nan_to_num(x), 1), oracle.float_mean_dim(np.nan_to_num(x), 1), H.REL_REDUCE, 1e-6, "mean")
+    H.assert_exact(reduce_axis(abi.RED_MAX, x, 1), oracle.float_max_dim(x, 1), "max")
+    H.assert_exact(reduce_axis(abi.RED_MIN, x, 1), oracle.float_min_dim(x, 1), "min")
+    H.assert_exact(reduce_axis(abi.RED_ARGMAX, x, 1, abi.I32), oracle.float_argmax(x, 1), "argmax")
+    H.assert_exact(reduce_axis(abi.RED_ARGMIN, x, 1, abi.I32), oracle.float_argmin(x, 1), "argmin")
+
+
 def test_max_min_dim_exact(dev):
     x = rnd((33, 130, 12), seed=2)
     x[1, 5, 3] = np.nan
