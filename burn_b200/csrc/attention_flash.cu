@@ -263,13 +263,35 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
             if (c0 + c >= P.Sk) s[c] = -INFINITY;
         }
       };
+      // warp-uniform: no mask byte set, no column beyond the causal limit of the warp's first row or past Sk, and a
+      // positive scale (so that max(s·scale) = max(s)·scale): the block needs one FMNMX per element for the row max and
+      // FFMA + MUFU.EX2 + FADD for the weight — the masked form below spends three times that
+      bool any_mask = false;
+      if (mrow && row_ok) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) any_mask |= mw[q] != 0u;
+      }
+      const bool fast = scale2 > 0.0f && col0 + kCols <= P.Sk && !(P.causal && col0 + kCols - 1 > q0 + quarter * 32 + (P.Sk - P.Sq)) &&
+                        !__any_sync(0xffffffffu, any_mask);
       float bm = -INFINITY;
+      if (fast) {
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-        float s[32];
-        load_scores(kb, s);
+        for (int kb = 0; kb < 2; ++kb) {
+          uint32_t r[32];
+          tmem_ld32(ts + kb * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) bm = fmaxf(bm, s[c]);
+          for (int c = 0; c < 32; ++c) bm = fmaxf(bm, __uint_as_float(r[c]));
+        }
+        bm = __fmul_rn(bm, scale2);
+      } else {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          float s[32];
+          load_scores(kb, s);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) bm = fmaxf(bm, s[c]);
+        }
       }
       const float m_new = fmaxf(m, bm);               // m starts at -FLT_MAX: the finfo.min clamp (attention.rs:70-72)
       const float alpha = ex2(m - m_new);
@@ -278,13 +300,27 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         float s[32];
-        load_scores(kb, s);
+        if (fast) {
+          uint32_t r[32];
+          tmem_ld32(ts + kb * 32, r);
+          tmem_ld_wait();
+          const float nm = -m_new;
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          s[c] = ex2(s[c] - m_new);
-          s[c + 1] = ex2(s[c + 1] - m_new);
-          acc0 += s[c];
-          acc1 += s[c + 1];
+          for (int c = 0; c < 32; c += 2) {
+            s[c] = ex2(__fmaf_rn(__uint_as_float(r[c]), scale2, nm));
+            s[c + 1] = ex2(__fmaf_rn(__uint_as_float(r[c + 1]), scale2, nm));
+            acc0 += s[c];
+            acc1 += s[c + 1];
+          }
+        } else {
+          load_scores(kb, s);
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            s[c] = ex2(s[c] - m_new);
+            s[c + 1] = ex2(s[c + 1] - m_new);
+            acc0 += s[c];
+            acc1 += s[c + 1];
+          }
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -367,14 +403,16 @@ constexpr int kBwdThreads = 320;   // issuer warp, TMEM-allocator warp, 8 row wa
 __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // K-major K_j / V_j tiles are DOUBLE-buffered (buffer j & 1): the load of block j+1 is in flight while block j is
-  // multiplied — with one buffer every iteration exposed a full TMA round trip between S_{j-1} retiring and S_j starting
-  uint8_t *sQ = smem, *sdO = sQ + kBig, *sKk = sdO + kBig, *sVk = sKk + 2 * kSmall, *sKmn = sVk + 2 * kSmall, *sdS = sKmn + kSmall;
-  float *sDelta = reinterpret_cast<float *>(sdS + kPBytes);          // [128] rowsum(dO ∘ O)
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sDelta + kRows);
-  uint64_t *bar_q = bars, *bar_kv = bars + 1 /* [2] */, *bar_mn = bars + 3, *bar_s0 = bars + 4, *bar_s1 = bars + 5, *bar_p = bars + 6,
-           *bar_o = bars + 7;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+  // sdS is DOUBLE-buffered (buffer j & 1): the row threads deliver dS_{j+1} while the tensor core still reads dS_j, so
+  // they only ever wait for the dQ product of block j-1 — two iterations of slack instead of a lock step with the MMA.
+  // Before the loop the first buffer receives the O tile (TMA), from which delta = rowsum(dO ∘ O) is computed in shared
+  // memory: no per-thread global row walks in the prologue.
+  uint8_t *sQ = smem, *sdO = sQ + kBig, *sKk = sdO + kBig, *sVk = sKk + kSmall, *sKmn = sVk + kSmall, *sdS = sKmn + kSmall;
+  float *sDelta = reinterpret_cast<float *>(sdS + 2 * kPBytes);      // [2][128] half-row partial sums
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sDelta + 2 * kRows);
+  uint64_t *bar_q = bars, *bar_kv = bars + 1, *bar_mn = bars + 2, *bar_s0 = bars + 3, *bar_s1 = bars + 4, *bar_p = bars + 5,
+           *bar_o0 = bars + 6, *bar_o1 = bars + 7, *bar_of = bars + 8;   // bar_o{b}: the dQ product that read dS buffer b retired
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int work = blockIdx.x;
@@ -394,14 +432,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
     tma_prefetch_desc(&P.tma_k);
     tma_prefetch_desc(&P.tma_v);
     tma_prefetch_desc(&P.tma_mn0);
+    tma_prefetch_desc(&P.tma_mn1);
     mbar_init(bar_q, 1);
+    mbar_init(bar_of, 1);
     mbar_init(bar_kv, 1);
-    mbar_init(bar_kv + 1, 1);
     mbar_init(bar_mn, 1);
     mbar_init(bar_s0, 1);
     mbar_init(bar_s1, 1);
     mbar_init(bar_p, 8);
-    mbar_init(bar_o, 1);
+    mbar_init(bar_o0, 1);
+    mbar_init(bar_o1, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -414,23 +454,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
     // TMA producers: lane 0 streams the K-major K_j / V_j tiles (free when S_j / dP_j retire), lane 1 the
     // MN-major K_j tile (free when the dQ MMA of block j retires)
     if (lane == 0 && nkv > 0) {
-      mbar_expect_tx(bar_q, 2 * kBig);
+      mbar_expect_tx(bar_of, 2 * kBig);                                // dO and O first: delta is the row threads' prologue
+      load_kmajor(sdO, &P.tma_do, bar_of, q0, h, b, kBig / 2);
+      load_kmajor(sdS, &P.tma_mn1, bar_of, q0, h, b, kBig / 2);         // O tile (K-major, 128 rows) into dS buffer 0
+      mbar_expect_tx(bar_q, kBig);
       load_kmajor(sQ, &P.tma_q, bar_q, q0, h, b, kBig / 2);
-      load_kmajor(sdO, &P.tma_do, bar_q, q0, h, b, kBig / 2);
       uint32_t ph_s0 = 0, ph_s1 = 0;
       for (int j = 0; j < nkv; ++j) {
-        const int buf = j & 1;
-        if (j >= 2) {   // buffer j & 1 is free once S_{j-2} / dP_{j-2} (same parity) have retired
-          if (buf) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+        if (j > 0) {
+          if ((j - 1) & 1) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
         }
-        mbar_expect_tx(bar_kv + buf, 2 * kSmall);
-        load_kmajor(sKk + buf * kSmall, &P.tma_k, bar_kv + buf, j * kCols, h, b, kSmall / 2);
-        load_kmajor(sVk + buf * kSmall, &P.tma_v, bar_kv + buf, j * kCols, h, b, kSmall / 2);
+        mbar_expect_tx(bar_kv, 2 * kSmall);
+        load_kmajor(sKk, &P.tma_k, bar_kv, j * kCols, h, b, kSmall / 2);
+        load_kmajor(sVk, &P.tma_v, bar_kv, j * kCols, h, b, kSmall / 2);
       }
     } else if (lane == 1 && nkv > 0) {
-      uint32_t ph_o = 0;
+      uint32_t ph_o0 = 0, ph_o1 = 0;
       for (int j = 0; j < nkv; ++j) {
-        if (j > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }
+        if (j > 0) {                                               // dQ product of block j-1 retired → sKmn is free
+          if ((j - 1) & 1) { mbar_wait(bar_o1, ph_o1); ph_o1 ^= 1; } else { mbar_wait(bar_o0, ph_o0); ph_o0 ^= 1; }
+        }
         mbar_expect_tx(bar_mn, kSmall);
         load_mnmajor(sKmn, &P.tma_mn0, bar_mn, j * kCols, h, b);
       }
@@ -442,25 +485,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
                      adS = smem_u32(sdS);
       auto mma_s_dp = [&](int buf) {
         tc_fence_after();
-        mma_kk(tmem + (buf ? 64u : 0u), aQ, kBig / 2, aKk + buf * kSmall, kSmall / 2, idesc, false);          // S = Q·Kᵀ
-        mma_kk(tmem + 128u + (buf ? 64u : 0u), adO, kBig / 2, aVk + buf * kSmall, kSmall / 2, idesc, false);  // dP = dO·Vᵀ
+        mma_kk(tmem + (buf ? 64u : 0u), aQ, kBig / 2, aKk, kSmall / 2, idesc, false);          // S = Q·Kᵀ
+        mma_kk(tmem + 128u + (buf ? 64u : 0u), adO, kBig / 2, aVk, kSmall / 2, idesc, false);  // dP = dO·Vᵀ
         umma_commit(buf ? bar_s1 : bar_s0);
       };
-      uint32_t ph_kv[2] = {0, 0}, ph_mn = 0, ph_p = 0;
+      uint32_t ph_kv = 0, ph_mn = 0, ph_p = 0;
       mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv, ph_kv[0]); ph_kv[0] ^= 1;
+      mbar_wait(bar_of, 0);
+      mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
       mma_s_dp(0);
       for (int j = 0; j < nkv; ++j) {
         const int cur = j & 1;
         if (j + 1 < nkv) {
-          mbar_wait(bar_kv + (cur ^ 1), ph_kv[cur ^ 1]); ph_kv[cur ^ 1] ^= 1;
+          mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
           mma_s_dp(cur ^ 1);
         }
         mbar_wait(bar_mn, ph_mn); ph_mn ^= 1;
         mbar_wait(bar_p, ph_p); ph_p ^= 1;                         // dS_j is in smem
         tc_fence_after();
-        mma_kmn(tmem + 256u, adS, aKmn, idesc_mn, j > 0);          // dQ += dS_j·K_j
-        umma_commit(bar_o);
+        mma_kmn(tmem + 256u, adS + cur * kPBytes, aKmn, idesc_mn, j > 0);   // dQ += dS_j·K_j
+        umma_commit(cur ? bar_o1 : bar_o0);
       }
     }
   } else if (warp >= 2) {
@@ -472,35 +516,33 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
     const uint8_t *mrow = P.mask ? P.mask + (int64_t)b * P.m_sb + (int64_t)h * P.m_sh + (int64_t)row * P.m_ss : nullptr;
     const float scale2 = P.scale * kLog2e, mask2 = P.mask_value * kLog2e;
     float4 *stat = P.stats + ((int64_t)b * P.H + h) * P.Sq + row;
-    float m2 = 0.0f, rinv = 0.0f, delta = 0.0f;
-    {
-      // delta = sum_d dO[row, d] * O[row, d]  (= rowsum(dP ∘ P)): each of the 8 row warps takes 16 rows and reads them
-      // coalesced (a row is 256 contiguous bytes: lane l holds columns 2l, 2l+1), instead of every thread walking its
-      // own row — 32 uncoalesced 16-byte loads per thread that kept the load/store unit queue full (ncu: lg_throttle)
-      const int w8 = warp - 2;
-#pragma unroll 4
-      for (int rr = 0; rr < 16; ++rr) {
-        const int rl = w8 * 16 + rr, rg = q0 + rl;
-        float part = 0.0f;
-        if (rg < P.Sq) {
-          const float2 ov = __ldg(reinterpret_cast<const float2 *>(P.o_fwd + (int64_t)b * P.of_sb + (int64_t)h * P.of_sh + (int64_t)rg * P.of_ss) + lane);
-          const float2 gv = __ldg(reinterpret_cast<const float2 *>(P.d_out + (int64_t)b * P.do_sb + (int64_t)h * P.do_sh + (int64_t)rg * P.do_ss) + lane);
-          part = __fadd_rn(__fmul_rn(ov.x, gv.x), __fmul_rn(ov.y, gv.y));
-        }
+    float nm2 = 0.0f, rinv = 0.0f, delta = 0.0f;
+    float4 st4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row_ok) st4 = *stat;                                         // in flight while the tiles land
+    if (nkv > 0) {
+      // delta = sum_d dO[row, d] * O[row, d]  (= rowsum(dP ∘ P)) from the two tiles in shared memory: this thread sums
+      // its half of the row (conflict-free: the 128-byte swizzle spreads 8 consecutive rows over all banks), the halves
+      // meet through sDelta.  Rows past Sq are zero-filled by TMA.
+      mbar_wait(bar_of, 0);
+      const uint8_t *pd = sdO + half * (kBig / 2) + r_in * 128, *po = sdS + half * (kBig / 2) + r_in * 128;
+      float part = 0.0f;
 #pragma unroll
-        for (int sft = 16; sft >= 1; sft >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, sft));
-        if (lane == 0) sDelta[rl] = part;
+      for (int q = 0; q < 8; ++q) {
+        const int off = (q ^ (r_in & 7)) << 4;
+        const float4 g = *reinterpret_cast<const float4 *>(pd + off), ov = *reinterpret_cast<const float4 *>(po + off);
+        part = __fadd_rn(part, __fadd_rn(__fadd_rn(__fmul_rn(ov.x, g.x), __fmul_rn(ov.y, g.y)),
+                                         __fadd_rn(__fmul_rn(ov.z, g.z), __fmul_rn(ov.w, g.w))));
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 row warps only
-      delta = sDelta[r_in];
+      sDelta[half * kRows + r_in] = part;
+      asm volatile("bar.sync 1, 256;" ::: "memory");                 // the 8 row warps: partials visible, O tile no longer read
+      delta = __fadd_rn(sDelta[r_in], sDelta[kRows + r_in]);
     }
     if (row_ok) {
-      const float4 st = *stat;
-      m2 = st.x;
-      rinv = st.y;
+      nm2 = -st4.x;
+      rinv = st4.y;
       if (half == 0) stat->z = delta;      // the dK/dV kernel (launched after this one) reads it per query column
     }
-    uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
+    uint32_t ph_s0 = 0, ph_s1 = 0, ph_o0 = 0, ph_o1 = 0;
     for (int j = 0; j < nkv; ++j) {
       const int cur = j & 1;
       const int col0 = j * kCols + half * 32;
@@ -521,26 +563,41 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
         const int first = causal_limit + 1 - col0;                 // first masked column of this chunk
         masked |= first <= 0 ? 0xFFFFFFFFu : (first >= 32 ? 0u : (0xFFFFFFFFu << first));
       }
+      // warp-uniform: nothing masked in this [32 rows x 32 columns] chunk and no column past Sk — 5 instructions per
+      // element instead of the masked form's dozen (the row warps' issue slots are what bounds this kernel)
+      const bool fast = (col0 + 32 <= P.Sk) && !__any_sync(0xffffffffu, masked != 0u);
       if (cur) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
       tc_fence_after();
       uint32_t rs[32], rp[32];
       tmem_ld32(tmem + (cur ? 64u : 0u) + lane_addr + half * 32, rs);
       tmem_ld32(tmem + 128u + (cur ? 64u : 0u) + lane_addr + half * 32, rp);
       tmem_ld_wait();
+      // dS WITHOUT the softmax scale: dQ = scale · Σ_j dS_j·K_j is scaled once per output element in the epilogue
       float ds[32];
+      if (fast) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const bool mk = (masked >> c) & 1u;
-        const float t = mk ? mask2 : __fmul_rn(__uint_as_float(rs[c]), scale2);
-        float p = __fmul_rn(ex2(t - m2), rinv);
-        if (col0 + c >= P.Sk) p = 0.0f;
-        const float d = __fmul_rn(__fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), delta)), P.scale);
-        ds[c] = mk ? 0.0f : d;                                     // mask_fill backward: no gradient through a filled score
+        for (int c = 0; c < 32; ++c) {
+          const float p = __fmul_rn(ex2(__fmaf_rn(__uint_as_float(rs[c]), scale2, nm2)), rinv);
+          ds[c] = __fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), delta));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const bool mk = (masked >> c) & 1u;
+          const float t = mk ? __fadd_rn(mask2, nm2) : __fmaf_rn(__uint_as_float(rs[c]), scale2, nm2);
+          float p = __fmul_rn(ex2(t), rinv);
+          if (col0 + c >= P.Sk) p = 0.0f;
+          const float d = __fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), delta));
+          ds[c] = mk ? 0.0f : d;                                     // mask_fill backward: no gradient through a filled score
+        }
       }
-      if (j > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }            // dQ MMA of block j-1 no longer reads sdS
+      if (j > 1) {                                                 // dQ MMA of block j-2 no longer reads this dS buffer
+        if (cur) { mbar_wait(bar_o1, ph_o1); ph_o1 ^= 1; } else { mbar_wait(bar_o0, ph_o0); ph_o0 ^= 1; }
+      }
+      uint8_t *dst = sdS + cur * kPBytes + half * (kPBytes / 2);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        store_a_chunk(sdS + half * (kPBytes / 2), r_in, q, make_float4(ds[q * 4], ds[q * 4 + 1], ds[q * 4 + 2], ds[q * 4 + 3]));
+        store_a_chunk(dst, r_in, q, make_float4(ds[q * 4], ds[q * 4 + 1], ds[q * 4 + 2], ds[q * 4 + 3]));
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -548,7 +605,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
     }
     float *grow_out = P.g0 + (int64_t)b * P.g0_sb + (int64_t)h * P.g0_sh + (int64_t)row * P.g0_ss + half * 32;
     if (nkv > 0) {
-      mbar_wait(bar_o, ph_o); ph_o ^= 1;
+      if ((nkv - 1) & 1) mbar_wait(bar_o1, ph_o1); else mbar_wait(bar_o0, ph_o0);   // last block: dQ is complete
       tc_fence_after();
       uint32_t r[32];
       tmem_ld32(tmem + 256u + lane_addr + half * 32, r);
@@ -556,7 +613,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
       if (row_ok) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          reinterpret_cast<uint4 *>(grow_out)[q] = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+          reinterpret_cast<float4 *>(grow_out)[q] =
+              make_float4(__fmul_rn(__uint_as_float(r[q * 4]), P.scale), __fmul_rn(__uint_as_float(r[q * 4 + 1]), P.scale),
+                          __fmul_rn(__uint_as_float(r[q * 4 + 2]), P.scale), __fmul_rn(__uint_as_float(r[q * 4 + 3]), P.scale));
       }
     } else if (row_ok) {
 #pragma unroll
@@ -576,15 +635,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
 __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // K-major Q_i / dO_i tiles are DOUBLE-buffered (buffer it & 1) so the load of query block it+1 overlaps the products of
-  // block it; the per-query statistics are read straight from global memory (one broadcast line per column) — staging
-  // them in shared memory is what the second tile buffer now occupies (224 KB of tiles + barriers)
-  uint8_t *sK = smem, *sV = sK + kBig, *sQk = sV + kBig, *sdOk = sQk + 2 * kSmall, *sQmn = sdOk + 2 * kSmall, *sdOmn = sQmn + kSmall,
+  uint8_t *sK = smem, *sV = sK + kBig, *sQk = sV + kBig, *sdOk = sQk + kSmall, *sQmn = sdOk + kSmall, *sdOmn = sQmn + kSmall,
           *sP = sdOmn + kSmall, *sdS = sP + kPBytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sdS + kPBytes);
-  uint64_t *bar_res = bars, *bar_qk = bars + 1 /* [2] */, *bar_mn = bars + 3, *bar_s0 = bars + 4, *bar_s1 = bars + 5, *bar_p = bars + 6,
-           *bar_o = bars + 7;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+  // [3][64] (m2, 1/l, delta, -) of the block's queries.  Three buffers: the producer refills buffer it % 3 once
+  // Sᵀ_{it-1} has retired, and that MMA is only issued after the row threads delivered block it-3 — the last
+  // reader of the buffer (with two buffers the refill could overtake the readers of block it-2).
+  float4 *sStats = reinterpret_cast<float4 *>(sdS + kPBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sStats + 3 * kCols);
+  uint64_t *bar_res = bars, *bar_qk = bars + 1, *bar_mn = bars + 2, *bar_s0 = bars + 3, *bar_s1 = bars + 4, *bar_p = bars + 5,
+           *bar_o = bars + 6, *bar_st = bars + 7;     // bar_st[3]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int work = blockIdx.x;
@@ -609,12 +669,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
     tma_prefetch_desc(&P.tma_mn1);
     mbar_init(bar_res, 1);
     mbar_init(bar_qk, 1);
-    mbar_init(bar_qk + 1, 1);
     mbar_init(bar_mn, 1);
     mbar_init(bar_s0, 1);
     mbar_init(bar_s1, 1);
     mbar_init(bar_p, 8);
     mbar_init(bar_o, 1);
+    mbar_init(bar_st, 1);
+    mbar_init(bar_st + 1, 1);
+    mbar_init(bar_st + 2, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -632,14 +694,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
       load_kmajor(sV, &P.tma_v, bar_res, kv0, h, b, kBig / 2);
       uint32_t ph_s0 = 0, ph_s1 = 0;
       for (int it = 0; it < n_it; ++it) {
-        const int buf = it & 1;
-        if (it >= 2) {   // buffer it & 1 is free once Sᵀ_{it-2} / dPᵀ_{it-2} (same parity) have retired
-          if (buf) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+        if (it > 0) {
+          if ((it - 1) & 1) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
         }
-        const int r0 = (i_start + it) * kCols;
-        mbar_expect_tx(bar_qk + buf, 2 * kSmall);
-        load_kmajor(sQk + buf * kSmall, &P.tma_q, bar_qk + buf, r0, h, b, kSmall / 2);
-        load_kmajor(sdOk + buf * kSmall, &P.tma_do, bar_qk + buf, r0, h, b, kSmall / 2);
+        const int r0 = (i_start + it) * kCols, buf = it % 3;
+        mbar_expect_tx(bar_qk, 2 * kSmall);
+        load_kmajor(sQk, &P.tma_q, bar_qk, r0, h, b, kSmall / 2);
+        load_kmajor(sdOk, &P.tma_do, bar_qk, r0, h, b, kSmall / 2);
+        // the block's per-query statistics: one bulk copy, clipped at the end of the sequence
+        const uint32_t bytes = (uint32_t)min(kCols, P.Sq - r0) * 16u;
+        uint64_t *bst = bar_st + buf;
+        mbar_expect_tx(bst, bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(sStats + buf * kCols)),
+                     "l"(P.stats + stat_base + r0), "r"(bytes), "r"(smem_u32(bst))
+                     : "memory");
       }
     } else if (lane == 1 && n_it > 0) {
       uint32_t ph_o = 0;
@@ -658,18 +727,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
                      adOmn = smem_u32(sdOmn), aP = smem_u32(sP), adS = smem_u32(sdS);
       auto mma_s_dp = [&](int buf) {
         tc_fence_after();
-        mma_kk(tmem + (buf ? 64u : 0u), aK, kBig / 2, aQk + buf * kSmall, kSmall / 2, idesc, false);          // Sᵀ = K·Qᵀ
-        mma_kk(tmem + 128u + (buf ? 64u : 0u), aV, kBig / 2, adOk + buf * kSmall, kSmall / 2, idesc, false);  // dPᵀ = V·dOᵀ
+        mma_kk(tmem + (buf ? 64u : 0u), aK, kBig / 2, aQk, kSmall / 2, idesc, false);          // Sᵀ = K·Qᵀ
+        mma_kk(tmem + 128u + (buf ? 64u : 0u), aV, kBig / 2, adOk, kSmall / 2, idesc, false);  // dPᵀ = V·dOᵀ
         umma_commit(buf ? bar_s1 : bar_s0);
       };
-      uint32_t ph_qk[2] = {0, 0}, ph_mn = 0, ph_p = 0;
+      uint32_t ph_qk = 0, ph_mn = 0, ph_p = 0;
       mbar_wait(bar_res, 0);
-      mbar_wait(bar_qk, ph_qk[0]); ph_qk[0] ^= 1;
+      mbar_wait(bar_qk, ph_qk); ph_qk ^= 1;
       mma_s_dp(0);
       for (int it = 0; it < n_it; ++it) {
         const int cur = it & 1;
         if (it + 1 < n_it) {
-          mbar_wait(bar_qk + (cur ^ 1), ph_qk[cur ^ 1]); ph_qk[cur ^ 1] ^= 1;
+          mbar_wait(bar_qk, ph_qk); ph_qk ^= 1;
           mma_s_dp(cur ^ 1);
         }
         mbar_wait(bar_mn, ph_mn); ph_mn ^= 1;
@@ -690,7 +759,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
     const float scale2 = P.scale * kLog2e, mask2 = P.mask_value * kLog2e;
     uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
     for (int it = 0; it < n_it; ++it) {
-      const int cur = it & 1;
+      const int cur = it & 1, sb = it % 3;
       const int qc0 = (i_start + it) * kCols + half * 32;
       uint32_t mbits = 0;                                           // bit c: explicit mask at (query qc0 + c, key kv)
       if (mcol && kv_ok) {                                          // fetched before the waits
@@ -698,25 +767,41 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
         for (int c = 0; c < 32; ++c)
           if (qc0 + c < P.Sq && __ldg(mcol + (int64_t)(qc0 + c) * P.m_ss)) mbits |= 1u << c;
       }
+      mbar_wait(bar_st + sb, (uint32_t)((it / 3) & 1));
       if (cur) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
       tc_fence_after();
       uint32_t rs[32], rp[32];
       tmem_ld32(tmem + (cur ? 64u : 0u) + lane_addr + half * 32, rs);
       tmem_ld32(tmem + 128u + (cur ? 64u : 0u) + lane_addr + half * 32, rp);
       tmem_ld_wait();
-      const float4 *st = P.stats + stat_base + qc0;                // same address for the whole warp: one broadcast line
+      const float4 *st = sStats + sb * kCols + half * 32;
+      // warp-uniform: every (key, query) pair of this [32 keys x 32 queries] chunk is in range and unmasked — 6
+      // instructions per element instead of the masked form's two dozen (the row warps' issue slots bound this kernel).
+      // dSᵀ is delivered WITHOUT the softmax scale: dK = scale · Σ_i dSᵀ_i·Q_i is scaled once per element in the epilogue.
+      const bool fast = (qc0 + 32 <= P.Sq) && (kv0 + quarter * 32 + 32 <= P.Sk) &&
+                        !(P.causal && kv0 + quarter * 32 + 31 > qc0 + shift) && !__any_sync(0xffffffffu, mbits != 0u);
       float pv[32], ds[32];
+      if (fast) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int q = qc0 + c;
-        const bool q_ok = q < P.Sq;
-        const float4 sq = q_ok ? __ldg(st + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool mk = (P.causal && kv > q + shift) || ((mbits >> c) & 1u);
-        const float t = mk ? mask2 : __fmul_rn(__uint_as_float(rs[c]), scale2);
-        float p = (q_ok && kv_ok) ? __fmul_rn(ex2(t - sq.x), sq.y) : 0.0f;
-        const float d = __fmul_rn(__fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), sq.z)), P.scale);
-        pv[c] = p;
-        ds[c] = (mk || !(q_ok && kv_ok)) ? 0.0f : d;
+        for (int c = 0; c < 32; ++c) {
+          const float4 sq = st[c];                                  // smem broadcast
+          const float p = __fmul_rn(ex2(__fmaf_rn(__uint_as_float(rs[c]), scale2, -sq.x)), sq.y);
+          pv[c] = p;
+          ds[c] = __fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), sq.z));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int q = qc0 + c;
+          const bool q_ok = q < P.Sq;
+          const float4 sq = st[c];                                  // smem broadcast; garbage past Sq is never used
+          const bool mk = (P.causal && kv > q + shift) || ((mbits >> c) & 1u);
+          const float t = mk ? __fsub_rn(mask2, sq.x) : __fmaf_rn(__uint_as_float(rs[c]), scale2, -sq.x);
+          float p = (q_ok && kv_ok) ? __fmul_rn(ex2(t), sq.y) : 0.0f;
+          const float d = __fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), sq.z));
+          pv[c] = p;
+          ds[c] = (mk || !(q_ok && kv_ok)) ? 0.0f : d;
+        }
       }
       if (it > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }            // dV / dK MMAs of block it-1 no longer read sP / sdS
 #pragma unroll
@@ -742,7 +827,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           reinterpret_cast<uint4 *>(dv_row)[q] = make_uint4(rv[q * 4], rv[q * 4 + 1], rv[q * 4 + 2], rv[q * 4 + 3]);
-          reinterpret_cast<uint4 *>(dk_row)[q] = make_uint4(rk[q * 4], rk[q * 4 + 1], rk[q * 4 + 2], rk[q * 4 + 3]);
+          reinterpret_cast<float4 *>(dk_row)[q] =
+              make_float4(__fmul_rn(__uint_as_float(rk[q * 4]), P.scale), __fmul_rn(__uint_as_float(rk[q * 4 + 1]), P.scale),
+                          __fmul_rn(__uint_as_float(rk[q * 4 + 2]), P.scale), __fmul_rn(__uint_as_float(rk[q * 4 + 3]), P.scale));
         }
       }
     } else if (kv_ok) {
@@ -907,13 +994,14 @@ extern "C" int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out
   if ((st = fa_map(&P.tma_k, k, false, fa::kCols, B, H)) != B200_OK) return st;
   if ((st = fa_map(&P.tma_v, v, false, fa::kCols, B, H)) != B200_OK) return st;
   if ((st = fa_map(&P.tma_mn0, k, true, 0, B, H)) != B200_OK) return st;
+  if ((st = fa_map(&P.tma_mn1, out, false, fa::kRows, B, H)) != B200_OK) return st;   // forward output tile, for delta
   P.g0 = reinterpret_cast<float *>(dq->ptr);
   P.g0_sb = dq->strides[0]; P.g0_sh = dq->strides[1]; P.g0_ss = dq->strides[2];
   P.blocks = (int32_t)((Sq + fa::kRows - 1) / fa::kRows);
   {
     const int64_t ctas = B * H * P.blocks;
     B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
-    const size_t smem = 1024 + 2 * fa::kBig + 5 * fa::kSmall + fa::kPBytes + fa::kRows * 4 + 128;
+    const size_t smem = 1024 + 2 * fa::kBig + 3 * fa::kSmall + 2 * fa::kPBytes + 2 * fa::kRows * 4 + 128;
     if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dq_kernel), smem)) != B200_OK) return st;
     fa::flash_bwd_dq_kernel<<<(unsigned)ctas, fa::kBwdThreads, smem, stream>>>(P);
     B200_LAUNCH_CHECK();
@@ -933,7 +1021,7 @@ extern "C" int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out
   {
     const int64_t ctas = B * H * P.blocks;
     B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
-    const size_t smem = 1024 + 2 * fa::kBig + 6 * fa::kSmall + 2 * fa::kPBytes + 128;
+    const size_t smem = 1024 + 2 * fa::kBig + 4 * fa::kSmall + 2 * fa::kPBytes + 3 * fa::kCols * 16 + 128;
     if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dkv_kernel), smem)) != B200_OK) return st;
     fa::flash_bwd_dkv_kernel<<<(unsigned)ctas, fa::kBwdThreads, smem, stream>>>(P);
     B200_LAUNCH_CHECK();
