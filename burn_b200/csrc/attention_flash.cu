@@ -34,6 +34,25 @@ namespace fa {
 
 using namespace mm;
 
+// Every mbarrier wait of these kernels is bounded: a protocol error traps (the launch fails with an error the host sees)
+// instead of hanging the device.  The try_wait carries a suspend-time hint, so a waiting thread sleeps in hardware until
+// the phase completes instead of polling — polls of the producer / issuer / early row warps compete with the row warps'
+// arithmetic for issue slots (a seven-instruction poll loop cost the forward kernel 35 %).
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .u32 n;\nmov.u32 n, 0;\n"
+      "FA_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra FA_WAIT_DONE;\n"
+      "add.u32 n, n, 1;\n"
+      "setp.lt.u32 p, n, %3;\n"
+      "@p bra FA_WAIT_LOOP;\n"
+      "trap;\n"
+      "FA_WAIT_DONE:\n}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u), "r"(1u << 24)
+      : "memory");
+}
+
 constexpr int HD = 64;
 constexpr int kRows = 128;                      // rows a CTA owns (= TMEM lanes)
 constexpr int kCols = 64;                       // columns per loop iteration
@@ -400,19 +419,30 @@ struct BwdParams {
 
 constexpr int kBwdThreads = 320;   // issuer warp, TMEM-allocator warp, 8 row warps (two per TMEM lane quarter)
 
+// D[128 x 64] (+)= A[128 x 64] (tensor memory: lanes = rows, 64 consecutive columns) · B[64 k x 64 n] (MN-major smem tile)
+__device__ __forceinline__ void mma_tmn(uint32_t tmem_d, uint32_t tmem_a, uint32_t b, uint32_t idesc_mn, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < kCols / 8; ++k) {
+    const uint64_t db = make_desc(b + (k >> 2) * 8192 + (k & 3) * 1024, 4096, 512, 1);
+    umma_ts_tf32(tmem_d, tmem_a + k * 8, db, idesc_mn, (accumulate || k) ? 1u : 0u);
+  }
+}
+
 __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // sdS is DOUBLE-buffered (buffer j & 1): the row threads deliver dS_{j+1} while the tensor core still reads dS_j, so
-  // they only ever wait for the dQ product of block j-1 — two iterations of slack instead of a lock step with the MMA.
-  // Before the loop the first buffer receives the O tile (TMA), from which delta = rowsum(dO ∘ O) is computed in shared
-  // memory: no per-thread global row walks in the prologue.
-  uint8_t *sQ = smem, *sdO = sQ + kBig, *sKk = sdO + kBig, *sVk = sKk + kSmall, *sKmn = sVk + kSmall, *sdS = sKmn + kSmall;
-  float *sDelta = reinterpret_cast<float *>(sdS + 2 * kPBytes);      // [2][128] half-row partial sums
+  // Every streamed tile is double-buffered (buffer j & 1) so that the TMA round trip of block j+1 is in flight while
+  // block j is multiplied.  dS never touches shared memory: the row threads overwrite the dP accumulator tile in
+  // tensor memory in place and the dQ product reads its A operand from there.  sO receives the forward output tile,
+  // from which delta = rowsum(dO ∘ O) is computed in shared memory (no per-thread global row walks in the prologue).
+  uint8_t *sQ = smem, *sdO = sQ + kBig, *sO = sdO + kBig, *sKk = sO + kBig, *sVk = sKk + 2 * kSmall, *sKmn = sVk + 2 * kSmall;
+  float *sDelta = reinterpret_cast<float *>(sKmn + 2 * kSmall);      // [2][128] half-row partial sums
   uint64_t *bars = reinterpret_cast<uint64_t *>(sDelta + 2 * kRows);
-  uint64_t *bar_q = bars, *bar_kv = bars + 1, *bar_mn = bars + 2, *bar_s0 = bars + 3, *bar_s1 = bars + 4, *bar_p = bars + 5,
-           *bar_o0 = bars + 6, *bar_o1 = bars + 7, *bar_of = bars + 8;   // bar_o{b}: the dQ product that read dS buffer b retired
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+  uint64_t *bar_q = bars, *bar_of = bars + 1, *bar_kv = bars + 2 /*[2]*/, *bar_mn = bars + 4 /*[2]*/, *bar_s = bars + 6 /*[2]*/,
+           *bar_o = bars + 8 /*[2]*/, *bar_p = bars + 10 /*[2]*/, *bar_done = bars + 12;
+  // bar_p is per buffer too: a row warp may deliver dS_{j+1} before a slower warp has delivered dS_j (S_{j+1} is issued
+  // ahead of the wait for dS_j); on a single barrier that early arrival would complete block j's phase one warp short
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int work = blockIdx.x;
@@ -433,79 +463,71 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
     tma_prefetch_desc(&P.tma_v);
     tma_prefetch_desc(&P.tma_mn0);
     tma_prefetch_desc(&P.tma_mn1);
-    mbar_init(bar_q, 1);
-    mbar_init(bar_of, 1);
-    mbar_init(bar_kv, 1);
-    mbar_init(bar_mn, 1);
-    mbar_init(bar_s0, 1);
-    mbar_init(bar_s1, 1);
-    mbar_init(bar_p, 8);
-    mbar_init(bar_o0, 1);
-    mbar_init(bar_o1, 1);
+    for (int i = 0; i < 13; ++i) mbar_init(bars + i, (i == 10 || i == 11) ? 8 : 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;        // S0 @0, S1 @64, dP0 @128, dP1 @192, dQ @256
+  const uint32_t tmem = *tmem_slot;        // S0 @0, S1 @64, dP0 / dS0 @128, dP1 / dS1 @192, dQ @256
 
   if (warp == 0) {
-    // TMA producers: lane 0 streams the K-major K_j / V_j tiles (free when S_j / dP_j retire), lane 1 the
-    // MN-major K_j tile (free when the dQ MMA of block j retires)
+    // TMA producers: lane 0 streams the K-major K_j / V_j tiles (buffer free when S_{j-2} / dP_{j-2} retired), lane 1
+    // the MN-major K_j tile (buffer free when the dQ product of block j-2 retired)
     if (lane == 0 && nkv > 0) {
       mbar_expect_tx(bar_of, 2 * kBig);                                // dO and O first: delta is the row threads' prologue
       load_kmajor(sdO, &P.tma_do, bar_of, q0, h, b, kBig / 2);
-      load_kmajor(sdS, &P.tma_mn1, bar_of, q0, h, b, kBig / 2);         // O tile (K-major, 128 rows) into dS buffer 0
+      load_kmajor(sO, &P.tma_mn1, bar_of, q0, h, b, kBig / 2);
       mbar_expect_tx(bar_q, kBig);
       load_kmajor(sQ, &P.tma_q, bar_q, q0, h, b, kBig / 2);
-      uint32_t ph_s0 = 0, ph_s1 = 0;
+      uint32_t ph[2] = {0, 0};
       for (int j = 0; j < nkv; ++j) {
-        if (j > 0) {
-          if ((j - 1) & 1) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
-        }
-        mbar_expect_tx(bar_kv, 2 * kSmall);
-        load_kmajor(sKk, &P.tma_k, bar_kv, j * kCols, h, b, kSmall / 2);
-        load_kmajor(sVk, &P.tma_v, bar_kv, j * kCols, h, b, kSmall / 2);
+        const int buf = j & 1;
+        if (j >= 2) { mbar_wait(bar_s + buf, ph[buf]); ph[buf] ^= 1; }
+        mbar_expect_tx(bar_kv + buf, 2 * kSmall);
+        load_kmajor(sKk + buf * kSmall, &P.tma_k, bar_kv + buf, j * kCols, h, b, kSmall / 2);
+        load_kmajor(sVk + buf * kSmall, &P.tma_v, bar_kv + buf, j * kCols, h, b, kSmall / 2);
       }
     } else if (lane == 1 && nkv > 0) {
-      uint32_t ph_o0 = 0, ph_o1 = 0;
+      uint32_t ph[2] = {0, 0};
       for (int j = 0; j < nkv; ++j) {
-        if (j > 0) {                                               // dQ product of block j-1 retired → sKmn is free
-          if ((j - 1) & 1) { mbar_wait(bar_o1, ph_o1); ph_o1 ^= 1; } else { mbar_wait(bar_o0, ph_o0); ph_o0 ^= 1; }
-        }
-        mbar_expect_tx(bar_mn, kSmall);
-        load_mnmajor(sKmn, &P.tma_mn0, bar_mn, j * kCols, h, b);
+        const int buf = j & 1;
+        if (j >= 2) { mbar_wait(bar_o + buf, ph[buf]); ph[buf] ^= 1; }
+        mbar_expect_tx(bar_mn + buf, kSmall);
+        load_mnmajor(sKmn + buf * kSmall, &P.tma_mn0, bar_mn + buf, j * kCols, h, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && nkv > 0) {
       const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
-      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKk = smem_u32(sKk), aVk = smem_u32(sVk), aKmn = smem_u32(sKmn),
-                     adS = smem_u32(sdS);
+      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKk = smem_u32(sKk), aVk = smem_u32(sVk), aKmn = smem_u32(sKmn);
       auto mma_s_dp = [&](int buf) {
         tc_fence_after();
-        mma_kk(tmem + (buf ? 64u : 0u), aQ, kBig / 2, aKk, kSmall / 2, idesc, false);          // S = Q·Kᵀ
-        mma_kk(tmem + 128u + (buf ? 64u : 0u), adO, kBig / 2, aVk, kSmall / 2, idesc, false);  // dP = dO·Vᵀ
-        umma_commit(buf ? bar_s1 : bar_s0);
+        mma_kk(tmem + buf * 64u, aQ, kBig / 2, aKk + buf * kSmall, kSmall / 2, idesc, false);           // S = Q·Kᵀ
+        mma_kk(tmem + 128u + buf * 64u, adO, kBig / 2, aVk + buf * kSmall, kSmall / 2, idesc, false);   // dP = dO·Vᵀ
+        umma_commit(bar_s + buf);
       };
-      uint32_t ph_kv = 0, ph_mn = 0, ph_p = 0;
+      uint32_t ph_kv[2] = {0, 0}, ph_mn[2] = {0, 0}, ph_p[2] = {0, 0};
       mbar_wait(bar_q, 0);
       mbar_wait(bar_of, 0);
-      mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
+      mbar_wait(bar_kv, ph_kv[0]); ph_kv[0] ^= 1;
       mma_s_dp(0);
       for (int j = 0; j < nkv; ++j) {
         const int cur = j & 1;
         if (j + 1 < nkv) {
-          mbar_wait(bar_kv, ph_kv); ph_kv ^= 1;
+          // S_{j+1} / dP_{j+1} overwrite the tiles of block j-1, whose dQ product was issued before them (the tensor
+          // pipe runs in issue order) and whose row threads are done (they delivered dS_{j-1})
+          mbar_wait(bar_kv + (cur ^ 1), ph_kv[cur ^ 1]); ph_kv[cur ^ 1] ^= 1;
           mma_s_dp(cur ^ 1);
         }
-        mbar_wait(bar_mn, ph_mn); ph_mn ^= 1;
-        mbar_wait(bar_p, ph_p); ph_p ^= 1;                         // dS_j is in smem
+        mbar_wait(bar_mn + cur, ph_mn[cur]); ph_mn[cur] ^= 1;
+        mbar_wait(bar_p + cur, ph_p[cur]); ph_p[cur] ^= 1;           // dS_j is in tensor memory (over dP_j)
         tc_fence_after();
-        mma_kmn(tmem + 256u, adS + cur * kPBytes, aKmn, idesc_mn, j > 0);   // dQ += dS_j·K_j
-        umma_commit(cur ? bar_o1 : bar_o0);
+        mma_tmn(tmem + 256u, tmem + 128u + cur * 64u, aKmn + cur * kSmall, idesc_mn, j > 0);   // dQ += dS_j·K_j
+        umma_commit(bar_o + cur);
       }
+      umma_commit(bar_done);
     }
   } else if (warp >= 2) {
     const int quarter = warp & 3, half = (warp - 2) >> 2;
@@ -524,7 +546,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
       // its half of the row (conflict-free: the 128-byte swizzle spreads 8 consecutive rows over all banks), the halves
       // meet through sDelta.  Rows past Sq are zero-filled by TMA.
       mbar_wait(bar_of, 0);
-      const uint8_t *pd = sdO + half * (kBig / 2) + r_in * 128, *po = sdS + half * (kBig / 2) + r_in * 128;
+      const uint8_t *pd = sdO + half * (kBig / 2) + r_in * 128, *po = sO + half * (kBig / 2) + r_in * 128;
       float part = 0.0f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -534,7 +556,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
                                          __fadd_rn(__fmul_rn(ov.z, g.z), __fmul_rn(ov.w, g.w))));
       }
       sDelta[half * kRows + r_in] = part;
-      asm volatile("bar.sync 1, 256;" ::: "memory");                 // the 8 row warps: partials visible, O tile no longer read
+      asm volatile("bar.sync 1, 256;" ::: "memory");                 // the 8 row warps: both half-row partials are visible
       delta = __fadd_rn(sDelta[r_in], sDelta[kRows + r_in]);
     }
     if (row_ok) {
@@ -542,7 +564,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
       rinv = st4.y;
       if (half == 0) stat->z = delta;      // the dK/dV kernel (launched after this one) reads it per query column
     }
-    uint32_t ph_s0 = 0, ph_s1 = 0, ph_o0 = 0, ph_o1 = 0;
+    uint32_t ph_s[2] = {0, 0};
     for (int j = 0; j < nkv; ++j) {
       const int cur = j & 1;
       const int col0 = j * kCols + half * 32;
@@ -564,21 +586,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
         masked |= first <= 0 ? 0xFFFFFFFFu : (first >= 32 ? 0u : (0xFFFFFFFFu << first));
       }
       // warp-uniform: nothing masked in this [32 rows x 32 columns] chunk and no column past Sk — 5 instructions per
-      // element instead of the masked form's dozen (the row warps' issue slots are what bounds this kernel)
+      // element instead of the masked form's dozen
       const bool fast = (col0 + 32 <= P.Sk) && !__any_sync(0xffffffffu, masked != 0u);
-      if (cur) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+      mbar_wait(bar_s + cur, ph_s[cur]); ph_s[cur] ^= 1;
       tc_fence_after();
+      const uint32_t t_dp = tmem + 128u + cur * 64u + lane_addr + half * 32;
       uint32_t rs[32], rp[32];
-      tmem_ld32(tmem + (cur ? 64u : 0u) + lane_addr + half * 32, rs);
-      tmem_ld32(tmem + 128u + (cur ? 64u : 0u) + lane_addr + half * 32, rp);
+      tmem_ld32(tmem + cur * 64u + lane_addr + half * 32, rs);
+      tmem_ld32(t_dp, rp);
       tmem_ld_wait();
       // dS WITHOUT the softmax scale: dQ = scale · Σ_j dS_j·K_j is scaled once per output element in the epilogue
-      float ds[32];
       if (fast) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const float p = __fmul_rn(ex2(__fmaf_rn(__uint_as_float(rs[c]), scale2, nm2)), rinv);
-          ds[c] = __fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), delta));
+          rp[c] = __float_as_uint(__fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), delta)));
         }
       } else {
 #pragma unroll
@@ -588,24 +610,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
           float p = __fmul_rn(ex2(t), rinv);
           if (col0 + c >= P.Sk) p = 0.0f;
           const float d = __fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), delta));
-          ds[c] = mk ? 0.0f : d;                                     // mask_fill backward: no gradient through a filled score
+          rp[c] = __float_as_uint(mk ? 0.0f : d);                   // mask_fill backward: no gradient through a filled score
         }
       }
-      if (j > 1) {                                                 // dQ MMA of block j-2 no longer reads this dS buffer
-        if (cur) { mbar_wait(bar_o1, ph_o1); ph_o1 ^= 1; } else { mbar_wait(bar_o0, ph_o0); ph_o0 ^= 1; }
-      }
-      uint8_t *dst = sdS + cur * kPBytes + half * (kPBytes / 2);
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        store_a_chunk(dst, r_in, q, make_float4(ds[q * 4], ds[q * 4 + 1], ds[q * 4 + 2], ds[q * 4 + 3]));
-      fence_proxy_async();
+      tmem_st32(t_dp, rp);                                          // dS_j over dP_j, in place
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
+      if (lane == 0) mbar_arrive(bar_p + cur);
     }
     float *grow_out = P.g0 + (int64_t)b * P.g0_sb + (int64_t)h * P.g0_sh + (int64_t)row * P.g0_ss + half * 32;
     if (nkv > 0) {
-      if ((nkv - 1) & 1) mbar_wait(bar_o1, ph_o1); else mbar_wait(bar_o0, ph_o0);   // last block: dQ is complete
+      mbar_wait(bar_done, 0);                                       // every product has retired: dQ is complete
       tc_fence_after();
       uint32_t r[32];
       tmem_ld32(tmem + 256u + lane_addr + half * 32, r);
@@ -1001,7 +1017,7 @@ extern "C" int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out
   {
     const int64_t ctas = B * H * P.blocks;
     B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
-    const size_t smem = 1024 + 2 * fa::kBig + 3 * fa::kSmall + 2 * fa::kPBytes + 2 * fa::kRows * 4 + 128;
+    const size_t smem = 1024 + 3 * fa::kBig + 6 * fa::kSmall + 2 * fa::kRows * 4 + 128;
     if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dq_kernel), smem)) != B200_OK) return st;
     fa::flash_bwd_dq_kernel<<<(unsigned)ctas, fa::kBwdThreads, smem, stream>>>(P);
     B200_LAUNCH_CHECK();

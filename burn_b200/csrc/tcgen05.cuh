@@ -29,12 +29,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // %2: suspend-time hint — sleep in hardware, do not poll
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -97,12 +97,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 // arrive on the LEADER CTA's copy of `bar` (no-op mask when executed by the leader itself)
@@ -179,6 +179,28 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: thread (= lane of its warp's lane quarter) writes 32 consecutive 32-bit columns of its own row
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] · B[smem descriptor], tf32: the A operand (M = 128 rows = TMEM lanes, K = 8 consecutive 32-bit
+// columns per instruction) is read from tensor memory — the layout an accumulator tile has, so a tile that the row
+// threads rewrote in place (weights over scores) feeds the next product without a trip through shared memory
+__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
