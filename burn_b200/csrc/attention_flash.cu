@@ -53,6 +53,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
 }
 
+// The issuer WARP runs converged and every lane executes the same issue code with warp-uniform operands; the single
+// issuing lane is chosen by elect.sync INSIDE the asm statement.  Issued from an `if (lane == 0)` region instead, the
+// compiler cannot prove the descriptors uniform and wraps every tcgen05.mma in a 16-instruction ELECT / R2UR.BROADCAST /
+// BRA.U.ANY waterfall — with [128 x 64 x 8] tf32 instructions (32-48 tensor-pipe cycles each) that single thread's issue
+// rate, not the tensor pipe or the softmax arithmetic, bounded all three kernels (ncu: tensor pipe active 20-23 %).
+__device__ __forceinline__ void umma_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p, q;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p, q;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void commit_e(uint64_t *bar) {
+  asm volatile(
+      "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 constexpr int HD = 64;
 constexpr int kRows = 128;                      // rows a CTA owns (= TMEM lanes)
 constexpr int kCols = 64;                       // columns per loop iteration
@@ -87,7 +113,7 @@ __device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a, uint32_t a_h
   for (int k = 0; k < HD / 8; ++k) {
     const uint64_t da = make_desc(a + (k >> 2) * a_half + (k & 3) * 32, 16, 1024);
     const uint64_t db = make_desc(b + (k >> 2) * b_half + (k & 3) * 32, 16, 1024);
-    umma<false>(tmem_d, da, db, idesc, (accumulate || k) ? 1u : 0u);
+    umma_e(tmem_d, da, db, idesc, (accumulate || k) ? 1u : 0u);
   }
 }
 // D[128 x 64] (+)= A[128 x 64] (K-major, halves kPBytes/2 apart) · B[64 k x 64 n] (MN-major tile)
@@ -96,7 +122,7 @@ __device__ __forceinline__ void mma_kmn(uint32_t tmem_d, uint32_t a, uint32_t b,
   for (int k = 0; k < kCols / 8; ++k) {
     const uint64_t da = make_desc(a + (k >> 2) * (kPBytes / 2) + (k & 3) * 32, 16, 1024);
     const uint64_t db = make_desc(b + (k >> 2) * 8192 + (k & 3) * 1024, 4096, 512, 1);
-    umma<false>(tmem_d, da, db, idesc_mn, (accumulate || k) ? 1u : 0u);
+    umma_e(tmem_d, da, db, idesc_mn, (accumulate || k) ? 1u : 0u);
   }
 }
 __device__ __forceinline__ uint32_t make_idesc() {
@@ -198,7 +224,7 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nkv > 0) {
+    if (nkv > 0) {   // the whole warp, converged: see umma_e
       // ===================== MMA issuer =====================
       const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
@@ -207,7 +233,7 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
       mbar_wait(bar_k, ph_k); ph_k ^= 1;
       tc_fence_after();
       mma_kk(tmem, aQ, kBig / 2, aK, kSmall / 2, idesc, false);
-      umma_commit(bar_s0);
+      commit_e(bar_s0);
       for (int j = 0; j < nkv; ++j) {
         const int cur = j & 1;
         if (j + 1 < nkv) {
@@ -216,13 +242,13 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
           mbar_wait(bar_k, ph_k); ph_k ^= 1;
           tc_fence_after();
           mma_kk(tmem + (cur ? 0u : 64u), aQ, kBig / 2, aK, kSmall / 2, idesc, false);
-          umma_commit(cur ? bar_s0 : bar_s1);
+          commit_e(cur ? bar_s0 : bar_s1);
         }
         mbar_wait(bar_v, ph_v); ph_v ^= 1;
         mbar_wait(bar_p, ph_p); ph_p ^= 1;                       // P_j is in smem; PV_{j-1} has been folded in
         tc_fence_after();
         mma_kmn(tmem + 128u + (cur ? 64u : 0u), aP, aV, idesc_mn, false);
-        umma_commit(bar_o);
+        commit_e(bar_o);
       }
     }
   } else if (warp >= 2) {
@@ -424,7 +450,7 @@ __device__ __forceinline__ void mma_tmn(uint32_t tmem_d, uint32_t tmem_a, uint32
 #pragma unroll
   for (int k = 0; k < kCols / 8; ++k) {
     const uint64_t db = make_desc(b + (k >> 2) * 8192 + (k & 3) * 1024, 4096, 512, 1);
-    umma_ts_tf32(tmem_d, tmem_a + k * 8, db, idesc_mn, (accumulate || k) ? 1u : 0u);
+    umma_ts_e(tmem_d, tmem_a + k * 8, db, idesc_mn, (accumulate || k) ? 1u : 0u);
   }
 }
 
@@ -499,14 +525,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nkv > 0) {
+    if (nkv > 0) {   // the whole warp, converged: see umma_e
       const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKk = smem_u32(sKk), aVk = smem_u32(sVk), aKmn = smem_u32(sKmn);
       auto mma_s_dp = [&](int buf) {
         tc_fence_after();
         mma_kk(tmem + buf * 64u, aQ, kBig / 2, aKk + buf * kSmall, kSmall / 2, idesc, false);           // S = Q·Kᵀ
         mma_kk(tmem + 128u + buf * 64u, adO, kBig / 2, aVk + buf * kSmall, kSmall / 2, idesc, false);   // dP = dO·Vᵀ
-        umma_commit(bar_s + buf);
+        commit_e(bar_s + buf);
       };
       uint32_t ph_kv[2] = {0, 0}, ph_mn[2] = {0, 0}, ph_p[2] = {0, 0};
       mbar_wait(bar_q, 0);
@@ -525,9 +551,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
         mbar_wait(bar_p + cur, ph_p[cur]); ph_p[cur] ^= 1;           // dS_j is in tensor memory (over dP_j)
         tc_fence_after();
         mma_tmn(tmem + 256u, tmem + 128u + cur * 64u, aKmn + cur * kSmall, idesc_mn, j > 0);   // dQ += dS_j·K_j
-        umma_commit(bar_o + cur);
+        commit_e(bar_o + cur);
       }
-      umma_commit(bar_done);
+      commit_e(bar_done);
     }
   } else if (warp >= 2) {
     const int quarter = warp & 3, half = (warp - 2) >> 2;
@@ -737,7 +763,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_it > 0) {
+    if (n_it > 0) {   // the whole warp, converged: see umma_e
       const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQk = smem_u32(sQk), adOk = smem_u32(sdOk), aQmn = smem_u32(sQmn),
                      adOmn = smem_u32(sdOmn), aP = smem_u32(sP), adS = smem_u32(sdS);
@@ -745,7 +771,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
         tc_fence_after();
         mma_kk(tmem + (buf ? 64u : 0u), aK, kBig / 2, aQk, kSmall / 2, idesc, false);          // Sᵀ = K·Qᵀ
         mma_kk(tmem + 128u + (buf ? 64u : 0u), aV, kBig / 2, adOk, kSmall / 2, idesc, false);  // dPᵀ = V·dOᵀ
-        umma_commit(buf ? bar_s1 : bar_s0);
+        commit_e(buf ? bar_s1 : bar_s0);
       };
       uint32_t ph_qk = 0, ph_mn = 0, ph_p = 0;
       mbar_wait(bar_res, 0);
@@ -762,7 +788,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
         tc_fence_after();
         mma_kmn(tmem + 256u, aP, adOmn, idesc_mn, it > 0);         // dV += Pᵀ·dO_i
         mma_kmn(tmem + 320u, adS, aQmn, idesc_mn, it > 0);         // dK += dSᵀ·Q_i
-        umma_commit(bar_o);
+        commit_e(bar_o);
       }
     }
   } else if (warp >= 2) {
