@@ -454,7 +454,12 @@ __device__ __forceinline__ void mma_tmn(uint32_t tmem_d, uint32_t tmem_a, uint32
   }
 }
 
-__global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __grid_constant__ BwdParams P) {
+// PARTS row threads share a query row, CW = 64 / PARTS score columns each (PARTS x 4 row warps: a TMEM lane quarter is
+// reachable from warps w with w % 4 == quarter).  Nothing in the backward couples the columns of a row — m, 1/l and delta
+// are per-row constants — so more, narrower row threads only add warps for the schedulers to hide MUFU / TMEM latency with.
+template <int PARTS>
+__global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_kernel(const __grid_constant__ BwdParams P) {
+  constexpr int CW = kCols / PARTS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // Every streamed tile is double-buffered (buffer j & 1) so that the TMA round trip of block j+1 is in flight while
@@ -462,8 +467,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
   // tensor memory in place and the dQ product reads its A operand from there.  sO receives the forward output tile,
   // from which delta = rowsum(dO ∘ O) is computed in shared memory (no per-thread global row walks in the prologue).
   uint8_t *sQ = smem, *sdO = sQ + kBig, *sO = sdO + kBig, *sKk = sO + kBig, *sVk = sKk + 2 * kSmall, *sKmn = sVk + 2 * kSmall;
-  float *sDelta = reinterpret_cast<float *>(sKmn + 2 * kSmall);      // [2][128] half-row partial sums
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sDelta + 2 * kRows);
+  float *sDelta = reinterpret_cast<float *>(sKmn + 2 * kSmall);      // [PARTS][128] partial row sums
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sDelta + PARTS * kRows);
   uint64_t *bar_q = bars, *bar_of = bars + 1, *bar_kv = bars + 2 /*[2]*/, *bar_mn = bars + 4 /*[2]*/, *bar_s = bars + 6 /*[2]*/,
            *bar_o = bars + 8 /*[2]*/, *bar_p = bars + 10 /*[2]*/, *bar_done = bars + 12;
   // bar_p is per buffer too: a row warp may deliver dS_{j+1} before a slower warp has delivered dS_j (S_{j+1} is issued
@@ -489,7 +494,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
     tma_prefetch_desc(&P.tma_v);
     tma_prefetch_desc(&P.tma_mn0);
     tma_prefetch_desc(&P.tma_mn1);
-    for (int i = 0; i < 13; ++i) mbar_init(bars + i, (i == 10 || i == 11) ? 8 : 1);
+    for (int i = 0; i < 13; ++i)   // bar_s: both the S and the dP issuer commit; bar_p: one arrival per row warp
+      mbar_init(bars + i, (i == 10 || i == 11) ? 4 * PARTS : ((i == 6 || i == 7) ? 2 : 1));
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -524,39 +530,54 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
         load_mnmajor(sKmn + buf * kSmall, &P.tma_mn0, bar_mn + buf, j * kCols, h, b);
       }
     }
-  } else if (warp == 1) {
-    if (nkv > 0) {   // the whole warp, converged: see umma_e
+  } else if (warp <= 3) {
+    // Three issuer warps, one product each, each on its own scheduler: with [128 x 64 x 8] tf32 instructions the issue
+    // path of a single thread (descriptor arithmetic + five R2UR per tcgen05.mma, ~120 cycles each against 32-48 cycles
+    // of tensor-pipe work) bounded the kernel at a quarter of the tensor rate.  tcgen05.commit tracks the issuing
+    // thread's own instructions, so every hand-over between the issuers goes through an mbarrier:
+    //   S_j   overwrites S_{j-2}   -> the row threads have read it               (bar_p of block j-2)
+    //   dP_j  overwrites dS_{j-2}  -> the dQ product of block j-2 has retired    (bar_o of block j-2)
+    //   dQ_j  reads dS_j           -> the row threads have delivered it          (bar_p of block j)
+    if (nkv > 0) {   // whole warps, converged: see umma_e
       const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
-      const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aKk = smem_u32(sKk), aVk = smem_u32(sVk), aKmn = smem_u32(sKmn);
-      auto mma_s_dp = [&](int buf) {
-        tc_fence_after();
-        mma_kk(tmem + buf * 64u, aQ, kBig / 2, aKk + buf * kSmall, kSmall / 2, idesc, false);           // S = Q·Kᵀ
-        mma_kk(tmem + 128u + buf * 64u, adO, kBig / 2, aVk + buf * kSmall, kSmall / 2, idesc, false);   // dP = dO·Vᵀ
-        commit_e(bar_s + buf);
-      };
-      uint32_t ph_kv[2] = {0, 0}, ph_mn[2] = {0, 0}, ph_p[2] = {0, 0};
-      mbar_wait(bar_q, 0);
-      mbar_wait(bar_of, 0);
-      mbar_wait(bar_kv, ph_kv[0]); ph_kv[0] ^= 1;
-      mma_s_dp(0);
-      for (int j = 0; j < nkv; ++j) {
-        const int cur = j & 1;
-        if (j + 1 < nkv) {
-          // S_{j+1} / dP_{j+1} overwrite the tiles of block j-1, whose dQ product was issued before them (the tensor
-          // pipe runs in issue order) and whose row threads are done (they delivered dS_{j-1})
-          mbar_wait(bar_kv + (cur ^ 1), ph_kv[cur ^ 1]); ph_kv[cur ^ 1] ^= 1;
-          mma_s_dp(cur ^ 1);
+      uint32_t ph_a = 0, ph_b = 0;           // bit b: phase of the per-buffer barrier pair this warp waits on
+      if (warp == 1) {
+        const uint32_t aQ = smem_u32(sQ), aKk = smem_u32(sKk);
+        mbar_wait(bar_q, 0);
+        for (int j = 0; j < nkv; ++j) {
+          const int buf = j & 1;
+          mbar_wait(bar_kv + buf, (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
+          if (j >= 2) { mbar_wait(bar_p + buf, (ph_b >> buf) & 1u); ph_b ^= 1u << buf; }
+          tc_fence_after();
+          mma_kk(tmem + buf * 64u, aQ, kBig / 2, aKk + buf * kSmall, kSmall / 2, idesc, false);           // S = Q·Kᵀ
+          commit_e(bar_s + buf);
         }
-        mbar_wait(bar_mn + cur, ph_mn[cur]); ph_mn[cur] ^= 1;
-        mbar_wait(bar_p + cur, ph_p[cur]); ph_p[cur] ^= 1;           // dS_j is in tensor memory (over dP_j)
-        tc_fence_after();
-        mma_tmn(tmem + 256u, tmem + 128u + cur * 64u, aKmn + cur * kSmall, idesc_mn, j > 0);   // dQ += dS_j·K_j
-        commit_e(bar_o + cur);
+      } else if (warp == 2) {
+        const uint32_t adO = smem_u32(sdO), aVk = smem_u32(sVk);
+        mbar_wait(bar_of, 0);
+        for (int j = 0; j < nkv; ++j) {
+          const int buf = j & 1;
+          mbar_wait(bar_kv + buf, (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
+          if (j >= 2) { mbar_wait(bar_o + buf, (ph_b >> buf) & 1u); ph_b ^= 1u << buf; }
+          tc_fence_after();
+          mma_kk(tmem + 128u + buf * 64u, adO, kBig / 2, aVk + buf * kSmall, kSmall / 2, idesc, false);   // dP = dO·Vᵀ
+          commit_e(bar_s + buf);
+        }
+      } else {
+        const uint32_t aKmn = smem_u32(sKmn);
+        for (int j = 0; j < nkv; ++j) {
+          const int cur = j & 1;
+          mbar_wait(bar_mn + cur, (ph_a >> cur) & 1u); ph_a ^= 1u << cur;
+          mbar_wait(bar_p + cur, (ph_b >> cur) & 1u); ph_b ^= 1u << cur;   // dS_j is in tensor memory (over dP_j)
+          tc_fence_after();
+          mma_tmn(tmem + 256u, tmem + 128u + cur * 64u, aKmn + cur * kSmall, idesc_mn, j > 0);   // dQ += dS_j·K_j
+          commit_e(bar_o + cur);
+        }
+        commit_e(bar_done);
       }
-      commit_e(bar_done);
     }
-  } else if (warp >= 2) {
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+  } else {
+    const int quarter = warp & 3, part = (warp - 4) >> 2;
     const int r_in = quarter * 32 + lane, row = q0 + r_in;
     const bool row_ok = row < P.Sq;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -572,32 +593,35 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
       // its half of the row (conflict-free: the 128-byte swizzle spreads 8 consecutive rows over all banks), the halves
       // meet through sDelta.  Rows past Sq are zero-filled by TMA.
       mbar_wait(bar_of, 0);
-      const uint8_t *pd = sdO + half * (kBig / 2) + r_in * 128, *po = sO + half * (kBig / 2) + r_in * 128;
-      float part = 0.0f;
+      const int c_first = part * CW;                                 // this thread's columns of the [128 x 64] tiles
+      const uint8_t *pd = sdO + (c_first >> 5) * (kBig / 2) + r_in * 128, *po = sO + (c_first >> 5) * (kBig / 2) + r_in * 128;
+      float psum = 0.0f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int qq = 0; qq < CW / 4; ++qq) {
+        const int q = ((c_first & 31) >> 2) + qq;
         const int off = (q ^ (r_in & 7)) << 4;
         const float4 g = *reinterpret_cast<const float4 *>(pd + off), ov = *reinterpret_cast<const float4 *>(po + off);
-        part = __fadd_rn(part, __fadd_rn(__fadd_rn(__fmul_rn(ov.x, g.x), __fmul_rn(ov.y, g.y)),
+        psum = __fadd_rn(psum, __fadd_rn(__fadd_rn(__fmul_rn(ov.x, g.x), __fmul_rn(ov.y, g.y)),
                                          __fadd_rn(__fmul_rn(ov.z, g.z), __fmul_rn(ov.w, g.w))));
       }
-      sDelta[half * kRows + r_in] = part;
-      asm volatile("bar.sync 1, 256;" ::: "memory");                 // the 8 row warps: both half-row partials are visible
-      delta = __fadd_rn(sDelta[r_in], sDelta[kRows + r_in]);
+      sDelta[part * kRows + r_in] = psum;
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * PARTS) : "memory");   // the row warps: all partial sums are visible
+#pragma unroll
+      for (int pp = 0; pp < PARTS; ++pp) delta = __fadd_rn(delta, sDelta[pp * kRows + r_in]);
     }
     if (row_ok) {
       nm2 = -st4.x;
       rinv = st4.y;
-      if (half == 0) stat->z = delta;      // the dK/dV kernel (launched after this one) reads it per query column
+      if (part == 0) stat->z = delta;      // the dK/dV kernel (launched after this one) reads it per query column
     }
-    uint32_t ph_s[2] = {0, 0};
+    uint32_t ph_s = 0;
     for (int j = 0; j < nkv; ++j) {
       const int cur = j & 1;
-      const int col0 = j * kCols + half * 32;
+      const int col0 = j * kCols + part * CW;
       uint32_t masked = 0;                                         // bit c: column col0 + c is masked
       if (mrow && row_ok) {                                        // fetched before the wait: latency overlaps it
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < CW / 4; ++q) {
           if (col0 + q * 4 < P.Sk) {
             const uint32_t mw = __ldg(reinterpret_cast<const uint32_t *>(mrow + col0) + q);
             if (mw & 0xFFu) masked |= 1u << (q * 4);
@@ -607,30 +631,30 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
           }
         }
       }
-      if (P.causal && col0 + 31 > causal_limit) {
+      if (P.causal && col0 + CW - 1 > causal_limit) {
         const int first = causal_limit + 1 - col0;                 // first masked column of this chunk
         masked |= first <= 0 ? 0xFFFFFFFFu : (first >= 32 ? 0u : (0xFFFFFFFFu << first));
       }
-      // warp-uniform: nothing masked in this [32 rows x 32 columns] chunk and no column past Sk — 5 instructions per
+      // warp-uniform: nothing masked in this [32 rows x CW columns] chunk and no column past Sk — 5 instructions per
       // element instead of the masked form's dozen
-      const bool fast = (col0 + 32 <= P.Sk) && !__any_sync(0xffffffffu, masked != 0u);
-      mbar_wait(bar_s + cur, ph_s[cur]); ph_s[cur] ^= 1;
+      const bool fast = (col0 + CW <= P.Sk) && !__any_sync(0xffffffffu, masked != 0u);
+      mbar_wait(bar_s + cur, (ph_s >> cur) & 1u); ph_s ^= 1u << cur;
       tc_fence_after();
-      const uint32_t t_dp = tmem + 128u + cur * 64u + lane_addr + half * 32;
-      uint32_t rs[32], rp[32];
-      tmem_ld32(tmem + cur * 64u + lane_addr + half * 32, rs);
-      tmem_ld32(t_dp, rp);
+      const uint32_t t_dp = tmem + 128u + cur * 64u + lane_addr + part * CW;
+      uint32_t rs[CW], rp[CW];
+      tmem_ldn(tmem + cur * 64u + lane_addr + part * CW, rs);
+      tmem_ldn(t_dp, rp);
       tmem_ld_wait();
       // dS WITHOUT the softmax scale: dQ = scale · Σ_j dS_j·K_j is scaled once per output element in the epilogue
       if (fast) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < CW; ++c) {
           const float p = __fmul_rn(ex2(__fmaf_rn(__uint_as_float(rs[c]), scale2, nm2)), rinv);
           rp[c] = __float_as_uint(__fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), delta)));
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < CW; ++c) {
           const bool mk = (masked >> c) & 1u;
           const float t = mk ? __fadd_rn(mask2, nm2) : __fmaf_rn(__uint_as_float(rs[c]), scale2, nm2);
           float p = __fmul_rn(ex2(t), rinv);
@@ -639,29 +663,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dq_kernel(const __gr
           rp[c] = __float_as_uint(mk ? 0.0f : d);                   // mask_fill backward: no gradient through a filled score
         }
       }
-      tmem_st32(t_dp, rp);                                          // dS_j over dP_j, in place
+      tmem_stn(t_dp, rp);                                          // dS_j over dP_j, in place
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p + cur);
     }
-    float *grow_out = P.g0 + (int64_t)b * P.g0_sb + (int64_t)h * P.g0_sh + (int64_t)row * P.g0_ss + half * 32;
+    float *grow_out = P.g0 + (int64_t)b * P.g0_sb + (int64_t)h * P.g0_sh + (int64_t)row * P.g0_ss + part * CW;
     if (nkv > 0) {
       mbar_wait(bar_done, 0);                                       // every product has retired: dQ is complete
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(tmem + 256u + lane_addr + half * 32, r);
+      uint32_t r[CW];
+      tmem_ldn(tmem + 256u + lane_addr + part * CW, r);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < CW / 4; ++q)
           reinterpret_cast<float4 *>(grow_out)[q] =
               make_float4(__fmul_rn(__uint_as_float(r[q * 4]), P.scale), __fmul_rn(__uint_as_float(r[q * 4 + 1]), P.scale),
                           __fmul_rn(__uint_as_float(r[q * 4 + 2]), P.scale), __fmul_rn(__uint_as_float(r[q * 4 + 3]), P.scale));
       }
     } else if (row_ok) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) reinterpret_cast<uint4 *>(grow_out)[q] = make_uint4(0, 0, 0, 0);
+      for (int q = 0; q < CW / 4; ++q) reinterpret_cast<uint4 *>(grow_out)[q] = make_uint4(0, 0, 0, 0);
     }
   }
 
@@ -1043,9 +1067,10 @@ extern "C" int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out
   {
     const int64_t ctas = B * H * P.blocks;
     B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
-    const size_t smem = 1024 + 3 * fa::kBig + 6 * fa::kSmall + 2 * fa::kRows * 4 + 128;
-    if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dq_kernel), smem)) != B200_OK) return st;
-    fa::flash_bwd_dq_kernel<<<(unsigned)ctas, fa::kBwdThreads, smem, stream>>>(P);
+    constexpr int kParts = 2;   // 8 row warps (16 measured no faster: the issue side bounds this kernel)
+    const size_t smem = 1024 + 3 * fa::kBig + 6 * fa::kSmall + kParts * fa::kRows * 4 + 128;
+    if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dq_kernel<kParts>), smem)) != B200_OK) return st;
+    fa::flash_bwd_dq_kernel<kParts><<<(unsigned)ctas, 128 + 128 * kParts, smem, stream>>>(P);
     B200_LAUNCH_CHECK();
   }
   // ---- kernel 2: dK, dV
