@@ -7,23 +7,35 @@
 // smallest normal), context = weights·v; the backward is what burn-autodiff's reverse walk over that chain
 // yields (matmul / mask_fill / softmax backward), with the mask_fill backward zeroing dS where masked.
 //
-// Head dim 64, f32 storage, tf32 tcgen05 products, f32 softmax in the base-2 domain (one FMUL + one
-// MUFU.EX2 per element).  Three kernels, each a TMA → tcgen05 → TMEM → row-thread pipeline in which one
-// elected thread issues every TMA load and MMA and the row threads (thread = TMEM lane) do the softmax math:
+// Head dim 64, f32 storage, tf32 tcgen05 products, f32 softmax in the base-2 domain (one FFMA + one
+// MUFU.EX2 per element).  Three kernels, each a TMA → tcgen05 → TMEM → row-thread pipeline: a producer warp
+// issues the TMA loads, converged issuer warps issue the products, the row threads (thread = TMEM lane) do the
+// softmax math.  What the measurements on B200 said (scripts/ubench/umma_issue.cu, -DFA_TRACE timelines, ncu
+// source pages) and the kernels now do:
+//   * a [128 x 64 x 8] tf32 instruction occupies the tensor pipe for 48 cycles with both operands in shared memory
+//     (the 6 KB of operand reads, not the math, bound it) and 32 cycles with A in tensor memory; the backward
+//     kernels therefore keep P / dS in TMEM — the row threads rewrite the S / dP accumulator tiles in place and the
+//     next product reads its A operand from there (no st.shared, no fence.proxy.async, 64 KB less shared memory);
+//   * every streamed tile is double-buffered: a single buffer exposes one TMA round trip per key block;
+//   * one issuer warp per product, each on its own scheduler, hand-overs through mbarriers (tcgen05.commit tracks
+//     the issuing thread's instructions only); the issuers run converged with elect.sync inside the asm;
+//   * mbarrier waits sleep in hardware (suspend-time hint) instead of polling, and are bounded (trap, not hang);
+//   * warp-uniform fast paths for blocks without any masked / out-of-range element; the softmax scale is applied
+//     once per dQ / dK element instead of once per dS element; delta comes from the TMA-staged O tile.
 //
 //   flash_fwd_kernel   CTA = 128 query rows, loop over 64-key blocks.  S_j = Q·K_jᵀ lands in one of two TMEM
 //                      buffers (S_{j+1} is issued before the row threads have finished S_j), online softmax:
 //                      P_j = 2^(s−m_j) goes to smem as the tf32 A operand, PV_j = P_j·V_j into one of two TMEM
 //                      buffers with no accumulation, and the row threads fold it into a register accumulator
 //                      O = O·2^(m_{j−1}−m_j) + PV_j while the tensor core already works on block j+1.
-//                      Saves stats[row] = (m, 1/l): weights are recomputed as 2^(s−m)·(1/l), exactly the
-//                      forward's values (no log-sum-exp cancellation when a row is masked with −1e9).
+//                      Saves stats[row] = (m, 1/l): weights are recomputed as 2^(s−m)·(1/l), the forward's
+//                      values (no log-sum-exp cancellation when a row is masked with −1e9).
 //                      96 KB smem + 256 TMEM columns: two CTAs per SM.
 //   flash_bwd_dq_kernel  CTA = 128 query rows, loop over 64-key blocks: S = Q·K_jᵀ and dP = dO·V_jᵀ (double
-//                      buffered in TMEM) → dS = P∘(dP − delta)·scale → smem → dQ += dS·K_j accumulated in TMEM.
-//                      delta = rowsum(dO∘O) is computed here and stored into stats[row].z for the second kernel.
+//                      buffered in TMEM) → dS = P∘(dP − delta) over dP in place → dQ += dS·K_j accumulated in TMEM,
+//                      scaled in the epilogue.  delta = rowsum(dO∘O) is stored into stats[row].z for the second kernel.
 //   flash_bwd_dkv_kernel CTA = 128 key rows, loop over 64-query blocks, everything transposed so the row thread
-//                      is a key: Sᵀ = K·Q_iᵀ, dPᵀ = V·dO_iᵀ → Pᵀ, dSᵀ → smem → dV += Pᵀ·dO_i, dK += dSᵀ·Q_i in
+//                      is a key: Sᵀ = K·Q_iᵀ, dPᵀ = V·dO_iᵀ → Pᵀ, dSᵀ in place → dV += Pᵀ·dO_i, dK += dSᵀ·Q_i in
 //                      TMEM.  Deterministic (no atomics): replicas stay bit-identical.
 // Algorithmic HBM bytes: forward q,k,v,out (+16 B/row); backward q,k,v,out,dO,dq,dk,dv — 4·B·H·S·D·4 and
 // 8·B·H·S·D·4 bytes; FLOPs 4·Sq·Sk·D forward, 14·Sq·Sk·D backward per head (7 products, S and dP twice).
@@ -443,7 +455,6 @@ struct BwdParams {
   float scale, mask_value;
 };
 
-constexpr int kBwdThreads = 320;   // issuer warp, TMEM-allocator warp, 8 row warps (two per TMEM lane quarter)
 
 // D[128 x 64] (+)= A[128 x 64] (tensor memory: lanes = rows, 64 consecutive columns) · B[64 k x 64 n] (MN-major smem tile)
 __device__ __forceinline__ void mma_tmn(uint32_t tmem_d, uint32_t tmem_a, uint32_t b, uint32_t idesc_mn, bool accumulate) {
@@ -457,6 +468,16 @@ __device__ __forceinline__ void mma_tmn(uint32_t tmem_d, uint32_t tmem_a, uint32
 // PARTS row threads share a query row, CW = 64 / PARTS score columns each (PARTS x 4 row warps: a TMEM lane quarter is
 // reachable from warps w with w % 4 == quarter).  Nothing in the backward couples the columns of a row — m, 1/l and delta
 // are per-row constants — so more, narrower row threads only add warps for the schedulers to hide MUFU / TMEM latency with.
+#ifdef FA_TRACE
+// debug build (-DFA_TRACE): block 0 prints, per role and key block, the SM clock at which each wait completed / each
+// product was issued, relative to the start of the role code — the pipeline's actual timeline
+#define FA_T(arr, j) do { if (blockIdx.x == 0 && (j) < 16) arr[(j)] = clock64() - fa_t0; } while (0)
+#define FA_DUMP(tag, n, a0, a1, a2) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) for (int jj = 0; jj < (n) && jj < 16; ++jj) \
+    printf("%s %2d %6lld %6lld %6lld\n", tag, jj, a0[jj], a1[jj], a2[jj]); } while (0)
+#else
+#define FA_T(arr, j) do { } while (0)
+#define FA_DUMP(tag, n, a0, a1, a2) do { } while (0)
+#endif
 template <int PARTS>
 __global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_kernel(const __grid_constant__ BwdParams P) {
   constexpr int CW = kCols / PARTS;
@@ -503,6 +524,11 @@ __global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_kernel(cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;        // S0 @0, S1 @64, dP0 / dS0 @128, dP1 / dS1 @192, dQ @256
+#ifdef FA_TRACE
+  const long long fa_t0 = clock64();
+  long long tr0[16], tr1[16], tr2[16];
+  for (int i = 0; i < 16; ++i) tr0[i] = tr1[i] = tr2[i] = 0;
+#endif
 
   if (warp == 0) {
     // TMA producers: lane 0 streams the K-major K_j / V_j tiles (buffer free when S_{j-2} / dP_{j-2} retired), lane 1
@@ -547,32 +573,44 @@ __global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_kernel(cons
         for (int j = 0; j < nkv; ++j) {
           const int buf = j & 1;
           mbar_wait(bar_kv + buf, (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
+          FA_T(tr0, j);
           if (j >= 2) { mbar_wait(bar_p + buf, (ph_b >> buf) & 1u); ph_b ^= 1u << buf; }
+          FA_T(tr1, j);
           tc_fence_after();
           mma_kk(tmem + buf * 64u, aQ, kBig / 2, aKk + buf * kSmall, kSmall / 2, idesc, false);           // S = Q·Kᵀ
           commit_e(bar_s + buf);
+          FA_T(tr2, j);
         }
+        FA_DUMP("S  kv/p/issued", nkv, tr0, tr1, tr2);
       } else if (warp == 2) {
         const uint32_t adO = smem_u32(sdO), aVk = smem_u32(sVk);
         mbar_wait(bar_of, 0);
         for (int j = 0; j < nkv; ++j) {
           const int buf = j & 1;
           mbar_wait(bar_kv + buf, (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
+          FA_T(tr0, j);
           if (j >= 2) { mbar_wait(bar_o + buf, (ph_b >> buf) & 1u); ph_b ^= 1u << buf; }
+          FA_T(tr1, j);
           tc_fence_after();
           mma_kk(tmem + 128u + buf * 64u, adO, kBig / 2, aVk + buf * kSmall, kSmall / 2, idesc, false);   // dP = dO·Vᵀ
           commit_e(bar_s + buf);
+          FA_T(tr2, j);
         }
+        FA_DUMP("dP kv/o/issued", nkv, tr0, tr1, tr2);
       } else {
         const uint32_t aKmn = smem_u32(sKmn);
         for (int j = 0; j < nkv; ++j) {
           const int cur = j & 1;
           mbar_wait(bar_mn + cur, (ph_a >> cur) & 1u); ph_a ^= 1u << cur;
+          FA_T(tr0, j);
           mbar_wait(bar_p + cur, (ph_b >> cur) & 1u); ph_b ^= 1u << cur;   // dS_j is in tensor memory (over dP_j)
+          FA_T(tr1, j);
           tc_fence_after();
           mma_tmn(tmem + 256u, tmem + 128u + cur * 64u, aKmn + cur * kSmall, idesc_mn, j > 0);   // dQ += dS_j·K_j
           commit_e(bar_o + cur);
+          FA_T(tr2, j);
         }
+        FA_DUMP("dQ mn/p/issued", nkv, tr0, tr1, tr2);
         commit_e(bar_done);
       }
     }
@@ -638,7 +676,9 @@ __global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_kernel(cons
       // warp-uniform: nothing masked in this [32 rows x CW columns] chunk and no column past Sk — 5 instructions per
       // element instead of the masked form's dozen
       const bool fast = (col0 + CW <= P.Sk) && !__any_sync(0xffffffffu, masked != 0u);
+      FA_T(tr0, j);
       mbar_wait(bar_s + cur, (ph_s >> cur) & 1u); ph_s ^= 1u << cur;
+      FA_T(tr1, j);
       tc_fence_after();
       const uint32_t t_dp = tmem + 128u + cur * 64u + lane_addr + part * CW;
       uint32_t rs[CW], rp[CW];
@@ -668,7 +708,9 @@ __global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_kernel(cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p + cur);
+      FA_T(tr2, j);
     }
+    if (warp == 4) FA_DUMP("row top/s/arrived", nkv, tr0, tr1, tr2);
     float *grow_out = P.g0 + (int64_t)b * P.g0_sb + (int64_t)h * P.g0_sh + (int64_t)row * P.g0_ss + part * CW;
     if (nkv > 0) {
       mbar_wait(bar_done, 0);                                       // every product has retired: dQ is complete
@@ -698,19 +740,23 @@ __global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_kernel(cons
   }
 }
 
-__global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __grid_constant__ BwdParams P) {
+constexpr int kDkvThreads = 13 * 32;   // TMA warp, four issuer warps (one product each), 8 row warps
+
+__global__ void __launch_bounds__(kDkvThreads, 1) flash_bwd_dkv_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *sK = smem, *sV = sK + kBig, *sQk = sV + kBig, *sdOk = sQk + kSmall, *sQmn = sdOk + kSmall, *sdOmn = sQmn + kSmall,
-          *sP = sdOmn + kSmall, *sdS = sP + kPBytes;
-  // [3][64] (m2, 1/l, delta, -) of the block's queries.  Three buffers: the producer refills buffer it % 3 once
-  // Sᵀ_{it-1} has retired, and that MMA is only issued after the row threads delivered block it-3 — the last
-  // reader of the buffer (with two buffers the refill could overtake the readers of block it-2).
-  float4 *sStats = reinterpret_cast<float4 *>(sdS + kPBytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sStats + 3 * kCols);
-  uint64_t *bar_res = bars, *bar_qk = bars + 1, *bar_mn = bars + 2, *bar_s0 = bars + 3, *bar_s1 = bars + 4, *bar_p = bars + 5,
-           *bar_o = bars + 6, *bar_st = bars + 7;     // bar_st[3]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
+  // K, V resident; the four streamed tiles of a query block (Q, dO in both operand layouts) double-buffered (buffer
+  // it & 1).  Pᵀ and dSᵀ never touch shared memory: the row threads rewrite the Sᵀ / dPᵀ accumulator tiles in tensor
+  // memory in place and the dV / dK products read their A operand from there.
+  uint8_t *sK = smem, *sV = sK + kBig, *sQk = sV + kBig, *sdOk = sQk + 2 * kSmall, *sQmn = sdOk + 2 * kSmall, *sdOmn = sQmn + 2 * kSmall;
+  // [4][64] (m2, 1/l, delta, -) of the block's queries.  Four buffers: the producer refills buffer it % 4 once
+  // Sᵀ_{it-2} has retired, and that product is only issued after the dV / dK products of block it-4 — issued after
+  // the row threads delivered block it-4, the last reader of the buffer — have retired.
+  float4 *sStats = reinterpret_cast<float4 *>(sdOmn + 2 * kSmall);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sStats + 4 * kCols);
+  uint64_t *bar_k = bars, *bar_v = bars + 1, *bar_qk = bars + 2 /*[2]*/, *bar_mn = bars + 4 /*[2]*/, *bar_s = bars + 6 /*[2]*/,
+           *bar_o = bars + 8 /*[2]*/, *bar_p = bars + 10 /*[2]*/, *bar_done = bars + 12, *bar_st = bars + 13 /*[4]*/;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int work = blockIdx.x;
@@ -733,99 +779,98 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
     tma_prefetch_desc(&P.tma_v);
     tma_prefetch_desc(&P.tma_mn0);
     tma_prefetch_desc(&P.tma_mn1);
-    mbar_init(bar_res, 1);
-    mbar_init(bar_qk, 1);
-    mbar_init(bar_mn, 1);
-    mbar_init(bar_s0, 1);
-    mbar_init(bar_s1, 1);
-    mbar_init(bar_p, 8);
-    mbar_init(bar_o, 1);
-    mbar_init(bar_st, 1);
-    mbar_init(bar_st + 1, 1);
-    mbar_init(bar_st + 2, 1);
+    for (int i = 0; i < 17; ++i)   // bar_s / bar_o / bar_done: two issuers commit; bar_p: one arrival per row warp
+      mbar_init(bars + i, (i == 10 || i == 11) ? 8 : ((i >= 6 && i <= 9) || i == 12 ? 2 : 1));
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;        // ST0 @0, ST1 @64, dPT0 @128, dPT1 @192, dV @256, dK @320
+  const uint32_t tmem = *tmem_slot;        // ST0 / PT0 @0, ST1 / PT1 @64, dPT0 / dST0 @128, dPT1 / dST1 @192, dV @256, dK @320
 
   if (warp == 0) {
-    // TMA producers: lane 0 streams the K-major Q_i / dO_i tiles + the block's row statistics (free when Sᵀ_i / dPᵀ_i
-    // retire), lane 1 the MN-major Q_i / dO_i tiles (free when the dV / dK MMAs of block i retire)
+    // TMA producers: lane 0 streams the K-major Q_i / dO_i tiles + the block's row statistics (buffer free when Sᵀ / dPᵀ
+    // of block i-2 retired), lane 1 the MN-major Q_i / dO_i tiles (buffer free when the dV / dK products of block i-2 retired)
     if (lane == 0 && n_it > 0) {
-      mbar_expect_tx(bar_res, 2 * kBig);
-      load_kmajor(sK, &P.tma_k, bar_res, kv0, h, b, kBig / 2);
-      load_kmajor(sV, &P.tma_v, bar_res, kv0, h, b, kBig / 2);
-      uint32_t ph_s0 = 0, ph_s1 = 0;
+      mbar_expect_tx(bar_k, kBig);
+      load_kmajor(sK, &P.tma_k, bar_k, kv0, h, b, kBig / 2);
+      mbar_expect_tx(bar_v, kBig);
+      load_kmajor(sV, &P.tma_v, bar_v, kv0, h, b, kBig / 2);
+      uint32_t ph = 0;
       for (int it = 0; it < n_it; ++it) {
-        if (it > 0) {
-          if ((it - 1) & 1) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
-        }
-        const int r0 = (i_start + it) * kCols, buf = it % 3;
-        mbar_expect_tx(bar_qk, 2 * kSmall);
-        load_kmajor(sQk, &P.tma_q, bar_qk, r0, h, b, kSmall / 2);
-        load_kmajor(sdOk, &P.tma_do, bar_qk, r0, h, b, kSmall / 2);
+        const int buf = it & 1;
+        if (it >= 2) { mbar_wait(bar_s + buf, (ph >> buf) & 1u); ph ^= 1u << buf; }
+        const int r0 = (i_start + it) * kCols;
+        mbar_expect_tx(bar_qk + buf, 2 * kSmall);
+        load_kmajor(sQk + buf * kSmall, &P.tma_q, bar_qk + buf, r0, h, b, kSmall / 2);
+        load_kmajor(sdOk + buf * kSmall, &P.tma_do, bar_qk + buf, r0, h, b, kSmall / 2);
         // the block's per-query statistics: one bulk copy, clipped at the end of the sequence
         const uint32_t bytes = (uint32_t)min(kCols, P.Sq - r0) * 16u;
-        uint64_t *bst = bar_st + buf;
+        uint64_t *bst = bar_st + (it & 3);
         mbar_expect_tx(bst, bytes);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(sStats + buf * kCols)),
+                         smem_u32(sStats + (it & 3) * kCols)),
                      "l"(P.stats + stat_base + r0), "r"(bytes), "r"(smem_u32(bst))
                      : "memory");
       }
     } else if (lane == 1 && n_it > 0) {
-      uint32_t ph_o = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < n_it; ++it) {
-        if (it > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }
+        const int buf = it & 1;
+        if (it >= 2) { mbar_wait(bar_o + buf, (ph >> buf) & 1u); ph ^= 1u << buf; }
         const int r0 = (i_start + it) * kCols;
-        mbar_expect_tx(bar_mn, 2 * kSmall);
-        load_mnmajor(sQmn, &P.tma_mn0, bar_mn, r0, h, b);
-        load_mnmajor(sdOmn, &P.tma_mn1, bar_mn, r0, h, b);
+        mbar_expect_tx(bar_mn + buf, 2 * kSmall);
+        load_mnmajor(sQmn + buf * kSmall, &P.tma_mn0, bar_mn + buf, r0, h, b);
+        load_mnmajor(sdOmn + buf * kSmall, &P.tma_mn1, bar_mn + buf, r0, h, b);
       }
     }
-  } else if (warp == 1) {
-    if (n_it > 0) {   // the whole warp, converged: see umma_e
+  } else if (warp <= 4) {
+    // Four issuer warps, one product each (see flash_bwd_dq_kernel).  Hand-overs:
+    //   Sᵀ_i  overwrites Pᵀ_{i-2},  dPᵀ_i overwrites dSᵀ_{i-2}  -> the dV / dK products of block i-2 retired  (bar_o)
+    //   dV_i reads Pᵀ_i, dK_i reads dSᵀ_i                        -> the row threads delivered them            (bar_p)
+    if (n_it > 0) {   // whole warps, converged: see umma_e
       const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQk = smem_u32(sQk), adOk = smem_u32(sdOk), aQmn = smem_u32(sQmn),
-                     adOmn = smem_u32(sdOmn), aP = smem_u32(sP), adS = smem_u32(sdS);
-      auto mma_s_dp = [&](int buf) {
-        tc_fence_after();
-        mma_kk(tmem + (buf ? 64u : 0u), aK, kBig / 2, aQk, kSmall / 2, idesc, false);          // Sᵀ = K·Qᵀ
-        mma_kk(tmem + 128u + (buf ? 64u : 0u), aV, kBig / 2, adOk, kSmall / 2, idesc, false);  // dPᵀ = V·dOᵀ
-        commit_e(buf ? bar_s1 : bar_s0);
-      };
-      uint32_t ph_qk = 0, ph_mn = 0, ph_p = 0;
-      mbar_wait(bar_res, 0);
-      mbar_wait(bar_qk, ph_qk); ph_qk ^= 1;
-      mma_s_dp(0);
-      for (int it = 0; it < n_it; ++it) {
-        const int cur = it & 1;
-        if (it + 1 < n_it) {
-          mbar_wait(bar_qk, ph_qk); ph_qk ^= 1;
-          mma_s_dp(cur ^ 1);
+      uint32_t ph_a = 0, ph_b = 0;
+      if (warp <= 2) {
+        const bool is_s = warp == 1;
+        const uint32_t aA = smem_u32(is_s ? sK : sV), aB = smem_u32(is_s ? sQk : sdOk);
+        const uint32_t td = tmem + (is_s ? 0u : 128u);
+        mbar_wait(is_s ? bar_k : bar_v, 0);
+        for (int it = 0; it < n_it; ++it) {
+          const int buf = it & 1;
+          mbar_wait(bar_qk + buf, (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
+          if (it >= 2) { mbar_wait(bar_o + buf, (ph_b >> buf) & 1u); ph_b ^= 1u << buf; }
+          tc_fence_after();
+          mma_kk(td + buf * 64u, aA, kBig / 2, aB + buf * kSmall, kSmall / 2, idesc, false);   // Sᵀ = K·Qᵀ | dPᵀ = V·dOᵀ
+          commit_e(bar_s + buf);
         }
-        mbar_wait(bar_mn, ph_mn); ph_mn ^= 1;
-        mbar_wait(bar_p, ph_p); ph_p ^= 1;                         // Pᵀ and dSᵀ are in smem
-        tc_fence_after();
-        mma_kmn(tmem + 256u, aP, adOmn, idesc_mn, it > 0);         // dV += Pᵀ·dO_i
-        mma_kmn(tmem + 320u, adS, aQmn, idesc_mn, it > 0);         // dK += dSᵀ·Q_i
-        commit_e(bar_o);
+      } else {
+        const bool is_v = warp == 3;
+        const uint32_t aB = smem_u32(is_v ? sdOmn : sQmn);
+        const uint32_t td = tmem + (is_v ? 256u : 320u), ta = tmem + (is_v ? 0u : 128u);
+        for (int it = 0; it < n_it; ++it) {
+          const int cur = it & 1;
+          mbar_wait(bar_mn + cur, (ph_a >> cur) & 1u); ph_a ^= 1u << cur;
+          mbar_wait(bar_p + cur, (ph_b >> cur) & 1u); ph_b ^= 1u << cur;    // Pᵀ_i and dSᵀ_i are in tensor memory
+          tc_fence_after();
+          mma_tmn(td, ta + cur * 64u, aB + cur * kSmall, idesc_mn, it > 0);   // dV += Pᵀ·dO_i | dK += dSᵀ·Q_i
+          commit_e(bar_o + cur);
+        }
+        commit_e(bar_done);
       }
     }
-  } else if (warp >= 2) {
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+  } else {
+    const int quarter = warp & 3, half = (warp - 5) >> 2;
     const int r_in = quarter * 32 + lane, kv = kv0 + r_in;
     const bool kv_ok = kv < P.Sk;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int shift = P.Sk - P.Sq;
     const uint8_t *mcol = P.mask ? P.mask + (int64_t)b * P.m_sb + (int64_t)h * P.m_sh + kv : nullptr;
     const float scale2 = P.scale * kLog2e, mask2 = P.mask_value * kLog2e;
-    uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
+    uint32_t ph_s = 0;
     for (int it = 0; it < n_it; ++it) {
-      const int cur = it & 1, sb = it % 3;
+      const int cur = it & 1, sb = it & 3;
       const int qc0 = (i_start + it) * kCols + half * 32;
       uint32_t mbits = 0;                                           // bit c: explicit mask at (query qc0 + c, key kv)
       if (mcol && kv_ok) {                                          // fetched before the waits
@@ -833,27 +878,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
         for (int c = 0; c < 32; ++c)
           if (qc0 + c < P.Sq && __ldg(mcol + (int64_t)(qc0 + c) * P.m_ss)) mbits |= 1u << c;
       }
-      mbar_wait(bar_st + sb, (uint32_t)((it / 3) & 1));
-      if (cur) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
-      tc_fence_after();
-      uint32_t rs[32], rp[32];
-      tmem_ld32(tmem + (cur ? 64u : 0u) + lane_addr + half * 32, rs);
-      tmem_ld32(tmem + 128u + (cur ? 64u : 0u) + lane_addr + half * 32, rp);
-      tmem_ld_wait();
-      const float4 *st = sStats + sb * kCols + half * 32;
       // warp-uniform: every (key, query) pair of this [32 keys x 32 queries] chunk is in range and unmasked — 6
-      // instructions per element instead of the masked form's two dozen (the row warps' issue slots bound this kernel).
+      // instructions per element instead of the masked form's two dozen.
       // dSᵀ is delivered WITHOUT the softmax scale: dK = scale · Σ_i dSᵀ_i·Q_i is scaled once per element in the epilogue.
       const bool fast = (qc0 + 32 <= P.Sq) && (kv0 + quarter * 32 + 32 <= P.Sk) &&
                         !(P.causal && kv0 + quarter * 32 + 31 > qc0 + shift) && !__any_sync(0xffffffffu, mbits != 0u);
-      float pv[32], ds[32];
+      mbar_wait(bar_st + sb, (uint32_t)((it >> 2) & 1));
+      mbar_wait(bar_s + cur, (ph_s >> cur) & 1u); ph_s ^= 1u << cur;
+      tc_fence_after();
+      const uint32_t t_s = tmem + cur * 64u + lane_addr + half * 32, t_dp = tmem + 128u + cur * 64u + lane_addr + half * 32;
+      uint32_t rs[32], rp[32];
+      tmem_ld32(t_s, rs);
+      tmem_ld32(t_dp, rp);
+      tmem_ld_wait();
+      const float4 *st = sStats + sb * kCols + half * 32;
       if (fast) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const float4 sq = st[c];                                  // smem broadcast
           const float p = __fmul_rn(ex2(__fmaf_rn(__uint_as_float(rs[c]), scale2, -sq.x)), sq.y);
-          pv[c] = p;
-          ds[c] = __fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), sq.z));
+          rs[c] = __float_as_uint(p);
+          rp[c] = __float_as_uint(__fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), sq.z)));
         }
       } else {
 #pragma unroll
@@ -863,27 +908,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_dkv_kernel(const __g
           const float4 sq = st[c];                                  // smem broadcast; garbage past Sq is never used
           const bool mk = (P.causal && kv > q + shift) || ((mbits >> c) & 1u);
           const float t = mk ? __fsub_rn(mask2, sq.x) : __fmaf_rn(__uint_as_float(rs[c]), scale2, -sq.x);
-          float p = (q_ok && kv_ok) ? __fmul_rn(ex2(t), sq.y) : 0.0f;
+          const float p = (q_ok && kv_ok) ? __fmul_rn(ex2(t), sq.y) : 0.0f;
           const float d = __fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), sq.z));
-          pv[c] = p;
-          ds[c] = (mk || !(q_ok && kv_ok)) ? 0.0f : d;
+          rs[c] = __float_as_uint(p);
+          rp[c] = __float_as_uint((mk || !(q_ok && kv_ok)) ? 0.0f : d);
         }
       }
-      if (it > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }            // dV / dK MMAs of block it-1 no longer read sP / sdS
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        store_a_chunk(sP + half * (kPBytes / 2), r_in, q, make_float4(pv[q * 4], pv[q * 4 + 1], pv[q * 4 + 2], pv[q * 4 + 3]));
-        store_a_chunk(sdS + half * (kPBytes / 2), r_in, q, make_float4(ds[q * 4], ds[q * 4 + 1], ds[q * 4 + 2], ds[q * 4 + 3]));
-      }
-      fence_proxy_async();
+      tmem_st32(t_s, rs);                                           // Pᵀ_i over Sᵀ_i, dSᵀ_i over dPᵀ_i, in place
+      tmem_st32(t_dp, rp);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
+      if (lane == 0) mbar_arrive(bar_p + cur);
     }
     float *dk_row = P.g0 + (int64_t)b * P.g0_sb + (int64_t)h * P.g0_sh + (int64_t)kv * P.g0_ss + half * 32;
     float *dv_row = P.g1 + (int64_t)b * P.g1_sb + (int64_t)h * P.g1_sh + (int64_t)kv * P.g1_ss + half * 32;
     if (n_it > 0) {
-      mbar_wait(bar_o, ph_o); ph_o ^= 1;
+      mbar_wait(bar_done, 0);                                       // every product has retired: dV and dK are complete
       tc_fence_after();
       uint32_t rv[32], rk[32];
       tmem_ld32(tmem + 256u + lane_addr + half * 32, rv);
@@ -1088,9 +1129,9 @@ extern "C" int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out
   {
     const int64_t ctas = B * H * P.blocks;
     B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
-    const size_t smem = 1024 + 2 * fa::kBig + 4 * fa::kSmall + 2 * fa::kPBytes + 3 * fa::kCols * 16 + 128;
+    const size_t smem = 1024 + 2 * fa::kBig + 8 * fa::kSmall + 4 * fa::kCols * 16 + 256;
     if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dkv_kernel), smem)) != B200_OK) return st;
-    fa::flash_bwd_dkv_kernel<<<(unsigned)ctas, fa::kBwdThreads, smem, stream>>>(P);
+    fa::flash_bwd_dkv_kernel<<<(unsigned)ctas, fa::kDkvThreads, smem, stream>>>(P);
     B200_LAUNCH_CHECK();
   }
   return B200_OK;
