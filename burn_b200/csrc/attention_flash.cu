@@ -1108,7 +1108,7 @@ extern "C" int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out
   {
     const int64_t ctas = B * H * P.blocks;
     B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
-    constexpr int kParts = 2;   // 8 row warps (16 measured no faster: the issue side bounds this kernel)
+    constexpr int kParts = 2;   // 8 row warps (16 measured 3 % slower: the tensor pipe and the tile traffic bound this kernel, not the row math)
     const size_t smem = 1024 + 3 * fa::kBig + 6 * fa::kSmall + kParts * fa::kRows * 4 + 128;
     if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dq_kernel<kParts>), smem)) != B200_OK) return st;
     fa::flash_bwd_dq_kernel<kParts><<<(unsigned)ctas, 128 + 128 * kParts, smem, stream>>>(P);

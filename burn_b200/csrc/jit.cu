@@ -326,7 +326,8 @@ extern "C" __global__ void __launch_bounds__(256) b200_jit_rows_warp(const JitPa
 extern "C" __global__ void __launch_bounds__(256) b200_jit_rows_cta(const JitParams P, const RedParams Q) { rows<256>(P, Q); }
 )";
   } else {
-    s += "extern \"C\" __global__ void __launch_bounds__(256) b200_jit_cols(const JitParams P, const RedParams Q) {\n" + prelude();
+    // 8 CTAs per SM (<= 32 registers): the fuse-on-read math is issue-bound, so resident warps are what it needs
+    s += "extern \"C\" __global__ void __launch_bounds__(256, 8) b200_jit_cols(const JitParams P, const RedParams Q) {\n" + prelude();
     s += R"(  // block (32, 8): 32 column vectors x 8 row groups; grid (outer * column tiles, splits)
   __shared__ float part[8][32][4];
   const uint32_t tiles = (Q.inner4 + 31) / 32;
@@ -408,7 +409,9 @@ int32_t jit_try_reduce(const CompiledTape &ct, const TapeParams &p, int rank_mod
   } else {
     Q.inner4 = (uint32_t)(inner / 4);
     const uint32_t tiles = (uint32_t)outer * ((Q.inner4 + 31) / 32);
-    while (splits < 64 && tiles * splits < (uint32_t)sms * 4u && R / (splits * 2) >= 64) splits *= 2;
+    // >= 4 waves of 8 resident CTAs per SM: with a single partial wave (1024 CTAs on 148 x 8 slots) the SMs that drew
+    // 6 CTAs idle while the others finish their 7th — ncu: 52 % warps active, 139 us against the row mapping's 108 us
+    while (splits < 64 && tiles * splits < (uint32_t)sms * 32u && R / (splits * 2) >= 64) splits *= 2;
     Q.per_split = (uint32_t)((R + splits - 1) / splits);
     splits = (uint32_t)((R + Q.per_split - 1) / Q.per_split);
     kname = "b200_jit_cols";
