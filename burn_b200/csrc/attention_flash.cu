@@ -137,6 +137,18 @@ __device__ __forceinline__ void mma_kmn(uint32_t tmem_d, uint32_t a, uint32_t b,
     umma_e(tmem_d, da, db, idesc_mn, (accumulate || k) ? 1u : 0u);
   }
 }
+// D[128 x 64] (+)= A[128 x 64] (tensor memory: lanes = rows, 64 consecutive columns) · B[64 k x 64 n] (MN-major smem tile)
+__device__ __forceinline__ void mma_tmn(uint32_t tmem_d, uint32_t tmem_a, uint32_t b, uint32_t idesc_mn, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < kCols / 8; ++k) {
+    const uint64_t db = make_desc(b + (k >> 2) * 8192 + (k & 3) * 1024, 4096, 512, 1);
+    umma_ts_e(tmem_d, tmem_a + k * 8, db, idesc_mn, (accumulate || k) ? 1u : 0u);
+  }
+}
+
+// PARTS row threads share a query row, CW = 64 / PARTS score columns each (PARTS x 4 row warps: a TMEM lane quarter is
+// reachable from warps w with w % 4 == quarter).  Nothing in the backward couples the columns of a row — m, 1/l and delta
+// are per-row constants — so more, narrower row threads only add warps for the schedulers to hide MUFU / TMEM latency with.
 __device__ __forceinline__ uint32_t make_idesc() {
   uint32_t idesc = 0;
   idesc |= 1u << 4;                       // D = f32
@@ -175,11 +187,13 @@ struct FwdParams {
 __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *sQ = smem, *sK = sQ + kBig, *sV = sK + kSmall, *sP = sV + kSmall;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + kPBytes);
-  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s0 = bars + 3, *bar_s1 = bars + 4, *bar_p = bars + 5,
-           *bar_o = bars + 6;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
+  // K_j / V_j double-buffered (buffer j & 1); the weights never touch shared memory: the row threads rewrite the S
+  // accumulator tile in tensor memory in place and the PV product reads its A operand from there
+  uint8_t *sQ = smem, *sK = sQ + kBig, *sV = sK + 2 * kSmall;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sV + 2 * kSmall);
+  uint64_t *bar_q = bars, *bar_k = bars + 1 /*[2]*/, *bar_v = bars + 3 /*[2]*/, *bar_s = bars + 5 /*[2]*/, *bar_p = bars + 7 /*[2]*/,
+           *bar_o = bars + 9 /*[2]*/;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int work = blockIdx.x;
@@ -197,20 +211,14 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
     tma_prefetch_desc(&P.tma_q);
     tma_prefetch_desc(&P.tma_k);
     tma_prefetch_desc(&P.tma_v);
-    mbar_init(bar_q, 1);
-    mbar_init(bar_k, 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_s0, 1);
-    mbar_init(bar_s1, 1);
-    mbar_init(bar_p, 4);
-    mbar_init(bar_o, 1);
+    for (int i = 0; i < 11; ++i) mbar_init(bars + i, (i == 7 || i == 8) ? 4 : 1);   // bar_p: one arrival per row warp
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;        // S0 @0, S1 @64, PV0 @128, PV1 @192
+  const uint32_t tmem = *tmem_slot;        // S0 / P0 @0, S1 / P1 @64, PV0 @128, PV1 @192
 
   if (warp == 0) {
     // ===================== TMA producers: lane 0 streams K tiles, lane 1 streams V tiles =====================
@@ -219,48 +227,49 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
     if (lane == 0 && nkv > 0) {
       mbar_expect_tx(bar_q, kBig);
       load_kmajor(sQ, &P.tma_q, bar_q, q0, h, b, kBig / 2);
-      uint32_t ph_s0 = 0, ph_s1 = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < nkv; ++j) {
-        if (j > 0) {                                              // S_{j-1} retired → sK is free
-          if ((j - 1) & 1) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
-        }
-        mbar_expect_tx(bar_k, kSmall);
-        load_kmajor(sK, &P.tma_k, bar_k, j * kCols, h, b, kSmall / 2);
+        const int buf = j & 1;
+        if (j >= 2) { mbar_wait(bar_s + buf, (ph >> buf) & 1u); ph ^= 1u << buf; }   // S_{j-2} retired → buffer free
+        mbar_expect_tx(bar_k + buf, kSmall);
+        load_kmajor(sK + buf * kSmall, &P.tma_k, bar_k + buf, j * kCols, h, b, kSmall / 2);
       }
     } else if (lane == 1 && nkv > 0) {
-      uint32_t ph_o = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < nkv; ++j) {
-        if (j > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }         // PV_{j-1} retired → sV is free
-        mbar_expect_tx(bar_v, kSmall);
-        load_mnmajor(sV, &P.tma_v, bar_v, j * kCols, h, b);
+        const int buf = j & 1;
+        if (j >= 2) { mbar_wait(bar_o + buf, (ph >> buf) & 1u); ph ^= 1u << buf; }   // PV_{j-2} retired → buffer free
+        mbar_expect_tx(bar_v + buf, kSmall);
+        load_mnmajor(sV + buf * kSmall, &P.tma_v, bar_v + buf, j * kCols, h, b);
       }
     }
   } else if (warp == 1) {
     if (nkv > 0) {   // the whole warp, converged: see umma_e
       // ===================== MMA issuer =====================
+      // S_{j+1} is issued before the wait for P_j, so the score products stay one block ahead of the row threads.  It
+      // overwrites P_{j-1}: the PV product that read it was issued earlier by this same thread (the tensor pipe runs a
+      // thread's instructions in order), and the row threads delivered P_{j-1} before that.
       const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
       uint32_t ph_k = 0, ph_v = 0, ph_p = 0;
       mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, ph_k); ph_k ^= 1;
+      mbar_wait(bar_k, 0); ph_k ^= 1u;
       tc_fence_after();
       mma_kk(tmem, aQ, kBig / 2, aK, kSmall / 2, idesc, false);
-      commit_e(bar_s0);
+      commit_e(bar_s);
       for (int j = 0; j < nkv; ++j) {
-        const int cur = j & 1;
+        const int cur = j & 1, nxt = cur ^ 1;
         if (j + 1 < nkv) {
-          // S_{j+1} into the other TMEM buffer while the row threads are still busy with S_j (they released
-          // that buffer when they delivered P_{j-1})
-          mbar_wait(bar_k, ph_k); ph_k ^= 1;
+          mbar_wait(bar_k + nxt, (ph_k >> nxt) & 1u); ph_k ^= 1u << nxt;
           tc_fence_after();
-          mma_kk(tmem + (cur ? 0u : 64u), aQ, kBig / 2, aK, kSmall / 2, idesc, false);
-          commit_e(cur ? bar_s0 : bar_s1);
+          mma_kk(tmem + nxt * 64u, aQ, kBig / 2, aK + nxt * kSmall, kSmall / 2, idesc, false);
+          commit_e(bar_s + nxt);
         }
-        mbar_wait(bar_v, ph_v); ph_v ^= 1;
-        mbar_wait(bar_p, ph_p); ph_p ^= 1;                       // P_j is in smem; PV_{j-1} has been folded in
+        mbar_wait(bar_v + cur, (ph_v >> cur) & 1u); ph_v ^= 1u << cur;
+        mbar_wait(bar_p + cur, (ph_p >> cur) & 1u); ph_p ^= 1u << cur;   // P_j is in tensor memory; PV_{j-2} has been folded in
         tc_fence_after();
-        mma_kmn(tmem + 128u + (cur ? 64u : 0u), aP, aV, idesc_mn, false);
-        commit_e(bar_o);
+        mma_tmn(tmem + 128u + cur * 64u, tmem + cur * 64u, aV + cur * kSmall, idesc_mn, false);
+        commit_e(bar_o + cur);
       }
     }
   } else if (warp >= 2) {
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
     const int causal_limit = row + (P.Sk - P.Sq);
     const uint8_t *mrow = P.mask ? P.mask + (int64_t)b * P.m_sb + (int64_t)h * P.m_sh + (int64_t)row * P.m_ss : nullptr;
     const float scale2 = P.scale * kLog2e, mask2 = P.mask_value * kLog2e;
-    uint32_t ph_s0 = 0, ph_s1 = 0, ph_o = 0;
+    uint32_t ph_s = 0, ph_o = 0;
     float m = -kFltMax, l = 0.0f, alpha_prev = 1.0f;
     float o[HD];
 #pragma unroll
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
         for (int q = 0; q < 16; ++q)
           mw[q] = (j * kCols + q * 4 < P.Sk) ? __ldg(reinterpret_cast<const uint32_t *>(mrow + j * kCols) + q) : 0u;
       }
-      if (cur) { mbar_wait(bar_s1, ph_s1); ph_s1 ^= 1; } else { mbar_wait(bar_s0, ph_s0); ph_s0 ^= 1; }
+      mbar_wait(bar_s + cur, (ph_s >> cur) & 1u); ph_s ^= 1u << cur;
       tc_fence_after();
       // Two passes over the S tile in TMEM (reads are ~free next to the exp math) keep 32 instead of 64 score
       // registers live beside the 64-wide output accumulator: pass 1 row max, pass 2 weights.
@@ -352,7 +361,6 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
       }
       const float m_new = fmaxf(m, bm);               // m starts at -FLT_MAX: the finfo.min clamp (attention.rs:70-72)
       const float alpha = ex2(m - m_new);
-      if (j > 0) { mbar_wait(bar_o, ph_o); ph_o ^= 1; }          // PV_{j-1} retired: sP is free, PV buffer readable
       float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
@@ -379,18 +387,20 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
             acc1 += s[c + 1];
           }
         }
+        uint32_t pb[32];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          store_a_chunk(sP + kb * (kPBytes / 2), r_in, q, make_float4(s[q * 4], s[q * 4 + 1], s[q * 4 + 2], s[q * 4 + 3]));
+        for (int c = 0; c < 32; ++c) pb[c] = __float_as_uint(s[c]);
+        tmem_st32(ts + kb * 32, pb);                               // P_j over S_j, in place
       }
       l = l * alpha + (acc0 + acc1);
       m = m_new;
-      fence_proxy_async();
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
+      if (lane == 0) mbar_arrive(bar_p + cur);
       if (j > 0) {
         // fold PV_{j-1} (other TMEM buffer) into the register accumulator while the tensor core runs block j
+        mbar_wait(bar_o + (cur ^ 1), (ph_o >> (cur ^ 1)) & 1u); ph_o ^= 1u << (cur ^ 1);
         tc_fence_after();
         const uint32_t to = tmem + 128u + (cur ? 0u : 64u) + lane_addr;
 #pragma unroll
@@ -409,7 +419,7 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
     const float rinv = __frcp_rn(l_fin);
     float *orow = P.out + (int64_t)b * P.o_sb + (int64_t)h * P.o_sh + (int64_t)row * P.o_ss;
     if (nkv > 0) {
-      mbar_wait(bar_o, ph_o); ph_o ^= 1;
+      mbar_wait(bar_o + ((nkv - 1) & 1), (ph_o >> ((nkv - 1) & 1)) & 1u);
       tc_fence_after();
       const uint32_t to = tmem + 128u + (((nkv - 1) & 1) ? 64u : 0u) + lane_addr;
 #pragma unroll
@@ -456,18 +466,6 @@ struct BwdParams {
 };
 
 
-// D[128 x 64] (+)= A[128 x 64] (tensor memory: lanes = rows, 64 consecutive columns) · B[64 k x 64 n] (MN-major smem tile)
-__device__ __forceinline__ void mma_tmn(uint32_t tmem_d, uint32_t tmem_a, uint32_t b, uint32_t idesc_mn, bool accumulate) {
-#pragma unroll
-  for (int k = 0; k < kCols / 8; ++k) {
-    const uint64_t db = make_desc(b + (k >> 2) * 8192 + (k & 3) * 1024, 4096, 512, 1);
-    umma_ts_e(tmem_d, tmem_a + k * 8, db, idesc_mn, (accumulate || k) ? 1u : 0u);
-  }
-}
-
-// PARTS row threads share a query row, CW = 64 / PARTS score columns each (PARTS x 4 row warps: a TMEM lane quarter is
-// reachable from warps w with w % 4 == quarter).  Nothing in the backward couples the columns of a row — m, 1/l and delta
-// are per-row constants — so more, narrower row threads only add warps for the schedulers to hide MUFU / TMEM latency with.
 #ifdef FA_TRACE
 // debug build (-DFA_TRACE): block 0 prints, per role and key block, the SM clock at which each wait completed / each
 // product was issued, relative to the start of the role code — the pipeline's actual timeline
@@ -1051,7 +1049,7 @@ extern "C" int32_t b200_launch_attention_flash(const b200_tensor *q, const b200_
   P.mask_value = (float)mask_value;
   const int64_t ctas = B * H * P.q_blocks;
   B200_REQUIRE(ctas < (1ll << 31), B200_ERR_UNSUPPORTED, "attention grid too large");
-  const size_t smem = 1024 + fa::kBig + 2 * fa::kSmall + fa::kPBytes + 128;
+  const size_t smem = 1024 + fa::kBig + 4 * fa::kSmall + 128;
   if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_fwd_kernel), smem, true)) != B200_OK) return st;
   fa::flash_fwd_kernel<<<(unsigned)ctas, 192, smem, resolve_stream(s)>>>(P);
   B200_LAUNCH_CHECK();
