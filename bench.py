@@ -440,13 +440,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": "configs[1]: fused chain mask_fill(gelu(a*b+c),m,0) + sum_dim(1) + sum_dim(0) + "
-                            "mean_dim(1) + argmax(1) + sum on [8192,8192] f32, per GPU",
-                "algorithmic_bytes_per_step": sb,
-                "l2": "inputs (1.14 GB per step) exceed the 126 MB L2; no explicit flush",
-                "parallelism": f"replicas x{world} (independent shards, no data-path collective)",
-            },
+            "config": bench_config(world, sb),
             "e2e": {"value": round(world * sb / (e2e_ms / args.steps * 1e-3) / 1e9, 2), "unit": "GB/s",
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": res_bytes,
                     "ms_per_step": round(e2e_ms / args.steps, 3),
@@ -561,6 +555,17 @@ def cpu_reference_run(rows: int, reps: int, arrays=None):
             "variants": variants, "host_cores_available": os.cpu_count()}
 
 
+def bench_config(world: int, sb: int) -> dict:
+    """`config` of the JSON line — one definition for both arms, so the driver compares like with like."""
+    return {
+        "workload": "configs[1]: fused chain mask_fill(gelu(a*b+c),m,0) + sum_dim(1) + sum_dim(0) + "
+                    "mean_dim(1) + argmax(1) + sum on [8192,8192] f32, per GPU",
+        "algorithmic_bytes_per_step": sb,
+        "l2": "inputs (1.14 GB per step) exceed the 126 MB L2; no explicit flush",
+        "parallelism": f"replicas x{world} (independent shards, no data-path collective)",
+    }
+
+
 def run_reference(args, rank: int, world: int):
     """The reference's CPU implementation of the path (restatement: no cargo here), all host threads it can use: the
     op-by-op step on independent row shards, one worker per core.  Each timed step is the full [8192, 8192] workload
@@ -594,13 +599,15 @@ def run_reference(args, rank: int, world: int):
     sb = step_bytes(rows, N_COLS)
     value = round(sb / sec / 1e9, 3)
     sample = (f"each step = the configs[1] workload on a [{rows}, {N_COLS}] f32 sample ({sb} algorithmic bytes), "
-              f"burn-ndarray restatement oracle/ndarray_oracle.c (gcc -O3 -march=native), op-by-op, {cores} threads over row shards")
+              f"CPU restatement of burn-ndarray oracle/ndarray_oracle.c (the Rust reference cannot be built here: no cargo, "
+              f"un-vendored crates), gcc -O3 -march=native, op-by-op, {cores} threads over row shards")
     line = {
         "impl": "reference", "metric": "fused elemwise/reduce GB/s vs HBM", "value": value, "unit": "GB/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] on the CPU restatement of burn-ndarray (the Rust reference cannot be "
-                               "built here: no cargo, un-vendored crates)", "sample_rows": rows},
+        # the arm's config IS the GPU arm's (same workload, same keys); what differs — the CPU restatement, the bounded
+        # sample when the step count asks for it — is in cpu_baseline.sample
+        "config": bench_config(world, step_bytes(N_ROWS, N_COLS)),
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
