@@ -49,7 +49,8 @@ using namespace mm;
 // Every mbarrier wait of these kernels is bounded: a protocol error traps (the launch fails with an error the host sees)
 // instead of hanging the device.  The try_wait carries a suspend-time hint, so a waiting thread sleeps in hardware until
 // the phase completes instead of polling — polls of the producer / issuer / early row warps compete with the row warps'
-// arithmetic for issue slots (a seven-instruction poll loop cost the forward kernel 35 %).
+// arithmetic for issue slots (a seven-instruction poll loop cost the forward kernel 35 %).  Hint 20 us x 2^19 polls: a
+// wedged wait traps after at most ~10 s; a real wait (microseconds) completes inside its first sleep.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n.reg .pred p;\n.reg .u32 n;\nmov.u32 n, 0;\n"
@@ -61,7 +62,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "@p bra FA_WAIT_LOOP;\n"
       "trap;\n"
       "FA_WAIT_DONE:\n}\n" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680u), "r"(1u << 24)
+      "r"(parity), "r"(20000u), "r"(1u << 19)
       : "memory");
 }
 
