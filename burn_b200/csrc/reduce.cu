@@ -531,7 +531,7 @@ static int32_t launch_fast(bool col, const fast::RowParams &rp, const fast::ColP
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = cp.splits;
+  attr[0].val.clusterDim.y = cp.partials ? 1 : cp.splits;      // partial-row mode: plain grid, no cluster combine
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
@@ -539,6 +539,23 @@ static int32_t launch_fast(bool col, const fast::RowParams &rp, const fast::ColP
   else if (cp.tx == 16) B200_CUDA(cudaLaunchKernelEx(&cfg, fast::reduce_col_fast_kernel<K, 16>, cp));
   else B200_CUDA(cudaLaunchKernelEx(&cfg, fast::reduce_col_fast_kernel<K, 8>, cp));
   B200_LAUNCH_CHECK();
+  if (cp.partials) {
+    // finish: [outer, splits <= 64, inner] -> [outer, inner] with the same tiled kernel (8 column-vectors x 32 row groups
+    // per CTA, no split); the mean divides by the full R.  Fixed order: replicas stay bit-identical.
+    fast::ColParams fp = cp;
+    fp.x = cp.partials;
+    fp.R = cp.splits;
+    fp.partials = nullptr;
+    fp.tx = 8;
+    fp.splits = 1;
+    fp.rows_per_split = fp.R;
+    cfg.gridDim = dim3(cp.outer * ((cp.inner4 + 7) / 8), 1, 1);
+    cfg.blockDim = dim3(8, fast::kBlock / 8, 1);
+    attr[0].val.clusterDim.y = 1;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, fast::reduce_col_fast_kernel<K, 8>, fp));
+    B200_LAUNCH_CHECK();
+    count_launch(1);
+  }
   return B200_OK;
 }
 
@@ -619,9 +636,31 @@ static int32_t try_fast_reduce(int32_t kind, int64_t outer, int64_t R, int64_t i
     const uint32_t tiles = cp.outer * ((cp.inner4 + tx - 1) / tx);
     uint32_t splits = 1;
     while (splits < 8 && tiles * splits < (uint32_t)sms * 6u && cp.R / (splits * 2) >= 64u) splits *= 2;
-    cp.splits = splits;
-    cp.rows_per_split = (cp.R + splits - 1) / splits;
-    grid = tiles;
+    // (measured, ncu launch list: [16384, 512] 16.6 us as a 128-CTA cluster launch, 8.5 + 4.1 us this way; at 256 cluster
+    //  CTAs — [8192, 1024] — the two-kernel form no longer wins, hence the < sms bound)
+    if (K == fast::kSum && tiles * 8u < (uint32_t)sms && cp.R >= 4096u) {
+      // tall and narrow: more row splits than a cluster holds -> partial rows + the short-axis finisher
+      uint32_t tx2 = 32;
+      while (tx2 > 8 && cp.outer * ((cp.inner4 + tx2 - 1) / tx2) * 64u < (uint32_t)sms * 2u) tx2 /= 2;
+      const uint32_t tiles2 = cp.outer * ((cp.inner4 + tx2 - 1) / tx2);
+      uint32_t s2 = std::min<uint32_t>(64u, ((uint32_t)sms * 4u + tiles2 - 1) / tiles2);
+      s2 = std::max(1u, std::min(s2, cp.R / 64u));
+      if (s2 > 8) {
+        cp.tx = tx2;
+        splits = s2;
+        const size_t pbytes = sizeof(float) * (size_t)cp.outer * s2 * (size_t)inner;
+        B200_CUDA(cudaMallocAsync(&ws, pbytes, stream));
+        cp.partials = reinterpret_cast<float *>(ws);
+        cp.splits = splits;
+        cp.rows_per_split = (cp.R + splits - 1) / splits;
+        grid = tiles2;
+      }
+    }
+    if (!cp.partials) {
+      cp.splits = splits;
+      cp.rows_per_split = (cp.R + splits - 1) / splits;
+      grid = tiles;
+    }
     const uint64_t colvecs = (uint64_t)cp.outer * cp.inner4;
     if (cp.R <= 64u && colvecs >= (uint64_t)sms * fast::kBlock * 2u) {
       cp.tx = 0;

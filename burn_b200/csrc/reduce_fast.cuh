@@ -308,6 +308,7 @@ struct ColParams {
   int32_t mean;
   float div;
   uint32_t tx;                 // column-vectors per CTA (32, 16 or 8)
+  float *partials;             // sum kinds, tall narrow inputs: [outer, splits, inner] partial sums instead of a cluster combine
 };
 
 // blockDim = (32, 8): 32 column-vectors (128 columns, 512 B per row) x 8 row
@@ -365,6 +366,16 @@ __global__ void __launch_bounds__(kBlock) reduce_col_fast_kernel(const ColParams
       a[j] = b;
       cta_result[threadIdx.x][j] = b;
     }
+  }
+  if (P.partials) {
+    // Tall, narrow inputs ([16384, 512] bias gradients): a cluster holds at most 8 row splits, i.e. 128 CTAs for 16 column
+    // tiles — under one CTA per SM and 2 TB/s.  Up to 64 splits write partial rows here and the short-axis kernel
+    // (reduce_col_short_kernel, fixed order) finishes them.
+    if (threadIdx.y == 0 && col_ok) {
+      float4 r = make_float4(a[0].v, a[1].v, a[2].v, a[3].v);
+      reinterpret_cast<float4 *>(P.partials)[((size_t)o * P.splits + blockIdx.y) * P.inner4 + c4] = r;
+    }
+    return;
   }
   if (P.splits > 1) {
     cgf::cluster_group cluster = cgf::this_cluster();

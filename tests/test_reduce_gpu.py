@@ -254,3 +254,18 @@ def test_large_fuse_on_read_reductions(dev, shape, axis, kind):
     n = shape[axis]
     abs_tol = {"sum": 2e-7 * n, "mean": 2e-7, "max": 2e-7, "min": 2e-7}[kind]     # erf 1-ulp allowance per element
     H.assert_close(out.numpy(), want, H.REL_REDUCE, abs_tol, f"fused {kind} over axis {axis} of {shape}")
+
+
+@pytest.mark.parametrize("shape", [(16384, 512), (8192, 1024), (4100, 768), (2, 8192, 256)])
+@pytest.mark.parametrize("kind", ["sum", "mean"])
+def test_tall_narrow_column_sums(dev, shape, kind):
+    """Bias-gradient shapes ([tokens, d_model] summed over the tokens): more row splits than a cluster holds, written as
+    partial rows and finished by the short-axis kernel (reduce_fast.cuh, ColParams::partials).  Against the oracle's
+    sum_axis / mean_axis (crates/burn-ndarray/src/ops/base.rs sum_dim / mean_dim)."""
+    x = rnd(shape, seed=31)
+    axis = len(shape) - 2
+    code = abi.RED_SUM if kind == "sum" else abi.RED_MEAN
+    got = reduce_axis(code, x, axis)
+    want = (oracle.float_sum_dim if kind == "sum" else oracle.float_mean_dim)(x, axis)
+    n = shape[axis]
+    H.assert_close(got, want, H.REL_REDUCE, 1e-6 * n if kind == "sum" else 1e-6, f"{kind} over axis {axis} of {shape}")
