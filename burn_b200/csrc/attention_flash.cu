@@ -198,8 +198,12 @@ __global__ void __launch_bounds__(192, 2) flash_fwd_kernel(const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int work = blockIdx.x;
-  const int qb = P.q_blocks - 1 - (work % P.q_blocks);      // heavy (late, under a causal mask) query blocks first
-  const int bh = work / P.q_blocks, h = bh % P.H, b = bh / P.H;
+  // Launch order = work order, globally: ALL heads' heaviest (latest, under a causal mask) query blocks first, so the
+  // hardware's in-order CTA dispatch is longest-processing-time-first list scheduling (per-head interleaving left the
+  // SMs that drew a heavy block last ~12 % behind; K/V locality across a head's blocks was measured not to matter)
+  const int n_bh = P.B * P.H;
+  const int qb = P.q_blocks - 1 - (work / n_bh);
+  const int bh = work % n_bh, h = bh % P.H, b = bh / P.H;
   const int q0 = qb * kRows;
   const int nkv_all = (P.Sk + kCols - 1) / kCols;
   int nkv = nkv_all;
@@ -497,8 +501,9 @@ __global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_kernel(cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int work = blockIdx.x;
-  const int qb = P.blocks - 1 - (work % P.blocks);
-  const int bh = work / P.blocks, h = bh % P.H, b = bh / P.H;
+  const int n_bh = P.B * P.H;                                        // heaviest blocks of all heads first (see flash_fwd_kernel)
+  const int qb = P.blocks - 1 - (work / n_bh);
+  const int bh = work % n_bh, h = bh % P.H, b = bh / P.H;
   const int q0 = qb * kRows;
   const int nkv_all = (P.Sk + kCols - 1) / kCols;
   int nkv = nkv_all;
@@ -739,6 +744,325 @@ __global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_kernel(cons
   }
 }
 
+// ---------------------------------------------------------------------------------- persistent dQ kernel
+// One CTA per SM walks a STATIC, balanced list of (batch, head, query block) items: the items sorted by work (under a
+// causal mask the late query blocks see the most keys), dealt to the CTAs in snake order — for [8,16,1024,64] causal the
+// heaviest CTA gets 64 key blocks against a mean of 62.3.  Barriers, the tensor-memory allocation and the tile rings
+// live for the whole kernel and every role runs the same item sequence, so the K/V prefetch, the first S / dP products
+// and the Q / dO / O loads of item n+1 overlap the last blocks and the dQ read-out of item n.  With one CTA per
+// (b, h, block) the per-CTA fixed cost (190 KB of prologue loads under load, allocation, the final barrier, the launch
+// order's imbalance) weighs most under a causal mask.  Measured on [8,16,1024,64]: causal 104 -> 94 us, unmasked 132 -> 137 us;
+// on the encoder's [64,8,256,64]: backward 162 -> 154 us.  B200_FA_PERSIST=0 selects the one-CTA-per-item kernel.
+struct DqItem {
+  int q0, h, b, nkv;
+  bool valid;
+};
+__device__ __forceinline__ DqItem dq_item(const BwdParams &P, int round) {
+  DqItem it;
+  const int G = (int)gridDim.x, c = (int)blockIdx.x;
+  const int n_bh = P.B * P.H, total = n_bh * P.blocks;
+  // (a head-major order — the eight blocks of a head on neighbouring CTAs, for L2 locality of K / V — was measured: no
+  //  faster without a mask, 12 % slower with the causal one, whose imbalance it brings back)
+  const int pos = round * G + ((round & 1) ? G - 1 - c : c);
+  it.valid = pos < total;
+  const int level = it.valid ? pos / n_bh : 0;               // 0 = heaviest
+  const int bh = it.valid ? pos - level * n_bh : 0;
+  const int qb = P.blocks - 1 - level;
+  it.q0 = qb * kRows;
+  it.h = bh % P.H;
+  it.b = bh / P.H;
+  const int nkv_all = (P.Sk + kCols - 1) / kCols;
+  it.nkv = nkv_all;
+  if (causal_skip(P.causal, P.Sq, P.Sk, P.mask_value)) {
+    const int last_col = min(P.Sk - 1, it.q0 + kRows - 1 + (P.Sk - P.Sq));
+    it.nkv = last_col < 0 ? 0 : min(nkv_all, last_col / kCols + 1);
+  }
+  return it;
+}
+
+template <int PARTS>
+__global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_persist_kernel(const __grid_constant__ BwdParams P) {
+  constexpr int CW = kCols / PARTS;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *sQ = smem, *sdO = sQ + kBig, *sO = sdO + kBig, *sKk = sO + kBig, *sVk = sKk + 2 * kSmall, *sKmn = sVk + 2 * kSmall;
+  float *sDelta = reinterpret_cast<float *>(sKmn + 2 * kSmall);      // [PARTS][128] partial row sums
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sDelta + PARTS * kRows);
+  // per item: bar_q, bar_do, bar_ot (tiles landed), bar_ofree (rows are done with the dO / O tiles: delta computed),
+  // bar_done (all dQ products of the item retired), bar_dqfree (rows have read the dQ accumulator);
+  // per key block, by TMEM buffer / tile stage g & 1 (g counts key blocks across items): bar_kv, bar_mn, bar_s, bar_o, bar_p
+  uint64_t *bar_q = bars, *bar_do = bars + 1, *bar_ot = bars + 2, *bar_ofree = bars + 3, *bar_done = bars + 4, *bar_dqfree = bars + 5,
+           *bar_kv = bars + 6 /*[2]*/, *bar_mn = bars + 8 /*[2]*/, *bar_s = bars + 10 /*[2]*/, *bar_o = bars + 12 /*[2]*/,
+           *bar_p = bars + 14 /*[2]*/;
+  constexpr int kBars = 16;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_items = P.B * P.H * P.blocks;
+  const int rounds = (total_items + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&P.tma_q);
+    tma_prefetch_desc(&P.tma_do);
+    tma_prefetch_desc(&P.tma_k);
+    tma_prefetch_desc(&P.tma_v);
+    tma_prefetch_desc(&P.tma_mn0);
+    tma_prefetch_desc(&P.tma_mn1);
+    for (int i = 0; i < kBars; ++i) {
+      uint32_t count = 1;
+      if (i == 3 || i == 5 || i >= 14) count = 4 * PARTS;    // bar_ofree, bar_dqfree, bar_p: one arrival per row warp
+      else if (i == 10 || i == 11) count = 2;                // bar_s: the S and the dP issuer commit
+      mbar_init(bars + i, count);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;        // S0 @0, S1 @64, dP0 / dS0 @128, dP1 / dS1 @192, dQ @256
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // K-major stream (K_g, V_g into stage g & 1: free when S_{g-2} and dP_{g-2} retired) + the per-item tiles
+      uint32_t ph_s = 0, ph_of = 0;
+      int s_waited = 0;                    // bar_s completions consumed so far (key blocks 0 .. s_waited-1, in order)
+      auto wait_s_upto = [&](int x) {      // the S and dP products of key block x (and all earlier ones) have retired
+        while (s_waited <= x) {
+          const int bf = s_waited & 1;
+          mbar_wait(bar_s + bf, (ph_s >> bf) & 1u);
+          ph_s ^= 1u << bf;
+          ++s_waited;
+        }
+      };
+      int g = 0, n = 0;
+      for (int r = 0; r < rounds; ++r) {
+        const DqItem it = dq_item(P, r);
+        if (!it.valid) break;
+        if (it.nkv == 0) continue;
+        for (int j = 0; j < it.nkv; ++j) {
+          const int gb = g + j, buf = gb & 1;
+          if (gb >= 2) wait_s_upto(gb - 2);
+          mbar_expect_tx(bar_kv + buf, 2 * kSmall);
+          load_kmajor(sKk + buf * kSmall, &P.tma_k, bar_kv + buf, j * kCols, it.h, it.b, kSmall / 2);
+          load_kmajor(sVk + buf * kSmall, &P.tma_v, bar_kv + buf, j * kCols, it.h, it.b, kSmall / 2);
+          if (j == 0) {
+            // the item's own tiles, after its first K/V block (whose stage frees earlier): sQ / sdO were read by the S /
+            // dP products of the previous item (all retired once block g-1 has), sdO / sO by its row threads (delta)
+            if (n > 0) {
+              wait_s_upto(g - 1);
+              mbar_wait(bar_ofree, ph_of);
+              ph_of ^= 1u;
+            }
+            mbar_expect_tx(bar_q, kBig);
+            load_kmajor(sQ, &P.tma_q, bar_q, it.q0, it.h, it.b, kBig / 2);
+            mbar_expect_tx(bar_do, kBig);
+            load_kmajor(sdO, &P.tma_do, bar_do, it.q0, it.h, it.b, kBig / 2);
+            mbar_expect_tx(bar_ot, kBig);
+            load_kmajor(sO, &P.tma_mn1, bar_ot, it.q0, it.h, it.b, kBig / 2);
+          }
+        }
+        g += it.nkv;
+        ++n;
+      }
+    } else if (lane == 1) {
+      // MN-major K stream (stage g & 1: free when the dQ product of block g-2 retired)
+      uint32_t ph = 0;
+      int g = 0;
+      for (int r = 0; r < rounds; ++r) {
+        const DqItem it = dq_item(P, r);
+        if (!it.valid) break;
+        for (int j = 0; j < it.nkv; ++j) {
+          const int gb = g + j, buf = gb & 1;
+          if (gb >= 2) { mbar_wait(bar_o + buf, (ph >> buf) & 1u); ph ^= 1u << buf; }
+          mbar_expect_tx(bar_mn + buf, kSmall);
+          load_mnmajor(sKmn + buf * kSmall, &P.tma_mn0, bar_mn + buf, j * kCols, it.h, it.b);
+        }
+        g += it.nkv;
+      }
+    }
+  } else if (warp <= 3) {
+    // issuer warps (whole warps, converged: see umma_e), one product each
+    const uint32_t idesc = make_idesc(), idesc_mn = idesc | (1u << 16);
+    uint32_t ph_a = 0, ph_b = 0, ph_item = 0;
+    int g = 0, n = 0;
+    for (int r = 0; r < rounds; ++r) {
+      const DqItem it = dq_item(P, r);
+      if (!it.valid) break;
+      if (it.nkv == 0) continue;
+      if (warp == 1) {
+        const uint32_t aQ = smem_u32(sQ), aKk = smem_u32(sKk);
+        mbar_wait(bar_q, ph_item);
+        for (int j = 0; j < it.nkv; ++j) {
+          const int gb = g + j, buf = gb & 1;
+          mbar_wait(bar_kv + buf, (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
+          if (gb >= 2) { mbar_wait(bar_p + buf, (ph_b >> buf) & 1u); ph_b ^= 1u << buf; }   // rows have read S_{g-2}
+          tc_fence_after();
+          mma_kk(tmem + buf * 64u, aQ, kBig / 2, aKk + buf * kSmall, kSmall / 2, idesc, false);           // S = Q·Kᵀ
+          commit_e(bar_s + buf);
+        }
+      } else if (warp == 2) {
+        const uint32_t adO = smem_u32(sdO), aVk = smem_u32(sVk);
+        mbar_wait(bar_do, ph_item);
+        for (int j = 0; j < it.nkv; ++j) {
+          const int gb = g + j, buf = gb & 1;
+          mbar_wait(bar_kv + buf, (ph_a >> buf) & 1u); ph_a ^= 1u << buf;
+          if (gb >= 2) { mbar_wait(bar_o + buf, (ph_b >> buf) & 1u); ph_b ^= 1u << buf; }   // dQ_{g-2} has read dS_{g-2}
+          tc_fence_after();
+          mma_kk(tmem + 128u + buf * 64u, adO, kBig / 2, aVk + buf * kSmall, kSmall / 2, idesc, false);   // dP = dO·Vᵀ
+          commit_e(bar_s + buf);
+        }
+      } else {
+        const uint32_t aKmn = smem_u32(sKmn);
+        if (n > 0) mbar_wait(bar_dqfree, ph_item ^ 1u);               // the rows have read the previous item's dQ
+        for (int j = 0; j < it.nkv; ++j) {
+          const int gb = g + j, cur = gb & 1;
+          mbar_wait(bar_mn + cur, (ph_a >> cur) & 1u); ph_a ^= 1u << cur;
+          mbar_wait(bar_p + cur, (ph_b >> cur) & 1u); ph_b ^= 1u << cur;   // dS_g is in tensor memory (over dP_g)
+          tc_fence_after();
+          mma_tmn(tmem + 256u, tmem + 128u + cur * 64u, aKmn + cur * kSmall, idesc_mn, j > 0);   // dQ += dS·K
+          commit_e(bar_o + cur);
+        }
+        commit_e(bar_done);
+      }
+      g += it.nkv;
+      ++n;
+      ph_item ^= 1u;
+    }
+  } else {
+    const int quarter = warp & 3, part = (warp - 4) >> 2;
+    const int r_in = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float scale2 = P.scale * kLog2e, mask2 = P.mask_value * kLog2e;
+    uint32_t ph_s = 0, ph_item = 0;
+    int g = 0;
+    for (int r = 0; r < rounds; ++r) {
+      const DqItem it = dq_item(P, r);
+      if (!it.valid) break;
+      const int row = it.q0 + r_in;
+      const bool row_ok = row < P.Sq;
+      float *grow_out = P.g0 + (int64_t)it.b * P.g0_sb + (int64_t)it.h * P.g0_sh + (int64_t)row * P.g0_ss + part * CW;
+      if (it.nkv == 0) {
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < CW / 4; ++q) reinterpret_cast<uint4 *>(grow_out)[q] = make_uint4(0, 0, 0, 0);
+        }
+        continue;
+      }
+      const int causal_limit = row + (P.Sk - P.Sq);
+      const uint8_t *mrow = P.mask ? P.mask + (int64_t)it.b * P.m_sb + (int64_t)it.h * P.m_sh + (int64_t)row * P.m_ss : nullptr;
+      float4 *stat = P.stats + ((int64_t)it.b * P.H + it.h) * P.Sq + row;
+      float nm2 = 0.0f, rinv = 0.0f, delta = 0.0f;
+      float4 st4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok) st4 = *stat;                                       // in flight while the tiles land
+      {
+        // delta = sum_d dO[row, d] * O[row, d] from the two tiles in shared memory (see flash_bwd_dq_kernel)
+        mbar_wait(bar_do, ph_item);
+        mbar_wait(bar_ot, ph_item);
+        const int c_first = part * CW;
+        const uint8_t *pd = sdO + (c_first >> 5) * (kBig / 2) + r_in * 128, *po = sO + (c_first >> 5) * (kBig / 2) + r_in * 128;
+        float psum = 0.0f;
+#pragma unroll
+        for (int qq = 0; qq < CW / 4; ++qq) {
+          const int q = ((c_first & 31) >> 2) + qq;
+          const int off = (q ^ (r_in & 7)) << 4;
+          const float4 gg = *reinterpret_cast<const float4 *>(pd + off), ov = *reinterpret_cast<const float4 *>(po + off);
+          psum = __fadd_rn(psum, __fadd_rn(__fadd_rn(__fmul_rn(ov.x, gg.x), __fmul_rn(ov.y, gg.y)),
+                                           __fadd_rn(__fmul_rn(ov.z, gg.z), __fmul_rn(ov.w, gg.w))));
+        }
+        sDelta[part * kRows + r_in] = psum;
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * PARTS) : "memory");   // the row warps: all partial sums are visible
+#pragma unroll
+        for (int pp = 0; pp < PARTS; ++pp) delta = __fadd_rn(delta, sDelta[pp * kRows + r_in]);
+        if (lane == 0) mbar_arrive(bar_ofree);                       // this warp no longer reads the dO / O tiles
+      }
+      if (row_ok) {
+        nm2 = -st4.x;
+        rinv = st4.y;
+        if (part == 0) stat->z = delta;    // the dK/dV kernel (launched after this one) reads it per query column
+      }
+      for (int j = 0; j < it.nkv; ++j) {
+        const int cur = (g + j) & 1;
+        const int col0 = j * kCols + part * CW;
+        uint32_t masked = 0;                                         // bit c: column col0 + c is masked
+        if (mrow && row_ok) {
+#pragma unroll
+          for (int q = 0; q < CW / 4; ++q) {
+            if (col0 + q * 4 < P.Sk) {
+              const uint32_t mw = __ldg(reinterpret_cast<const uint32_t *>(mrow + col0) + q);
+              if (mw & 0xFFu) masked |= 1u << (q * 4);
+              if (mw & 0xFF00u) masked |= 2u << (q * 4);
+              if (mw & 0xFF0000u) masked |= 4u << (q * 4);
+              if (mw & 0xFF000000u) masked |= 8u << (q * 4);
+            }
+          }
+        }
+        if (P.causal && col0 + CW - 1 > causal_limit) {
+          const int first = causal_limit + 1 - col0;                 // first masked column of this chunk
+          masked |= first <= 0 ? 0xFFFFFFFFu : (first >= 32 ? 0u : (0xFFFFFFFFu << first));
+        }
+        const bool fast = (col0 + CW <= P.Sk) && !__any_sync(0xffffffffu, masked != 0u);
+        mbar_wait(bar_s + cur, (ph_s >> cur) & 1u); ph_s ^= 1u << cur;
+        tc_fence_after();
+        const uint32_t t_dp = tmem + 128u + cur * 64u + lane_addr + part * CW;
+        uint32_t rs[CW], rp[CW];
+        tmem_ldn(tmem + cur * 64u + lane_addr + part * CW, rs);
+        tmem_ldn(t_dp, rp);
+        tmem_ld_wait();
+        if (fast) {
+#pragma unroll
+          for (int c = 0; c < CW; ++c) {
+            const float p = __fmul_rn(ex2(__fmaf_rn(__uint_as_float(rs[c]), scale2, nm2)), rinv);
+            rp[c] = __float_as_uint(__fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), delta)));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < CW; ++c) {
+            const bool mk = (masked >> c) & 1u;
+            const float t = mk ? __fadd_rn(mask2, nm2) : __fmaf_rn(__uint_as_float(rs[c]), scale2, nm2);
+            float p = __fmul_rn(ex2(t), rinv);
+            if (col0 + c >= P.Sk) p = 0.0f;
+            const float d = __fmul_rn(p, __fsub_rn(__uint_as_float(rp[c]), delta));
+            rp[c] = __float_as_uint(mk ? 0.0f : d);                 // mask_fill backward: no gradient through a filled score
+          }
+        }
+        tmem_stn(t_dp, rp);                                         // dS over dP, in place
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p + cur);
+      }
+      {
+        mbar_wait(bar_done, ph_item);                               // every dQ product of the item has retired
+        tc_fence_after();
+        uint32_t rq[CW];
+        tmem_ldn(tmem + 256u + lane_addr + part * CW, rq);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dqfree);                     // the accumulator may be overwritten by the next item
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < CW / 4; ++q)
+            reinterpret_cast<float4 *>(grow_out)[q] =
+                make_float4(__fmul_rn(__uint_as_float(rq[q * 4]), P.scale), __fmul_rn(__uint_as_float(rq[q * 4 + 1]), P.scale),
+                            __fmul_rn(__uint_as_float(rq[q * 4 + 2]), P.scale), __fmul_rn(__uint_as_float(rq[q * 4 + 3]), P.scale));
+        }
+      }
+      g += it.nkv;
+      ph_item ^= 1u;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 constexpr int kDkvThreads = 13 * 32;   // TMA warp, four issuer warps (one product each), 8 row warps
 
 __global__ void __launch_bounds__(kDkvThreads, 1) flash_bwd_dkv_kernel(const __grid_constant__ BwdParams P) {
@@ -759,8 +1083,9 @@ __global__ void __launch_bounds__(kDkvThreads, 1) flash_bwd_dkv_kernel(const __g
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int work = blockIdx.x;
-  const int kb_ = work % P.blocks;                                  // early key tiles see the most queries under a causal mask
-  const int bh = work / P.blocks, h = bh % P.H, b = bh / P.H;
+  const int n_bh = P.B * P.H;             // early key tiles see the most queries under a causal mask: all heads' first
+  const int kb_ = work / n_bh;
+  const int bh = work % n_bh, h = bh % P.H, b = bh / P.H;
   const int kv0 = kb_ * kRows;
   const int nq = (P.Sq + kCols - 1) / kCols;
   int i_start = 0;
@@ -1110,6 +1435,15 @@ extern "C" int32_t b200_launch_attention_flash_backward(const b200_tensor *d_out
     constexpr int kParts = 2;   // 8 row warps (16 measured 3 % slower: the tensor pipe and the tile traffic bound this kernel, not the row math)
     const size_t smem = 1024 + 3 * fa::kBig + 6 * fa::kSmall + kParts * fa::kRows * 4 + 128;
     if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dq_kernel<kParts>), smem)) != B200_OK) return st;
+    static const bool persist = [] { const char *e = std::getenv("B200_FA_PERSIST"); return !(e && e[0] == '0'); }();
+    // where it was measured to win: causal masks (balance) and short key loops (per-item cost dominates)
+    const bool skip_blocks = P.causal && !(Sq > Sk && P.mask_value > -INFINITY);
+    if (persist && (skip_blocks || (Sk + fa::kCols - 1) / fa::kCols <= 8)) {
+      const size_t psmem = smem + 64;
+      if ((st = ensure_dyn_smem(reinterpret_cast<const void *>(fa::flash_bwd_dq_persist_kernel<kParts>), psmem)) != B200_OK) return st;
+      const unsigned grid = (unsigned)std::min<int64_t>(ctas, sm_count());
+      fa::flash_bwd_dq_persist_kernel<kParts><<<grid, 128 + 128 * kParts, psmem, stream>>>(P);
+    } else
     fa::flash_bwd_dq_kernel<kParts><<<(unsigned)ctas, 128 + 128 * kParts, smem, stream>>>(P);
     B200_LAUNCH_CHECK();
   }

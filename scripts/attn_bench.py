@@ -6,7 +6,7 @@ from burn_b200 import _abi as abi, device as dv, ops
 from burn_b200.device import DeviceTensor, TapeBuilder
 from tests import helpers as H
 dv.init(0); lib = abi.load()
-B, Hh, S, dk = 8, 16, 1024, 64
+B, Hh, S, dk = (int(x) for x in os.environ.get("ATTN_SHAPE", "8,16,1024,64").split(","))
 rng = np.random.default_rng(0)
 heads = lambda: H.up((rng.standard_normal((B, S, Hh * dk)) * 0.5).astype(np.float32)).reshape((B, S, Hh, dk)).swap_dims(1, 2)
 q, k, v = heads(), heads(), heads()
