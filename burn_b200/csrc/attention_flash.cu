@@ -22,6 +22,9 @@
 //   * mbarrier waits sleep in hardware (suspend-time hint) instead of polling, and are bounded (trap, not hang);
 //   * warp-uniform fast paths for blocks without any masked / out-of-range element; the softmax scale is applied
 //     once per dQ / dK element instead of once per dS element; delta comes from the TMA-staged O tile.
+//   * CTAs are dispatched heaviest-first over ALL heads (in-order dispatch = LPT list scheduling under a causal mask);
+//     the dQ kernel also exists as a persistent kernel (one CTA per SM, static balanced item deal, everything alive
+//     across items) that the host picks for causal masks and short key loops.
 //
 //   flash_fwd_kernel   CTA = 128 query rows, loop over 64-key blocks.  S_j = Q·K_jᵀ lands in one of two TMEM
 //                      buffers (S_{j+1} is issued before the row threads have finished S_j), online softmax:
