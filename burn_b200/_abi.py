@@ -34,7 +34,7 @@ LOG1P_F SQRT_F RECIP_F SIN_F COS_F TAN_F TANH_F ERF_F FLOOR_F CEIL_F ROUND_F TRU
 COSH_F ASIN_F ACOS_F ATAN_F ASINH_F ACOSH_F ATANH_F SIGMOID_F CLAMP_F EQ_F NE_F LT_F LE_F GT_F GE_F
 ISNAN_F ISINF_F ADD_I SUB_I MUL_I DIV_I REM_I MIN_I MAX_I NEG_I ABS_I SIGN_I AND_I OR_I XOR_I NOT_I
 SHL_I SHR_I CLAMP_I EQ_I NE_I LT_I LE_I GT_I GE_I AND_B OR_B XOR_B NOT_B SELECT F2I I2F B2F B2I F2B
-I2B""".split()
+I2B REMT_F""".split()
 OP = {name: i for i, name in enumerate(_OPCODES)}
 OP_COUNT = len(_OPCODES)
 

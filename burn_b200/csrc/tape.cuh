@@ -401,7 +401,7 @@ static inline int op_arity(int op) {
   switch (op) {
     case B200_OP_ADD_F: case B200_OP_SUB_F: case B200_OP_MUL_F: case B200_OP_DIV_F:
     case B200_OP_REM_F: case B200_OP_POW_F: case B200_OP_MIN_F: case B200_OP_MAX_F:
-    case B200_OP_ATAN2_F:
+    case B200_OP_ATAN2_F: case B200_OP_REMT_F:
     case B200_OP_EQ_F: case B200_OP_NE_F: case B200_OP_LT_F: case B200_OP_LE_F:
     case B200_OP_GT_F: case B200_OP_GE_F:
     case B200_OP_ADD_I: case B200_OP_SUB_I: case B200_OP_MUL_I: case B200_OP_DIV_I:
@@ -517,6 +517,7 @@ __device__ __forceinline__ void run_tape(const TapeParams &p, const SlotFile<VEC
         break;
       }
       case B200_OP_REM_F: B200_BIN(rem_floor(x, y)) break;
+      case B200_OP_REMT_F: B200_BIN(rem_tensor(x, y)) break;
       case B200_OP_POW_F: B200_BIN(pow_f(x, y)) break;
       case B200_OP_MIN_F: B200_BIN((x != x || y != y) ? __int_as_float(0x7fc00000) : fminf(x, y)) break;
       case B200_OP_MAX_F: B200_BIN((x != x || y != y) ? __int_as_float(0x7fc00000) : fmaxf(x, y)) break;

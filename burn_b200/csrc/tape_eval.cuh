@@ -39,6 +39,7 @@ __device__ __forceinline__ uint32_t eval_op(uint32_t a, uint32_t b, uint32_t c) 
       return u_of(__fmul_rn(__fmul_rn(y, __fadd_rn(e, 1.0f)), 0.5f));
     }
     case B200_OP_REM_F: return u_of(rem_floor(x, y));
+    case B200_OP_REMT_F: return u_of(rem_tensor(x, y));
     case B200_OP_POW_F: return u_of(pow_f(x, y));
     case B200_OP_MIN_F: return u_of((x != x || y != y) ? __int_as_float(0x7fc00000) : fminf(x, y));
     case B200_OP_MAX_F: return u_of((x != x || y != y) ? __int_as_float(0x7fc00000) : fmaxf(x, y));

@@ -103,6 +103,12 @@ __device__ __forceinline__ float rem_floor(float x, float y) {
   return fmodf(fmodf(x, y) + y, y);
 }
 
+// tensor-tensor `remainder` of the reference: a - b*floor(a/b) in f64, then rounded (base.rs:909-922)
+__device__ __forceinline__ float rem_tensor(float x, float y) {
+  const double a = (double)x, b = (double)y;
+  return (float)__dsub_rn(a, __dmul_rn(b, floor(__ddiv_rn(a, b))));   // no FMA contraction: Rust rounds the product
+}
+
 __device__ __forceinline__ int32_t irem_floor(int32_t x, int32_t y) {
   if (y == 0) return 0;
   return ((x % y) + y) % y;

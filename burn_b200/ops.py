@@ -66,7 +66,7 @@ def float_add(a, b): return _binary("ADD_F", a, b)
 def float_sub(a, b): return _binary("SUB_F", a, b)
 def float_mul(a, b): return _binary("MUL_F", a, b)
 def float_div(a, b): return _binary("DIV_F", a, b)
-def float_remainder(a, b): return _binary("REM_F", a, b)
+def float_remainder(a, b): return _binary("REMT_F", a, b)   # tensor-tensor form: a - b*floor(a/b) in f64
 def float_powf(a, b): return _binary("POW_F", a, b)
 def float_add_scalar(a, s): return _scalar("ADD_F", a, s)
 def float_sub_scalar(a, s): return _scalar("SUB_F", a, s)

@@ -185,6 +185,10 @@ typedef enum {
   B200_OP_SELECT,
   /* casts (FuseOp::Assign with a dtype change; Rust `as` semantics) */
   B200_OP_F2I, B200_OP_I2F, B200_OP_B2F, B200_OP_B2I, B200_OP_F2B, B200_OP_I2B,
+  /* tensor-tensor float remainder: a - b*floor(a/b) evaluated in f64 (crates/burn-ndarray/src/ops/base.rs:909-922).
+   * The REM_F opcode above is remainder_scalar's ((x % y) + y) % y (base.rs:924-930); the two differ in rounding, in the sign of
+   * zero and for infinite divisors.  Appended so that the existing opcode values stay what they were. */
+  B200_OP_REMT_F,
   B200_OP_COUNT
 } b200_opcode;
 

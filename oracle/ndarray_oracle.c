@@ -36,7 +36,7 @@
 
 /* ---- elementwise -------------------------------------------------------- */
 /* op codes are private to the oracle (oracle/oracle.py mirrors them) */
-enum { O_ADD = 0, O_SUB, O_MUL, O_DIV, O_REM, O_POW, O_MIN, O_MAX };
+enum { O_ADD = 0, O_SUB, O_MUL, O_DIV, O_REM, O_POW, O_MIN, O_MAX, O_REMT };
 
 static inline float bin_f32(int op, float x, float y) {
   switch (op) {
@@ -44,8 +44,10 @@ static inline float bin_f32(int op, float x, float y) {
     case O_SUB: return x - y;
     case O_MUL: return x * y;
     case O_DIV: return x / y;
-    /* crates/burn-ndarray/src/ops/base.rs remainder: ((x % y) + y) % y */
+    /* crates/burn-ndarray/src/ops/base.rs:924-930 remainder_scalar: ((x % y) + y) % y */
     case O_REM: return fmodf(fmodf(x, y) + y, y);
+    /* crates/burn-ndarray/src/ops/base.rs:909-922 remainder (tensor-tensor): a - b*floor(a/b) in f64 */
+    case O_REMT: { const double a = (double)x, b = (double)y; return (float)(a - b * floor(a / b)); }
     case O_POW: return powf(x, y);
     case O_MIN: return (x != x || y != y) ? NAN : (x < y ? x : y);
     case O_MAX: return (x != x || y != y) ? NAN : (x > y ? x : y);

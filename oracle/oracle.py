@@ -26,7 +26,7 @@ LIB = HERE / "_build" / "libndarray_oracle.so"
 
 _lib = None
 
-_BIN = {"add": 0, "sub": 1, "mul": 2, "div": 3, "rem": 4, "pow": 5, "min": 6, "max": 7}
+_BIN = {"add": 0, "sub": 1, "mul": 2, "div": 3, "rem": 4, "pow": 5, "min": 6, "max": 7, "remt": 8}
 _UN = {n: i for i, n in enumerate(
     "exp log log1p sqrt tanh erf sin cos tan recip abs neg floor ceil round trunc sinh cosh asin "
     "acos atan asinh acosh atanh sign".split())}
@@ -108,7 +108,7 @@ def float_add(a, b): return _binary("add", a, b)
 def float_sub(a, b): return _binary("sub", a, b)
 def float_mul(a, b): return _binary("mul", a, b)
 def float_div(a, b): return _binary("div", a, b)
-def float_remainder(a, b): return _binary("rem", a, b)
+def float_remainder(a, b): return _binary("remt", a, b)    # base.rs:909-922 (the scalar form is a different formula)
 def float_powf(a, b): return _binary("pow", a, b)
 def float_add_scalar(a, s): return _binary_scalar("add", a, s)
 def float_sub_scalar(a, s): return _binary_scalar("sub", a, s)

@@ -43,6 +43,23 @@ def test_binary_broadcast(dev, sa, sb):
     H.assert_exact(H.binary("MUL_F", H.up(a), H.up(b)), oracle.float_mul(a, b), "mul broadcast")
 
 
+def test_tensor_remainder_is_the_f64_floor_form(dev):
+    """Tensor-tensor `remainder` is a - b*floor(a/b) evaluated in f64 (crates/burn-ndarray/src/ops/base.rs:909-922);
+    `remainder_scalar` is ((x % y) + y) % y (base.rs:924-930).  The two differ for infinite divisors, in the sign of
+    zero and in rounding — separate opcodes (REMT_F / REM_F), each bit-exact against the oracle; the literals of
+    crates/burn-backend-tests/tests/tensor/float/ops/remainder.rs:7-19,35-52 on top."""
+    a = np.concatenate([rnd((2000,), -20, 20), np.float32([5.0, -5.0, 7.5, -7.5, 0.0, -0.0, 1e30, 3.0, -3.0, 6.0])])
+    b = np.concatenate([rnd((2000,), 0.25, 4.0) * np.where(np.arange(2000) % 3 == 0, -1, 1).astype(np.float32),
+                        np.float32([np.inf, np.inf, -np.inf, 2.5, 3.0, 3.0, 7.0, -3.0, 3.0, -1.5])])
+    with np.errstate(all="ignore"):
+        want = oracle.float_remainder(a, b)
+        got = H.binary("REMT_F", H.up(a), H.up(b))
+        H.assert_exact(got, want, "tensor remainder")
+        H.assert_exact(H.binary_scalar("REM_F", H.up(a), -1.5), oracle.float_remainder_scalar(a, -1.5), "scalar remainder")
+    lhs, rhs = np.float32([-3.0, -2.0, -1.0, 1.0, 2.0, 3.0]), np.float32([2.0, 3.0, 1.0, 2.0, 1.0, 3.0])
+    H.assert_exact(H.binary("REMT_F", H.up(lhs), H.up(rhs)), np.float32([1.0, 1.0, 0.0, 1.0, 0.0, 0.0]))   # remainder.rs:7-19
+
+
 def test_scalar_ops(dev):
     a = rnd((5, 40))
     H.assert_exact(H.binary_scalar("ADD_F", H.up(a), 2.5), oracle.float_add_scalar(a, 2.5))

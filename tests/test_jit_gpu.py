@@ -46,7 +46,7 @@ run(tb, [da, db, dc, dm])
 for name in ["NEG_F", "ABS_F", "EXP_F", "LOG_F", "LOG1P_F", "SQRT_F", "RECIP_F", "TANH_F", "ERF_F", "FLOOR_F", "CEIL_F",
              "ROUND_F", "TRUNC_F", "SIGN_F", "SIGMOID_F", "SIN_F", "COS_F", "ATAN_F"]:
     run(TapeBuilder().op(name, ("in", 0), out=0), [dc if name in ("LOG_F", "SQRT_F") else da])
-for name in ["ADD_F", "SUB_F", "MUL_F", "DIV_F", "REM_F", "POW_F", "MIN_F", "MAX_F", "ATAN2_F"]:
+for name in ["ADD_F", "SUB_F", "MUL_F", "DIV_F", "REM_F", "REMT_F", "POW_F", "MIN_F", "MAX_F", "ATAN2_F"]:
     run(TapeBuilder().op(name, ("in", 0), ("in", 1), out=0), [dc if name == "POW_F" else da, db])
 for name in ["EQ_F", "NE_F", "LT_F", "LE_F", "GT_F", "GE_F"]:
     run(TapeBuilder().op(name, ("in", 0), ("in", 1), out=0), [da, db], dts=(abi.BOOL,))
