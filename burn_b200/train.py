@@ -172,6 +172,7 @@ def add(tape: Tape, a: Var, b: Var) -> Var:
 
 
 GELU_BWD_EXACT = os.environ.get("B200_GELU_BWD", "reference") == "exact"
+_SYNC_DEFER = os.environ.get("B200_SYNC_DEFER", "0") == "1"
 
 
 def gelu_backward_tape() -> TapeBuilder:
@@ -626,6 +627,7 @@ class ParamArena:
         self.peer, self.fused, self.opt = peer, bool(fused and peer is not None), None
         self.buckets: list[dict] = []
         self.slot: dict[int, dict] = {}
+        self._pending: list[dict] = []
         lib = abi.load()
         members, size = [], 0
         order = list(reversed(list(params)))
@@ -679,6 +681,15 @@ class ParamArena:
             p.g = p.grad_slot
         b["arrived"] += 1
         if b["arrived"] == b["n"]:
+            if _SYNC_DEFER:             # experiment: no overlap — every bucket's sync kernel fires after backward, in wait()
+                self._pending.append(b)
+                b["arrived"] = 0
+                return
+            self._fire(b)
+            b["arrived"] = 0
+
+    def _fire(self, b: dict) -> None:
+        if True:
             if self.fused:
                 # reduce-scatter → Adam on this rank's 1/N → all-gather of the new parameters, one kernel, beside backward.
                 # Safe to update p now: every backward consumer of these parameters has already been launched (a
@@ -695,7 +706,6 @@ class ParamArena:
             elif self.comm is not None:
                 self.comm.all_reduce(b["g"], mean=True)
                 abi.check(abi.load().b200_collective_mark(self.comm.handle, b["done"]))
-            b["arrived"] = 0
 
     def attach_optimizer(self, opt: "Adam") -> None:
         self.opt = opt
@@ -706,6 +716,9 @@ class ParamArena:
         for b in self.buckets:
             if b["arrived"]:
                 raise RuntimeError("a gradient bucket is incomplete: some parameter received no gradient")
+        for b in self._pending:
+            self._fire(b)
+        self._pending.clear()
 
     def fence(self, b: dict) -> None:
         """The compute stream waits for bucket b's all-reduce only."""
