@@ -136,7 +136,7 @@ extern "C" int32_t b200_comm_init(b200_comm *out, const uint8_t id[B200_NCCL_UNI
     B200_NCCL(g_nccl.CommInitRank(&c->comm, world_size, uid, rank));
     int lo = 0, hi = 0;
     B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    B200_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+    B200_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, coll_stream_priority(lo, hi)));
     B200_CUDA(cudaEventCreateWithFlags(&c->fence, cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
     return B200_OK;
@@ -190,7 +190,7 @@ extern "C" int32_t b200_comm_init_all(b200_comm *out, const int32_t *devices, in
       B200_CUDA(cudaSetDevice(devs[i]));
       int lo = 0, hi = 0;
       B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      B200_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+      B200_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, coll_stream_priority(lo, hi)));
       B200_CUDA(cudaEventCreateWithFlags(&c->fence, cudaEventDisableTiming));
       B200_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
     }

@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "burn_b200.h"
 
 namespace b200 {
@@ -15,6 +16,12 @@ int32_t fail_cuda(cudaError_t e, const char *what, const char *file, int line);
 cudaStream_t resolve_stream(b200_stream s);
 void count_launch(int n = 1);
 int sm_count();
+// Priority of the collective streams: highest by default (a bucket's sync starts the moment it is complete);
+// B200_COLL_PRIORITY=low makes them background streams — compute kernels get free SM slots first.
+static inline int coll_stream_priority(int lo, int hi) {
+  const char *e = getenv("B200_COLL_PRIORITY");
+  return (e && e[0] == 'l') ? lo : hi;
+}
 int max_smem_optin();
 // sticky device-side error flag (host-mapped pinned int32): kernels store one of these codes, the next
 // synchronising ABI call reports it as B200_ERR_SHAPE and clears it

@@ -241,7 +241,7 @@ static int32_t fill_common(Group *g, Args &A, uint64_t count, int32_t slot, int3
 static int32_t make_streams(Group *g) {
   int lo = 0, hi = 0;
   B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  B200_CUDA(cudaStreamCreateWithPriority(&g->stream, cudaStreamNonBlocking, hi));
+  B200_CUDA(cudaStreamCreateWithPriority(&g->stream, cudaStreamNonBlocking, coll_stream_priority(lo, hi)));
   B200_CUDA(cudaEventCreateWithFlags(&g->fence, cudaEventDisableTiming));
   B200_CUDA(cudaEventCreateWithFlags(&g->done, cudaEventDisableTiming));
   return B200_OK;
