@@ -100,7 +100,6 @@ constexpr int kRows = 128;                      // rows a CTA owns (= TMEM lanes
 constexpr int kCols = 64;                       // columns per loop iteration
 constexpr uint32_t kBig = kRows * HD * 4;       // [128 x 64] f32 tile: 32 KB
 constexpr uint32_t kSmall = kCols * HD * 4;     // [64 x 64] f32 tile: 16 KB
-constexpr uint32_t kPBytes = kRows * kCols * 4; // [128 x 64] f32 weights tile: 32 KB
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kFltMax = 3.402823466e+38f, kMinPos = 1.175494351e-38f;
 
@@ -132,15 +131,6 @@ __device__ __forceinline__ void mma_kk(uint32_t tmem_d, uint32_t a, uint32_t a_h
     umma_e(tmem_d, da, db, idesc, (accumulate || k) ? 1u : 0u);
   }
 }
-// D[128 x 64] (+)= A[128 x 64] (K-major, halves kPBytes/2 apart) · B[64 k x 64 n] (MN-major tile)
-__device__ __forceinline__ void mma_kmn(uint32_t tmem_d, uint32_t a, uint32_t b, uint32_t idesc_mn, bool accumulate) {
-#pragma unroll
-  for (int k = 0; k < kCols / 8; ++k) {
-    const uint64_t da = make_desc(a + (k >> 2) * (kPBytes / 2) + (k & 3) * 32, 16, 1024);
-    const uint64_t db = make_desc(b + (k >> 2) * 8192 + (k & 3) * 1024, 4096, 512, 1);
-    umma_e(tmem_d, da, db, idesc_mn, (accumulate || k) ? 1u : 0u);
-  }
-}
 // D[128 x 64] (+)= A[128 x 64] (tensor memory: lanes = rows, 64 consecutive columns) · B[64 k x 64 n] (MN-major smem tile)
 __device__ __forceinline__ void mma_tmn(uint32_t tmem_d, uint32_t tmem_a, uint32_t b, uint32_t idesc_mn, bool accumulate) {
 #pragma unroll
@@ -161,10 +151,6 @@ __device__ __forceinline__ uint32_t make_idesc() {
   idesc |= (uint32_t)(kCols >> 3) << 17;  // N = 64
   idesc |= (uint32_t)(kRows >> 4) << 24;  // M = 128
   return idesc;
-}
-// K-major A operand, 128-byte swizzle: 16-byte chunk q of row r lives at chunk q ^ (r & 7)
-__device__ __forceinline__ void store_a_chunk(uint8_t *tile_half, int r_in, int q, float4 v) {
-  *reinterpret_cast<float4 *>(tile_half + r_in * 128 + ((q ^ (r_in & 7)) << 4)) = v;
 }
 
 // Key blocks entirely above the causal diagonal are skipped: a filled score contributes 2^(fill - max) = 0
@@ -747,6 +733,9 @@ __global__ void __launch_bounds__(128 + 128 * PARTS, 1) flash_bwd_dq_kernel(cons
   }
 }
 
+// (The row-thread block bodies of the persistent kernels repeat those of the per-item kernels on purpose: factored into
+//  shared device functions — tried — the per-item dK/dV kernel compiled 10 % slower, 140 -> 155 us, from a different
+//  register allocation around the 64 live score registers.)
 // ---------------------------------------------------------------------------------- persistent dQ kernel
 // One CTA per SM walks a STATIC, balanced list of (batch, head, query block) items: the items sorted by work (under a
 // causal mask the late query blocks see the most keys), dealt to the CTAs in snake order — for [8,16,1024,64] causal the

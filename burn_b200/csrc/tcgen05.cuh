@@ -203,16 +203,6 @@ __device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&r)[32]) { tm
 __device__ __forceinline__ void tmem_stn(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
 __device__ __forceinline__ void tmem_stn(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st32(taddr, r); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem] · B[smem descriptor], tf32: the A operand (M = 128 rows = TMEM lanes, K = 8 consecutive 32-bit
-// columns per instruction) is read from tensor memory — the layout an accumulator tile has, so a tile that the row
-// threads rewrote in place (weights over scores) feeds the next product without a trip through shared memory
-__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
