@@ -140,3 +140,17 @@ def test_flash_full_config4_shape(dev):
         want = grads_reference(q[sl], k[sl], v[sl], g[sl], None, 0.125, -1.0e9, True)
         for got, ref in zip((gq[sl], gk[sl], gv[sl]), want):
             assert np.abs(got - ref).max() <= 3e-3 * np.abs(ref).max()
+
+
+def test_per_item_backward_kernels_stay_covered(dev):
+    """The host picks the persistent dQ / dK/dV kernels for causal masks and short loops; B200_FA_PERSIST=0 (read once
+    per process) forces the one-CTA-per-item kernels for every shape.  Run the causal backward cases under it in a child
+    process so that both kernel families are held to the float64 reference."""
+    import os, subprocess, sys
+    env = dict(os.environ, B200_FA_PERSIST="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-m", "gpu", "-q", "-x", "--timeout", "100",
+                        "-k", "test_flash_backward_matches_reference and causal", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=300,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
