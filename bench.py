@@ -413,6 +413,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             enc = train_bench.run("encoder", steps=args.train_steps, warmup=3, rank=rank, world=world,
                                   local_rank=local_rank, mm="tf32", use_graph=True, init_device=False, sync=grad_sync)
             train["encoder_configs3"] = {k: enc[k] for k in ("value", "unit", "ms_per_step", "model_tflops_per_s", "config")}
+            if world > 1:
+                # what the gradient sync costs, measured on the same GPUs in the same run: every rank repeats the LM step
+                # WITHOUT synchronisation (local Adam, world = 1 code path); exposed = synced step - slowest local step
+                solo = train_bench.run("lm", steps=args.train_steps, warmup=3, rank=rank, world=1, local_rank=local_rank,
+                                       mm="tf32", use_graph=True, init_device=False, sync=None)
+                solo_ms = max_over_ranks(float(solo["ms_per_step"]))
+                train["no_sync_ms_per_step"] = round(solo_ms, 3)
+                train["exposed_sync_ms"] = round(float(train["ms_per_step"]) - solo_ms, 3)
+                train["efficiency_vs_no_sync"] = round(solo_ms / float(train["ms_per_step"]), 4)
+                train["sync_path"] = ("fused / peer: the library's own kernels over NVLink peer memory, no NCCL on the data path"
+                                      if grad_sync in (None, "fused", "peer") else
+                                      "nccl: ncclAllReduce(avg) per bucket (observed on this pool: ring, LL128, 32 channels)")
             if world == 1:
                 train["mnist_fc_head_configs0"] = train_bench.run_fc_head()
         except Exception as e:  # the headline metric above stands on its own
